@@ -1,0 +1,973 @@
+// libhyperb200.so -- C-ABI (include/hyperb200.h) over the sm_100a kernels.
+// Host-side bookkeeping mirrors what the reference's CeresOptimizer keeps in ceres::Problem
+// (reference internal/hyper/optimizers/ceres/optimizer.cpp:189-382) but flattened: one set of
+// device arrays per variable family and two factor lists.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/hyperb200.h"
+#include "hb200_solve.cuh"
+
+using namespace hb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define HB_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t err__ = (expr);                                                                         \
+    if (err__ != cudaSuccess) return fail(100 + static_cast<int>(err__), "%s: %s", #expr, cudaGetErrorString(err__)); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+void compute_basis(Basis* b, int k) {
+  // Blending matrix of the uniform B-spline of order k and its cumulative form.
+  auto binom = [](int n, int r) { double v = 1; if (r < 0 || r > n) return 0.0; for (int i = 1; i <= r; ++i) v = v * (n - r + i) / i; return v; };
+  double M[kMaxOrder][kMaxOrder];
+  double fact = 1;
+  for (int i = 2; i <= k - 1; ++i) fact *= i;
+  for (int s = 0; s < k; ++s)
+    for (int n = 0; n < k; ++n) {
+      double sum = 0;
+      for (int l = s; l <= k - 1; ++l) {
+        double pw = 1;
+        for (int i = 0; i < k - 1 - n; ++i) pw *= static_cast<double>(k - 1 - l);
+        sum += ((l - s) % 2 ? -1.0 : 1.0) * binom(k, l - s) * pw;
+      }
+      M[s][n] = binom(k - 1, n) / fact * sum;
+    }
+  b->k = k;
+  for (int j = 0; j < k; ++j)
+    for (int n = 0; n < k; ++n) {
+      double s = 0;
+      for (int r = j; r < k; ++r) s += M[r][n];
+      b->Mc[j * k + n] = s;
+    }
+}
+
+}  // namespace
+
+struct hb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool use_graph = true;
+  int num_sms = 0;
+  long long launches = 0;
+  long long launches_per_iteration = 0;
+
+  // window state (index 0 = current, 1 = trial)
+  int k = 0, K = 0, kb = 4, Kbg = 0, Kba = 0, C = 0, L = 0;
+  Basis basis{}, bias_basis{};
+  DevBuf<double> knots[2], bg[2], ba[2], grav[2], lms[2], tab[2];
+  DevBuf<double> cams, imu, cam_tab, imu_tab;
+  DevBuf<unsigned char> fixed;
+  std::vector<unsigned char> h_knot_const;
+  int gravity_const = 0, bias_const = 0;
+  bool have_imu = false, have_gravity = false;
+  double huber = 0.5, imu_scale = 1.6e-5, radius0 = 1e4;
+
+  // factors (host copies in user order; device copies in bound order)
+  int Nv = 0, Ni = 0;
+  std::vector<double> h_v_stamp, h_v_pixel, h_i_stamp, h_i_meas;
+  std::vector<int> h_v_cam, h_v_lm;
+  DevBuf<double> v_stamp, v_pixel, i_stamp, i_meas;
+  DevBuf<int> v_cam, v_lm;
+  DevBuf<int4> v_idx, i_idx;
+  std::vector<int4> h_v_idx, h_i_idx;       // bound order
+  std::vector<int> v_perm, i_perm;          // bound position -> user index
+  DevBuf<int> seg_off, run_off, lm_off, lm_obs, d_invalid;
+  int nseg = 0, nruns = 0, max_rows = 6;
+  bool bound = false;
+
+  // outputs
+  DevBuf<double> v_r, v_Jp, v_Jl, i_r, i_Jp, i_wg, i_wa, i_Jg;
+  DevBuf<double> cp_pix[2], cp_imu[2];
+  int n_pix_blocks = 0, n_imu_blocks = 0;
+  bool evaluated_J = false;
+  // host mirror for hb200_factor_evaluate
+  bool mirror_valid = false;
+  std::vector<double> m_v_r, m_v_Jp, m_v_Jl, m_i_r, m_i_Jp, m_i_wg, m_i_wa, m_i_Jg, m_grav;
+
+  // system
+  int n = 0;
+  DevBuf<double> sys, D, Lw, Ldiag, dp, dl, Vinv, gl, Dl, lm_part, scal;
+  DevBuf<int> spd;
+  DevBuf<SolverState> st, records;
+  int max_records = 64;
+  int n_lm_blocks = 0;
+  bool system_built = false;
+
+  hb200_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_valid = false;
+
+  int o_bg() const { return 6 * K; }
+  int o_ba() const { return 6 * K + 3 * Kbg; }
+  int o_g() const { return 6 * K + 3 * Kbg + 3 * Kba; }
+  void invalidate() { graph_valid = false; system_built = false; evaluated_J = false; mirror_valid = false; }
+};
+
+namespace {
+
+int check_launch(hb200_ctx* c, const char* what) {
+  c->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(100 + static_cast<int>(e), "launch %s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+#define HB_LAUNCH(ctx, what)                       \
+  do {                                             \
+    int rc__ = check_launch(ctx, what);            \
+    if (rc__) return rc__;                         \
+  } while (0)
+
+int update_fixed(hb200_ctx* c) {
+  c->n = 6 * c->K + 3 * c->Kbg + 3 * c->Kba + 2;
+  std::vector<unsigned char> f(c->n, 0);
+  for (int j = 0; j < c->K && j < static_cast<int>(c->h_knot_const.size()); ++j)
+    if (c->h_knot_const[j]) for (int a = 0; a < 6; ++a) f[6 * j + a] = 1;
+  if (c->bias_const) for (int a = c->o_bg(); a < c->o_g(); ++a) f[a] = 1;
+  if (c->gravity_const) { f[c->o_g()] = 1; f[c->o_g() + 1] = 1; }
+  HB_CUDA(c->fixed.ensure(c->n));
+  HB_CUDA(cudaMemcpyAsync(c->fixed.p, f.data(), c->n, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ensure_system(hb200_ctx* c) {
+  const size_t n = c->n;
+  const size_t T = (n + kCholNB - 1) / kCholNB;
+  HB_CUDA(c->sys.ensure(n * n + 3 * n + 2));
+  HB_CUDA(c->D.ensure(n));
+  HB_CUDA(c->Lw.ensure((T * kCholNB + 1) * n));
+  HB_CUDA(c->Ldiag.ensure(T * kCholNB * kCholNB));
+  HB_CUDA(c->dp.ensure(n));
+  HB_CUDA(c->dl.ensure(3 * static_cast<size_t>(std::max(c->L, 1))));
+  HB_CUDA(c->Vinv.ensure(9 * static_cast<size_t>(std::max(c->L, 1))));
+  HB_CUDA(c->gl.ensure(3 * static_cast<size_t>(std::max(c->L, 1))));
+  HB_CUDA(c->Dl.ensure(3 * static_cast<size_t>(std::max(c->L, 1))));
+  c->n_lm_blocks = (c->L + 127) / 128;
+  HB_CUDA(c->lm_part.ensure(2 * static_cast<size_t>(std::max(c->n_lm_blocks, 1))));
+  HB_CUDA(c->scal.ensure(4));
+  HB_CUDA(c->spd.ensure(1));
+  HB_CUDA(c->records.ensure(c->max_records));
+  return 0;
+}
+
+int reset_solver_state(hb200_ctx* c) {
+  SolverState s{};
+  s.radius = c->radius0; s.decrease_factor = 2.0; s.spd = 1;
+  HB_CUDA(c->st.ensure(1));
+  HB_CUDA(cudaMemcpyAsync(c->st.p, &s, sizeof(s), cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- kernel dispatch on (order, bias order) -------------------------------------------------
+template <int K, bool J>
+int launch_pixel(hb200_ctx* c, int sel) {
+  if (c->Nv == 0) return 0;
+  PixelArgs a{};
+  a.n = c->Nv; a.stamp = c->v_stamp.p; a.pixel = reinterpret_cast<const double2*>(c->v_pixel.p); a.idx = c->v_idx.p;
+  a.tab = c->tab[sel].p; a.cam_tab = c->cam_tab.p; a.landmarks = c->lms[sel].p;
+  a.r = J ? c->v_r.p : nullptr; a.Jp = c->v_Jp.p; a.Jl = c->v_Jl.p; a.cost_partial = c->cp_pix[J ? 0 : 1].p; a.huber = c->huber; a.K_knots = c->K;
+  pixel_eval_kernel<K, J><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
+  HB_LAUNCH(c, "pixel_eval_kernel");
+  return 0;
+}
+template <int K, bool J>
+int launch_inertial(hb200_ctx* c, int sel) {
+  if (c->Ni == 0) return 0;
+  InertialArgs a{};
+  a.n = c->Ni; a.stamp = c->i_stamp.p; a.meas = c->i_meas.p; a.idx = c->i_idx.p; a.tab = c->tab[sel].p; a.imu_tab = c->imu_tab.p;
+  a.bg = c->bg[sel].p; a.ba = c->ba[sel].p; a.gravity = c->grav[sel].p;
+  a.r = J ? c->i_r.p : nullptr; a.Jp = c->i_Jp.p; a.wg = c->i_wg.p; a.wa = c->i_wa.p; a.Jg = c->i_Jg.p;
+  a.cost_partial = c->cp_imu[J ? 0 : 1].p; a.loss_scale = c->imu_scale;
+  inertial_eval_kernel<K, 4, J><<<c->n_imu_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis, c->bias_basis);
+  HB_LAUNCH(c, "inertial_eval_kernel");
+  return 0;
+}
+
+int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel) {
+  prep_kernel<<<(c->K + 63) / 64, 64, 0, c->stream>>>(c->K, c->knots[sel].p, c->tab[sel].p);
+  HB_LAUNCH(c, "prep_kernel");
+  int rc = 0;
+  if (c->k == 4) { rc = want_J ? launch_pixel<4, true>(c, sel) : launch_pixel<4, false>(c, sel); if (rc) return rc; rc = want_J ? launch_inertial<4, true>(c, sel) : launch_inertial<4, false>(c, sel); }
+  else if (c->k == 6) { rc = want_J ? launch_pixel<6, true>(c, sel) : launch_pixel<6, false>(c, sel); if (rc) return rc; rc = want_J ? launch_inertial<6, true>(c, sel) : launch_inertial<6, false>(c, sel); }
+  else return fail(-4, "spline order %d not supported (4 or 6)", c->k);
+  return rc;
+}
+
+int enqueue_build(hb200_ctx* c) {
+  const size_t n = c->n;
+  HB_CUDA(cudaMemsetAsync(c->sys.p, 0, (n * n + 3 * n + 2) * sizeof(double), c->stream));
+  if (c->Nv) {
+    if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n);
+    else pixel_hessian_kernel<6><<<c->nseg, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n);
+    HB_LAUNCH(c, "pixel_hessian_kernel");
+  }
+  if (c->Ni) {
+    if (c->k == 4)
+      inertial_hessian_kernel<4, 4><<<c->nruns, kHessThreads, 0, c->stream>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g());
+    else
+      inertial_hessian_kernel<6, 4><<<c->nruns, kHessThreads, 0, c->stream>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g());
+    HB_LAUNCH(c, "inertial_hessian_kernel");
+  }
+  diag_cost_kernel<<<std::max(1, (c->n + 255) / 256), 256, 0, c->stream>>>(c->sys.p, c->n, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p,
+                                                                         c->Ni ? c->n_imu_blocks : 0);
+  HB_LAUNCH(c, "diag_cost_kernel");
+  if (c->Nv && c->L) {
+    const size_t smem = 2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double);
+    if (c->k == 4)
+      schur_kernel<4><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber, c->st.p,
+                                                                c->sys.p, c->n, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
+    else
+      schur_kernel<6><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber, c->st.p,
+                                                                c->sys.p, c->n, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
+    HB_LAUNCH(c, "schur_kernel");
+  }
+  return 0;
+}
+
+int enqueue_finalize(hb200_ctx* c) {
+  const size_t total = static_cast<size_t>(c->n + 1) * c->n;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(c->num_sms) * 8));
+  finalize_kernel<<<blocks, 256, 0, c->stream>>>(c->sys.p, c->n, c->st.p, c->fixed.p, c->D.p, c->Lw.p, c->spd.p);
+  HB_LAUNCH(c, "finalize_kernel");
+  return 0;
+}
+
+int enqueue_solve(hb200_ctx* c) {
+  {
+    int n = c->n;
+    double* Lw = c->Lw.p; double* Ld = c->Ldiag.p; int* spd = c->spd.p;
+    void* args[] = {&Lw, &Ld, &n, &spd};
+    const int T = (n + kCholNB - 1) / kCholNB;
+    const long long tiles = static_cast<long long>(T) * (T + 1) / 2 + T;
+    int blocks = static_cast<int>(std::min<long long>(c->num_sms, std::max<long long>(1, (tiles + kCholWarps - 1) / kCholWarps)));
+    HB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cholesky_kernel), dim3(blocks), dim3(kCholThreads), args, kCholSmem, c->stream));
+    c->launches += 1;
+  }
+  backsolve_kernel<<<1, 1024, 0, c->stream>>>(c->Lw.p, c->Ldiag.p, c->n, c->dp.p);
+  HB_LAUNCH(c, "backsolve_kernel");
+  if (c->L) {
+    if (c->Nv) {
+      if (c->k == 4)
+        lm_backsub_kernel<4><<<c->n_lm_blocks, 128, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber,
+                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p);
+      else
+        lm_backsub_kernel<6><<<c->n_lm_blocks, 128, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber,
+                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p);
+      HB_LAUNCH(c, "lm_backsub_kernel");
+    } else {
+      HB_CUDA(cudaMemsetAsync(c->dl.p, 0, 3 * static_cast<size_t>(c->L) * sizeof(double), c->stream));
+      HB_CUDA(cudaMemsetAsync(c->lm_part.p, 0, 2 * static_cast<size_t>(c->n_lm_blocks) * sizeof(double), c->stream));
+    }
+  }
+  return 0;
+}
+
+int enqueue_retract(hb200_ctx* c) {
+  const int m = std::max(std::max(c->K, c->L), std::max(std::max(c->Kbg, c->Kba), 1));
+  retract_kernel<<<(m + 127) / 128, 128, 0, c->stream>>>(c->K, c->Kbg, c->Kba, c->L, c->dp.p, c->dl.p, c->knots[0].p, c->bg[0].p, c->ba[0].p, c->grav[0].p,
+                                                        c->lms[0].p, c->knots[1].p, c->bg[1].p, c->ba[1].p, c->grav[1].p, c->lms[1].p);
+  HB_LAUNCH(c, "retract_kernel");
+  return 0;
+}
+
+int enqueue_scalars(hb200_ctx* c) {
+  scalars_kernel<<<1, 256, 0, c->stream>>>(c->cp_pix[1].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[1].p, c->Ni ? c->n_imu_blocks : 0, c->lm_part.p,
+                                          (c->L && c->Nv) ? c->n_lm_blocks : 0, c->scal.p);
+  HB_LAUNCH(c, "scalars_kernel");
+  return 0;
+}
+
+int enqueue_accept(hb200_ctx* c) {
+  accept_kernel<<<1, 256, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records);
+  HB_LAUNCH(c, "accept_kernel");
+  struct Item { size_t count; const double* src; double* dst; };
+  const Item items[] = {{8 * static_cast<size_t>(c->K), c->knots[1].p, c->knots[0].p}, {4 * static_cast<size_t>(c->Kbg), c->bg[1].p, c->bg[0].p},
+                        {4 * static_cast<size_t>(c->Kba), c->ba[1].p, c->ba[0].p},      {3, c->grav[1].p, c->grav[0].p},
+                        {3 * static_cast<size_t>(c->L), c->lms[1].p, c->lms[0].p}};
+  for (const Item& it : items) {
+    if (!it.count) continue;
+    const int blocks = static_cast<int>(std::min<size_t>((it.count + 255) / 256, static_cast<size_t>(c->num_sms) * 4));
+    commit_kernel<<<blocks, 256, 0, c->stream>>>(c->st.p, it.count, it.src, it.dst);
+    HB_LAUNCH(c, "commit_kernel");
+  }
+  return 0;
+}
+
+// One LM iteration enqueued on the stream; the two optional all-reduce callbacks split it in three
+// graph-capturable segments.
+int enqueue_segment(hb200_ctx* c, int segment) {
+  int rc = 0;
+  if (segment == 0) {
+    if ((rc = enqueue_evaluate(c, true, 0))) return rc;
+    if ((rc = enqueue_build(c))) return rc;
+  } else if (segment == 1) {
+    if ((rc = enqueue_finalize(c))) return rc;
+    if ((rc = enqueue_solve(c))) return rc;
+    if ((rc = enqueue_retract(c))) return rc;
+    if ((rc = enqueue_evaluate(c, false, 1))) return rc;
+    if ((rc = enqueue_scalars(c))) return rc;
+  } else {
+    if ((rc = enqueue_accept(c))) return rc;
+  }
+  return 0;
+}
+
+int check_ready(hb200_ctx* c) {
+  if (!c) return fail(-1, "null context");
+  if (c->K == 0) return fail(-2, "spline not set");
+  if (!c->bound) return fail(-2, "factors not bound (call hb200_bind)");
+  if (c->Ni && (!c->have_imu || !c->have_gravity || c->Kbg == 0 || c->Kba == 0)) return fail(-2, "inertial factors need IMU calibration, bias splines and gravity");
+  if (c->Nv && (c->C == 0 || c->L == 0)) return fail(-2, "pixel factors need cameras and landmarks");
+  return 0;
+}
+
+int ensure_placeholders(hb200_ctx* c) {
+  // Kernels take these pointers even when a factor family is absent.
+  for (int s = 0; s < 2; ++s) {
+    HB_CUDA(c->bg[s].ensure(4)); HB_CUDA(c->ba[s].ensure(4)); HB_CUDA(c->grav[s].ensure(4)); HB_CUDA(c->lms[s].ensure(3));
+    HB_CUDA(c->cp_pix[s].ensure(1)); HB_CUDA(c->cp_imu[s].ensure(1));
+  }
+  HB_CUDA(c->imu_tab.ensure(kImuStride)); HB_CUDA(c->cam_tab.ensure(kCamStride));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hb200_last_error_string(void) { return g_error.c_str(); }
+
+int hb200_create(const hb200_options* options, hb200_ctx** out) {
+  if (!out) return fail(-1, "null output pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(100 + static_cast<int>(e), "no CUDA device: %s (libhyperb200 has no CPU fallback)", cudaGetErrorString(e));
+  hb200_ctx* c = new hb200_ctx();
+  c->device = options ? options->device : 0;
+  if (c->device < 0 || c->device >= count) { delete c; return fail(-1, "invalid device %d", c->device); }
+  HB_CUDA(cudaSetDevice(c->device));
+  cudaDeviceProp prop{};
+  HB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major < 10) { const int maj = prop.major, mnr = prop.minor; delete c; return fail(-5, "device sm_%d%d is not Blackwell (built for sm_100a only)", maj, mnr); }
+  c->num_sms = prop.multiProcessorCount;
+  c->use_graph = options ? options->use_graph != 0 : true;
+  if (options && options->stream) { c->stream = static_cast<cudaStream_t>(options->stream); c->own_stream = false; }
+  else { HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  int rc = ensure_placeholders(c);
+  if (rc) { delete c; return rc; }
+  HB_CUDA(cudaFuncSetAttribute(cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCholSmem)));
+  rc = reset_solver_state(c);
+  if (rc) { delete c; return rc; }
+  *out = c;
+  return 0;
+}
+
+void hb200_destroy(hb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->graph) cudaGraphDestroy(c->graph);
+  for (int s = 0; s < 2; ++s) { c->knots[s].release(); c->bg[s].release(); c->ba[s].release(); c->grav[s].release(); c->lms[s].release(); c->tab[s].release(); c->cp_pix[s].release(); c->cp_imu[s].release(); }
+  c->cams.release(); c->imu.release(); c->cam_tab.release(); c->imu_tab.release(); c->fixed.release();
+  c->v_stamp.release(); c->v_pixel.release(); c->i_stamp.release(); c->i_meas.release(); c->v_cam.release(); c->v_lm.release(); c->v_idx.release(); c->i_idx.release();
+  c->seg_off.release(); c->run_off.release(); c->lm_off.release(); c->lm_obs.release(); c->d_invalid.release();
+  c->v_r.release(); c->v_Jp.release(); c->v_Jl.release(); c->i_r.release(); c->i_Jp.release(); c->i_wg.release(); c->i_wa.release(); c->i_Jg.release();
+  c->sys.release(); c->D.release(); c->Lw.release(); c->Ldiag.release(); c->dp.release(); c->dl.release(); c->Vinv.release(); c->gl.release(); c->Dl.release();
+  c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int hb200_synchronize(hb200_ctx* c) {
+  if (!c) return fail(-1, "null context");
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+void* hb200_stream(hb200_ctx* c) { return c ? c->stream : nullptr; }
+long long hb200_launch_count(hb200_ctx* c) { return c ? c->launches : 0; }
+
+int hb200_set_spline(hb200_ctx* c, int order, int K, const double* knots) {
+  if (!c || !knots) return fail(-1, "null argument");
+  if (order != 4 && order != 6) return fail(-4, "spline order %d not supported (4 or 6)", order);
+  if (K < order) return fail(-1, "need at least %d knots, got %d", order, K);
+  for (int j = 1; j < K; ++j)
+    if (!(knots[8 * j + 7] > knots[8 * (j - 1) + 7])) return fail(-1, "knot stamps must be strictly increasing (knot %d)", j);
+  HB_CUDA(cudaSetDevice(c->device));
+  const bool reshape = (order != c->k) || (K != c->K);
+  c->k = order; c->K = K;
+  compute_basis(&c->basis, order);
+  for (int s = 0; s < 2; ++s) { HB_CUDA(c->knots[s].ensure(8 * static_cast<size_t>(K))); HB_CUDA(c->tab[s].ensure(static_cast<size_t>(K) * kTabStride)); }
+  HB_CUDA(cudaMemcpyAsync(c->knots[0].p, knots, 8 * sizeof(double) * K, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  if (reshape) { c->h_knot_const.assign(K, 0); c->bound = false; c->invalidate(); int rc = update_fixed(c); if (rc) return rc; }
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  return 0;
+}
+
+int hb200_set_bias_splines(hb200_ctx* c, int order, int Kg, const double* gyro, int Ka, const double* accel) {
+  if (!c || !gyro || !accel) return fail(-1, "null argument");
+  if (order != 4) return fail(-4, "bias spline order %d not supported (4)", order);
+  if (Kg < order || Ka < order) return fail(-1, "need at least %d bias knots", order);
+  HB_CUDA(cudaSetDevice(c->device));
+  const bool reshape = (Kg != c->Kbg) || (Ka != c->Kba);
+  c->kb = order; c->Kbg = Kg; c->Kba = Ka;
+  compute_basis(&c->bias_basis, order);
+  for (int s = 0; s < 2; ++s) { HB_CUDA(c->bg[s].ensure(4 * static_cast<size_t>(Kg))); HB_CUDA(c->ba[s].ensure(4 * static_cast<size_t>(Ka))); }
+  HB_CUDA(cudaMemcpyAsync(c->bg[0].p, gyro, 4 * sizeof(double) * Kg, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->ba[0].p, accel, 4 * sizeof(double) * Ka, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  if (reshape) { c->bound = false; c->invalidate(); int rc = update_fixed(c); if (rc) return rc; }
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  return 0;
+}
+
+int hb200_set_gravity(hb200_ctx* c, const double* g) {
+  if (!c || !g) return fail(-1, "null argument");
+  HB_CUDA(cudaSetDevice(c->device));
+  HB_CUDA(cudaMemcpyAsync(c->grav[0].p, g, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_gravity = true;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  return 0;
+}
+
+int hb200_set_cameras(hb200_ctx* c, int C, const double* cams) {
+  if (!c || !cams || C <= 0) return fail(-1, "invalid cameras");
+  HB_CUDA(cudaSetDevice(c->device));
+  if (C != c->C) { c->bound = false; c->invalidate(); }
+  c->C = C;
+  HB_CUDA(c->cams.ensure(15 * static_cast<size_t>(C)));
+  HB_CUDA(c->cam_tab.ensure(kCamStride * static_cast<size_t>(C)));
+  HB_CUDA(cudaMemcpyAsync(c->cams.p, cams, 15 * sizeof(double) * C, cudaMemcpyHostToDevice, c->stream));
+  calib_kernel<<<(C + 63) / 64, 64, 0, c->stream>>>(C, c->cams.p, c->cam_tab.p, nullptr, nullptr);
+  HB_LAUNCH(c, "calib_kernel");
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  return 0;
+}
+
+int hb200_set_imu(hb200_ctx* c, const double* imu) {
+  if (!c || !imu) return fail(-1, "null argument");
+  HB_CUDA(cudaSetDevice(c->device));
+  HB_CUDA(c->imu.ensure(37));
+  HB_CUDA(cudaMemcpyAsync(c->imu.p, imu, 37 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  calib_kernel<<<1, 64, 0, c->stream>>>(0, nullptr, nullptr, c->imu.p, c->imu_tab.p);
+  HB_LAUNCH(c, "calib_kernel");
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_imu = true;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  return 0;
+}
+
+int hb200_set_landmarks(hb200_ctx* c, int L, const double* xyz) {
+  if (!c || (L > 0 && !xyz) || L < 0) return fail(-1, "invalid landmarks");
+  HB_CUDA(cudaSetDevice(c->device));
+  if (L != c->L) { c->bound = false; c->invalidate(); }
+  c->L = L;
+  for (int s = 0; s < 2; ++s) HB_CUDA(c->lms[s].ensure(3 * static_cast<size_t>(std::max(L, 1))));
+  if (L) HB_CUDA(cudaMemcpyAsync(c->lms[0].p, xyz, 3 * sizeof(double) * L, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  return 0;
+}
+
+int hb200_set_constant(hb200_ctx* c, const unsigned char* knot_constant, int gravity_constant, int bias_constant) {
+  if (!c) return fail(-1, "null context");
+  if (c->K == 0) return fail(-2, "spline not set");
+  HB_CUDA(cudaSetDevice(c->device));
+  if (knot_constant) c->h_knot_const.assign(knot_constant, knot_constant + c->K);
+  else c->h_knot_const.assign(c->K, 0);
+  c->gravity_const = gravity_constant; c->bias_const = bias_constant;
+  c->system_built = false;
+  return update_fixed(c);
+}
+
+int hb200_set_options(hb200_ctx* c, double huber_pixel, double imu_loss_scale, double radius) {
+  if (!c) return fail(-1, "null context");
+  if (!(huber_pixel > 0) || !(imu_loss_scale > 0) || !(radius > 0)) return fail(-1, "options must be positive");
+  HB_CUDA(cudaSetDevice(c->device));
+  if (huber_pixel != c->huber || imu_loss_scale != c->imu_scale) c->graph_valid = false;  // baked into kernel arguments
+  c->huber = huber_pixel; c->imu_scale = imu_loss_scale; c->radius0 = radius;
+  c->system_built = false; c->evaluated_J = false;
+  return reset_solver_state(c);
+}
+
+int hb200_set_pixel_factors(hb200_ctx* c, int n, const double* stamp, const int* camera, const int* landmark, const double* pixel) {
+  if (!c || n < 0 || (n > 0 && (!stamp || !camera || !landmark || !pixel))) return fail(-1, "invalid pixel factors");
+  c->Nv = n;
+  c->h_v_stamp.assign(stamp, stamp + n); c->h_v_cam.assign(camera, camera + n); c->h_v_lm.assign(landmark, landmark + n);
+  c->h_v_pixel.assign(pixel, pixel + 2 * static_cast<size_t>(n));
+  c->bound = false; c->invalidate();
+  return 0;
+}
+
+int hb200_set_inertial_factors(hb200_ctx* c, int n, const double* stamp, const double* meas) {
+  if (!c || n < 0 || (n > 0 && (!stamp || !meas))) return fail(-1, "invalid inertial factors");
+  c->Ni = n;
+  c->h_i_stamp.assign(stamp, stamp + n); c->h_i_meas.assign(meas, meas + 6 * static_cast<size_t>(n));
+  c->bound = false; c->invalidate();
+  return 0;
+}
+
+int hb200_bind(hb200_ctx* c, int* num_invalid) {
+  if (!c) return fail(-1, "null context");
+  if (c->K == 0) return fail(-2, "spline not set");
+  if (c->Ni && (c->Kbg == 0 || c->Kba == 0)) return fail(-2, "bias splines not set");
+  if (c->Nv && (c->C == 0 || c->L == 0)) return fail(-2, "cameras / landmarks not set");
+  HB_CUDA(cudaSetDevice(c->device));
+  const int Nv = c->Nv, Ni = c->Ni;
+  HB_CUDA(c->d_invalid.ensure(1));
+  HB_CUDA(cudaMemsetAsync(c->d_invalid.p, 0, sizeof(int), c->stream));
+  HB_CUDA(c->v_stamp.ensure(std::max(Nv, 1))); HB_CUDA(c->v_pixel.ensure(2 * static_cast<size_t>(std::max(Nv, 1))));
+  HB_CUDA(c->v_cam.ensure(std::max(Nv, 1))); HB_CUDA(c->v_lm.ensure(std::max(Nv, 1))); HB_CUDA(c->v_idx.ensure(std::max(Nv, 1)));
+  HB_CUDA(c->i_stamp.ensure(std::max(Ni, 1))); HB_CUDA(c->i_meas.ensure(6 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_idx.ensure(std::max(Ni, 1)));
+  c->h_v_idx.assign(Nv, make_int4(0, 0, 0, 0)); c->h_i_idx.assign(Ni, make_int4(0, 0, 0, 0));
+  // pass 1: index maps in user order (device), a2/a4
+  if (Nv) {
+    HB_CUDA(cudaMemcpyAsync(c->v_stamp.p, c->h_v_stamp.data(), sizeof(double) * Nv, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->v_cam.p, c->h_v_cam.data(), sizeof(int) * Nv, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->v_lm.p, c->h_v_lm.data(), sizeof(int) * Nv, cudaMemcpyHostToDevice, c->stream));
+    bind_pixel_kernel<<<(Nv + 127) / 128, 128, 0, c->stream>>>(Nv, c->v_stamp.p, c->v_cam.p, c->v_lm.p, c->knots[0].p, c->K, c->k, c->C, c->L, c->v_idx.p, c->d_invalid.p);
+    HB_LAUNCH(c, "bind_pixel_kernel");
+    HB_CUDA(cudaMemcpyAsync(c->h_v_idx.data(), c->v_idx.p, sizeof(int4) * Nv, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (Ni) {
+    HB_CUDA(cudaMemcpyAsync(c->i_stamp.p, c->h_i_stamp.data(), sizeof(double) * Ni, cudaMemcpyHostToDevice, c->stream));
+    bind_inertial_kernel<<<(Ni + 127) / 128, 128, 0, c->stream>>>(Ni, c->i_stamp.p, c->knots[0].p, c->K, c->k, c->bg[0].p, c->Kbg, c->ba[0].p, c->Kba, c->kb,
+                                                               c->i_idx.p, c->d_invalid.p);
+    HB_LAUNCH(c, "bind_inertial_kernel");
+    HB_CUDA(cudaMemcpyAsync(c->h_i_idx.data(), c->i_idx.p, sizeof(int4) * Ni, cudaMemcpyDeviceToHost, c->stream));
+  }
+  int invalid = 0;
+  HB_CUDA(cudaMemcpyAsync(&invalid, c->d_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  if (num_invalid) *num_invalid = invalid;
+  if (invalid) return fail(2, "%d factor(s) reference a stamp outside the spline's valid range or an invalid camera / landmark", invalid);
+
+  // pass 2: bound order = stable sort by knot base index (pixel) / (base, gyro base, accel base)
+  c->v_perm.resize(Nv); std::iota(c->v_perm.begin(), c->v_perm.end(), 0);
+  c->i_perm.resize(Ni); std::iota(c->i_perm.begin(), c->i_perm.end(), 0);
+  {
+    const std::vector<int4>& id = c->h_v_idx;
+    if (!std::is_sorted(id.begin(), id.end(), [](const int4& a, const int4& b) { return a.x < b.x; }))
+      std::stable_sort(c->v_perm.begin(), c->v_perm.end(), [&](int a, int b) { return id[a].x < id[b].x; });
+    auto key = [](const int4& a, const int4& b) { return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); };
+    const std::vector<int4>& ii = c->h_i_idx;
+    if (!std::is_sorted(ii.begin(), ii.end(), key)) std::stable_sort(c->i_perm.begin(), c->i_perm.end(), [&](int a, int b) { return key(ii[a], ii[b]); });
+  }
+  {
+    std::vector<double> st(Nv), px(2 * static_cast<size_t>(Nv));
+    std::vector<int4> id(Nv);
+    for (int p = 0; p < Nv; ++p) { const int u = c->v_perm[p]; st[p] = c->h_v_stamp[u]; px[2 * p] = c->h_v_pixel[2 * u]; px[2 * p + 1] = c->h_v_pixel[2 * u + 1]; id[p] = c->h_v_idx[u]; }
+    c->h_v_idx = id;
+    if (Nv) {
+      HB_CUDA(cudaMemcpyAsync(c->v_stamp.p, st.data(), sizeof(double) * Nv, cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(c->v_pixel.p, px.data(), sizeof(double) * 2 * Nv, cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(c->v_idx.p, id.data(), sizeof(int4) * Nv, cudaMemcpyHostToDevice, c->stream));
+    }
+    std::vector<double> is(Ni), im(6 * static_cast<size_t>(Ni));
+    std::vector<int4> iid(Ni);
+    for (int p = 0; p < Ni; ++p) { const int u = c->i_perm[p]; is[p] = c->h_i_stamp[u]; for (int q = 0; q < 6; ++q) im[6 * p + q] = c->h_i_meas[6 * u + q]; iid[p] = c->h_i_idx[u]; }
+    c->h_i_idx = iid;
+    if (Ni) {
+      HB_CUDA(cudaMemcpyAsync(c->i_stamp.p, is.data(), sizeof(double) * Ni, cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(c->i_meas.p, im.data(), sizeof(double) * 6 * Ni, cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(c->i_idx.p, iid.data(), sizeof(int4) * Ni, cudaMemcpyHostToDevice, c->stream));
+    }
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  // segment offsets (pixel), runs (inertial), landmark incidence (CSR)
+  c->nseg = c->K - c->k + 1;
+  std::vector<int> seg(c->nseg + 1, 0);
+  for (int p = 0; p < Nv; ++p) seg[c->h_v_idx[p].x + 1] += 1;
+  for (int s = 0; s < c->nseg; ++s) seg[s + 1] += seg[s];
+  std::vector<int> runs;
+  for (int p = 0; p < Ni; ++p) {
+    const int4& a = c->h_i_idx[p];
+    if (p == 0 || a.x != c->h_i_idx[p - 1].x || a.y != c->h_i_idx[p - 1].y || a.z != c->h_i_idx[p - 1].z) runs.push_back(p);
+  }
+  c->nruns = static_cast<int>(runs.size());
+  runs.push_back(Ni);
+  std::vector<int> off(c->L + 1, 0), obs(std::max(Nv, 1));
+  for (int p = 0; p < Nv; ++p) off[c->h_v_idx[p].y + 1] += 1;
+  for (int l = 0; l < c->L; ++l) off[l + 1] += off[l];
+  {
+    std::vector<int> cur(off.begin(), off.end() - 1);
+    for (int p = 0; p < Nv; ++p) obs[cur[c->h_v_idx[p].y]++] = p;
+  }
+  c->max_rows = 6 * c->k;
+  for (int l = 0; l < c->L; ++l)
+    if (off[l + 1] > off[l]) c->max_rows = std::max(c->max_rows, 6 * (c->h_v_idx[obs[off[l + 1] - 1]].x + c->k - c->h_v_idx[obs[off[l]]].x));
+  if (2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double) > 200 * 1024) return fail(-6, "landmark track spans %d control-point dofs; exceeds the Schur kernel's shared-memory tile", c->max_rows);
+  HB_CUDA(c->seg_off.ensure(seg.size())); HB_CUDA(c->run_off.ensure(runs.size())); HB_CUDA(c->lm_off.ensure(off.size())); HB_CUDA(c->lm_obs.ensure(obs.size()));
+  HB_CUDA(cudaMemcpyAsync(c->seg_off.p, seg.data(), sizeof(int) * seg.size(), cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->run_off.p, runs.data(), sizeof(int) * runs.size(), cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->lm_off.p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->lm_obs.p, obs.data(), sizeof(int) * obs.size(), cudaMemcpyHostToDevice, c->stream));
+  // outputs
+  const size_t k = c->k;
+  HB_CUDA(c->v_r.ensure(2 * static_cast<size_t>(std::max(Nv, 1)))); HB_CUDA(c->v_Jp.ensure(12 * k * std::max(Nv, 1))); HB_CUDA(c->v_Jl.ensure(6 * static_cast<size_t>(std::max(Nv, 1))));
+  HB_CUDA(c->i_r.ensure(6 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_Jp.ensure(36 * k * std::max(Ni, 1)));
+  HB_CUDA(c->i_wg.ensure(4 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_wa.ensure(4 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_Jg.ensure(12 * static_cast<size_t>(std::max(Ni, 1))));
+  c->n_pix_blocks = (Nv + kEvalThreads - 1) / kEvalThreads;
+  c->n_imu_blocks = (Ni + kEvalThreads - 1) / kEvalThreads;
+  for (int s = 0; s < 2; ++s) { HB_CUDA(c->cp_pix[s].ensure(std::max(c->n_pix_blocks, 1))); HB_CUDA(c->cp_imu[s].ensure(std::max(c->n_imu_blocks, 1))); }
+  if (c->max_rows * 6 * sizeof(double) > 48 * 1024) {
+    const int smem = static_cast<int>(2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double));
+    HB_CUDA(cudaFuncSetAttribute(schur_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HB_CUDA(cudaFuncSetAttribute(schur_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  int rc = update_fixed(c);
+  if (rc) return rc;
+  rc = ensure_system(c);
+  if (rc) return rc;
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->bound = true;
+  c->invalidate();
+  return 0;
+}
+
+int hb200_get_index_maps(hb200_ctx* c, int* pixel_base, int* inertial_base, int* gyro_bias_base, int* accel_bias_base) {
+  if (!c || !c->bound) return fail(-2, "not bound");
+  for (int p = 0; p < c->Nv; ++p) if (pixel_base) pixel_base[c->v_perm[p]] = c->h_v_idx[p].x;
+  for (int p = 0; p < c->Ni; ++p) {
+    const int u = c->i_perm[p];
+    if (inertial_base) inertial_base[u] = c->h_i_idx[p].x;
+    if (gyro_bias_base) gyro_bias_base[u] = c->h_i_idx[p].y;
+    if (accel_bias_base) accel_bias_base[u] = c->h_i_idx[p].z;
+  }
+  return 0;
+}
+
+int hb200_evaluate(hb200_ctx* c, int flags) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  HB_CUDA(cudaSetDevice(c->device));
+  const bool J = flags & HB200_EVAL_JACOBIANS;
+  const int sel = (flags & HB200_EVAL_TRIAL) ? 1 : 0;
+  rc = enqueue_evaluate(c, J, sel);
+  if (rc) return rc;
+  if (J && sel == 0) c->evaluated_J = true;
+  c->mirror_valid = false; c->system_built = false;
+  return 0;
+}
+
+int hb200_get_pixel_outputs(hb200_ctx* c, double* r, double* Jp, double* Jl) {
+  if (!c || !c->bound) return fail(-2, "not bound");
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t N = c->Nv, w = 12 * static_cast<size_t>(c->k);
+  std::vector<double> tr(2 * N), tJ(Jp ? w * N : 0), tl(Jl ? 6 * N : 0);
+  if (N) {
+    HB_CUDA(cudaMemcpyAsync(tr.data(), c->v_r.p, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, c->stream));
+    if (Jp) HB_CUDA(cudaMemcpyAsync(tJ.data(), c->v_Jp.p, sizeof(double) * w * N, cudaMemcpyDeviceToHost, c->stream));
+    if (Jl) HB_CUDA(cudaMemcpyAsync(tl.data(), c->v_Jl.p, sizeof(double) * 6 * N, cudaMemcpyDeviceToHost, c->stream));
+  }
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t p = 0; p < N; ++p) {
+    const size_t u = c->v_perm[p];
+    if (r) { r[2 * u] = tr[2 * p]; r[2 * u + 1] = tr[2 * p + 1]; }
+    if (Jp) std::memcpy(Jp + w * u, tJ.data() + w * p, sizeof(double) * w);
+    if (Jl) std::memcpy(Jl + 6 * u, tl.data() + 6 * p, sizeof(double) * 6);
+  }
+  return 0;
+}
+
+int hb200_get_inertial_outputs(hb200_ctx* c, double* r, double* Jp, double* wg, double* wa, double* Jg) {
+  if (!c || !c->bound) return fail(-2, "not bound");
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t N = c->Ni, w = 36 * static_cast<size_t>(c->k);
+  std::vector<double> tr(6 * N), tJ(Jp ? w * N : 0), tg(wg ? 4 * N : 0), ta(wa ? 4 * N : 0), tG(Jg ? 12 * N : 0);
+  if (N) {
+    HB_CUDA(cudaMemcpyAsync(tr.data(), c->i_r.p, sizeof(double) * 6 * N, cudaMemcpyDeviceToHost, c->stream));
+    if (Jp) HB_CUDA(cudaMemcpyAsync(tJ.data(), c->i_Jp.p, sizeof(double) * w * N, cudaMemcpyDeviceToHost, c->stream));
+    if (wg) HB_CUDA(cudaMemcpyAsync(tg.data(), c->i_wg.p, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, c->stream));
+    if (wa) HB_CUDA(cudaMemcpyAsync(ta.data(), c->i_wa.p, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, c->stream));
+    if (Jg) HB_CUDA(cudaMemcpyAsync(tG.data(), c->i_Jg.p, sizeof(double) * 12 * N, cudaMemcpyDeviceToHost, c->stream));
+  }
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t p = 0; p < N; ++p) {
+    const size_t u = c->i_perm[p];
+    if (r) std::memcpy(r + 6 * u, tr.data() + 6 * p, sizeof(double) * 6);
+    if (Jp) std::memcpy(Jp + w * u, tJ.data() + w * p, sizeof(double) * w);
+    if (wg) std::memcpy(wg + 4 * u, tg.data() + 4 * p, sizeof(double) * 4);
+    if (wa) std::memcpy(wa + 4 * u, ta.data() + 4 * p, sizeof(double) * 4);
+    if (Jg) std::memcpy(Jg + 12 * u, tG.data() + 12 * p, sizeof(double) * 12);
+  }
+  return 0;
+}
+
+int hb200_factor_evaluate(hb200_ctx* c, int kind, int index, const double* const* parameters, double* residuals, double** jacobians) {
+  if (!c || !c->bound) return fail(-2, "not bound");
+  if (!c->evaluated_J) return fail(-2, "call hb200_evaluate(HB200_EVAL_JACOBIANS) first");
+  if (!parameters || !residuals) return fail(-1, "null argument");
+  if (!c->mirror_valid) {
+    const size_t k = c->k;
+    c->m_v_r.resize(2 * static_cast<size_t>(c->Nv)); c->m_v_Jp.resize(12 * k * c->Nv); c->m_v_Jl.resize(6 * static_cast<size_t>(c->Nv));
+    c->m_i_r.resize(6 * static_cast<size_t>(c->Ni)); c->m_i_Jp.resize(36 * k * c->Ni); c->m_i_wg.resize(4 * static_cast<size_t>(c->Ni));
+    c->m_i_wa.resize(4 * static_cast<size_t>(c->Ni)); c->m_i_Jg.resize(12 * static_cast<size_t>(c->Ni)); c->m_grav.resize(3);
+    int rc = hb200_get_pixel_outputs(c, c->m_v_r.data(), c->m_v_Jp.data(), c->m_v_Jl.data());
+    if (rc) return rc;
+    rc = hb200_get_inertial_outputs(c, c->m_i_r.data(), c->m_i_Jp.data(), c->m_i_wg.data(), c->m_i_wa.data(), c->m_i_Jg.data());
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpy(c->m_grav.data(), c->grav[0].p, 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    c->mirror_valid = true;
+  }
+  const int k = c->k, kb = c->kb;
+  const int nr = (kind == HB200_PIXEL) ? 2 : 6;
+  const int N = (kind == HB200_PIXEL) ? c->Nv : c->Ni;
+  if (kind != HB200_PIXEL && kind != HB200_INERTIAL) return fail(-1, "unknown factor kind %d", kind);
+  if (index < 0 || index >= N) return fail(-1, "factor index %d out of range", index);
+  const double* r = (kind == HB200_PIXEL) ? &c->m_v_r[2 * static_cast<size_t>(index)] : &c->m_i_r[6 * static_cast<size_t>(index)];
+  for (int i = 0; i < nr; ++i) residuals[i] = r[i];
+  if (!jacobians) return 0;
+  const double* Jp = (kind == HB200_PIXEL) ? &c->m_v_Jp[12 * static_cast<size_t>(k) * index] : &c->m_i_Jp[36 * static_cast<size_t>(k) * index];
+  // state blocks: [J_theta * A_q(q_m) | J_rho | 0]  (ambient 8, row-major nr x 8)
+  for (int m = 0; m < k; ++m) {
+    if (!jacobians[m]) continue;
+    const double* q = parameters[m];
+    const double Aq[12] = {2 * q[3], -2 * q[2], 2 * q[1], -2 * q[0], 2 * q[2], 2 * q[3], -2 * q[0], -2 * q[1], -2 * q[1], 2 * q[0], 2 * q[3], -2 * q[2]};
+    for (int row = 0; row < nr; ++row) {
+      const double* jt = Jp + row * 6 * k + 6 * m;
+      double* o = jacobians[m] + 8 * row;
+      for (int col = 0; col < 4; ++col) o[col] = jt[0] * Aq[col] + jt[1] * Aq[4 + col] + jt[2] * Aq[8 + col];
+      o[4] = jt[3]; o[5] = jt[4]; o[6] = jt[5]; o[7] = 0.0;
+    }
+  }
+  if (kind == HB200_PIXEL) {
+    const int sizes[4] = {7, 4, 4, 3};
+    for (int b = 0; b < 4; ++b) {
+      double* o = jacobians[k + b];
+      if (!o) continue;
+      if (b < 3) std::fill(o, o + 2 * sizes[b], 0.0);  // calibration is constant in the live configuration (reference optimizer.cpp:59)
+      else std::memcpy(o, &c->m_v_Jl[6 * static_cast<size_t>(index)], 6 * sizeof(double));
+    }
+  } else {
+    const int sizes[5] = {7, 6, 6, 9, 9};
+    for (int b = 0; b < 5; ++b) if (jacobians[k + b]) std::fill(jacobians[k + b], jacobians[k + b] + 6 * sizes[b], 0.0);
+    for (int m = 0; m < kb; ++m) {
+      if (double* o = jacobians[k + 5 + m]) {
+        std::fill(o, o + 24, 0.0);
+        for (int a = 0; a < 3; ++a) o[4 * a + a] = c->m_i_wg[4 * static_cast<size_t>(index) + m];
+      }
+      if (double* o = jacobians[k + 5 + kb + m]) {
+        std::fill(o, o + 24, 0.0);
+        for (int a = 0; a < 3; ++a) o[4 * (3 + a) + a] = c->m_i_wa[4 * static_cast<size_t>(index) + m];
+      }
+    }
+    if (double* o = jacobians[k + 5 + 2 * kb]) {
+      // minimal-norm ambient Jacobian: J_tangent * PlusJacobian^T / |g|^2  (PlusJacobian^T PlusJacobian = |g|^2 I)
+      const double* x = parameters[k + 5 + 2 * kb];
+      const double sigma = x[0] * x[0] + x[1] * x[1];
+      double v[3] = {x[0], x[1], 1.0}, beta = 0.0;
+      if (sigma <= 2.220446049250313e-16) { if (x[2] < 0.0) beta = 2.0; }
+      else {
+        const double mu = std::sqrt(x[2] * x[2] + sigma);
+        const double vp = (x[2] <= 0.0) ? (x[2] - mu) : (-sigma / (x[2] + mu));
+        beta = 2.0 * vp * vp / (sigma + vp * vp);
+        v[0] /= vp; v[1] /= vp;
+      }
+      const double nx = std::sqrt(sigma + x[2] * x[2]);
+      double PJ[6];
+      for (int cc = 0; cc < 2; ++cc) for (int rr = 0; rr < 3; ++rr) PJ[2 * rr + cc] = nx * ((rr == cc ? 1.0 : 0.0) - beta * v[cc] * v[rr]);
+      const double* Jg = &c->m_i_Jg[12 * static_cast<size_t>(index)];
+      for (int row = 0; row < 6; ++row)
+        for (int col = 0; col < 3; ++col) o[3 * row + col] = (Jg[2 * row] * PJ[2 * col] + Jg[2 * row + 1] * PJ[2 * col + 1]) / (nx * nx);
+    }
+  }
+  return 0;
+}
+
+int hb200_reduced_size(hb200_ctx* c) { return c ? 6 * c->K + 3 * c->Kbg + 3 * c->Kba + 2 : -1; }
+
+int hb200_build_system(hb200_ctx* c) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!c->evaluated_J) return fail(-2, "call hb200_evaluate(HB200_EVAL_JACOBIANS) first");
+  HB_CUDA(cudaSetDevice(c->device));
+  if ((rc = enqueue_build(c))) return rc;
+  if (c->allreduce) {
+    rc = c->allreduce(c->allreduce_user, c->sys.p, static_cast<long long>(c->n) * c->n + 3LL * c->n + 2, c->stream);
+    if (rc) return fail(200 + rc, "all-reduce callback failed (%d)", rc);
+  }
+  if ((rc = enqueue_finalize(c))) return rc;
+  c->system_built = true;
+  return 0;
+}
+
+int hb200_get_system(hb200_ctx* c, double* S, double* b) {
+  if (!c || !c->system_built) return fail(-2, "system not built");
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t n = c->n;
+  if (S) HB_CUDA(cudaMemcpyAsync(S, c->sys.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+  if (b) HB_CUDA(cudaMemcpyAsync(b, c->sys.p + n * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int hb200_solve(hb200_ctx* c) {
+  if (!c || !c->system_built) return fail(-2, "system not built");
+  HB_CUDA(cudaSetDevice(c->device));
+  return enqueue_solve(c);
+}
+
+int hb200_get_delta(hb200_ctx* c, double* dp, double* dl) {
+  if (!c || !c->bound) return fail(-2, "not bound");
+  HB_CUDA(cudaSetDevice(c->device));
+  if (dp) HB_CUDA(cudaMemcpyAsync(dp, c->dp.p, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->stream));
+  if (dl && c->L) HB_CUDA(cudaMemcpyAsync(dl, c->dl.p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int hb200_iterate(hb200_ctx* c, int iterations, hb200_iteration* records) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (iterations < 0 || iterations > c->max_records) return fail(-1, "iterations must be in [0, %d]", c->max_records);
+  HB_CUDA(cudaSetDevice(c->device));
+  // records[] index = SolverState.iteration modulo nothing: reset the device-side counter first.
+  {
+    SolverState s{};
+    HB_CUDA(cudaMemcpyAsync(&s, c->st.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    s.iteration = 0;
+    HB_CUDA(cudaMemcpyAsync(c->st.p, &s, sizeof(s), cudaMemcpyHostToDevice, c->stream));
+  }
+  const bool graph_ok = c->use_graph && !c->allreduce;
+  for (int it = 0; it < iterations; ++it) {
+    if (graph_ok) {
+      if (!c->graph_valid) {
+        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+        HB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const long long before = c->launches;
+        rc = enqueue_segment(c, 0);
+        if (!rc) rc = enqueue_segment(c, 1);
+        if (!rc) rc = enqueue_segment(c, 2);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &c->graph);
+        c->launches = before;  // capture does not execute
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(100 + static_cast<int>(e), "graph capture: %s", cudaGetErrorString(e));
+        HB_CUDA(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+        c->graph_valid = true;
+        c->launches_per_iteration = 0;
+        size_t nodes = 0;
+        HB_CUDA(cudaGraphGetNodes(c->graph, nullptr, &nodes));
+        cudaGraphNode_t* nd = new cudaGraphNode_t[nodes];
+        HB_CUDA(cudaGraphGetNodes(c->graph, nd, &nodes));
+        for (size_t i = 0; i < nodes; ++i) { cudaGraphNodeType t; if (cudaGraphNodeGetType(nd[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) c->launches_per_iteration += 1; }
+        delete[] nd;
+      }
+      HB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
+      c->launches += c->launches_per_iteration;
+    } else {
+      if ((rc = enqueue_segment(c, 0))) return rc;
+      if (c->allreduce) {
+        rc = c->allreduce(c->allreduce_user, c->sys.p, static_cast<long long>(c->n) * c->n + 3LL * c->n + 2, c->stream);
+        if (rc) return fail(200 + rc, "all-reduce callback failed (%d)", rc);
+      }
+      if ((rc = enqueue_segment(c, 1))) return rc;
+      if (c->allreduce) {
+        rc = c->allreduce(c->allreduce_user, c->scal.p, 4, c->stream);
+        if (rc) return fail(200 + rc, "all-reduce callback failed (%d)", rc);
+      }
+      if ((rc = enqueue_segment(c, 2))) return rc;
+    }
+  }
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  if (records && iterations) {
+    std::vector<SolverState> rec(iterations);
+    HB_CUDA(cudaMemcpyAsync(rec.data(), c->records.p, sizeof(SolverState) * iterations, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < iterations; ++i) {
+      records[i].cost = rec[i].cost; records[i].cost_new = rec[i].cost_new; records[i].model_change = rec[i].model_change; records[i].rho = rec[i].rho;
+      records[i].radius = rec[i].radius; records[i].accepted = rec[i].accepted; records[i].spd = rec[i].spd;
+    }
+  }
+  return 0;
+}
+
+int hb200_cost(hb200_ctx* c, double* cost) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!cost) return fail(-1, "null argument");
+  HB_CUDA(cudaSetDevice(c->device));
+  if ((rc = enqueue_evaluate(c, false, 0))) return rc;
+  if ((rc = enqueue_scalars(c))) return rc;
+  double s[4];
+  HB_CUDA(cudaMemcpyAsync(s, c->scal.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  *cost = s[0];
+  return 0;
+}
+
+int hb200_get_state(hb200_ctx* c, double* knots, double* gyro, double* accel, double* gravity, double* landmarks) {
+  if (!c) return fail(-1, "null context");
+  HB_CUDA(cudaSetDevice(c->device));
+  if (knots && c->K) HB_CUDA(cudaMemcpyAsync(knots, c->knots[0].p, sizeof(double) * 8 * c->K, cudaMemcpyDeviceToHost, c->stream));
+  if (gyro && c->Kbg) HB_CUDA(cudaMemcpyAsync(gyro, c->bg[0].p, sizeof(double) * 4 * c->Kbg, cudaMemcpyDeviceToHost, c->stream));
+  if (accel && c->Kba) HB_CUDA(cudaMemcpyAsync(accel, c->ba[0].p, sizeof(double) * 4 * c->Kba, cudaMemcpyDeviceToHost, c->stream));
+  if (gravity) HB_CUDA(cudaMemcpyAsync(gravity, c->grav[0].p, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
+  if (landmarks && c->L) HB_CUDA(cudaMemcpyAsync(landmarks, c->lms[0].p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int hb200_set_allreduce(hb200_ctx* c, hb200_allreduce_fn fn, void* user) {
+  if (!c) return fail(-1, "null context");
+  c->allreduce = fn; c->allreduce_user = user;
+  return 0;
+}
+
+void* hb200_system_device_ptr(hb200_ctx* c, long long* count) {
+  if (!c) return nullptr;
+  if (count) *count = static_cast<long long>(c->n) * c->n + 3LL * c->n + 2;
+  return c->sys.p;
+}
+
+}  // extern "C"

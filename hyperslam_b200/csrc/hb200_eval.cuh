@@ -1,0 +1,729 @@
+// Factor evaluation kernels (sm_100a): knot table, index maps, stereo-pixel and inertial
+// residual + Jacobian.  One factor per thread; a CTA's knot-table tile is staged to shared memory
+// with one TMA bulk copy (cp.async.bulk + mbarrier).  Replaces, for a whole factor list at once,
+//   ExteroceptiveCost::Evaluate           reference internal/hyper/optimizers/ceres/costs/exteroceptive.cpp:101-160
+//   VisualPixelEvaluator<SE3>::evaluate   reference internal/hyper/optimizers/evaluators/pixel.cpp:16-146
+//   InertialEvaluator<SE3>::evaluate      reference internal/hyper/optimizers/evaluators/inertial.cpp:13-205
+//   AbstractState::evaluate (HyperState)  call sites pixel.cpp:74-75, inertial.cpp:93-94
+// and projects Jacobians straight into the tangent space the Ceres manifolds would project them to
+// (reference include/hyper/optimizers/ceres/manifolds/variables/wrapper.hpp:36-42).
+#pragma once
+#include "hb200_math.cuh"
+#include "hb200_types.cuh"
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------------
+// TMA (1-D bulk copy) + mbarrier helpers
+// ---------------------------------------------------------------------------------------------
+HB_DI uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+HB_DI void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+HB_DI void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+HB_DI void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+HB_DI void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+HB_DI void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Stage knot-table rows [row_lo, row_lo + rows) into s_tab with one bulk copy.  Call from all threads.
+HB_DI void stage_table(double* s_tab, uint64_t* bar, const double* g_tab, int row_lo, int rows) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = static_cast<uint32_t>(rows) * kTabStride * sizeof(double);
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(s_tab, g_tab + static_cast<size_t>(row_lo) * kTabStride, bytes, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+// Block-wide min / max of an int (blockDim.x <= 1024).
+HB_DI void block_min_max(int v_min, int v_max, int* s_red /*2 ints*/, int* out_min, int* out_max) {
+  if (threadIdx.x == 0) { s_red[0] = 0x7fffffff; s_red[1] = -0x7fffffff; }
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v_min = min(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
+    v_max = max(v_max, __shfl_xor_sync(0xffffffffu, v_max, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&s_red[0], v_min); atomicMax(&s_red[1], v_max); }
+  __syncthreads();
+  *out_min = s_red[0];
+  *out_max = s_red[1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2 / a4: knot base index of a stamp (bit-exact with the oracle's segment_base()).
+// ---------------------------------------------------------------------------------------------
+HB_DI int segment_base(const double* knots, int stride, int stamp_off, int K, int k, double t) {
+  if (K < k) return -1;
+  const double t0 = knots[stamp_off], t1 = knots[stride + stamp_off];
+  long long j = static_cast<long long>(floor((t - t0) / (t1 - t0)));
+  if (j < 0) j = 0;
+  if (j > K - 2) j = K - 2;
+  while (j > 0 && knots[static_cast<size_t>(j) * stride + stamp_off] > t) --j;
+  while (j < K - 2 && knots[static_cast<size_t>(j + 1) * stride + stamp_off] <= t) ++j;
+  if (!(knots[static_cast<size_t>(j) * stride + stamp_off] <= t && t < knots[static_cast<size_t>(j + 1) * stride + stamp_off])) return -1;
+  const int base = static_cast<int>(j) - (k - 1) / 2;
+  if (base < 0 || base + k - 1 > K - 1) return -1;
+  return base;
+}
+
+__global__ void bind_pixel_kernel(int n, const double* __restrict__ stamp, const int* __restrict__ cam, const int* __restrict__ lm,
+                                  const double* __restrict__ knots, int K, int k, int C, int L, int4* __restrict__ idx,
+                                  int* __restrict__ num_invalid) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const int base = segment_base(knots, 8, 7, K, k, stamp[f]);
+  const int c = cam[f], l = lm[f];
+  idx[f] = make_int4(base, l, c, 0);
+  if (base < 0 || c < 0 || c >= C || l < 0 || l >= L) atomicAdd(num_invalid, 1);
+}
+
+__global__ void bind_inertial_kernel(int n, const double* __restrict__ stamp, const double* __restrict__ knots, int K, int k,
+                                     const double* __restrict__ bg, int Kbg, const double* __restrict__ ba, int Kba, int kb,
+                                     int4* __restrict__ idx, int* __restrict__ num_invalid) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const double t = stamp[f];
+  const int base = segment_base(knots, 8, 7, K, k, t);
+  const int g = segment_base(bg, 4, 3, Kbg, kb, t);
+  const int a = segment_base(ba, 4, 3, Kba, kb, t);
+  idx[f] = make_int4(base, g, a, 0);
+  if (base < 0 || g < 0 || a < 0) atomicAdd(num_invalid, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Knot table: one thread per control point (a3, per-segment part shared by all factors).
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_kernel(int K, const double* __restrict__ knots, double* __restrict__ tab) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= K) return;
+  const double* kn = knots + 8 * static_cast<size_t>(j);
+  double* row = tab + static_cast<size_t>(j) * kTabStride;
+  double q[4] = {kn[0], kn[1], kn[2], kn[3]};
+  double R[9];
+  quat_to_rot(q, R);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) row[i] = R[i];
+  row[9] = kn[4]; row[10] = kn[5]; row[11] = kn[6];
+  double d[3] = {0, 0, 0}, G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (j > 0) {
+    const double* kp = kn - 8;
+    const double qc[4] = {-kp[0], -kp[1], -kp[2], kp[3]};
+    double qr[4], Ji[9];
+    quat_mul(qc, q, qr);
+    quat_log(qr, d);
+    so3_Jr_inv(d, Ji);
+    m3_mult(Ji, R, G);
+  }
+  row[12] = d[0]; row[13] = d[1]; row[14] = d[2];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) row[15 + i] = G[i];
+  row[24] = kn[7]; row[25] = 0; row[26] = 0; row[27] = 0;
+}
+
+// Calibration tables (once per set_cameras / set_imu).
+__global__ void calib_kernel(int C, const double* __restrict__ cams, double* __restrict__ cam_tab, const double* __restrict__ imu,
+                             double* __restrict__ imu_tab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < C) {
+    const double* c = cams + 15 * t;
+    double* o = cam_tab + kCamStride * t;
+    double R[9];
+    quat_to_rot(c, R);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) o[3 * i + j] = R[3 * j + i];  // R_sb = R_bs^T
+    o[9] = c[4]; o[10] = c[5]; o[11] = c[6];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[12 + i] = c[7 + i];
+  }
+  if (t == 0 && imu != nullptr) {
+    double R[9], Rsb[9];
+    quat_to_rot(imu, R);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Rsb[3 * i + j] = R[3 * j + i];
+    const double* ig = imu + 7;
+    const double* ia = imu + 13;
+    const double Ig[9] = {ig[0], 0, 0, ig[3], ig[1], 0, ig[4], ig[5], ig[2]};
+    const double Ia[9] = {ia[0], 0, 0, ia[3], ia[1], 0, ia[4], ia[5], ia[2]};
+    double IgR[9], IaR[9];
+    m3_mul(Ig, Rsb, IgR);
+    m3_mul(Ia, Rsb, IaR);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { imu_tab[i] = Rsb[i]; imu_tab[12 + i] = IgR[i]; imu_tab[21 + i] = IaR[i]; }
+    imu_tab[9] = imu[4]; imu_tab[10] = imu[5]; imu_tab[11] = imu[6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        imu_tab[30 + 3 * i + j] = imu[19 + i + 3 * j];            // S_g row-major from column-major
+        imu_tab[39 + 3 * i + j] = imu[28 + j + 3 * i] + imu[4 + j];  // lever arm c_i = X_a[:, i] + t_bs
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Basis evaluation (Horner), lam[0] = 1, lam[K] = 0.
+// ---------------------------------------------------------------------------------------------
+template <int K, bool DERIV>
+HB_DI void basis_eval(const Basis& b, double u, double inv_dt, double* lam, double* lamd, double* lamdd) {
+  lam[0] = 1.0; lam[K] = 0.0;
+  if (DERIV) { lamd[0] = lamdd[0] = 0.0; lamd[K] = lamdd[K] = 0.0; }
+#pragma unroll
+  for (int j = 1; j < K; ++j) {
+    double v = 0, d1 = 0, d2 = 0;
+#pragma unroll
+    for (int n = K - 1; n >= 0; --n) {
+      if (DERIV) { d2 = d2 * u + 2.0 * d1; d1 = d1 * u + v; }
+      v = v * u + b.Mc[j * K + n];
+    }
+    lam[j] = v;
+    if (DERIV) { lamd[j] = d1 * inv_dt; lamdd[j] = d2 * inv_dt * inv_dt; }
+  }
+}
+
+HB_DI double huber_rho(double s, double delta, double* weight) {
+  if (s <= delta * delta) { *weight = 1.0; return s; }
+  const double rt = sqrt(s);
+  *weight = delta / rt;
+  return 2.0 * delta * rt - delta * delta;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pixel factor (a5 + a3 + a7..a10 fused).  T: table origin (row r at T + r*kTabStride).
+// ---------------------------------------------------------------------------------------------
+template <int K, bool WANT_J>
+HB_DI void pixel_factor(const double* __restrict__ T, const Basis& B, int base, double t, double zx, double zy,
+                        const double* __restrict__ cam, const double* __restrict__ lmk, double* r, double* __restrict__ Jp,
+                        double* __restrict__ Jl) {
+  constexpr int left = (K - 1) / 2;
+  const double* row0 = T + static_cast<size_t>(base) * kTabStride;
+  const double t0 = row0[left * kTabStride + 24], t1 = row0[(left + 1) * kTabStride + 24];
+  const double inv_dt = 1.0 / (t1 - t0);
+  const double u = (t - t0) * inv_dt;
+  double lam[K + 1];
+  basis_eval<K, false>(B, u, inv_dt, lam, nullptr, nullptr);
+
+  double P[9], p[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) P[i] = row0[i];
+  p[0] = row0[9]; p[1] = row0[10]; p[2] = row0[11];
+  double M[(K - 1) * 9];
+#pragma unroll
+  for (int j = 1; j < K; ++j) {
+    const double* rj = row0 + j * kTabStride;
+    const double w[3] = {lam[j] * rj[12], lam[j] * rj[13], lam[j] * rj[14]};
+    double A[9], Jr[9], Pn[9];
+    so3_exp_and_Jr(w, A, WANT_J ? Jr : nullptr);
+    m3_mul(P, A, Pn);
+    if (WANT_J) {
+      double G[9], JG[9], PJG[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) G[i] = rj[15 + i];
+      m3_mul(Jr, G, JG);
+      m3_mul(Pn, JG, PJG);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) M[(j - 1) * 9 + i] = lam[j] * PJG[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) P[i] = Pn[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] += lam[j] * (rj[9 + c] - rj[9 + c - kTabStride]);
+  }
+  // p_s = R_sb (R^T (p_w - p) - t_bs)
+  const double q[3] = {lmk[0] - p[0], lmk[1] - p[1], lmk[2] - p[2]};
+  double pb[3], ps[3];
+  m3_tvec(P, q, pb);
+  const double pbt[3] = {pb[0] - cam[9], pb[1] - cam[10], pb[2] - cam[11]};
+  m3_vec(cam, pbt, ps);
+  const double iz = 1.0 / ps[2];
+  const double x = ps[0] * iz, y = ps[1] * iz;
+  const double cx = cam[12], cy = cam[13], fx = cam[14], fy = cam[15];
+  const double k1 = cam[16], k2 = cam[17], p1 = cam[18], p2 = cam[19];
+  const double r2 = x * x + y * y;
+  const double rad = 1.0 + k1 * r2 + k2 * r2 * r2;
+  const double dx = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+  const double dy = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+  r[0] = fx * dx + cx - zx;
+  r[1] = fy * dy + cy - zy;
+  if (!WANT_J) return;
+
+  const double g = k1 + 2.0 * k2 * r2;
+  const double drx = 2.0 * x * g, dry = 2.0 * y * g;
+  // J_r_n = diag(fx, fy) * d(distort)/dn
+  const double a00 = fx * (rad + x * drx + 2.0 * p1 * y + 6.0 * p2 * x);
+  const double a01 = fx * (x * dry + 2.0 * p1 * x + 2.0 * p2 * y);
+  const double a10 = fy * (y * drx + 2.0 * p1 * x + 2.0 * p2 * y);
+  const double a11 = fy * (rad + y * dry + 6.0 * p1 * y + 2.0 * p2 * x);
+  // J_n_p = [iz 0 -x iz; 0 iz -y iz]
+  const double Jps[6] = {a00 * iz, a01 * iz, -(a00 * x + a01 * y) * iz, a10 * iz, a11 * iz, -(a10 * x + a11 * y) * iz};
+  double Jpb[6], F[6], E[6];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Jpb[3 * i + j] = Jps[3 * i] * cam[j] + Jps[3 * i + 1] * cam[3 + j] + Jps[3 * i + 2] * cam[6 + j];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) F[3 * i + j] = Jpb[3 * i] * P[3 * j] + Jpb[3 * i + 1] * P[3 * j + 1] + Jpb[3 * i + 2] * P[3 * j + 2];  // Jpb R^T
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {  // E = F hat(q)
+    E[3 * i] = F[3 * i + 1] * q[2] - F[3 * i + 2] * q[1];
+    E[3 * i + 1] = F[3 * i + 2] * q[0] - F[3 * i] * q[2];
+    E[3 * i + 2] = F[3 * i] * q[1] - F[3 * i + 1] * q[0];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) Jl[i] = F[i];
+  // E M_j (2x3 each)
+  double EM[(K - 1) * 6];
+#pragma unroll
+  for (int j = 0; j < K - 1; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        EM[j * 6 + 3 * i + c] = E[3 * i] * M[j * 9 + c] + E[3 * i + 1] * M[j * 9 + 3 + c] + E[3 * i + 2] * M[j * 9 + 6 + c];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    double2* out = reinterpret_cast<double2*>(Jp + i * 6 * K);
+#pragma unroll
+    for (int m = 0; m < K; ++m) {
+      double v[6];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double cur = (m == 0) ? E[3 * i + c] : EM[(m - 1) * 6 + 3 * i + c];
+        const double nxt = (m + 1 < K) ? EM[m * 6 + 3 * i + c] : 0.0;
+        v[c] = cur - nxt;
+        v[3 + c] = -(lam[m] - lam[m + 1]) * F[3 * i + c];
+      }
+      out[3 * m] = make_double2(v[0], v[1]);
+      out[3 * m + 1] = make_double2(v[2], v[3]);
+      out[3 * m + 2] = make_double2(v[4], v[5]);
+    }
+  }
+}
+
+struct PixelArgs {
+  int n;
+  const double* stamp;
+  const double2* pixel;
+  const int4* idx;        // (base, landmark, camera, -)
+  const double* tab;      // knot table of the evaluated state
+  const double* cam_tab;
+  const double* landmarks;
+  double* r;              // [n][2]
+  double* Jp;             // [n][2][6K]
+  double* Jl;             // [n][2][3]
+  double* cost_partial;   // [gridDim.x]
+  double huber;
+  int K_knots;
+};
+
+template <int K, bool WANT_J>
+__global__ void __launch_bounds__(kEvalThreads) pixel_eval_kernel(PixelArgs a, Basis B) {
+  __shared__ __align__(16) double s_tab[kTileRows * kTabStride];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_red[2];
+  __shared__ double s_cost[kEvalThreads / 32];
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = f < a.n;
+  int4 id = make_int4(0, 0, 0, 0);
+  if (active) id = a.idx[f];
+  int bmin, bmax;
+  block_min_max(active ? id.x : 0x7fffffff, active ? id.x : -0x7fffffff, s_red, &bmin, &bmax);
+  const int rows = bmax - bmin + K;
+  const bool staged = rows <= kTileRows;
+  if (staged) stage_table(s_tab, &s_bar, a.tab, bmin, rows);
+  double cost = 0.0;
+  if (active) {
+    const double t = a.stamp[f];
+    const double2 z = a.pixel[f];
+    const double* cam = a.cam_tab + kCamStride * id.z;
+    const double* lmk = a.landmarks + 3 * static_cast<size_t>(id.y);
+    double r[2];
+    double* Jp = WANT_J ? a.Jp + static_cast<size_t>(f) * 12 * K : nullptr;
+    double* Jl = WANT_J ? a.Jl + static_cast<size_t>(f) * 6 : nullptr;
+    if (staged) pixel_factor<K, WANT_J>(s_tab - static_cast<ptrdiff_t>(bmin) * kTabStride, B, id.x, t, z.x, z.y, cam, lmk, r, Jp, Jl);
+    else pixel_factor<K, WANT_J>(a.tab, B, id.x, t, z.x, z.y, cam, lmk, r, Jp, Jl);
+    if (a.r) reinterpret_cast<double2*>(a.r)[f] = make_double2(r[0], r[1]);
+    double wgt;
+    cost = 0.5 * huber_rho(r[0] * r[0] + r[1] * r[1], a.huber, &wgt);
+  }
+  // deterministic block reduction of the cost
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+  if ((threadIdx.x & 31) == 0) s_cost[threadIdx.x >> 5] = cost;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0;
+    for (int w = 0; w < kEvalThreads / 32; ++w) c += s_cost[w];
+    a.cost_partial[blockIdx.x] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inertial factor (a6 + a3 with value/velocity/acceleration Jacobian stacks fused).
+// ---------------------------------------------------------------------------------------------
+struct InertialArgs {
+  int n;
+  const double* stamp;
+  const double* meas;      // [n][6]
+  const int4* idx;         // (base, gyro bias base, accel bias base, -)
+  const double* tab;
+  const double* imu_tab;
+  const double* bg;        // [Kbg][4]
+  const double* ba;        // [Kba][4]
+  const double* gravity;   // [3]
+  double* r;               // [n][6]
+  double* Jp;              // [n][6][6K]
+  double* wg;              // [n][KB]
+  double* wa;              // [n][KB]
+  double* Jg;              // [n][6][2]
+  double* cost_partial;
+  double loss_scale;
+};
+
+// Ceres SphereManifold<3> plus-Jacobian (3x2): |x| (I - beta v v^T)[:, 0:2].
+HB_DI void sphere_plus_jacobian(const double* x, double* J /*3x2*/) {
+  const double sigma = x[0] * x[0] + x[1] * x[1];
+  double v[3] = {x[0], x[1], 1.0};
+  double beta = 0.0;
+  const double xp = x[2];
+  if (sigma <= 2.220446049250313e-16) {
+    if (xp < 0.0) beta = 2.0;
+  } else {
+    const double mu = sqrt(xp * xp + sigma);
+    const double vp = (xp <= 0.0) ? (xp - mu) : (-sigma / (xp + mu));
+    beta = 2.0 * vp * vp / (sigma + vp * vp);
+    v[0] /= vp; v[1] /= vp;
+  }
+  const double nx = sqrt(sigma + xp * xp);
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) J[2 * r + c] = nx * ((r == c ? 1.0 : 0.0) - beta * v[c] * v[r]);
+}
+
+template <int K, int KB, bool WANT_J>
+HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const Basis& BB, int base, int gb, int ab, double t,
+                           const double* __restrict__ z, const double* __restrict__ I, const double* __restrict__ bg,
+                           const double* __restrict__ ba, const double* __restrict__ grav, double* r, double* __restrict__ Jp,
+                           double* __restrict__ wg_out, double* __restrict__ wa_out, double* __restrict__ Jg) {
+  constexpr int left = (K - 1) / 2;
+  const double* row0 = T + static_cast<size_t>(base) * kTabStride;
+  const double t0 = row0[left * kTabStride + 24], t1 = row0[(left + 1) * kTabStride + 24];
+  const double inv_dt = 1.0 / (t1 - t0);
+  const double u = (t - t0) * inv_dt;
+  double lam[K + 1], lamd[K + 1], lamdd[K + 1];
+  basis_eval<K, true>(B, u, inv_dt, lam, lamd, lamdd);
+
+  // ---- forward sweep: pose, body rates (Sommer et al. recursion) ----
+  double P[9], pdd[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 9; ++i) P[i] = row0[i];
+  double A[(K - 1) * 9], LJ[(K - 1) * 9];          // A_j, lambda_j Jr(lambda_j d_j)
+  double ATw[(K - 1) * 3], ATwd[(K - 1) * 3], Wat[(K - 1) * 3];
+  double w[3] = {0, 0, 0}, wd[3] = {0, 0, 0};
+#pragma unroll
+  for (int j = 1; j < K; ++j) {
+    const double* rj = row0 + j * kTabStride;
+    const double d[3] = {rj[12], rj[13], rj[14]};
+    const double lw[3] = {lam[j] * d[0], lam[j] * d[1], lam[j] * d[2]};
+    double Jr[9], Pn[9];
+    so3_exp_and_Jr(lw, &A[(j - 1) * 9], WANT_J ? Jr : nullptr);
+    if (WANT_J) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) LJ[(j - 1) * 9 + i] = lam[j] * Jr[i];
+    }
+    m3_mul(P, &A[(j - 1) * 9], Pn);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) P[i] = Pn[i];
+    double aw[3], awd[3], wn[3], cr[3];
+    m3_tvec(&A[(j - 1) * 9], w, aw);
+    m3_tvec(&A[(j - 1) * 9], wd, awd);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) wn[c] = aw[c] + lamd[j] * d[c];
+    cross(wn, d, cr);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      wd[c] = awd[c] + lamd[j] * cr[c] + lamdd[j] * d[c];
+      w[c] = wn[c];
+      ATw[(j - 1) * 3 + c] = aw[c]; ATwd[(j - 1) * 3 + c] = awd[c]; Wat[(j - 1) * 3 + c] = wn[c];
+      pdd[c] += lamdd[j] * (rj[9 + c] - rj[9 + c - kTabStride]);
+    }
+  }
+  // ---- bias splines (value + basis weights) ----
+  double bgv[3] = {0, 0, 0}, bav[3] = {0, 0, 0};
+  {
+    constexpr int lb = (KB - 1) / 2;
+    double lb_[KB + 1];
+    const double* g0 = bg + 4 * static_cast<size_t>(gb);
+    const double s0 = g0[4 * lb + 3], s1 = g0[4 * (lb + 1) + 3];
+    basis_eval<KB, false>(BB, (t - s0) / (s1 - s0), 0.0, lb_, nullptr, nullptr);
+#pragma unroll
+    for (int m = 0; m < KB; ++m) {
+      const double wv = lb_[m] - lb_[m + 1];
+      if (WANT_J) wg_out[m] = wv;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) bgv[c] += wv * g0[4 * m + c];
+    }
+    const double* a0 = ba + 4 * static_cast<size_t>(ab);
+    const double u0 = a0[4 * lb + 3], u1 = a0[4 * (lb + 1) + 3];
+    basis_eval<KB, false>(BB, (t - u0) / (u1 - u0), 0.0, lb_, nullptr, nullptr);
+#pragma unroll
+    for (int m = 0; m < KB; ++m) {
+      const double wv = lb_[m] - lb_[m + 1];
+      if (WANT_J) wa_out[m] = wv;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) bav[c] += wv * a0[4 * m + c];
+    }
+  }
+  // ---- residual (reference inertial.cpp:62-79) ----
+  const double* Rsb = I;
+  const double* IgR = I + 12;
+  const double* IaR = I + 21;
+  const double* Sg = I + 30;
+  const double* lever = I + 39;  // row i = c_i
+  const double gm[3] = {pdd[0] - grav[0], pdd[1] - grav[1], pdd[2] - grav[2]};
+  double a_i[3], a_m[3];
+  m3_tvec(P, gm, a_i);  // R^T (pdd - g) = A_lin - R_bw g
+  double Fa[9];
+  {
+    const double ww = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Fa[3 * i + j] = w[i] * w[j] - (i == j ? ww : 0.0);
+    Fa[1] -= wd[2]; Fa[2] += wd[1]; Fa[3] += wd[2]; Fa[5] -= wd[0]; Fa[6] -= wd[1]; Fa[7] += wd[0];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) a_m[i] = a_i[i] + Fa[3 * i] * lever[3 * i] + Fa[3 * i + 1] * lever[3 * i + 1] + Fa[3 * i + 2] * lever[3 * i + 2];
+  {
+    double t1v[3], t2v[3], t3v[3];
+    m3_vec(IgR, w, t1v);
+    m3_vec(Sg, a_m, t2v);
+    m3_vec(IaR, a_m, t3v);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      r[c] = t1v[c] + t2v[c] + bgv[c] - z[c];
+      r[3 + c] = t3v[c] + bav[c] - z[3 + c];
+    }
+  }
+  if (!WANT_J) return;
+
+  // ---- coefficient matrices: rows 0-2 gyro, 3-5 accel ----
+  // d a_m / d theta = hat(a_i) R^T ; d a_m / d omega = Kw ; d a_m / d alpha = Kal ; d a_m / d pdd_w = R^T
+  double Bm[9];  // hat(a_i) R^T
+  {
+    double Rt[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Rt[3 * i + j] = P[3 * j + i];
+    hat_mul(a_i, Rt, Bm);
+  }
+  double Kw[9], Kal[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double* c = lever + 3 * i;
+    // row i of -(2 w^ c^ - c^ w^) ; (w^ c^) = c w^T - (w.c) I ; (c^ w^) = w c^T - (w.c) I
+    const double wc = w[0] * c[0] + w[1] * c[1] + w[2] * c[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double wxcx = c[i] * w[j] - (i == j ? wc : 0.0);
+      const double cxwx = w[i] * c[j] - (i == j ? wc : 0.0);
+      Kw[3 * i + j] = -(2.0 * wxcx - cxwx);
+    }
+    // row i of -c^
+    Kal[3 * i] = (i == 0) ? 0.0 : (i == 1 ? -c[2] : c[1]);
+    Kal[3 * i + 1] = (i == 0) ? c[2] : (i == 1 ? 0.0 : -c[0]);
+    Kal[3 * i + 2] = (i == 0) ? -c[1] : (i == 1 ? c[0] : 0.0);
+  }
+  double Cth[18], Cw[18], Cal[18], Cp[18];
+  m3_mul(Sg, Bm, &Cth[0]);
+  m3_mul(IaR, Bm, &Cth[9]);
+  m3_mul(Sg, Kw, &Cw[0]);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Cw[i] += IgR[i];
+  m3_mul(IaR, Kw, &Cw[9]);
+  m3_mul(Sg, Kal, &Cal[0]);
+  m3_mul(IaR, Kal, &Cal[9]);
+  m3_mult(Sg, P, &Cp[0]);   // S_g R^T
+  m3_mult(IaR, P, &Cp[9]);  // I_a R_sb R^T
+  (void)Rsb;
+  // gravity tangent Jacobian: -(Cp) * PlusJacobian_sphere(g)   (6x2)
+  {
+    double PJ[6];
+    sphere_plus_jacobian(grav, PJ);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) Jg[2 * i + c] = -(Cp[3 * i] * PJ[c] + Cp[3 * i + 1] * PJ[2 + c] + Cp[3 * i + 2] * PJ[4 + c]);
+  }
+  // ---- backward sweep over j = K-1 .. 1 ----
+  double Pc[9], QT[9], Z[9], Dprev[18];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { Pc[i] = P[i]; QT[i] = (i % 4 == 0) ? 1.0 : 0.0; Z[i] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < 18; ++i) Dprev[i] = 0.0;
+#pragma unroll
+  for (int j = K - 1; j >= 1; --j) {
+    const double* rj = row0 + j * kTabStride;
+    const double d[3] = {rj[12], rj[13], rj[14]};
+    const double* lj = &LJ[(j - 1) * 9];
+    double X[9], Y[9], tmp[9], tmp2[9];
+    hat_mul(&ATw[(j - 1) * 3], lj, X);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) X[4 * i] += lamd[j];
+    hat_mul(&ATwd[(j - 1) * 3], lj, Y);
+    hat_mul(d, X, tmp);
+    hat(&Wat[(j - 1) * 3], tmp2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Y[i] += lamd[j] * (tmp2[i] - tmp[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Y[4 * i] += lamdd[j];
+    double Xf[9], Yf[9], Tf[9];
+    m3_mul(QT, X, Xf);
+    m3_mul(Z, X, Yf);
+    m3_mul(QT, Y, tmp);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Yf[i] += tmp[i];
+    m3_mul(Pc, lj, Tf);
+    double G[9], TG[9], XG[9], YG[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] = rj[15 + i];
+    m3_mul(Tf, G, TG);
+    m3_mul(Xf, G, XG);
+    m3_mul(Yf, G, YG);
+    double D[18];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        D[3 * i + c] = Cth[3 * i] * TG[c] + Cth[3 * i + 1] * TG[3 + c] + Cth[3 * i + 2] * TG[6 + c] + Cw[3 * i] * XG[c] +
+                       Cw[3 * i + 1] * XG[3 + c] + Cw[3 * i + 2] * XG[6 + c] + Cal[3 * i] * YG[c] + Cal[3 * i + 1] * YG[3 + c] +
+                       Cal[3 * i + 2] * YG[6 + c];
+    // block m = j : rotation = D_j - D_{j+1}, translation = (lamdd_m - lamdd_{m+1}) * Cp
+    {
+      const double wdd = lamdd[j] - lamdd[j + 1];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double2* out = reinterpret_cast<double2*>(Jp + i * 6 * K + 6 * j);
+        out[0] = make_double2(D[3 * i] - Dprev[3 * i], D[3 * i + 1] - Dprev[3 * i + 1]);
+        out[1] = make_double2(D[3 * i + 2] - Dprev[3 * i + 2], wdd * Cp[3 * i]);
+        out[2] = make_double2(wdd * Cp[3 * i + 1], wdd * Cp[3 * i + 2]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) Dprev[i] = D[i];
+    // Pc <- Pc A_j^T ; Z <- (Z - lamd_j QT d^) A_j^T ; QT <- QT A_j^T
+    const double* Aj = &A[(j - 1) * 9];
+    m3_mult(Pc, Aj, tmp);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Pc[i] = tmp[i];
+    mul_hat(QT, d, tmp);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tmp2[i] = Z[i] - lamd[j] * tmp[i];
+    m3_mult(tmp2, Aj, Z);
+    m3_mult(QT, Aj, tmp);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) QT[i] = tmp[i];
+  }
+  // block m = 0 : rotation = Cth - D_1
+  {
+    const double wdd = lamdd[0] - lamdd[1];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double2* out = reinterpret_cast<double2*>(Jp + i * 6 * K);
+      out[0] = make_double2(Cth[3 * i] - Dprev[3 * i], Cth[3 * i + 1] - Dprev[3 * i + 1]);
+      out[1] = make_double2(Cth[3 * i + 2] - Dprev[3 * i + 2], wdd * Cp[3 * i]);
+      out[2] = make_double2(wdd * Cp[3 * i + 1], wdd * Cp[3 * i + 2]);
+    }
+  }
+}
+
+template <int K, int KB, bool WANT_J>
+__global__ void __launch_bounds__(kEvalThreads) inertial_eval_kernel(InertialArgs a, Basis B, Basis BB) {
+  __shared__ __align__(16) double s_tab[kTileRows * kTabStride];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_red[2];
+  __shared__ double s_cost[kEvalThreads / 32];
+  __shared__ double s_imu[kImuStride];
+  __shared__ double s_grav[3];
+  if (threadIdx.x < kImuStride) s_imu[threadIdx.x] = a.imu_tab[threadIdx.x];
+  if (threadIdx.x < 3) s_grav[threadIdx.x] = a.gravity[threadIdx.x];
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = f < a.n;
+  int4 id = make_int4(0, 0, 0, 0);
+  if (active) id = a.idx[f];
+  int bmin, bmax;
+  block_min_max(active ? id.x : 0x7fffffff, active ? id.x : -0x7fffffff, s_red, &bmin, &bmax);
+  const int rows = bmax - bmin + K;
+  const bool staged = rows <= kTileRows;
+  if (staged) stage_table(s_tab, &s_bar, a.tab, bmin, rows);
+  double cost = 0.0;
+  if (active) {
+    const double t = a.stamp[f];
+    double z[6];
+    {
+      const double2* zp = reinterpret_cast<const double2*>(a.meas + 6 * static_cast<size_t>(f));
+      const double2 z0 = zp[0], z1 = zp[1], z2 = zp[2];
+      z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y; z[4] = z2.x; z[5] = z2.y;
+    }
+    double r[6];
+    double* Jp = WANT_J ? a.Jp + static_cast<size_t>(f) * 36 * K : nullptr;
+    double* wg = WANT_J ? a.wg + static_cast<size_t>(f) * KB : nullptr;
+    double* wa = WANT_J ? a.wa + static_cast<size_t>(f) * KB : nullptr;
+    double* Jg = WANT_J ? a.Jg + static_cast<size_t>(f) * 12 : nullptr;
+    if (staged)
+      inertial_factor<K, KB, WANT_J>(s_tab - static_cast<ptrdiff_t>(bmin) * kTabStride, B, BB, id.x, id.y, id.z, t, z, s_imu, a.bg, a.ba,
+                                     s_grav, r, Jp, wg, wa, Jg);
+    else
+      inertial_factor<K, KB, WANT_J>(a.tab, B, BB, id.x, id.y, id.z, t, z, s_imu, a.bg, a.ba, s_grav, r, Jp, wg, wa, Jg);
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s += r[i] * r[i];
+    cost = 0.5 * a.loss_scale * s;
+    if (a.r) {
+      double2* ro = reinterpret_cast<double2*>(a.r + 6 * static_cast<size_t>(f));
+      ro[0] = make_double2(r[0], r[1]); ro[1] = make_double2(r[2], r[3]); ro[2] = make_double2(r[4], r[5]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+  if ((threadIdx.x & 31) == 0) s_cost[threadIdx.x >> 5] = cost;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0;
+    for (int w = 0; w < kEvalThreads / 32; ++w) c += s_cost[w];
+    a.cost_partial[blockIdx.x] = c;
+  }
+}
+
+}  // namespace hb

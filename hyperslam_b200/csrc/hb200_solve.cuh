@@ -1,0 +1,666 @@
+// Normal equations, landmark Schur complement, dense Cholesky, back-substitution, retraction and
+// LM step control (sm_100a).  Replaces the inside of ceres::Solve for the reference's problem
+// (reference internal/hyper/optimizers/ceres/optimizer.cpp:38-54,276-280): loss correction
+// (Huber 0.5 / ScaledLoss 1.6e-5, optimizer.cpp:226,267-268), J^T J / J^T r, the linear solve
+// (SPARSE_NORMAL_CHOLESKY there, landmark Schur + dense Cholesky here), Manifold::Plus
+// (reference manifolds/variables/wrapper.hpp:32-34) and the trust-region update.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "hb200_eval.cuh"
+
+namespace hb {
+
+namespace cg = cooperative_groups;
+
+// Packed system buffer: [S n*n | b n | diagH n | g n | cost | pad]
+struct SysView {
+  double* S; double* b; double* diagH; double* g; double* cost;
+  int n;
+};
+HB_DI SysView sys_view(double* base, int n) {
+  SysView v;
+  v.S = base; v.b = base + static_cast<size_t>(n) * n; v.diagH = v.b + n; v.g = v.diagH + n; v.cost = v.g + n; v.n = n;
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// J^T J / J^T r of the pixel factors, one CTA per spline segment (factors are sorted by knot base
+// index, so a segment's factors are contiguous and share the same 6K x 6K block of H).
+// ---------------------------------------------------------------------------------------------
+constexpr int kHessThreads = 128;
+
+template <int K>
+__global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* __restrict__ seg_off, const double* __restrict__ r,
+                                                                     const double* __restrict__ Jp, double huber, double* sys, int n) {
+  constexpr int NB = 6 * K;
+  constexpr int CH = 16;
+  constexpr int EPT = (NB * NB + kHessThreads - 1) / kHessThreads;
+  __shared__ double sJ[CH][2][NB];
+  __shared__ double sr[CH][2];
+  const int seg = blockIdx.x;
+  const int lo = seg_off[seg], hi = seg_off[seg + 1];
+  if (lo >= hi) return;
+  double acc[EPT], gacc = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) acc[e] = 0.0;
+  for (int f0 = lo; f0 < hi; f0 += CH) {
+    const int cnt = min(CH, hi - f0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * 2 * NB; e += kHessThreads) {
+      const int ff = e / (2 * NB), rem = e - ff * 2 * NB;
+      const int f = f0 + ff;
+      const double r0 = r[2 * f], r1 = r[2 * f + 1];
+      double wgt;
+      huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
+      const double sw = sqrt(wgt);
+      sJ[ff][rem / NB][rem % NB] = sw * Jp[static_cast<size_t>(f) * 2 * NB + rem];
+      if (rem < 2) sr[ff][rem] = sw * (rem == 0 ? r0 : r1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int id = threadIdx.x + e * kHessThreads;
+      if (id < NB * NB) {
+        const int a = id / NB, b = id - a * NB;
+        double s = 0;
+        for (int ff = 0; ff < cnt; ++ff) s += sJ[ff][0][a] * sJ[ff][0][b] + sJ[ff][1][a] * sJ[ff][1][b];
+        acc[e] += s;
+      }
+    }
+    if (threadIdx.x < NB) {
+      double s = 0;
+      for (int ff = 0; ff < cnt; ++ff) s += sJ[ff][0][threadIdx.x] * sr[ff][0] + sJ[ff][1][threadIdx.x] * sr[ff][1];
+      gacc += s;
+    }
+  }
+  SysView v = sys_view(sys, n);
+  const int c0 = 6 * seg;  // segment index == knot base index
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int id = threadIdx.x + e * kHessThreads;
+    if (id < NB * NB) {
+      const int a = id / NB, b = id - a * NB;
+      atomicAdd(&v.S[static_cast<size_t>(c0 + a) * n + c0 + b], acc[e]);
+    }
+  }
+  if (threadIdx.x < NB) atomicAdd(&v.g[c0 + threadIdx.x], gacc);
+}
+
+// Inertial factors: one CTA per run of identical (pose base, gyro-bias base, accel-bias base).
+template <int K, int KB>
+__global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const int* __restrict__ run_off, const int4* __restrict__ idx,
+                                                                        const double* __restrict__ r, const double* __restrict__ Jp,
+                                                                        const double* __restrict__ wg, const double* __restrict__ wa,
+                                                                        const double* __restrict__ Jg, double loss_scale, double* sys,
+                                                                        int n, int o_bg, int o_ba, int o_g) {
+  constexpr int NP = 6 * K;
+  constexpr int NI = NP + 6 * KB + 2;
+  constexpr int CH = 8;
+  constexpr int EPT = (NI * NI + kHessThreads - 1) / kHessThreads;
+  __shared__ double sJ[CH][6][NI];
+  __shared__ double sr[CH][6];
+  __shared__ int scol[NI];
+  const int run = blockIdx.x;
+  const int lo = run_off[run], hi = run_off[run + 1];
+  if (lo >= hi) return;
+  const int4 id0 = idx[lo];
+  for (int c = threadIdx.x; c < NI; c += kHessThreads) {
+    int col;
+    if (c < NP) col = 6 * id0.x + c;
+    else if (c < NP + 3 * KB) col = o_bg + 3 * id0.y + (c - NP);
+    else if (c < NP + 6 * KB) col = o_ba + 3 * id0.z + (c - NP - 3 * KB);
+    else col = o_g + (c - NP - 6 * KB);
+    scol[c] = col;
+  }
+  const double sw = sqrt(loss_scale);
+  double acc[EPT], gacc = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) acc[e] = 0.0;
+  for (int f0 = lo; f0 < hi; f0 += CH) {
+    const int cnt = min(CH, hi - f0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * 6 * NI; e += kHessThreads) {
+      const int ff = e / (6 * NI), rem = e - ff * 6 * NI;
+      const int row = rem / NI, c = rem - row * NI;
+      const size_t f = f0 + ff;
+      double v;
+      if (c < NP) v = Jp[f * 6 * NP + row * NP + c];
+      else if (c < NP + 3 * KB) { const int m = (c - NP) / 3, a = (c - NP) % 3; v = (row == a) ? wg[f * KB + m] : 0.0; }
+      else if (c < NP + 6 * KB) { const int m = (c - NP - 3 * KB) / 3, a = (c - NP - 3 * KB) % 3; v = (row == 3 + a) ? wa[f * KB + m] : 0.0; }
+      else v = Jg[f * 12 + 2 * row + (c - NP - 6 * KB)];
+      sJ[ff][row][c] = sw * v;
+      if (c == 0) sr[ff][row] = sw * r[f * 6 + row];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int id = threadIdx.x + e * kHessThreads;
+      if (id < NI * NI) {
+        const int a = id / NI, b = id - a * NI;
+        double s = 0;
+        for (int ff = 0; ff < cnt; ++ff)
+#pragma unroll
+          for (int row = 0; row < 6; ++row) s += sJ[ff][row][a] * sJ[ff][row][b];
+        acc[e] += s;
+      }
+    }
+    if (threadIdx.x < NI) {
+      double s = 0;
+      for (int ff = 0; ff < cnt; ++ff)
+#pragma unroll
+        for (int row = 0; row < 6; ++row) s += sJ[ff][row][threadIdx.x] * sr[ff][row];
+      gacc += s;
+    }
+  }
+  SysView v = sys_view(sys, n);
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int id = threadIdx.x + e * kHessThreads;
+    if (id < NI * NI) {
+      const int a = id / NI, b = id - a * NI;
+      if (acc[e] != 0.0) atomicAdd(&v.S[static_cast<size_t>(scol[a]) * n + scol[b]], acc[e]);
+    }
+  }
+  if (threadIdx.x < NI) atomicAdd(&v.g[scol[threadIdx.x]], gacc);
+}
+
+// diagH = diag(H), b = -g, cost = sum of the evaluation kernels' per-block partials (fixed order).
+__global__ void diag_cost_kernel(double* sys, int n, const double* __restrict__ cp_pix, int n_pix_blocks, const double* __restrict__ cp_imu,
+                                 int n_imu_blocks) {
+  SysView v = sys_view(sys, n);
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+    v.diagH[a] = v.S[static_cast<size_t>(a) * n + a];
+    v.b[a] = -v.g[a];
+  }
+  if (blockIdx.x == 0) {
+    __shared__ double s[256];
+    double c = 0;
+    for (int i = threadIdx.x; i < n_pix_blocks; i += blockDim.x) c += cp_pix[i];
+    for (int i = threadIdx.x; i < n_imu_blocks; i += blockDim.x) c += cp_imu[i];
+    s[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { v.cost[0] = s[0]; v.cost[1] = 0.0; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Landmark Schur complement: one CTA per landmark.
+//   V = sum w Jl^T Jl + mu D_l ; W = sum w Jp^T Jl (rows of the control points the landmark's
+//   observations touch) ; S -= W V^-1 W^T ; b += W V^-1 g_l.
+// Dynamic shared memory: 2 * max_rows * 3 doubles.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSchurThreads = 128;
+
+template <int K>
+__global__ void __launch_bounds__(kSchurThreads) schur_kernel(const int* __restrict__ lm_off, const int* __restrict__ lm_obs,
+                                                              const int4* __restrict__ idx, const double* __restrict__ r,
+                                                              const double* __restrict__ Jp, const double* __restrict__ Jl, double huber,
+                                                              const SolverState* __restrict__ st, double* sys, int n,
+                                                              double* __restrict__ Vinv, double* __restrict__ gl, double* __restrict__ Dl,
+                                                              int max_rows) {
+  constexpr int NB = 6 * K;
+  extern __shared__ double s_dyn[];
+  double* W = s_dyn;                  // [rows][3]
+  double* WV = s_dyn + 3 * max_rows;  // [rows][3]
+  __shared__ double sV[12];           // V (9) + g_l (3)
+  __shared__ double sVi[9];
+  const int l = blockIdx.x;
+  const int o_lo = lm_off[l], o_hi = lm_off[l + 1];
+  if (o_lo >= o_hi) {
+    if (threadIdx.x < 9) Vinv[9 * static_cast<size_t>(l) + threadIdx.x] = 0.0;
+    if (threadIdx.x < 3) { gl[3 * static_cast<size_t>(l) + threadIdx.x] = 0.0; Dl[3 * static_cast<size_t>(l) + threadIdx.x] = 1e-6; }
+    return;
+  }
+  const int cp_lo = idx[lm_obs[o_lo]].x;
+  const int cp_hi = idx[lm_obs[o_hi - 1]].x + K;
+  const int rows = 6 * (cp_hi - cp_lo);
+  // V and g_l
+  if (threadIdx.x < 12) {
+    double s = 0;
+    for (int o = o_lo; o < o_hi; ++o) {
+      const int f = lm_obs[o];
+      const double r0 = r[2 * f], r1 = r[2 * f + 1];
+      double wgt;
+      huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
+      const double* jl = Jl + 6 * static_cast<size_t>(f);
+      if (threadIdx.x < 9) { const int a = threadIdx.x / 3, b = threadIdx.x % 3; s += wgt * (jl[a] * jl[b] + jl[3 + a] * jl[3 + b]); }
+      else { const int a = threadIdx.x - 9; s += wgt * (jl[a] * r0 + jl[3 + a] * r1); }
+    }
+    sV[threadIdx.x] = s;
+  }
+  // W rows
+  for (int e = threadIdx.x; e < rows * 3; e += kSchurThreads) {
+    const int row = e / 3, c = e - 3 * row;
+    double s = 0;
+    for (int o = o_lo; o < o_hi; ++o) {
+      const int f = lm_obs[o];
+      const int a = row - 6 * (idx[f].x - cp_lo);
+      if (a >= 0 && a < NB) {
+        const double r0 = r[2 * f], r1 = r[2 * f + 1];
+        double wgt;
+        huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
+        const double* jp = Jp + static_cast<size_t>(f) * 2 * NB;
+        const double* jl = Jl + 6 * static_cast<size_t>(f);
+        s += wgt * (jp[a] * jl[c] + jp[NB + a] * jl[3 + c]);
+      }
+    }
+    W[e] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double mu = 1.0 / st->radius;
+    double V[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) V[i] = sV[i];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double d = fmin(fmax(V[4 * a], 1e-6), 1e32);
+      Dl[3 * static_cast<size_t>(l) + a] = d;
+      V[4 * a] += mu * d;
+    }
+    const double a = V[0], b = V[1], c = V[2], d = V[4], e = V[5], f = V[8];
+    const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+    const double det = a * c00 + b * c01 + c * c02;
+    const double id = 1.0 / det;
+    sVi[0] = c00 * id; sVi[1] = c01 * id; sVi[2] = c02 * id;
+    sVi[3] = sVi[1]; sVi[4] = (a * f - c * c) * id; sVi[5] = (b * c - a * e) * id;
+    sVi[6] = sVi[2]; sVi[7] = sVi[5]; sVi[8] = (a * d - b * b) * id;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Vinv[9 * static_cast<size_t>(l) + i] = sVi[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) gl[3 * static_cast<size_t>(l) + i] = sV[9 + i];
+  }
+  __syncthreads();
+  SysView v = sys_view(sys, n);
+  const int r0g = 6 * cp_lo;
+  for (int e = threadIdx.x; e < rows * 3; e += kSchurThreads) {
+    const int row = e / 3, c = e - 3 * row;
+    WV[e] = W[3 * row] * sVi[c] + W[3 * row + 1] * sVi[3 + c] + W[3 * row + 2] * sVi[6 + c];
+  }
+  __syncthreads();
+  for (int row = threadIdx.x; row < rows; row += kSchurThreads) {
+    const double val = WV[3 * row] * sV[9] + WV[3 * row + 1] * sV[10] + WV[3 * row + 2] * sV[11];
+    if (val != 0.0) atomicAdd(&v.b[r0g + row], val);
+  }
+  for (int e = threadIdx.x; e < rows * rows; e += kSchurThreads) {
+    const int a = e / rows, b = e - a * rows;
+    const double val = WV[3 * a] * W[3 * b] + WV[3 * a + 1] * W[3 * b + 1] + WV[3 * a + 2] * W[3 * b + 2];
+    if (val != 0.0) atomicAdd(&v.S[static_cast<size_t>(r0g + a) * n + r0g + b], -val);
+  }
+}
+
+// LM damping + constant dofs; writes the damped system back to S/b and the factorisation work
+// copy Lw ((n+1) x n, last row = b).
+__global__ void finalize_kernel(double* sys, int n, const SolverState* __restrict__ st, const unsigned char* __restrict__ fixed,
+                                double* __restrict__ D, double* __restrict__ Lw, int* __restrict__ spd_flag) {
+  SysView v = sys_view(sys, n);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *spd_flag = 1;
+  const size_t brow = static_cast<size_t>((n + 31) / 32) * 32;  // row of Lw holding b (own tile row)
+  const double mu = 1.0 / st->radius;
+  const size_t total = static_cast<size_t>(n + 1) * n;
+  for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total; e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(e / n), j = static_cast<int>(e - static_cast<size_t>(i) * n);
+    if (i < n) {
+      double s = v.S[e];
+      if (i == j) {
+        const double d = fmin(fmax(v.diagH[i], 1e-6), 1e32);
+        D[i] = d;
+        s += mu * d;
+      }
+      if (fixed[i] || fixed[j]) s = (i == j) ? 1.0 : 0.0;
+      v.S[e] = s;
+      Lw[e] = s;
+    } else {
+      const double bb = fixed[j] ? 0.0 : v.b[j];
+      v.b[j] = bb;
+      Lw[brow * n + j] = bb;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense blocked Cholesky (right-looking, 32 x 32 tiles) of the augmented matrix [S ; b^T] stored
+// as (32*T + 1) x n (rows n..32T-1 unused, b^T in row 32T so that it owns a tile row): after the
+// call the strictly-lower tiles hold L, Ldiag holds the diagonal tiles and row 32T holds y = L^-1 b.  Cooperative launch (grid sync between panel phases).
+// ---------------------------------------------------------------------------------------------
+constexpr int kCholNB = 32;
+constexpr int kCholThreads = 256;
+constexpr int kCholWarps = kCholThreads / 32;
+constexpr size_t kCholSmem = sizeof(double) * (kCholNB * (kCholNB + 1)) * (1 + kCholWarps);
+
+HB_DI void chol_tile32(double (*s)[kCholNB + 1], int lane) {
+  // In-place Cholesky of a 32x32 SPD tile in shared memory by one warp; lane = row.
+  double row[kCholNB];
+#pragma unroll
+  for (int c = 0; c < kCholNB; ++c) row[c] = s[lane][c];
+#pragma unroll
+  for (int c = 0; c < kCholNB; ++c) {
+    const double dcc = __shfl_sync(0xffffffffu, row[c], c);
+    const double inv = rsqrt(dcc);
+    const double lrc = (lane == c) ? dcc * inv : row[c] * inv;  // sqrt(dcc) on the diagonal
+    row[c] = lrc;
+    s[lane][c] = (lane >= c) ? lrc : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int cc = c + 1; cc < kCholNB; ++cc) row[cc] -= lrc * s[cc][c];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kCholThreads) cholesky_kernel(double* __restrict__ Lw, double* __restrict__ Ldiag, int n, int* __restrict__ spd_flag) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double s_chol[];
+  double (*sL)[kCholNB + 1] = reinterpret_cast<double (*)[kCholNB + 1]>(s_chol);
+  double (*sA)[kCholNB][kCholNB + 1] = reinterpret_cast<double (*)[kCholNB][kCholNB + 1]>(s_chol + kCholNB * (kCholNB + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (n + kCholNB - 1) / kCholNB;  // column tiles
+  const int TR = T + 1;                       // row tiles (last one = augmented row only)
+  const int brow = T * kCholNB;
+  const int gwarp = blockIdx.x * kCholWarps + warp;
+  const int nwarps = gridDim.x * kCholWarps;
+  for (int p = 0; p < T; ++p) {
+    const int c0 = p * kCholNB;
+    // ---- phase A: every CTA with TRSM work factors the diagonal tile, then solves its row tiles ----
+    const int ntr = TR - (p + 1);
+    const bool has_work = (blockIdx.x == 0) || (blockIdx.x * kCholWarps < ntr);
+    if (has_work) {
+      for (int e = threadIdx.x; e < kCholNB * kCholNB; e += kCholThreads) {
+        const int i = e / kCholNB, j = e - i * kCholNB;
+        const int gi = c0 + i, gj = c0 + j;
+        double val = (i == j) ? 1.0 : 0.0;
+        if (gi < n && gj < n) val = Lw[static_cast<size_t>(gi) * n + gj];
+        sL[i][j] = val;
+      }
+      __syncthreads();
+      if (warp == 0) chol_tile32(sL, lane);
+      __syncthreads();
+      if (blockIdx.x == 0) {
+        bool bad = false;
+        for (int e = threadIdx.x; e < kCholNB * kCholNB; e += kCholThreads) {
+          const int i = e / kCholNB, j = e - i * kCholNB;
+          const double val = sL[i][j];
+          Ldiag[static_cast<size_t>(p) * kCholNB * kCholNB + e] = val;
+          if (i == j && !(val > 0.0)) bad = true;
+        }
+        if (bad) atomicExch(spd_flag, 0);
+      }
+      // TRSM: row tile i (> p, incl. the augmented row): X = A_ip L_pp^-T, lane = row of the tile
+      for (int it = gwarp; it < ntr; it += nwarps) {
+        const int i = p + 1 + it;
+        const int gi = i * kCholNB + lane;
+        double a[kCholNB];
+        if (gi < n || gi == brow) {
+#pragma unroll
+          for (int c = 0; c < kCholNB; ++c) a[c] = (c0 + c < n) ? Lw[static_cast<size_t>(gi) * n + c0 + c] : 0.0;
+        } else {
+#pragma unroll
+          for (int c = 0; c < kCholNB; ++c) a[c] = 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < kCholNB; ++c) {
+          double x = a[c];
+#pragma unroll
+          for (int q = 0; q < c; ++q) x -= a[q] * sL[c][q];
+          a[c] = x / sL[c][c];
+        }
+        if (gi < n || gi == brow) {
+#pragma unroll
+          for (int c = 0; c < kCholNB; ++c)
+            if (c0 + c < n) Lw[static_cast<size_t>(gi) * n + c0 + c] = a[c];
+        }
+      }
+    }
+    grid.sync();
+    // ---- phase B: trailing update A_ij -= A_ip A_jp^T for p < j <= i (i over row tiles) ----
+    const int nt = TR - (p + 1);   // row tiles below the panel
+    const int ntc = T - (p + 1);   // column tiles right of the panel
+    // enumerate (ii, jj) with jj < ntc, ii >= jj, ii < nt
+    const long long ntiles = static_cast<long long>(ntc) * nt - static_cast<long long>(ntc) * (ntc - 1) / 2;
+    for (long long tix = gwarp; tix < ntiles; tix += nwarps) {
+      // decode: column jj has (nt - jj) tiles
+      int jj = 0;
+      long long rem = tix;
+      while (rem >= nt - jj) { rem -= nt - jj; ++jj; }
+      const int ii = jj + static_cast<int>(rem);
+      const int i = p + 1 + ii, j = p + 1 + jj;
+      // stage A_ip into this warp's smem tile, keep row `lane` of A_jp in registers
+      double (*sa)[kCholNB + 1] = sA[warp];
+      for (int rr = 0; rr < kCholNB; ++rr) {
+        const int gi = i * kCholNB + rr;
+        sa[rr][lane] = ((gi < n || gi == brow) && c0 + lane < n) ? Lw[static_cast<size_t>(gi) * n + c0 + lane] : 0.0;
+      }
+      double bj[kCholNB];
+      {
+        const int gj = j * kCholNB + lane;
+#pragma unroll
+        for (int q = 0; q < kCholNB; ++q) bj[q] = (gj < n && c0 + q < n) ? Lw[static_cast<size_t>(gj) * n + c0 + q] : 0.0;
+      }
+      __syncwarp();
+      const int gcol = j * kCholNB + lane;
+      for (int rr = 0; rr < kCholNB; ++rr) {
+        const int gi = i * kCholNB + rr;
+        if (!(gi < n || gi == brow)) continue;
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < kCholNB; ++q) s += sa[rr][q] * bj[q];
+        if (gcol < n && (gi >= gcol)) Lw[static_cast<size_t>(gi) * n + gcol] -= s;
+      }
+      __syncwarp();
+    }
+    grid.sync();
+  }
+}
+
+// Back-substitution L^T x = y (y = row n of Lw), single CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) backsolve_kernel(const double* __restrict__ Lw, const double* __restrict__ Ldiag, int n,
+                                                         double* __restrict__ x) {
+  __shared__ double part[32][kCholNB + 1];
+  __shared__ double sx[kCholNB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (n + kCholNB - 1) / kCholNB;
+  for (int p = T - 1; p >= 0; --p) {
+    const int c0 = p * kCholNB;
+    double acc = 0.0;
+    const int col = c0 + lane;
+    for (int row = (p + 1) * kCholNB + warp; row < n; row += 32)
+      if (col < n) acc += Lw[static_cast<size_t>(row) * n + col] * x[row];
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      double rhs = (col < n) ? Lw[static_cast<size_t>(T) * kCholNB * n + col] : 0.0;
+      for (int w = 0; w < 32; ++w) rhs -= part[w][lane];
+      const double* Ld = Ldiag + static_cast<size_t>(p) * kCholNB * kCholNB;
+      double xv = 0.0;
+      for (int q = kCholNB - 1; q >= 0; --q) {
+        // x_q = rhs_q / L[q][q]; rhs_c -= L[q][c] x_q for c < q
+        const double dq = Ld[q * kCholNB + q];
+        const double xq = __shfl_sync(0xffffffffu, rhs, q) / dq;
+        if (lane == q) xv = xq;
+        if (lane < q) rhs -= Ld[q * kCholNB + lane] * xq;
+      }
+      if (col < n) x[col] = xv;
+      sx[lane] = xv;
+    }
+    __syncthreads();
+  }
+}
+
+// Landmark back-substitution: dl = V^-1 (-g_l - W^T dp); also partial sums of dl.g_l and dl.D_l.dl.
+template <int K>
+__global__ void lm_backsub_kernel(int L, const int* __restrict__ lm_off, const int* __restrict__ lm_obs, const int4* __restrict__ idx,
+                                  const double* __restrict__ r, const double* __restrict__ Jp, const double* __restrict__ Jl, double huber,
+                                  const double* __restrict__ Vinv, const double* __restrict__ gl, const double* __restrict__ Dl,
+                                  const double* __restrict__ dp, double* __restrict__ dl, double* __restrict__ part /*[grid][2]*/) {
+  constexpr int NB = 6 * K;
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  double s_g = 0, s_d = 0;
+  if (l < L) {
+    double rhs[3] = {-gl[3 * static_cast<size_t>(l)], -gl[3 * static_cast<size_t>(l) + 1], -gl[3 * static_cast<size_t>(l) + 2]};
+    for (int o = lm_off[l]; o < lm_off[l + 1]; ++o) {
+      const int f = lm_obs[o];
+      const double r0 = r[2 * f], r1 = r[2 * f + 1];
+      double wgt;
+      huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
+      const double* jp = Jp + static_cast<size_t>(f) * 2 * NB;
+      const double* jl = Jl + 6 * static_cast<size_t>(f);
+      const double* d = dp + 6 * idx[f].x;
+      double t0 = 0, t1 = 0;
+#pragma unroll
+      for (int a = 0; a < NB; ++a) { t0 += jp[a] * d[a]; t1 += jp[NB + a] * d[a]; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rhs[c] -= wgt * (jl[c] * t0 + jl[3 + c] * t1);
+    }
+    const double* Vi = Vinv + 9 * static_cast<size_t>(l);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double v = Vi[3 * c] * rhs[0] + Vi[3 * c + 1] * rhs[1] + Vi[3 * c + 2] * rhs[2];
+      dl[3 * static_cast<size_t>(l) + c] = v;
+      s_g += v * gl[3 * static_cast<size_t>(l) + c];
+      s_d += v * v * Dl[3 * static_cast<size_t>(l) + c];
+    }
+  }
+  __shared__ double sg[8], sd[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s_g += __shfl_xor_sync(0xffffffffu, s_g, o); s_d += __shfl_xor_sync(0xffffffffu, s_d, o); }
+  if ((threadIdx.x & 31) == 0) { sg[threadIdx.x >> 5] = s_g; sd[threadIdx.x >> 5] = s_d; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { a += sg[w]; b += sd[w]; }
+    part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// Ceres SphereManifold<3>::Plus.
+HB_DI void sphere_plus(const double* x, const double* delta, double* out) {
+  const double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1]);
+  if (nd == 0.0) { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; return; }
+  const double sigma = x[0] * x[0] + x[1] * x[1];
+  double v[3] = {x[0], x[1], 1.0};
+  double beta = 0.0;
+  const double xp = x[2];
+  if (sigma <= 2.220446049250313e-16) {
+    if (xp < 0.0) beta = 2.0;
+  } else {
+    const double mu = sqrt(xp * xp + sigma);
+    const double vp = (xp <= 0.0) ? (xp - mu) : (-sigma / (xp + mu));
+    beta = 2.0 * vp * vp / (sigma + vp * vp);
+    v[0] /= vp; v[1] /= vp;
+  }
+  const double nx = sqrt(sigma + xp * xp);
+  const double s = sin(nd) / nd;
+  const double y[3] = {s * delta[0], s * delta[1], cos(nd)};
+  const double vy = v[0] * y[0] + v[1] * y[1] + v[2] * y[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) out[i] = nx * (y[i] - v[i] * beta * vy);
+}
+
+// Manifold::Plus on every variable block: trial = current (+) delta.
+__global__ void retract_kernel(int K, int Kbg, int Kba, int L, const double* __restrict__ dp, const double* __restrict__ dl,
+                               const double* __restrict__ knots, const double* __restrict__ bg, const double* __restrict__ ba,
+                               const double* __restrict__ grav, const double* __restrict__ lms, double* __restrict__ knots_t,
+                               double* __restrict__ bg_t, double* __restrict__ ba_t, double* __restrict__ grav_t, double* __restrict__ lms_t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K) {
+    const double* kn = knots + 8 * static_cast<size_t>(i);
+    const double* d = dp + 6 * static_cast<size_t>(i);
+    double qe[4], qn[4];
+    const double th[3] = {d[0], d[1], d[2]};
+    const double q[4] = {kn[0], kn[1], kn[2], kn[3]};
+    quat_exp(th, qe);
+    quat_mul(qe, q, qn);
+    double* o = knots_t + 8 * static_cast<size_t>(i);
+    o[0] = qn[0]; o[1] = qn[1]; o[2] = qn[2]; o[3] = qn[3];
+    o[4] = kn[4] + d[3]; o[5] = kn[5] + d[4]; o[6] = kn[6] + d[5]; o[7] = kn[7];
+  }
+  if (i < Kbg) {
+    const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(i);
+    for (int c = 0; c < 3; ++c) bg_t[4 * i + c] = bg[4 * i + c] + d[c];
+    bg_t[4 * i + 3] = bg[4 * i + 3];
+  }
+  if (i < Kba) {
+    const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(Kbg) + 3 * static_cast<size_t>(i);
+    for (int c = 0; c < 3; ++c) ba_t[4 * i + c] = ba[4 * i + c] + d[c];
+    ba_t[4 * i + 3] = ba[4 * i + 3];
+  }
+  if (i == 0) {
+    const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(Kbg) + 3 * static_cast<size_t>(Kba);
+    const double x[3] = {grav[0], grav[1], grav[2]};
+    const double dd[2] = {d[0], d[1]};
+    double o[3];
+    sphere_plus(x, dd, o);
+    grav_t[0] = o[0]; grav_t[1] = o[1]; grav_t[2] = o[2];
+  }
+  if (i < L) {
+    for (int c = 0; c < 3; ++c) lms_t[3 * static_cast<size_t>(i) + c] = lms[3 * static_cast<size_t>(i) + c] + dl[3 * static_cast<size_t>(i) + c];
+  }
+}
+
+// scal = [cost_new, dl.g_l, dl.D_l.dl, 0] (rank-local partial sums, fixed order).
+__global__ void scalars_kernel(const double* __restrict__ cp_pix, int n_pix_blocks, const double* __restrict__ cp_imu, int n_imu_blocks,
+                               const double* __restrict__ lm_part, int n_lm_blocks, double* __restrict__ scal) {
+  __shared__ double s[3][256];
+  double c = 0, a = 0, b = 0;
+  for (int i = threadIdx.x; i < n_pix_blocks; i += blockDim.x) c += cp_pix[i];
+  for (int i = threadIdx.x; i < n_imu_blocks; i += blockDim.x) c += cp_imu[i];
+  for (int i = threadIdx.x; i < n_lm_blocks; i += blockDim.x) { a += lm_part[2 * i]; b += lm_part[2 * i + 1]; }
+  s[0][threadIdx.x] = c; s[1][threadIdx.x] = a; s[2][threadIdx.x] = b;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s[0][threadIdx.x] += s[0][threadIdx.x + o]; s[1][threadIdx.x] += s[1][threadIdx.x + o]; s[2][threadIdx.x] += s[2][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { scal[0] = s[0][0]; scal[1] = s[1][0]; scal[2] = s[2][0]; scal[3] = 0.0; }
+}
+
+// Step acceptance (Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy::StepAccepted/Rejected).
+__global__ void accept_kernel(const double* __restrict__ sys, int n, const double* __restrict__ scal, const double* __restrict__ dp,
+                              const double* __restrict__ D, const unsigned char* __restrict__ fixed, SolverState* st,
+                              const int* __restrict__ spd_flag, SolverState* __restrict__ record, int max_records) {
+  __shared__ double s[2][256];
+  const double* g = sys + static_cast<size_t>(n) * n + 2 * static_cast<size_t>(n);
+  double a = 0, b = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (!fixed[i]) { a += dp[i] * g[i]; b += dp[i] * dp[i] * D[i]; }
+  s[0][threadIdx.x] = a; s[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s[0][threadIdx.x] += s[0][threadIdx.x + o]; s[1][threadIdx.x] += s[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mu = 1.0 / st->radius;
+    const double cost = sys[static_cast<size_t>(n) * n + 3 * static_cast<size_t>(n)];
+    const double cost_new = scal[0];
+    const double dg = s[0][0] + scal[1], dDd = s[1][0] + scal[2];
+    const double model = 0.5 * (-dg + mu * dDd);
+    const double rho = (cost - cost_new) / model;
+    const int spd = *spd_flag;
+    st->cost = cost; st->cost_new = cost_new; st->model_change = model; st->rho = rho; st->spd = spd;
+    if (spd && model > 0.0 && rho > 1e-3) {
+      st->accepted = 1;
+      const double t = 2.0 * rho - 1.0;
+      st->radius = fmin(1e16, st->radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+      st->decrease_factor = 2.0;
+    } else {
+      st->accepted = 0;
+      st->radius = st->radius / st->decrease_factor;
+      st->decrease_factor *= 2.0;
+    }
+    st->iteration += 1;
+    if (record && st->iteration <= max_records) record[st->iteration - 1] = *st;
+  }
+}
+
+__global__ void commit_kernel(const SolverState* __restrict__ st, size_t count, const double* __restrict__ src, double* __restrict__ dst) {
+  if (!st->accepted) return;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < count; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
+}  // namespace hb

@@ -1,0 +1,126 @@
+/* hyperb200.h -- C-ABI of the B200-native HyperSLAM hot path (libhyperb200.so).
+ *
+ * Drop-in boundary: one context owns the flattened sliding window that the
+ * reference's optimizer holds as a pointer graph, and runs what ceres::Solve runs per iteration --
+ * every residual block's Evaluate(), the normal equations and the linear solve -- as batched sm_100a
+ * kernels.  All pointers are plain host pointers unless a name says "device"; buffers are copied in
+ * or out, never aliased across calls.  Every function returns 0 on success, <0 for an invalid
+ * argument, >0 for a CUDA / numerical failure; hb200_last_error_string() describes the last one.
+ * (The reference aborts through glog CHECKs and Evaluate() always returns true,
+ * reference internal/hyper/optimizers/ceres/costs/exteroceptive.cpp:159,162-178.)
+ * A context is not thread-safe (the reference runs everything optimiser-side on one backend thread,
+ * reference internal/hyper/system/components/backend.cpp:124-158).
+ */
+#ifndef HYPERB200_H_
+#define HYPERB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb200_ctx hb200_ctx;
+
+typedef struct hb200_options {
+  int device;        /* CUDA device ordinal */
+  void* stream;      /* cudaStream_t to run on; NULL => the context creates its own */
+  int use_graph;     /* capture hb200_iterate() in a CUDA graph (1) or launch kernels directly (0) */
+  int reserved;
+} hb200_options;
+
+/* Per-iteration record, the analogue of ceres::IterationSummary printed through
+ * summary.BriefReport() (reference internal/hyper/optimizers/ceres/optimizer.cpp:279). */
+typedef struct hb200_iteration {
+  double cost;          /* 1/2 sum rho(|r|^2) at the linearisation point */
+  double cost_new;      /* cost at the trial point */
+  double model_change;  /* predicted decrease of the quadratic model */
+  double rho;           /* (cost - cost_new) / model_change */
+  double radius;        /* trust-region radius after the update */
+  int accepted;         /* step accepted */
+  int spd;              /* reduced system was positive definite */
+} hb200_iteration;
+
+enum { HB200_PIXEL = 0, HB200_INERTIAL = 1 };
+enum { HB200_EVAL_JACOBIANS = 1, HB200_EVAL_TRIAL = 2 };
+
+int hb200_create(const hb200_options* options, hb200_ctx** out);
+void hb200_destroy(hb200_ctx* ctx);
+const char* hb200_last_error_string(void);
+int hb200_synchronize(hb200_ctx* ctx);
+
+/* ---- window state: replaces the parameter blocks Ceres aliases ------------------------------
+ * knots  [K][8] = Stamped<SE3> blocks [qx qy qz qw px py pz | stamp] ordered by stamp
+ *         (reference optimizer.cpp:287-305 AddParameterBlock per state element; storage order
+ *         reference settings.yaml:34-36, stamped.hpp:35-36).  order = layout().outer.size.      */
+int hb200_set_spline(hb200_ctx* ctx, int order, int num_knots, const double* knots);
+/* bias control points [Kb][4] = Stamped<R3> [bx by bz | stamp] (reference imu.cpp:64-80). */
+int hb200_set_bias_splines(hb200_ctx* ctx, int order, int num_gyro, const double* gyro, int num_accel, const double* accel);
+/* gravity parameter block, 3 doubles on the sphere (reference optimizer.cpp:104). */
+int hb200_set_gravity(hb200_ctx* ctx, const double* gravity);
+/* cameras [C][15] = T_bs(7) | intrinsics cx cy fx fy | radtan k1 k2 p1 p2
+ * (Sensor::parameters order, reference pixel.cpp:43-45). */
+int hb200_set_cameras(hb200_ctx* ctx, int num_cameras, const double* cameras);
+/* IMU static blocks (37) = T_bs(7) | i_g(6) | i_a(6) | S_g(9) | X_a(9) (reference inertial.cpp:35-39,45-49). */
+int hb200_set_imu(hb200_ctx* ctx, const double* imu);
+/* landmark position blocks [L][3] (reference optimizer.cpp:347-358). */
+int hb200_set_landmarks(hb200_ctx* ctx, int num_landmarks, const double* xyz);
+/* constancy: SetParameterBlockConstant on state elements (reference optimizer.cpp:322-328),
+ * setGravityConstant (reference abstract.cpp:57-61), bias manifolds (reference optimizer.cpp:62-63). */
+int hb200_set_constant(hb200_ctx* ctx, const unsigned char* knot_constant, int gravity_constant, int bias_constant);
+/* losses: HuberLoss(huber_pixel) (reference optimizer.cpp:226), ScaledLoss(NULL, imu_loss_scale)
+ * (:267-268); radius = initial trust-region radius (Ceres default 1e4). */
+int hb200_set_options(hb200_ctx* ctx, double huber_pixel, double imu_loss_scale, double radius);
+
+/* ---- factor lists: replace problem_.AddResidualBlock (reference optimizer.cpp:212-232,253-274) */
+int hb200_set_pixel_factors(hb200_ctx* ctx, int n, const double* stamp, const int* camera, const int* landmark, const double* pixel);
+int hb200_set_inertial_factors(hb200_ctx* ctx, int n, const double* stamp, const double* measurement /* [n][6] gyro|accel */);
+/* ExteroceptiveCost::update() for every factor (reference exteroceptive.cpp:25-99): resolves the
+ * knot base index of each stamp and the segment / landmark incidence lists.  num_invalid receives
+ * the number of factors whose stamp or indices fall outside the window (they are an error). */
+int hb200_bind(hb200_ctx* ctx, int* num_invalid);
+int hb200_get_index_maps(hb200_ctx* ctx, int* pixel_base, int* inertial_base, int* gyro_bias_base, int* accel_bias_base);
+
+/* ---- the hot path --------------------------------------------------------------------------
+ * hb200_evaluate: residual (+ Jacobian) of every factor at the current state (flags 0 / JACOBIANS)
+ * or at the trial state (TRIAL).  Compact outputs (DESIGN.md "HBM layout"):
+ *   pixel   : r[n][2], Jp[n][2][6k], Jl[n][2][3]
+ *   inertial: r[n][6], Jp[n][6][6k], wg[n][kb], wa[n][kb], Jg[n][6][2]                       */
+int hb200_evaluate(hb200_ctx* ctx, int flags);
+int hb200_get_pixel_outputs(hb200_ctx* ctx, double* r, double* Jp, double* Jl);
+int hb200_get_inertial_outputs(hb200_ctx* ctx, double* r, double* Jp, double* wg, double* wa, double* Jg);
+/* Ceres-shaped copy-out of one factor after hb200_evaluate(JACOBIANS): same signature, block order
+ * and row-major ambient Jacobians as ExteroceptiveCost::Evaluate (reference exteroceptive.hpp:31,
+ * exteroceptive.cpp:149-156).  parameters must be the blocks the window was uploaded from; blocks
+ * that are constant in the live configuration (calibration) get zero Jacobians. */
+int hb200_factor_evaluate(hb200_ctx* ctx, int kind, int index, const double* const* parameters, double* residuals, double** jacobians);
+
+/* normal equations + landmark Schur complement at the current linearisation point;
+ * requires hb200_evaluate(JACOBIANS).  System layout: [6K pose | 3Kbg | 3Kba | 2 gravity]. */
+int hb200_reduced_size(hb200_ctx* ctx);
+int hb200_build_system(hb200_ctx* ctx);
+int hb200_get_system(hb200_ctx* ctx, double* S /* n x n */, double* b /* n */);
+/* dense Cholesky of the reduced system, back-substitution, landmark back-substitution. */
+int hb200_solve(hb200_ctx* ctx);
+int hb200_get_delta(hb200_ctx* ctx, double* delta_pose /* n */, double* delta_landmark /* 3L */);
+/* full LM iterations: evaluate -> build -> [allreduce] -> solve -> retract -> cost at trial ->
+ * accept/reject, all on the device.  records may be NULL. */
+int hb200_iterate(hb200_ctx* ctx, int iterations, hb200_iteration* records);
+int hb200_cost(hb200_ctx* ctx, double* cost);
+int hb200_get_state(hb200_ctx* ctx, double* knots, double* gyro, double* accel, double* gravity, double* landmarks);
+
+/* ---- multi-GPU hook -------------------------------------------------------------------------
+ * The packed reduced system [S (n*n) | b (n) | cost (1) | pad (1)] lives in one device buffer;
+ * when factors are sharded over ranks the caller sums it across ranks between build and solve
+ * (one all-reduce per iteration).  The callback runs on the context's
+ * stream inside hb200_iterate; it must enqueue work on that stream only. */
+typedef int (*hb200_allreduce_fn)(void* user, void* device_buffer, long long count_doubles, void* stream);
+int hb200_set_allreduce(hb200_ctx* ctx, hb200_allreduce_fn fn, void* user);
+void* hb200_system_device_ptr(hb200_ctx* ctx, long long* count_doubles);
+void* hb200_stream(hb200_ctx* ctx);
+
+/* kernel-launch counter (number of this library's kernels launched since creation). */
+long long hb200_launch_count(hb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPERB200_H_ */
