@@ -13,7 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/hyperb200.h"
-#include "hb200_solve.cuh"
+#include "hb200_band.cuh"
 
 using namespace hb;
 
@@ -110,6 +110,10 @@ struct hb200_ctx {
   std::vector<int> v_perm, i_perm;          // bound position -> user index
   DevBuf<int> seg_off, run_off, lm_off, lm_obs, d_invalid;
   int nseg = 0, nruns = 0, max_rows = 6;
+  int pix_splits = 1, imu_splits = 1;
+  int beta = 3;
+  bool band_solver = true, band_smem = true, force_dense = false;
+  DevBuf<double> band_ws;
   bool bound = false;
 
   // outputs
@@ -133,6 +137,16 @@ struct hb200_ctx {
   hb200_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
 
+  // profiling (hb200_profile_iteration)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<std::string> prof_names;
+  size_t prof_used = 0;
+  // snapshot
+  DevBuf<double> snap_knots, snap_bg, snap_ba, snap_grav, snap_lms;
+  DevBuf<SolverState> snap_st;
+  bool have_snapshot = false;
+
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
@@ -145,8 +159,17 @@ struct hb200_ctx {
 
 namespace {
 
+void prof_mark(hb200_ctx* c, const char* what) {
+  if (!c->profiling) return;
+  if (c->prof_used == c->prof_events.size()) { cudaEvent_t e; cudaEventCreate(&e); c->prof_events.push_back(e); c->prof_names.emplace_back(); }
+  cudaEventRecord(c->prof_events[c->prof_used], c->stream);
+  c->prof_names[c->prof_used] = what;
+  c->prof_used += 1;
+}
+
 int check_launch(hb200_ctx* c, const char* what) {
   c->launches += 1;
+  prof_mark(c, what);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(100 + static_cast<int>(e), "launch %s: %s", what, cudaGetErrorString(e));
   return 0;
@@ -183,11 +206,25 @@ int ensure_system(hb200_ctx* c) {
   HB_CUDA(c->Vinv.ensure(9 * static_cast<size_t>(std::max(c->L, 1))));
   HB_CUDA(c->gl.ensure(3 * static_cast<size_t>(std::max(c->L, 1))));
   HB_CUDA(c->Dl.ensure(3 * static_cast<size_t>(std::max(c->L, 1))));
-  c->n_lm_blocks = (c->L + 127) / 128;
+  c->n_lm_blocks = (c->L + kLmWarps - 1) / kLmWarps;
   HB_CUDA(c->lm_part.ensure(2 * static_cast<size_t>(std::max(c->n_lm_blocks, 1))));
   HB_CUDA(c->scal.ensure(4));
   HB_CUDA(c->spd.ensure(1));
   HB_CUDA(c->records.ensure(c->max_records));
+  // solver selection: block-banded + arrowhead (one CTA) unless the band is wide on a large system
+  c->beta = std::max(c->k - 1, c->max_rows / 6 - 1);
+  c->beta = std::min(c->beta, std::max(c->K - 1, 0));
+  const size_t ws = band_workspace_doubles(c->K, c->beta, c->n - 6 * c->K) * sizeof(double);
+  c->band_solver = !c->force_dense && ((c->n <= 512) || (12 * (c->beta + 1) <= 6 * c->K));
+  c->band_smem = ws <= 220 * 1024;
+  if (c->band_solver) {
+    if (c->band_smem) HB_CUDA(cudaFuncSetAttribute(band_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ws)));
+    else HB_CUDA(c->band_ws.ensure(ws / sizeof(double)));
+  }
+  HB_CUDA(c->band_ws.ensure(1));
+  // parallelism of the J^T J kernels: aim at ~2 CTAs per SM
+  c->pix_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nseg, 1) - 1) / std::max(c->nseg, 1), std::max(1, c->Nv / (16 * std::max(c->nseg, 1)))));
+  c->imu_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nruns, 1) - 1) / std::max(c->nruns, 1), std::max(1, c->Ni / (8 * std::max(c->nruns, 1)))));
   return 0;
 }
 
@@ -238,18 +275,19 @@ int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel) {
 int enqueue_build(hb200_ctx* c) {
   const size_t n = c->n;
   HB_CUDA(cudaMemsetAsync(c->sys.p, 0, (n * n + 3 * n + 2) * sizeof(double), c->stream));
+  prof_mark(c, "memset(system)");
   if (c->Nv) {
-    if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n);
-    else pixel_hessian_kernel<6><<<c->nseg, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n);
+    if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n, c->pix_splits);
+    else pixel_hessian_kernel<6><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n, c->pix_splits);
     HB_LAUNCH(c, "pixel_hessian_kernel");
   }
   if (c->Ni) {
     if (c->k == 4)
-      inertial_hessian_kernel<4, 4><<<c->nruns, kHessThreads, 0, c->stream>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g());
+      inertial_hessian_kernel<4, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, c->stream>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     else
-      inertial_hessian_kernel<6, 4><<<c->nruns, kHessThreads, 0, c->stream>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g());
+      inertial_hessian_kernel<6, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, c->stream>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     HB_LAUNCH(c, "inertial_hessian_kernel");
   }
   diag_cost_kernel<<<std::max(1, (c->n + 255) / 256), 256, 0, c->stream>>>(c->sys.p, c->n, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p,
@@ -277,7 +315,11 @@ int enqueue_finalize(hb200_ctx* c) {
 }
 
 int enqueue_solve(hb200_ctx* c) {
-  {
+  if (c->band_solver) {
+    const size_t smem = c->band_smem ? band_workspace_doubles(c->K, c->beta, c->n - 6 * c->K) * sizeof(double) : 0;
+    band_solve_kernel<<<1, kBandThreads, smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_smem ? 1 : 0, c->band_ws.p, c->dp.p, c->spd.p);
+    HB_LAUNCH(c, "band_solve_kernel");
+  } else {
     int n = c->n;
     double* Lw = c->Lw.p; double* Ld = c->Ldiag.p; int* spd = c->spd.p;
     void* args[] = {&Lw, &Ld, &n, &spd};
@@ -286,16 +328,17 @@ int enqueue_solve(hb200_ctx* c) {
     int blocks = static_cast<int>(std::min<long long>(c->num_sms, std::max<long long>(1, (tiles + kCholWarps - 1) / kCholWarps)));
     HB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cholesky_kernel), dim3(blocks), dim3(kCholThreads), args, kCholSmem, c->stream));
     c->launches += 1;
+    prof_mark(c, "cholesky_kernel");
+    backsolve_kernel<<<1, 1024, 0, c->stream>>>(c->Lw.p, c->Ldiag.p, c->n, c->dp.p);
+    HB_LAUNCH(c, "backsolve_kernel");
   }
-  backsolve_kernel<<<1, 1024, 0, c->stream>>>(c->Lw.p, c->Ldiag.p, c->n, c->dp.p);
-  HB_LAUNCH(c, "backsolve_kernel");
   if (c->L) {
     if (c->Nv) {
       if (c->k == 4)
-        lm_backsub_kernel<4><<<c->n_lm_blocks, 128, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber,
+        lm_backsub_kernel<4><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber,
                                                                     c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p);
       else
-        lm_backsub_kernel<6><<<c->n_lm_blocks, 128, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber,
+        lm_backsub_kernel<6><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber,
                                                                     c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p);
       HB_LAUNCH(c, "lm_backsub_kernel");
     } else {
@@ -324,16 +367,15 @@ int enqueue_scalars(hb200_ctx* c) {
 int enqueue_accept(hb200_ctx* c) {
   accept_kernel<<<1, 256, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records);
   HB_LAUNCH(c, "accept_kernel");
-  struct Item { size_t count; const double* src; double* dst; };
-  const Item items[] = {{8 * static_cast<size_t>(c->K), c->knots[1].p, c->knots[0].p}, {4 * static_cast<size_t>(c->Kbg), c->bg[1].p, c->bg[0].p},
-                        {4 * static_cast<size_t>(c->Kba), c->ba[1].p, c->ba[0].p},      {3, c->grav[1].p, c->grav[0].p},
-                        {3 * static_cast<size_t>(c->L), c->lms[1].p, c->lms[0].p}};
-  for (const Item& it : items) {
-    if (!it.count) continue;
-    const int blocks = static_cast<int>(std::min<size_t>((it.count + 255) / 256, static_cast<size_t>(c->num_sms) * 4));
-    commit_kernel<<<blocks, 256, 0, c->stream>>>(c->st.p, it.count, it.src, it.dst);
-    HB_LAUNCH(c, "commit_kernel");
-  }
+  CommitArgs a{};
+  const size_t counts[5] = {8 * static_cast<size_t>(c->K), 4 * static_cast<size_t>(c->Kbg), 4 * static_cast<size_t>(c->Kba), 3, 3 * static_cast<size_t>(c->L)};
+  const double* srcs[5] = {c->knots[1].p, c->bg[1].p, c->ba[1].p, c->grav[1].p, c->lms[1].p};
+  double* dsts[5] = {c->knots[0].p, c->bg[0].p, c->ba[0].p, c->grav[0].p, c->lms[0].p};
+  size_t mx = 1;
+  for (int i = 0; i < 5; ++i) { a.count[i] = counts[i]; a.src[i] = srcs[i]; a.dst[i] = dsts[i]; mx = std::max(mx, counts[i]); }
+  const int blocks = static_cast<int>(std::min<size_t>((mx + 255) / 256, static_cast<size_t>(c->num_sms) * 4));
+  commit_kernel<<<blocks, 256, 0, c->stream>>>(c->st.p, a);
+  HB_LAUNCH(c, "commit_kernel");
   return 0;
 }
 
@@ -395,6 +437,7 @@ int hb200_create(const hb200_options* options, hb200_ctx** out) {
   if (prop.major < 10) { const int maj = prop.major, mnr = prop.minor; delete c; return fail(-5, "device sm_%d%d is not Blackwell (built for sm_100a only)", maj, mnr); }
   c->num_sms = prop.multiProcessorCount;
   c->use_graph = options ? options->use_graph != 0 : true;
+  c->force_dense = options ? (options->reserved & 1) != 0 : false;
   if (options && options->stream) { c->stream = static_cast<cudaStream_t>(options->stream); c->own_stream = false; }
   else { HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   int rc = ensure_placeholders(c);
@@ -418,7 +461,7 @@ void hb200_destroy(hb200_ctx* c) {
   c->seg_off.release(); c->run_off.release(); c->lm_off.release(); c->lm_obs.release(); c->d_invalid.release();
   c->v_r.release(); c->v_Jp.release(); c->v_Jl.release(); c->i_r.release(); c->i_Jp.release(); c->i_wg.release(); c->i_wa.release(); c->i_Jg.release();
   c->sys.release(); c->D.release(); c->Lw.release(); c->Ldiag.release(); c->dp.release(); c->dl.release(); c->Vinv.release(); c->gl.release(); c->Dl.release();
-  c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
+  c->band_ws.release(); c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -865,19 +908,16 @@ int hb200_get_delta(hb200_ctx* c, double* dp, double* dl) {
   return 0;
 }
 
-int hb200_iterate(hb200_ctx* c, int iterations, hb200_iteration* records) {
-  int rc = check_ready(c);
-  if (rc) return rc;
-  if (iterations < 0 || iterations > c->max_records) return fail(-1, "iterations must be in [0, %d]", c->max_records);
-  HB_CUDA(cudaSetDevice(c->device));
-  // records[] index = SolverState.iteration modulo nothing: reset the device-side counter first.
-  {
-    SolverState s{};
-    HB_CUDA(cudaMemcpyAsync(&s, c->st.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
-    HB_CUDA(cudaStreamSynchronize(c->stream));
-    s.iteration = 0;
-    HB_CUDA(cudaMemcpyAsync(c->st.p, &s, sizeof(s), cudaMemcpyHostToDevice, c->stream));
-  }
+}  // extern "C"
+
+namespace {
+__global__ void reset_iteration_kernel(SolverState* st) { st->iteration = 0; }
+
+int iterate_enqueue(hb200_ctx* c, int iterations) {
+  int rc = 0;
+  // records[] index = SolverState.iteration: reset the device-side counter first.
+  reset_iteration_kernel<<<1, 1, 0, c->stream>>>(c->st.p);
+  HB_LAUNCH(c, "reset_iteration_kernel");
   const bool graph_ok = c->use_graph && !c->allreduce;
   for (int it = 0; it < iterations; ++it) {
     if (graph_ok) {
@@ -920,15 +960,55 @@ int hb200_iterate(hb200_ctx* c, int iterations, hb200_iteration* records) {
     }
   }
   c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  return 0;
+}
+
+void convert_records(const std::vector<SolverState>& rec, hb200_iteration* records) {
+  for (size_t i = 0; i < rec.size(); ++i) {
+    records[i].cost = rec[i].cost; records[i].cost_new = rec[i].cost_new; records[i].model_change = rec[i].model_change; records[i].rho = rec[i].rho;
+    records[i].radius = rec[i].radius; records[i].accepted = rec[i].accepted; records[i].spd = rec[i].spd;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int hb200_iterate(hb200_ctx* c, int iterations, hb200_iteration* records) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (iterations < 0 || iterations > c->max_records) return fail(-1, "iterations must be in [0, %d]", c->max_records);
+  HB_CUDA(cudaSetDevice(c->device));
+  if ((rc = iterate_enqueue(c, iterations))) return rc;
   if (records && iterations) {
     std::vector<SolverState> rec(iterations);
     HB_CUDA(cudaMemcpyAsync(rec.data(), c->records.p, sizeof(SolverState) * iterations, cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < iterations; ++i) {
-      records[i].cost = rec[i].cost; records[i].cost_new = rec[i].cost_new; records[i].model_change = rec[i].model_change; records[i].rho = rec[i].rho;
-      records[i].radius = rec[i].radius; records[i].accepted = rec[i].accepted; records[i].spd = rec[i].spd;
-    }
+    convert_records(rec, records);
   }
+  return 0;
+}
+
+int hb200_optimize(hb200_ctx* c, int iterations, double* knots, double* gyro, double* accel, double* gravity, double* landmarks,
+                   hb200_iteration* records) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (iterations < 0 || iterations > c->max_records) return fail(-1, "iterations must be in [0, %d]", c->max_records);
+  HB_CUDA(cudaSetDevice(c->device));
+  if (knots) HB_CUDA(cudaMemcpyAsync(c->knots[0].p, knots, sizeof(double) * 8 * c->K, cudaMemcpyHostToDevice, c->stream));
+  if (gyro && c->Kbg) HB_CUDA(cudaMemcpyAsync(c->bg[0].p, gyro, sizeof(double) * 4 * c->Kbg, cudaMemcpyHostToDevice, c->stream));
+  if (accel && c->Kba) HB_CUDA(cudaMemcpyAsync(c->ba[0].p, accel, sizeof(double) * 4 * c->Kba, cudaMemcpyHostToDevice, c->stream));
+  if (gravity) { HB_CUDA(cudaMemcpyAsync(c->grav[0].p, gravity, sizeof(double) * 3, cudaMemcpyHostToDevice, c->stream)); c->have_gravity = true; }
+  if (landmarks && c->L) HB_CUDA(cudaMemcpyAsync(c->lms[0].p, landmarks, sizeof(double) * 3 * c->L, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = iterate_enqueue(c, iterations))) return rc;
+  if (knots) HB_CUDA(cudaMemcpyAsync(knots, c->knots[0].p, sizeof(double) * 8 * c->K, cudaMemcpyDeviceToHost, c->stream));
+  if (gyro && c->Kbg) HB_CUDA(cudaMemcpyAsync(gyro, c->bg[0].p, sizeof(double) * 4 * c->Kbg, cudaMemcpyDeviceToHost, c->stream));
+  if (accel && c->Kba) HB_CUDA(cudaMemcpyAsync(accel, c->ba[0].p, sizeof(double) * 4 * c->Kba, cudaMemcpyDeviceToHost, c->stream));
+  if (gravity) HB_CUDA(cudaMemcpyAsync(gravity, c->grav[0].p, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
+  if (landmarks && c->L) HB_CUDA(cudaMemcpyAsync(landmarks, c->lms[0].p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<SolverState> rec(records ? iterations : 0);
+  if (records && iterations) HB_CUDA(cudaMemcpyAsync(rec.data(), c->records.p, sizeof(SolverState) * iterations, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  if (records && iterations) convert_records(rec, records);
   return 0;
 }
 
@@ -943,6 +1023,76 @@ int hb200_cost(hb200_ctx* c, double* cost) {
   HB_CUDA(cudaMemcpyAsync(s, c->scal.p, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   *cost = s[0];
+  return 0;
+}
+
+__global__ void hb200_spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {}
+}
+
+int hb200_profile_iteration(hb200_ctx* c, int reps, int max_entries, char* names, double* ms, int* count) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (reps <= 0 || !names || !ms || !count) return fail(-1, "invalid argument");
+  HB_CUDA(cudaSetDevice(c->device));
+  std::vector<double> acc;
+  std::vector<std::string> nm;
+  for (int rep = 0; rep < reps; ++rep) {
+    c->prof_used = 0;
+    // keep the GPU busy while the host enqueues the whole iteration, so kernels run back to back
+    hb200_spin_kernel<<<1, 1, 0, c->stream>>>(600000);
+    c->profiling = true;
+    prof_mark(c, "start");
+    rc = enqueue_segment(c, 0);
+    if (!rc) rc = enqueue_segment(c, 1);
+    if (!rc) rc = enqueue_segment(c, 2);
+    c->profiling = false;
+    if (rc) return rc;
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (rep == 0) { acc.assign(c->prof_used, 0.0); nm.assign(c->prof_names.begin(), c->prof_names.begin() + c->prof_used); }
+    for (size_t i = 1; i < c->prof_used && i < acc.size(); ++i) {
+      float t = 0;
+      HB_CUDA(cudaEventElapsedTime(&t, c->prof_events[i - 1], c->prof_events[i]));
+      acc[i] += t;
+    }
+  }
+  int n_out = 0;
+  for (size_t i = 1; i < acc.size() && n_out < max_entries; ++i, ++n_out) {
+    std::snprintf(names + 32 * n_out, 32, "%s", nm[i].c_str());
+    ms[n_out] = acc[i] / reps;
+  }
+  *count = n_out;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  return 0;
+}
+
+int hb200_snapshot(hb200_ctx* c) {
+  if (!c || c->K == 0) return fail(-2, "spline not set");
+  HB_CUDA(cudaSetDevice(c->device));
+  HB_CUDA(c->snap_knots.ensure(8 * static_cast<size_t>(c->K))); HB_CUDA(c->snap_bg.ensure(4 * static_cast<size_t>(std::max(c->Kbg, 1))));
+  HB_CUDA(c->snap_ba.ensure(4 * static_cast<size_t>(std::max(c->Kba, 1)))); HB_CUDA(c->snap_grav.ensure(4)); HB_CUDA(c->snap_lms.ensure(3 * static_cast<size_t>(std::max(c->L, 1))));
+  HB_CUDA(c->snap_st.ensure(1));
+  HB_CUDA(cudaMemcpyAsync(c->snap_knots.p, c->knots[0].p, sizeof(double) * 8 * c->K, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->Kbg) HB_CUDA(cudaMemcpyAsync(c->snap_bg.p, c->bg[0].p, sizeof(double) * 4 * c->Kbg, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->Kba) HB_CUDA(cudaMemcpyAsync(c->snap_ba.p, c->ba[0].p, sizeof(double) * 4 * c->Kba, cudaMemcpyDeviceToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->snap_grav.p, c->grav[0].p, sizeof(double) * 3, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->L) HB_CUDA(cudaMemcpyAsync(c->snap_lms.p, c->lms[0].p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->snap_st.p, c->st.p, sizeof(SolverState), cudaMemcpyDeviceToDevice, c->stream));
+  c->have_snapshot = true;
+  return 0;
+}
+
+int hb200_restore(hb200_ctx* c) {
+  if (!c || !c->have_snapshot) return fail(-2, "no snapshot");
+  HB_CUDA(cudaSetDevice(c->device));
+  HB_CUDA(cudaMemcpyAsync(c->knots[0].p, c->snap_knots.p, sizeof(double) * 8 * c->K, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->Kbg) HB_CUDA(cudaMemcpyAsync(c->bg[0].p, c->snap_bg.p, sizeof(double) * 4 * c->Kbg, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->Kba) HB_CUDA(cudaMemcpyAsync(c->ba[0].p, c->snap_ba.p, sizeof(double) * 4 * c->Kba, cudaMemcpyDeviceToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->grav[0].p, c->snap_grav.p, sizeof(double) * 3, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->L) HB_CUDA(cudaMemcpyAsync(c->lms[0].p, c->snap_lms.p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->st.p, c->snap_st.p, sizeof(SolverState), cudaMemcpyDeviceToDevice, c->stream));
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
   return 0;
 }
 

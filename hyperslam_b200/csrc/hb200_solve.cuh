@@ -32,14 +32,16 @@ constexpr int kHessThreads = 128;
 
 template <int K>
 __global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* __restrict__ seg_off, const double* __restrict__ r,
-                                                                     const double* __restrict__ Jp, double huber, double* sys, int n) {
+                                                                     const double* __restrict__ Jp, double huber, double* sys, int n, int splits) {
   constexpr int NB = 6 * K;
   constexpr int CH = 16;
   constexpr int EPT = (NB * NB + kHessThreads - 1) / kHessThreads;
   __shared__ double sJ[CH][2][NB];
   __shared__ double sr[CH][2];
-  const int seg = blockIdx.x;
-  const int lo = seg_off[seg], hi = seg_off[seg + 1];
+  const int seg = blockIdx.x / splits, part = blockIdx.x - seg * splits;
+  const int slo = seg_off[seg], shi = seg_off[seg + 1];
+  const int len = (shi - slo + splits - 1) / splits;
+  const int lo = slo + part * len, hi = min(shi, lo + len);
   if (lo >= hi) return;
   double acc[EPT], gacc = 0.0;
 #pragma unroll
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
                                                                         const double* __restrict__ r, const double* __restrict__ Jp,
                                                                         const double* __restrict__ wg, const double* __restrict__ wa,
                                                                         const double* __restrict__ Jg, double loss_scale, double* sys,
-                                                                        int n, int o_bg, int o_ba, int o_g) {
+                                                                        int n, int o_bg, int o_ba, int o_g, int splits) {
   constexpr int NP = 6 * K;
   constexpr int NI = NP + 6 * KB + 2;
   constexpr int CH = 8;
@@ -101,8 +103,10 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
   __shared__ double sJ[CH][6][NI];
   __shared__ double sr[CH][6];
   __shared__ int scol[NI];
-  const int run = blockIdx.x;
-  const int lo = run_off[run], hi = run_off[run + 1];
+  const int run = blockIdx.x / splits, part = blockIdx.x - run * splits;
+  const int rlo = run_off[run], rhi = run_off[run + 1];
+  const int len = (rhi - rlo + splits - 1) / splits;
+  const int lo = rlo + part * len, hi = min(rhi, lo + len);
   if (lo >= hi) return;
   const int4 id0 = idx[lo];
   for (int c = threadIdx.x; c < NI; c += kHessThreads) {
@@ -491,47 +495,74 @@ __global__ void __launch_bounds__(1024) backsolve_kernel(const double* __restric
 }
 
 // Landmark back-substitution: dl = V^-1 (-g_l - W^T dp); also partial sums of dl.g_l and dl.D_l.dl.
+// One warp per landmark: 8 observations x 4 column groups in flight per pass.
+constexpr int kLmWarps = 4;
+
 template <int K>
-__global__ void lm_backsub_kernel(int L, const int* __restrict__ lm_off, const int* __restrict__ lm_obs, const int4* __restrict__ idx,
-                                  const double* __restrict__ r, const double* __restrict__ Jp, const double* __restrict__ Jl, double huber,
-                                  const double* __restrict__ Vinv, const double* __restrict__ gl, const double* __restrict__ Dl,
-                                  const double* __restrict__ dp, double* __restrict__ dl, double* __restrict__ part /*[grid][2]*/) {
+__global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const int* __restrict__ lm_off, const int* __restrict__ lm_obs,
+                                                                  const int4* __restrict__ idx, const double* __restrict__ r,
+                                                                  const double* __restrict__ Jp, const double* __restrict__ Jl, double huber,
+                                                                  const double* __restrict__ Vinv, const double* __restrict__ gl,
+                                                                  const double* __restrict__ Dl, const double* __restrict__ dp,
+                                                                  double* __restrict__ dl, double* __restrict__ part /*[grid][2]*/) {
   constexpr int NB = 6 * K;
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int CG = NB / 4;  // columns per lane group
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int l = blockIdx.x * kLmWarps + warp;
   double s_g = 0, s_d = 0;
   if (l < L) {
-    double rhs[3] = {-gl[3 * static_cast<size_t>(l)], -gl[3 * static_cast<size_t>(l) + 1], -gl[3 * static_cast<size_t>(l) + 2]};
-    for (int o = lm_off[l]; o < lm_off[l + 1]; ++o) {
-      const int f = lm_obs[o];
-      const double r0 = r[2 * f], r1 = r[2 * f + 1];
-      double wgt;
-      huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
-      const double* jp = Jp + static_cast<size_t>(f) * 2 * NB;
-      const double* jl = Jl + 6 * static_cast<size_t>(f);
-      const double* d = dp + 6 * idx[f].x;
-      double t0 = 0, t1 = 0;
+    const int o_lo = lm_off[l], o_hi = lm_off[l + 1];
+    const int og = lane >> 2, cg = lane & 3;
+    double rhs[3] = {0, 0, 0};
+    for (int o0 = o_lo; o0 < o_hi; o0 += 8) {
+      const int o = o0 + og;
+      double t0 = 0, t1 = 0, wgt = 0, jl[6] = {0, 0, 0, 0, 0, 0};
+      if (o < o_hi) {
+        const int f = lm_obs[o];
+        const double r0 = r[2 * f], r1 = r[2 * f + 1];
+        huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
+        const double* jp = Jp + static_cast<size_t>(f) * 2 * NB + cg * CG;
+        const double* d = dp + 6 * idx[f].x + cg * CG;
 #pragma unroll
-      for (int a = 0; a < NB; ++a) { t0 += jp[a] * d[a]; t1 += jp[NB + a] * d[a]; }
+        for (int a = 0; a < CG; ++a) { const double dv = d[a]; t0 += jp[a] * dv; t1 += jp[NB + a] * dv; }
+        if (cg == 0) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) rhs[c] -= wgt * (jl[c] * t0 + jl[3 + c] * t1);
+          for (int c = 0; c < 6; ++c) jl[c] = Jl[6 * static_cast<size_t>(f) + c];
+        }
+      }
+      t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+      t0 += __shfl_xor_sync(0xffffffffu, t0, 2); t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+      if (cg == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rhs[c] -= wgt * (jl[c] * t0 + jl[3 + c] * t1);
+      }
     }
-    const double* Vi = Vinv + 9 * static_cast<size_t>(l);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const double v = Vi[3 * c] * rhs[0] + Vi[3 * c + 1] * rhs[1] + Vi[3 * c + 2] * rhs[2];
-      dl[3 * static_cast<size_t>(l) + c] = v;
-      s_g += v * gl[3 * static_cast<size_t>(l) + c];
-      s_d += v * v * Dl[3 * static_cast<size_t>(l) + c];
+      rhs[c] += __shfl_xor_sync(0xffffffffu, rhs[c], 4);
+      rhs[c] += __shfl_xor_sync(0xffffffffu, rhs[c], 8);
+      rhs[c] += __shfl_xor_sync(0xffffffffu, rhs[c], 16);
+    }
+    if (lane == 0) {
+      const double* g = gl + 3 * static_cast<size_t>(l);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rhs[c] -= g[c];
+      const double* Vi = Vinv + 9 * static_cast<size_t>(l);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double v = Vi[3 * c] * rhs[0] + Vi[3 * c + 1] * rhs[1] + Vi[3 * c + 2] * rhs[2];
+        dl[3 * static_cast<size_t>(l) + c] = v;
+        s_g += v * g[c];
+        s_d += v * v * Dl[3 * static_cast<size_t>(l) + c];
+      }
     }
   }
-  __shared__ double sg[8], sd[8];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { s_g += __shfl_xor_sync(0xffffffffu, s_g, o); s_d += __shfl_xor_sync(0xffffffffu, s_d, o); }
-  if ((threadIdx.x & 31) == 0) { sg[threadIdx.x >> 5] = s_g; sd[threadIdx.x >> 5] = s_d; }
+  __shared__ double sg[kLmWarps], sd[kLmWarps];
+  if (lane == 0) { sg[warp] = s_g; sd[warp] = s_d; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double a = 0, b = 0;
-    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { a += sg[w]; b += sd[w]; }
+    for (int w = 0; w < kLmWarps; ++w) { a += sg[w]; b += sd[w]; }
     part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
   }
 }
@@ -657,10 +688,17 @@ __global__ void accept_kernel(const double* __restrict__ sys, int n, const doubl
   }
 }
 
-__global__ void commit_kernel(const SolverState* __restrict__ st, size_t count, const double* __restrict__ src, double* __restrict__ dst) {
+struct CommitArgs {
+  size_t count[5];
+  const double* src[5];
+  double* dst[5];
+};
+__global__ void commit_kernel(const SolverState* __restrict__ st, CommitArgs a) {
   if (!st->accepted) return;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < count; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    dst[i] = src[i];
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+#pragma unroll
+  for (int s = 0; s < 5; ++s)
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < a.count[s]; i += stride) a.dst[s][i] = a.src[s][i];
 }
 
 }  // namespace hb

@@ -38,7 +38,8 @@ EXPORTS = [
     "hb200_get_index_maps", "hb200_evaluate", "hb200_get_pixel_outputs", "hb200_get_inertial_outputs",
     "hb200_factor_evaluate", "hb200_reduced_size", "hb200_build_system", "hb200_get_system", "hb200_solve",
     "hb200_get_delta", "hb200_iterate", "hb200_cost", "hb200_get_state", "hb200_set_allreduce",
-    "hb200_system_device_ptr", "hb200_stream", "hb200_launch_count",
+    "hb200_system_device_ptr", "hb200_stream", "hb200_launch_count", "hb200_optimize", "hb200_snapshot", "hb200_restore",
+    "hb200_profile_iteration",
 ]
 
 _lib = None
@@ -81,10 +82,10 @@ def _f64(a):
 class Context:
     """One sliding-window problem on one GPU (wraps an hb200_ctx)."""
 
-    def __init__(self, device: int = 0, stream: int | None = None, use_graph: bool = True):
+    def __init__(self, device: int = 0, stream: int | None = None, use_graph: bool = True, force_dense: bool = False):
         self.lib = load_library()
         self.h = C.c_void_p()
-        opts = Options(device, stream, int(use_graph), 0)
+        opts = Options(device, stream, int(use_graph), int(force_dense))
         self._check(self.lib.hb200_create(C.byref(opts), C.byref(self.h)))
         self._cb = None
         self.order = self.K = self.Kbg = self.Kba = self.L = self.Nv = self.Ni = 0
@@ -234,6 +235,31 @@ class Context:
             return None
         return [dict(cost=r.cost, cost_new=r.cost_new, model_change=r.model_change, rho=r.rho, radius=r.radius,
                      accepted=r.accepted, spd=r.spd) for r in rec[:iterations]]
+
+    def optimize(self, iterations, knots, gyro, accel, gravity, landmarks, records=True):
+        """hb200_optimize: host (ideally pinned) float64 arrays, updated in place."""
+        rec = (Iteration * max(iterations, 1))()
+        self._check(self.lib.hb200_optimize(self.h, int(iterations), _d(knots), _d(gyro), _d(accel), _d(gravity), _d(landmarks),
+                                            rec if records else None))
+        return [dict(cost=r.cost, cost_new=r.cost_new, rho=r.rho, radius=r.radius, accepted=r.accepted, spd=r.spd)
+                for r in rec[:iterations]] if records else None
+
+    def snapshot(self):
+        self._check(self.lib.hb200_snapshot(self.h))
+
+    def restore(self):
+        self._check(self.lib.hb200_restore(self.h))
+
+    def profile_iteration(self, reps=5, max_entries=64):
+        names = C.create_string_buffer(32 * max_entries)
+        ms = np.zeros(max_entries)
+        cnt = C.c_int(0)
+        self._check(self.lib.hb200_profile_iteration(self.h, int(reps), max_entries, names, _d(ms), C.byref(cnt)))
+        out = []
+        for i in range(cnt.value):
+            raw = names.raw[32 * i: 32 * (i + 1)]
+            out.append((raw.split(b"\0", 1)[0].decode(), float(ms[i])))
+        return out
 
     def cost(self):
         c = C.c_double(0)

@@ -24,7 +24,7 @@ typedef struct hb200_options {
   int device;        /* CUDA device ordinal */
   void* stream;      /* cudaStream_t to run on; NULL => the context creates its own */
   int use_graph;     /* capture hb200_iterate() in a CUDA graph (1) or launch kernels directly (0) */
-  int reserved;
+  int reserved;      /* bit 0: force the dense cooperative Cholesky instead of the banded-arrow solver */
 } hb200_options;
 
 /* Per-iteration record, the analogue of ceres::IterationSummary printed through
@@ -105,6 +105,20 @@ int hb200_get_delta(hb200_ctx* ctx, double* delta_pose /* n */, double* delta_la
  * accept/reject, all on the device.  records may be NULL. */
 int hb200_iterate(hb200_ctx* ctx, int iterations, hb200_iteration* records);
 int hb200_cost(hb200_ctx* ctx, double* cost);
+/* The drop-in for CeresOptimizer::optimize() (reference optimizer.cpp:276-280) with the parameter
+ * blocks in HOST memory, as Ceres aliases them: uploads the five variable families, runs
+ * `iterations` LM iterations on the device, downloads the updated blocks into the same buffers and
+ * synchronises once.  Factor lists stay bound.  Buffers should be pinned for asynchronous copies. */
+int hb200_optimize(hb200_ctx* ctx, int iterations, double* knots, double* gyro, double* accel, double* gravity, double* landmarks,
+                   hb200_iteration* records);
+/* device-side snapshot / restore of the variable blocks and the trust-region state (benchmarks,
+ * step rejection experiments). */
+int hb200_snapshot(hb200_ctx* ctx);
+int hb200_restore(hb200_ctx* ctx);
+/* Runs `reps` LM iterations with a CUDA event after every kernel and returns the average duration of
+ * each launch in issue order (names are kernel names, 32 chars each).  Not for timing the step --
+ * for attributing it (bench.py roofline / kernel shares). */
+int hb200_profile_iteration(hb200_ctx* ctx, int reps, int max_entries, char* names /* [max_entries][32] */, double* ms, int* count);
 int hb200_get_state(hb200_ctx* ctx, double* knots, double* gyro, double* accel, double* gravity, double* landmarks);
 
 /* ---- multi-GPU hook -------------------------------------------------------------------------

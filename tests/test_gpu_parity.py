@@ -114,13 +114,14 @@ def test_edge_cases(built):
     ctx.close(); ctx2.close(); ctx3.close()
 
 
+@pytest.mark.parametrize("force_dense", [False, True])
 @pytest.mark.parametrize("name", ["k4", "k6", "k4_generic_calib", "cfg0_plumbing", "pixel_only"])
-def test_system_and_step_parity(built, name):
+def test_system_and_step_parity(built, name, force_dense):
     kw = dict(CASES[name])
     win = synthetic.make_window(seed=synthetic.SEED_BASE + 200, constant_knots=2, **kw)
     ow = ol.OracleWindow(win)
     o = ow.iterate(apply=False)
-    ctx = make_ctx(win)
+    ctx = make_ctx(win, force_dense=force_dense)
     ctx.evaluate()
     ctx.build_system()
     S, b = ctx.system()
@@ -138,11 +139,11 @@ def test_system_and_step_parity(built, name):
     ctx.close()
 
 
-@pytest.mark.parametrize("use_graph", [True, False])
-def test_iterate_parity(built, use_graph):
+@pytest.mark.parametrize("use_graph,force_dense", [(True, False), (False, False), (True, True)])
+def test_iterate_parity(built, use_graph, force_dense):
     win = synthetic.make_window(order=4, num_knots=20, num_landmarks=150, num_imu=400, seed=synthetic.SEED_BASE + 201, constant_knots=2)
     ow = ol.OracleWindow(win)
-    ctx = make_ctx(win, use_graph=use_graph)
+    ctx = make_ctx(win, use_graph=use_graph, force_dense=force_dense)
     recs = ctx.iterate(5)
     for it, rec in enumerate(recs):
         o = ow.iterate(apply=True)
