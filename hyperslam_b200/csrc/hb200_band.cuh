@@ -16,7 +16,7 @@
 
 namespace hb {
 
-constexpr int kBandThreads = 1024;
+constexpr int kBandThreads = 512;
 
 __host__ __device__ inline size_t band_workspace_doubles(int K, int beta, int m) {
   const size_t h = 6 + 6 * static_cast<size_t>(beta);
@@ -112,27 +112,50 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       for (int q = 0; q < 6; ++q) a[q] = v[q];
     }
     __syncthreads();
-    // trailing update: target(u, v) -= X_u . X_v for v <= u over the R panel rows
-    const int Rp = (R + 31) & ~31;  // v index padded to a warp multiple: u is warp-uniform
-    for (int e = tid; e < R * Rp; e += kBandThreads) {
-      const int u = e / Rp, v = e - u * Rp;
-      if (v > u) continue;
-      const double* xu = (u < nb) ? (Wc + static_cast<size_t>(6 + u) * 6) : (AR + static_cast<size_t>(u - nb) * np + 6 * c);
-      const double* xv = (v < nb) ? (Wc + static_cast<size_t>(6 + v) * 6) : (AR + static_cast<size_t>(v - nb) * np + 6 * c);
-      double s = 0.0;
+    // trailing update in 6x6 tiles: groups = band blocks below the diagonal, then arrow rows in sixes
+    // (the rhs row is the last arrow row).  Thread = (tile, row i of the tile): 6 dots of length 6.
+    {
+      const int nbk = nb / 6;
+      const int ng = (m + 1 + 5) / 6;
+      const int G = nbk + ng;
+      const int ntiles = G * (G + 1) / 2;
+      for (int t = tid; t < ntiles * 6; t += kBandThreads) {
+        const int tile = t / 6, i = t - 6 * tile;
+        int gu = static_cast<int>((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
+        while (gu * (gu + 1) / 2 > tile) --gu;
+        while ((gu + 1) * (gu + 2) / 2 <= tile) ++gu;
+        const int gv = tile - gu * (gu + 1) / 2;
+        const bool ub = gu < nbk, vb = gv < nbk;
+        const int ru = ub ? 0 : 6 * (gu - nbk) + i;   // arrow row index of u
+        if (!ub && ru > m) continue;
+        const double* xu = ub ? (Wc + static_cast<size_t>(6 + 6 * gu + i) * 6) : (AR + static_cast<size_t>(ru) * np + 6 * c);
+        double a[6], sd[6];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) s += xu[q] * xv[q];
-      double* tgt;
-      if (u < nb) {  // both band rows: row = 6(c+1)+u, col = 6(c+1)+v
-        const int cb = v / 6, jl = v - 6 * cb;
-        tgt = W + (static_cast<size_t>(c + 1 + cb) * h + (u - 6 * cb)) * 6 + jl;
-      } else if (v < nb) {  // arrow row x band column
-        tgt = AR + static_cast<size_t>(u - nb) * np + 6 * (c + 1) + v;
-      } else {  // arrow x arrow (rhs row m never appears as v)
-        if (v - nb >= m) continue;
-        tgt = CC + static_cast<size_t>(u - nb) * m + (v - nb);
+        for (int q = 0; q < 6; ++q) a[q] = xu[q];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int rv = vb ? 0 : 6 * (gv - nbk) + j;
+          const double* xv = vb ? (Wc + static_cast<size_t>(6 + 6 * gv + j) * 6) : (AR + static_cast<size_t>(min(rv, m)) * np + 6 * c);
+          double acc = 0.0;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) acc += a[q] * xv[q];
+          sd[j] = acc;
+        }
+        if (ub) {  // band x band
+          double* tgt = W + (static_cast<size_t>(c + 1 + gv) * h + (6 * (gu - gv) + i)) * 6;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) tgt[j] -= sd[j];
+        } else if (vb) {  // arrow x band
+          double* tgt = AR + static_cast<size_t>(ru) * np + 6 * (c + 1 + gv);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) tgt[j] -= sd[j];
+        } else {  // arrow x arrow (columns are arrow dofs < m)
+          double* tgt = CC + static_cast<size_t>(ru) * m + 6 * (gv - nbk);
+#pragma unroll
+          for (int j = 0; j < 6; ++j)
+            if (6 * (gv - nbk) + j < m) tgt[j] -= sd[j];
+        }
       }
-      *tgt -= s;
     }
     __syncthreads();
   }

@@ -427,4 +427,122 @@ inline void window_iterate(Window* w, IterationOutput* out, int apply) {
   out->radius = w->radius;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Sharded form of the normal equations (multi-GPU layout, DESIGN.md "Multi-GPU"): each rank builds
+//   packed = [ S (n*n) | b (n) | diagH (n) | g (n) | cost | pad ]
+// from ITS factors only -- S = H_pp - sum_l W_l (V_l + mu D_l)^-1 W_l^T without pose damping,
+// b = -g + sum_l W_l (V_l + mu D_l)^-1 g_l -- the packed buffers are summed across ranks, and
+// packed_finalize() then applies the pose damping mu * clamp(diagH) and the constant-dof mask.
+// Exact (not approximate) as long as all observations of a landmark live on one rank.
+// ---------------------------------------------------------------------------------------------
+inline void window_build_packed(const Window& w, std::vector<double>* packed) {
+  const int k = w.k, kb = w.k_b, K = w.K, n = reduced_size(w), L = w.L;
+  const int o_bg = 6 * K, o_ba = o_bg + 3 * w.Kbg, o_g = o_ba + 3 * w.Kba;
+  packed->assign((size_t)n * n + 3 * (size_t)n + 2, 0.0);
+  double* S = packed->data();
+  double* b = S + (size_t)n * n;
+  double* diagH = b + n;
+  double* g = diagH + n;
+  double* cost = g + n;
+  std::vector<double> V((size_t)9 * L, 0.0), gl((size_t)3 * L, 0.0);
+  struct Obs { int lm; int base; double Jp[2 * 6 * kMaxOrder]; double Jl[6]; double r[2]; };
+  std::vector<Obs> obs(w.Nv);
+  const int nc = 6 * k;
+  for (int f = 0; f < w.Nv; ++f) {
+    Obs& o = obs[f];
+    o.lm = w.v_lm[f]; o.base = w.v_base[f];
+    window_eval_pixel(w, f, true, o.r, o.Jp, o.Jl);
+    double rho;
+    const double wgt = huber_weight(o.r[0] * o.r[0] + o.r[1] * o.r[1], w.huber_pixel, &rho);
+    *cost += 0.5 * rho;
+    const double sw = std::sqrt(wgt);
+    for (int i = 0; i < 2 * nc; ++i) o.Jp[i] *= sw;
+    for (int i = 0; i < 6; ++i) o.Jl[i] *= sw;
+    o.r[0] *= sw; o.r[1] *= sw;
+    const int c0 = 6 * o.base;
+    for (int a = 0; a < nc; ++a) {
+      g[c0 + a] += o.Jp[a] * o.r[0] + o.Jp[nc + a] * o.r[1];
+      for (int bc = 0; bc < nc; ++bc) S[(size_t)(c0 + a) * n + c0 + bc] += o.Jp[a] * o.Jp[bc] + o.Jp[nc + a] * o.Jp[nc + bc];
+    }
+    for (int a = 0; a < 3; ++a) {
+      gl[3 * o.lm + a] += o.Jl[a] * o.r[0] + o.Jl[3 + a] * o.r[1];
+      for (int bc = 0; bc < 3; ++bc) V[9 * o.lm + 3 * a + bc] += o.Jl[a] * o.Jl[bc] + o.Jl[3 + a] * o.Jl[3 + bc];
+    }
+  }
+  {
+    const double sw = std::sqrt(w.imu_loss_scale);
+    const int ncol = 6 * k + 6 * kb + 2;
+    std::vector<double> J((size_t)6 * ncol);
+    std::vector<int> idx(ncol);
+    for (int f = 0; f < w.Ni; ++f) {
+      double r[6], Jp[6 * 6 * kMaxOrder], wg[kMaxOrder], wa[kMaxOrder], Jg[12];
+      window_eval_inertial(w, f, true, r, Jp, wg, wa, Jg);
+      double s2 = 0;
+      for (int i = 0; i < 6; ++i) s2 += r[i] * r[i];
+      *cost += 0.5 * w.imu_loss_scale * s2;
+      std::fill(J.begin(), J.end(), 0.0);
+      int c = 0;
+      for (int a = 0; a < 6 * k; ++a, ++c) { idx[c] = 6 * w.i_base[f] + a; for (int rr = 0; rr < 6; ++rr) J[(size_t)rr * ncol + c] = sw * Jp[rr * 6 * k + a]; }
+      for (int m = 0; m < kb; ++m) for (int a = 0; a < 3; ++a, ++c) { idx[c] = o_bg + 3 * (w.i_bg_base[f] + m) + a; J[(size_t)a * ncol + c] = sw * wg[m]; }
+      for (int m = 0; m < kb; ++m) for (int a = 0; a < 3; ++a, ++c) { idx[c] = o_ba + 3 * (w.i_ba_base[f] + m) + a; J[(size_t)(3 + a) * ncol + c] = sw * wa[m]; }
+      for (int a = 0; a < 2; ++a, ++c) { idx[c] = o_g + a; for (int rr = 0; rr < 6; ++rr) J[(size_t)rr * ncol + c] = sw * Jg[2 * rr + a]; }
+      for (int a = 0; a < ncol; ++a) {
+        double ga = 0;
+        for (int rr = 0; rr < 6; ++rr) ga += J[(size_t)rr * ncol + a] * sw * r[rr];
+        g[idx[a]] += ga;
+        for (int bc = 0; bc < ncol; ++bc) {
+          double hh = 0;
+          for (int rr = 0; rr < 6; ++rr) hh += J[(size_t)rr * ncol + a] * J[(size_t)rr * ncol + bc];
+          S[(size_t)idx[a] * n + idx[bc]] += hh;
+        }
+      }
+    }
+  }
+  for (int a = 0; a < n; ++a) { diagH[a] = S[(size_t)a * n + a]; b[a] = -g[a]; }
+  const double mu = 1.0 / w.radius;
+  std::vector<std::vector<int>> lm_obs(L);
+  for (int f = 0; f < w.Nv; ++f) lm_obs[obs[f].lm].push_back(f);
+  for (int l = 0; l < L; ++l) {
+    if (lm_obs[l].empty()) continue;
+    double Vd[9], Vi[9];
+    for (int i = 0; i < 9; ++i) Vd[i] = V[9 * l + i];
+    for (int a = 0; a < 3; ++a) Vd[4 * a] += mu * std::min(std::max(V[9 * l + 4 * a], 1e-6), 1e32);
+    if (!inv3_sym(Vd, Vi)) continue;
+    std::vector<double> Wl((size_t)n * 3, 0.0);
+    for (int f : lm_obs[l]) {
+      const Obs& o = obs[f];
+      for (int a = 0; a < nc; ++a)
+        for (int c = 0; c < 3; ++c) Wl[(size_t)(6 * o.base + a) * 3 + c] += o.Jp[a] * o.Jl[c] + o.Jp[nc + a] * o.Jl[3 + c];
+    }
+    std::vector<int> rows;
+    for (int a = 0; a < n; ++a) if (Wl[3 * a] != 0 || Wl[3 * a + 1] != 0 || Wl[3 * a + 2] != 0) rows.push_back(a);
+    for (int a : rows) {
+      double WV[3];
+      for (int c = 0; c < 3; ++c) WV[c] = Wl[3 * a] * Vi[c] + Wl[3 * a + 1] * Vi[3 + c] + Wl[3 * a + 2] * Vi[6 + c];
+      b[a] += WV[0] * gl[3 * l] + WV[1] * gl[3 * l + 1] + WV[2] * gl[3 * l + 2];
+      for (int bb : rows) S[(size_t)a * n + bb] -= WV[0] * Wl[3 * bb] + WV[1] * Wl[3 * bb + 1] + WV[2] * Wl[3 * bb + 2];
+    }
+  }
+}
+
+inline void packed_finalize(const Window& w, std::vector<double>* packed) {
+  const int n = reduced_size(w), K = w.K;
+  const int o_bg = 6 * K, o_g = o_bg + 3 * w.Kbg + 3 * w.Kba;
+  double* S = packed->data();
+  double* b = S + (size_t)n * n;
+  const double* diagH = b + n;
+  const double mu = 1.0 / w.radius;
+  std::vector<uint8_t> fixed(n, 0);
+  for (int j = 0; j < K; ++j) if (w.knot_const[j]) for (int a = 0; a < 6; ++a) fixed[6 * j + a] = 1;
+  if (w.bias_const) for (int a = o_bg; a < o_g; ++a) fixed[a] = 1;
+  if (w.gravity_const) { fixed[o_g] = fixed[o_g + 1] = 1; }
+  for (int a = 0; a < n; ++a) S[(size_t)a * n + a] += mu * std::min(std::max(diagH[a], 1e-6), 1e32);
+  for (int a = 0; a < n; ++a)
+    if (fixed[a]) {
+      for (int c = 0; c < n; ++c) { S[(size_t)a * n + c] = 0; S[(size_t)c * n + a] = 0; }
+      S[(size_t)a * n + a] = 1.0; b[a] = 0.0;
+    }
+}
+
 }  // namespace ho

@@ -107,7 +107,7 @@ int ho_cost_evaluate(int kind, double stamp, const double* meas, int k, int k_bg
 // manifold_ids: per block BlockManifold.  results: [relative_ok, absolute_ok, max_rel_err, max_abs_norm_err]
 // per_block_err (optional): num_blocks x 2.
 int ho_probe(int kind, double stamp, const double* meas, int k, int k_bg, int k_ba, const double* params,
-             const int* manifold_ids, double tolerance, int quirks, double* results, double* per_block_err) {
+             const int* manifold_ids, double tolerance, int quirks, double* results, double* per_block_err, int richardson) {
   Factor f = make_factor(kind, stamp, meas, k, k_bg, k_ba);
   Layout L; layout_update(f, &L);
   Basis b, bb; basis_init(&b, k); basis_init(&bb, k_bg);
@@ -131,18 +131,32 @@ int ho_probe(int kind, double stamp, const double* meas, int k, int k_bg, int k_
       manifold_plus_jacobian(m, x.data() + L.offsets[blk], PJ.data());
       mat_mul(jptrs[blk], PJ.data(), Ja.data(), nr, na, nt);
       std::vector<double> save(x.begin() + L.offsets[blk], x.begin() + L.offsets[blk] + na), delta(nt), xp(na);
+      // richardson = 0: plain central difference with the reference's step (evaluator.hpp:26-32);
+      // richardson = 1: one Richardson extrapolation from steps 2e-4 / 1e-4 (O(h^4), ~100x less
+      // round-off) -- used where a block's Jacobian is tiny (edge control points of a quintic spline).
       for (int c = 0; c < nt; ++c) {
-        double rp[6], rm[6];
-        std::fill(delta.begin(), delta.end(), 0.0);
-        delta[c] = h;
-        manifold_plus(m, save.data(), delta.data(), xp.data());
-        std::copy(xp.begin(), xp.end(), x.begin() + L.offsets[blk]);
-        cost_evaluate(f, L, b, bb, ptrs, rp, nullptr, quirks);
-        delta[c] = -h;
-        manifold_plus(m, save.data(), delta.data(), xp.data());
-        std::copy(xp.begin(), xp.end(), x.begin() + L.offsets[blk]);
-        cost_evaluate(f, L, b, bb, ptrs, rm, nullptr, quirks);
-        for (int r = 0; r < nr; ++r) Jn[r * nt + c] = (rp[r] - rm[r]) / (2 * h);
+        auto central = [&](double step, double* out) {
+          double rp[6], rm[6];
+          std::fill(delta.begin(), delta.end(), 0.0);
+          delta[c] = step;
+          manifold_plus(m, save.data(), delta.data(), xp.data());
+          std::copy(xp.begin(), xp.end(), x.begin() + L.offsets[blk]);
+          cost_evaluate(f, L, b, bb, ptrs, rp, nullptr, quirks);
+          delta[c] = -step;
+          manifold_plus(m, save.data(), delta.data(), xp.data());
+          std::copy(xp.begin(), xp.end(), x.begin() + L.offsets[blk]);
+          cost_evaluate(f, L, b, bb, ptrs, rm, nullptr, quirks);
+          for (int r = 0; r < nr; ++r) out[r] = (rp[r] - rm[r]) / (2 * step);
+        };
+        double d1[6], d2[6];
+        if (!richardson) {
+          central(h, d1);
+          for (int r = 0; r < nr; ++r) Jn[r * nt + c] = d1[r];
+        } else {
+          central(2e-4, d1);
+          central(1e-4, d2);
+          for (int r = 0; r < nr; ++r) Jn[r * nt + c] = (4.0 * d2[r] - d1[r]) / 3.0;
+        }
       }
       std::copy(save.begin(), save.end(), x.begin() + L.offsets[blk]);
       double na2 = 0, nn2 = 0;

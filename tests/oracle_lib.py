@@ -100,14 +100,14 @@ def cost_evaluate(kind, stamp, meas, params, k=4, k_bg=4, k_ba=4, jac=True, jac_
     return r, blocks
 
 
-def probe(kind, stamp, meas, params, manifold_ids, k=4, k_bg=4, k_ba=4, tol=1e-5, quirks=0):
+def probe(kind, stamp, meas, params, manifold_ids, k=4, k_bg=4, k_ba=4, tol=1e-5, quirks=0, richardson=False):
     L = layout(kind, k, k_bg, k_ba)
     params = np.ascontiguousarray(params, dtype=np.float64)
     meas = np.ascontiguousarray(meas, dtype=np.float64)
     ids = np.ascontiguousarray(manifold_ids, dtype=np.int32)
     res = np.zeros(4)
     per = np.zeros((L["num_blocks"], 2))
-    rc = lib().ho_probe(kind, C.c_double(stamp), _d(meas), k, k_bg, k_ba, _d(params), _i(ids), C.c_double(tol), quirks, _d(res), _d(per))
+    rc = lib().ho_probe(kind, C.c_double(stamp), _d(meas), k, k_bg, k_ba, _d(params), _i(ids), C.c_double(tol), quirks, _d(res), _d(per), int(richardson))
     return rc == 0, res, per
 
 
@@ -201,6 +201,18 @@ class OracleWindow:
         lib().ho_window_iterate(self.h, int(apply), _d(S), _d(b), _d(dp), _d(dl), _d(stats), nthreads)
         return dict(S=S, b=b, delta_p=dp, delta_l=dl, cost=stats[0], cost_new=stats[1], model_change=stats[2], rho=stats[3],
                     radius=stats[4], accepted=int(stats[5]), spd=int(stats[6]), stats=stats)
+
+    def build_packed(self):
+        n = self.n
+        packed = np.zeros(n * n + 3 * n + 2)
+        lib().ho_window_build_packed(self.h, _d(packed))
+        return packed
+
+    def finalize_packed(self, packed):
+        packed = np.ascontiguousarray(packed, dtype=np.float64).copy()
+        lib().ho_window_finalize_packed(self.h, _d(packed))
+        n = self.n
+        return packed[: n * n].reshape(n, n), packed[n * n: n * n + n]
 
     def state(self):
         w = self.win

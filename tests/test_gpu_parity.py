@@ -216,3 +216,21 @@ def test_full_size_properties(built):
     assert all(r["spd"] == 1 for r in recs)
     assert recs[-1]["cost_new"] < 0.2 * recs[0]["cost"]
     ctx.close()
+
+
+def test_gpu_matches_mpmath_golden(built):
+    """CUDA path vs the 80-digit known-answer vectors (independent of the oracle)."""
+    import glob
+    import json
+    import os
+    from test_oracle import check_against_golden, window_from_golden
+    paths = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.json")))
+    assert len(paths) >= 4
+    for path in paths:
+        with open(path) as f:
+            case = json.load(f)
+        win = window_from_golden(case)
+        ctx = make_ctx(win)
+        ctx.evaluate()
+        check_against_golden(case, ctx.outputs(), ctx.index_maps())
+        ctx.close()
