@@ -1067,6 +1067,36 @@ int hb200_profile_iteration(hb200_ctx* c, int reps, int max_entries, char* names
   return 0;
 }
 
+int hb200_interpolate(hb200_ctx* c, int n, const double* stamps, double* pose, double* velocity, double* acceleration, int* num_invalid) {
+  if (!c || n < 0 || (n > 0 && (!stamps || !pose))) return fail(-1, "invalid argument");
+  if (c->K == 0) return fail(-2, "spline not set");
+  HB_CUDA(cudaSetDevice(c->device));
+  if (num_invalid) *num_invalid = 0;
+  if (n == 0) return 0;
+  DevBuf<double> d_t, d_p, d_v, d_a;
+  HB_CUDA(d_t.ensure(n)); HB_CUDA(d_p.ensure(7 * static_cast<size_t>(n)));
+  if (velocity) HB_CUDA(d_v.ensure(6 * static_cast<size_t>(n)));
+  if (acceleration) HB_CUDA(d_a.ensure(6 * static_cast<size_t>(n)));
+  HB_CUDA(c->d_invalid.ensure(1));
+  HB_CUDA(cudaMemsetAsync(c->d_invalid.p, 0, sizeof(int), c->stream));
+  HB_CUDA(cudaMemcpyAsync(d_t.p, stamps, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  prep_kernel<<<(c->K + 63) / 64, 64, 0, c->stream>>>(c->K, c->knots[0].p, c->tab[0].p);
+  HB_LAUNCH(c, "prep_kernel");
+  if (c->k == 4) interpolate_kernel<4><<<(n + 127) / 128, 128, 0, c->stream>>>(n, d_t.p, c->knots[0].p, c->tab[0].p, c->K, c->basis, d_p.p, d_v.p, d_a.p, c->d_invalid.p);
+  else interpolate_kernel<6><<<(n + 127) / 128, 128, 0, c->stream>>>(n, d_t.p, c->knots[0].p, c->tab[0].p, c->K, c->basis, d_p.p, d_v.p, d_a.p, c->d_invalid.p);
+  HB_LAUNCH(c, "interpolate_kernel");
+  int bad = 0;
+  HB_CUDA(cudaMemcpyAsync(pose, d_p.p, sizeof(double) * 7 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (velocity) HB_CUDA(cudaMemcpyAsync(velocity, d_v.p, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (acceleration) HB_CUDA(cudaMemcpyAsync(acceleration, d_a.p, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaMemcpyAsync(&bad, c->d_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  d_t.release(); d_p.release(); d_v.release(); d_a.release();
+  if (e != cudaSuccess) return fail(100 + static_cast<int>(e), "interpolate: %s", cudaGetErrorString(e));
+  if (num_invalid) *num_invalid = bad;
+  return 0;
+}
+
 int hb200_snapshot(hb200_ctx* c) {
   if (!c || c->K == 0) return fail(-2, "spline not set");
   HB_CUDA(cudaSetDevice(c->device));

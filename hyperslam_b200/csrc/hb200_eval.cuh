@@ -726,4 +726,71 @@ __global__ void __launch_bounds__(kEvalThreads) inertial_eval_kernel(InertialArg
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Plain spline interpolation at arbitrary stamps (no Jacobians): pose [q|p], body velocity
+// [omega | R^T pdot], body acceleration [alpha | R^T pddot].  Serves the reference's trajectory
+// dump (reference apps/hyperslam/main.cpp:69-80: state->evaluate(StateQuery{stamp, kValueIndex})).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void interpolate_kernel(int n, const double* __restrict__ stamps, const double* __restrict__ knots, const double* __restrict__ tab,
+                                   int Kn, Basis B, double* __restrict__ pose, double* __restrict__ vel, double* __restrict__ acc,
+                                   int* __restrict__ num_invalid) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const double t = stamps[f];
+  const int base = segment_base(knots, 8, 7, Kn, K, t);
+  if (base < 0) {
+    atomicAdd(num_invalid, 1);
+    for (int i = 0; i < 7; ++i) pose[7 * static_cast<size_t>(f) + i] = (i == 3) ? 1.0 : 0.0;
+    if (vel) for (int i = 0; i < 6; ++i) vel[6 * static_cast<size_t>(f) + i] = 0.0;
+    if (acc) for (int i = 0; i < 6; ++i) acc[6 * static_cast<size_t>(f) + i] = 0.0;
+    return;
+  }
+  constexpr int left = (K - 1) / 2;
+  const double* row0 = tab + static_cast<size_t>(base) * kTabStride;
+  const double t0 = row0[left * kTabStride + 24], t1 = row0[(left + 1) * kTabStride + 24];
+  const double inv_dt = 1.0 / (t1 - t0);
+  double lam[K + 1], lamd[K + 1], lamdd[K + 1];
+  basis_eval<K, true>(B, (t - t0) * inv_dt, inv_dt, lam, lamd, lamdd);
+  const double* k0 = knots + 8 * static_cast<size_t>(base);
+  double q[4] = {k0[0], k0[1], k0[2], k0[3]};
+  double p[3] = {k0[4], k0[5], k0[6]}, pd[3] = {0, 0, 0}, pdd[3] = {0, 0, 0};
+  double w[3] = {0, 0, 0}, wd[3] = {0, 0, 0};
+#pragma unroll
+  for (int j = 1; j < K; ++j) {
+    const double* rj = row0 + j * kTabStride;
+    const double d[3] = {rj[12], rj[13], rj[14]};
+    const double lw[3] = {lam[j] * d[0], lam[j] * d[1], lam[j] * d[2]};
+    double qe[4], qn[4], A[9], aw[3], awd[3], wn[3], cr[3];
+    quat_exp(lw, qe);
+    quat_mul(q, qe, qn);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = qn[i];
+    so3_exp_and_Jr(lw, A, nullptr);
+    m3_tvec(A, w, aw);
+    m3_tvec(A, wd, awd);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) wn[c] = aw[c] + lamd[j] * d[c];
+    cross(wn, d, cr);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      wd[c] = awd[c] + lamd[j] * cr[c] + lamdd[j] * d[c];
+      w[c] = wn[c];
+      const double dp = rj[9 + c] - rj[9 + c - kTabStride];
+      p[c] += lam[j] * dp; pd[c] += lamd[j] * dp; pdd[c] += lamdd[j] * dp;
+    }
+  }
+  double* o = pose + 7 * static_cast<size_t>(f);
+  o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3]; o[4] = p[0]; o[5] = p[1]; o[6] = p[2];
+  if (vel || acc) {
+    double R[9], v[3], a[3];
+    quat_to_rot(q, R);
+    m3_tvec(R, pd, v);
+    m3_tvec(R, pdd, a);
+    if (vel) { double* ov = vel + 6 * static_cast<size_t>(f); ov[0] = w[0]; ov[1] = w[1]; ov[2] = w[2]; ov[3] = v[0]; ov[4] = v[1]; ov[5] = v[2]; }
+    if (acc) { double* oa = acc + 6 * static_cast<size_t>(f); oa[0] = wd[0]; oa[1] = wd[1]; oa[2] = wd[2]; oa[3] = a[0]; oa[4] = a[1]; oa[5] = a[2]; }
+  }
+}
+
 }  // namespace hb

@@ -39,7 +39,7 @@ EXPORTS = [
     "hb200_factor_evaluate", "hb200_reduced_size", "hb200_build_system", "hb200_get_system", "hb200_solve",
     "hb200_get_delta", "hb200_iterate", "hb200_cost", "hb200_get_state", "hb200_set_allreduce",
     "hb200_system_device_ptr", "hb200_stream", "hb200_launch_count", "hb200_optimize", "hb200_snapshot", "hb200_restore",
-    "hb200_profile_iteration",
+    "hb200_profile_iteration", "hb200_interpolate",
 ]
 
 _lib = None
@@ -271,6 +271,16 @@ class Context:
         g, lm = np.zeros(3), np.zeros((self.L, 3))
         self._check(self.lib.hb200_get_state(self.h, _d(knots), _d(bg), _d(ba), _d(g), _d(lm)))
         return dict(knots=knots, gyro_bias=bg, accel_bias=ba, gravity=g, landmarks=lm)
+
+    def interpolate(self, stamps, derivatives=True):
+        stamps = _f64(stamps)
+        n = stamps.size
+        pose = np.zeros((n, 7))
+        vel = np.zeros((n, 6)) if derivatives else None
+        acc = np.zeros((n, 6)) if derivatives else None
+        bad = C.c_int(0)
+        self._check(self.lib.hb200_interpolate(self.h, n, _d(stamps), _d(pose), _d(vel), _d(acc), C.byref(bad)))
+        return pose, vel, acc, bad.value
 
     def synchronize(self):
         self._check(self.lib.hb200_synchronize(self.h))

@@ -119,6 +119,11 @@ int hb200_restore(hb200_ctx* ctx);
  * each launch in issue order (names are kernel names, 32 chars each).  Not for timing the step --
  * for attributing it (bench.py roofline / kernel shares). */
 int hb200_profile_iteration(hb200_ctx* ctx, int reps, int max_entries, char* names /* [max_entries][32] */, double* ms, int* count);
+/* Spline interpolation of the current state at `n` stamps (device kernel): pose [n][7] = [q|p], and
+ * optionally (may be NULL) body velocity [n][6] = [omega | R^T pdot] and acceleration [n][6]. Stamps
+ * outside the valid span give identity/zero rows and are counted in num_invalid.  Replaces
+ * state->evaluate(StateQuery{stamp, derivative}) for trajectory dumps (reference apps/hyperslam/main.cpp:69-80). */
+int hb200_interpolate(hb200_ctx* ctx, int n, const double* stamps, double* pose, double* velocity, double* acceleration, int* num_invalid);
 int hb200_get_state(hb200_ctx* ctx, double* knots, double* gyro, double* accel, double* gravity, double* landmarks);
 
 /* ---- multi-GPU hook -------------------------------------------------------------------------

@@ -234,3 +234,22 @@ def test_gpu_matches_mpmath_golden(built):
         ctx.evaluate()
         check_against_golden(case, ctx.outputs(), ctx.index_maps())
         ctx.close()
+
+
+def test_interpolate_matches_oracle_state_evaluate(built):
+    for order in (4, 6):
+        win = synthetic.make_window(order=order, num_knots=14, num_landmarks=5, num_imu=5, seed=synthetic.SEED_BASE + 400)
+        ctx = make_ctx(win)
+        left = (order - 1) // 2
+        t = np.linspace(win.knots[left, 7], win.knots[14 - order + left, 7], 57, endpoint=False)
+        t = np.concatenate([t, [win.knots[-1, 7] + 5.0]])            # one stamp outside the span
+        pose, vel, acc, bad = ctx.interpolate(t)
+        assert bad == 1 and np.array_equal(pose[-1], [0, 0, 0, 1, 0, 0, 0])
+        ow = ol.OracleWindow(win)
+        for i in range(t.size - 1):
+            j = int(np.searchsorted(win.knots[:, 7], t[i], side="right") - 1) - left
+            v, ve, ac, _ = ol.state_evaluate(win.knots[j:j + order], t[i], 2, False)
+            assert np.abs(pose[i] - v).max() < 1e-12
+            assert np.abs(vel[i] - ve).max() < 1e-9 * max(1.0, np.abs(ve).max())
+            assert np.abs(acc[i] - ac).max() < 1e-8 * max(1.0, np.abs(ac).max())
+        ctx.close()
