@@ -1,0 +1,65 @@
+"""Worker for tests/test_gpu_multi.py: every rank runs LM iterations on its factor shard with the
+NCCL all-reduce hook; rank 0 compares records and final state with the single-process oracle."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from hyperslam_b200 import runtime, synthetic  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    win = synthetic.make_window(order=4, num_knots=20, num_landmarks=160, num_imu=400, seed=synthetic.SEED_BASE + 700, constant_knots=2)
+    ctx = runtime.Context(local, use_graph=False)
+    ctx.load_window(win.shard(rank, world))
+    ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    cache = {}
+
+    def allreduce(ptr, count, stream):
+        if (ptr, count) not in cache:
+            class _Arr:
+                __cuda_array_interface__ = dict(shape=(count,), typestr="<f8", data=(ptr, False), version=2)
+            cache[(ptr, count)] = torch.as_tensor(_Arr(), device=torch.device("cuda", local))
+        with torch.cuda.stream(ext):
+            dist.all_reduce(cache[(ptr, count)])
+        return 0
+
+    ctx.set_allreduce(allreduce)
+    recs = ctx.iterate(4)
+    state = ctx.state()
+    ok, msg = True, ""
+    if rank == 0:
+        import oracle_lib as ol
+        ow = ol.OracleWindow(win)
+        for it, rec in enumerate(recs):
+            o = ow.iterate(apply=True)
+            if not (abs(rec["cost"] - o["cost"]) <= 1e-7 * o["cost"] and abs(rec["cost_new"] - o["cost_new"]) <= 1e-6 * abs(o["cost_new"])
+                    and rec["accepted"] == o["accepted"] and rec["spd"] == 1):
+                ok, msg = False, f"iteration {it}: {rec} vs oracle cost {o['cost']} -> {o['cost_new']} accepted {o['accepted']}"
+        so = ow.state()
+        if np.abs(state["knots"] - so["knots"]).max() > 1e-6:
+            ok, msg = False, "knots differ"
+    # every rank holds the same replicated knots; landmarks are updated by their owner only
+    knots = torch.from_numpy(state["knots"]).cuda()
+    ref = knots.clone()
+    dist.broadcast(ref, 0)
+    same = bool(torch.equal(knots, ref))
+    flag = torch.tensor([1.0 if (ok and same) else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps(dict(ok=bool(flag.item() == 1.0), msg=msg, replicas_identical=same, world=world)))
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
