@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -114,6 +115,7 @@ struct hb200_ctx {
   int beta = 3;
   bool band_solver = true, band_smem = true, force_dense = false;
   DevBuf<double> band_ws;
+  DevBuf<long long> band_dbg;   // optional phase timings of band_solve_kernel (HB200_BAND_TIMING=1)
   bool bound = false;
 
   // outputs
@@ -218,10 +220,11 @@ int ensure_system(hb200_ctx* c) {
   c->band_solver = !c->force_dense && ((c->n <= 512) || (12 * (c->beta + 1) <= 6 * c->K));
   c->band_smem = ws <= 220 * 1024;
   if (c->band_solver) {
-    if (c->band_smem) HB_CUDA(cudaFuncSetAttribute(band_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ws)));
+    if (c->band_smem) HB_CUDA(cudaFuncSetAttribute(band_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ws)));
     else HB_CUDA(c->band_ws.ensure(ws / sizeof(double)));
   }
   HB_CUDA(c->band_ws.ensure(1));
+  if (getenv("HB200_BAND_TIMING")) HB_CUDA(c->band_dbg.ensure(8));
   // parallelism of the J^T J kernels: aim at ~2 CTAs per SM
   c->pix_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nseg, 1) - 1) / std::max(c->nseg, 1), std::max(1, c->Nv / (16 * std::max(c->nseg, 1)))));
   c->imu_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nruns, 1) - 1) / std::max(c->nruns, 1), std::max(1, c->Ni / (8 * std::max(c->nruns, 1)))));
@@ -317,7 +320,8 @@ int enqueue_finalize(hb200_ctx* c) {
 int enqueue_solve(hb200_ctx* c) {
   if (c->band_solver) {
     const size_t smem = c->band_smem ? band_workspace_doubles(c->K, c->beta, c->n - 6 * c->K) * sizeof(double) : 0;
-    band_solve_kernel<<<1, kBandThreads, smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_smem ? 1 : 0, c->band_ws.p, c->dp.p, c->spd.p);
+    if (c->band_smem) band_solve_kernel<true><<<1, kBandThreads, smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p);
+    else band_solve_kernel<false><<<1, kBandThreads, 0, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p);
     HB_LAUNCH(c, "band_solve_kernel");
   } else {
     int n = c->n;
@@ -461,7 +465,7 @@ void hb200_destroy(hb200_ctx* c) {
   c->seg_off.release(); c->run_off.release(); c->lm_off.release(); c->lm_obs.release(); c->d_invalid.release();
   c->v_r.release(); c->v_Jp.release(); c->v_Jl.release(); c->i_r.release(); c->i_Jp.release(); c->i_wg.release(); c->i_wa.release(); c->i_Jg.release();
   c->sys.release(); c->D.release(); c->Lw.release(); c->Ldiag.release(); c->dp.release(); c->dl.release(); c->Vinv.release(); c->gl.release(); c->Dl.release();
-  c->band_ws.release(); c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
+  c->band_ws.release(); c->band_dbg.release(); c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1094,6 +1098,12 @@ int hb200_interpolate(hb200_ctx* c, int n, const double* stamps, double* pose, d
   d_t.release(); d_p.release(); d_v.release(); d_a.release();
   if (e != cudaSuccess) return fail(100 + static_cast<int>(e), "interpolate: %s", cudaGetErrorString(e));
   if (num_invalid) *num_invalid = bad;
+  return 0;
+}
+
+int hb200_debug_band_timing(hb200_ctx* c, long long* cycles /*[8]*/) {
+  if (!c || !c->band_dbg.p) return fail(-2, "set HB200_BAND_TIMING=1 before hb200_bind");
+  HB_CUDA(cudaMemcpy(cycles, c->band_dbg.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -9,8 +9,8 @@
 //   memory (global-memory workspace when it does not fit).
 //
 // Workspace (doubles): W[K][h][6] band block-columns (h = 6 + 6 beta rows each: diagonal block first),
-//   AR[m+1][np] arrow rows (+ the rhs as last row), CC[m+1][m] corner (+ rhs row), LI[K][8] reciprocal
-//   diagonals of the diagonal Cholesky blocks, X[n].
+//   AR[m+1][np] arrow rows (+ the rhs as last row), CC[m+1][m] corner (+ rhs row), LI[K][48] reciprocal
+//   diagonals (6) and inverses (36, at +8) of the diagonal Cholesky blocks, X[n].
 #pragma once
 #include "hb200_solve.cuh"
 
@@ -21,7 +21,7 @@ constexpr int kBandThreads = 512;
 __host__ __device__ inline size_t band_workspace_doubles(int K, int beta, int m) {
   const size_t h = 6 + 6 * static_cast<size_t>(beta);
   const size_t np = 6 * static_cast<size_t>(K);
-  return static_cast<size_t>(K) * h * 6 + (m + 1) * np + static_cast<size_t>(m + 1) * m + static_cast<size_t>(K) * 8 + np + m;
+  return static_cast<size_t>(K) * h * 6 + (m + 1) * np + static_cast<size_t>(m + 1) * m + static_cast<size_t>(K) * 48 + np + m;
 }
 
 // Right-looking Cholesky of a 6x6 SPD block (lower, row-major with stride ld), division-free:
@@ -54,56 +54,67 @@ HB_DI bool chol6(double* A, int ld, double* inv /*6*/) {
   return ok;
 }
 
-__global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* __restrict__ sys, int n, int K, int beta, int use_smem,
+template <bool SMEM>
+__global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* __restrict__ sys, int n, int K, int beta,
                                                                   double* __restrict__ ws_global, double* __restrict__ x_out,
-                                                                  int* __restrict__ spd_flag) {
+                                                                  int* __restrict__ spd_flag, long long* __restrict__ dbg) {
   extern __shared__ double s_band[];
-  double* ws = use_smem ? s_band : ws_global;
+  double* ws = SMEM ? s_band : ws_global;
   const int np = 6 * K, m = n - np, h = 6 + 6 * beta;
   double* W = ws;
   double* AR = W + static_cast<size_t>(K) * h * 6;
   double* CC = AR + static_cast<size_t>(m + 1) * np;
   double* LI = CC + static_cast<size_t>(m + 1) * m;
-  double* X = LI + static_cast<size_t>(K) * 8;
+  double* X = LI + static_cast<size_t>(K) * 48;
   const double* S = sys;
   const double* b = sys + static_cast<size_t>(n) * n;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   __shared__ int s_ok;
   if (tid == 0) s_ok = 1;
   // ---- gather the band, the arrow and the corner from the dense system ----
-  for (int e = tid; e < K * h * 6; e += kBandThreads) {
-    const int c = e / (h * 6), rem = e - c * h * 6;
-    const int i = rem / 6, j = rem - 6 * i;
-    const int row = 6 * c + i, col = 6 * c + j;
-    W[e] = (row < np) ? S[static_cast<size_t>(row) * n + col] : 0.0;
-  }
-  for (int e = tid; e < (m + 1) * np; e += kBandThreads) {
-    const int r = e / np, col = e - r * np;
-    AR[e] = (r < m) ? S[static_cast<size_t>(np + r) * n + col] : b[col];
-  }
-  for (int e = tid; e < (m + 1) * m; e += kBandThreads) {
-    const int r = e / m, q = e - r * m;
-    CC[e] = (r < m) ? S[static_cast<size_t>(np + r) * n + np + q] : b[np + q];
+  {
+    const int h6 = h * 6;
+    for (int e = tid; e < K * h6; e += kBandThreads) {
+      const int c = e / h6, rem = e - c * h6;
+      const int i = rem / 6, j = rem - 6 * i;
+      const int row = 6 * c + i, col = 6 * c + j;
+      W[e] = (row < np) ? S[static_cast<size_t>(row) * n + col] : 0.0;
+    }
+    for (int e = tid; e < (m + 1) * np; e += kBandThreads) {
+      const int r = e / np, col = e - r * np;
+      AR[e] = (r < m) ? S[static_cast<size_t>(np + r) * n + col] : b[col];
+    }
+    for (int e = tid; e < (m + 1) * m; e += kBandThreads) {
+      const int r = e / m, q = e - r * m;
+      CC[e] = (r < m) ? S[static_cast<size_t>(np + r) * n + np + q] : b[np + q];
+    }
   }
   __syncthreads();
-  // ---- factorisation + forward substitution, one control-point block column per step ----
+  long long t_mark = clock64(), t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define HB_TICK(i) do { if (dbg && tid == 0) { const long long now = clock64(); t_acc[i] += now - t_mark; t_mark = now; } } while (0)
+  HB_TICK(0);
+  // ---- factorisation + forward substitution, one control-point block column per step.  The 6x6
+  // Cholesky of the NEXT diagonal block is done by warp 0 inside the trailing-update phase, as soon
+  // as that block has received its update (look-ahead), so it is off the critical path. ----
+  if (tid == 0 && K > 0) {
+    if (!chol6(W, 6, LI)) s_ok = 0;
+  }
+  __syncthreads();
+  HB_TICK(1);
+  const int ng = (m + 1 + 5) / 6;
   for (int c = 0; c < K; ++c) {
     double* Wc = W + static_cast<size_t>(c) * h * 6;
-    double* Lic = LI + static_cast<size_t>(c) * 8;
-    if (tid == 0) {
-      if (!chol6(Wc, 6, Lic)) s_ok = 0;
-    }
-    __syncthreads();
+    const double* Lic = LI + static_cast<size_t>(c) * 48;
     const int nb = min(h - 6, np - 6 * (c + 1));  // band rows below the diagonal block
     const int R = nb + m + 1;                      // + arrow rows + rhs row
-    // panel: X_row = A_row * L^-T  (6 values per row)
+    // panel: solve x L^T = a for every row (right-looking, reciprocal diagonal in Lic)
     for (int t = tid; t < R; t += kBandThreads) {
       double* a = (t < nb) ? (Wc + static_cast<size_t>(6 + t) * 6) : (AR + static_cast<size_t>(t - nb) * np + 6 * c);
       double v[6];
 #pragma unroll
       for (int q = 0; q < 6; ++q) v[q] = a[q];
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {  // x L^T = a  (right-looking forward substitution)
+      for (int j = 0; j < 6; ++j) {
         v[j] *= Lic[j];
 #pragma unroll
         for (int q = j + 1; q < 6; ++q) v[q] -= v[j] * Wc[q * 6 + j];
@@ -112,14 +123,24 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       for (int q = 0; q < 6; ++q) a[q] = v[q];
     }
     __syncthreads();
+    HB_TICK(2);
     // trailing update in 6x6 tiles: groups = band blocks below the diagonal, then arrow rows in sixes
     // (the rhs row is the last arrow row).  Thread = (tile, row i of the tile): 6 dots of length 6.
     {
       const int nbk = nb / 6;
-      const int ng = (m + 1 + 5) / 6;
       const int G = nbk + ng;
       const int ntiles = G * (G + 1) / 2;
-      for (int t = tid; t < ntiles * 6; t += kBandThreads) {
+      const bool look = (c + 1 < K);   // then tile 0 is the next diagonal block and belongs to warp 0
+      // warp 0 handles tile 0 only (when looking ahead); the other warps share tiles [first, ntiles)
+      const int first = look ? 1 : 0;
+      int t;
+      int stride;
+      if (look) {
+        if (warp == 0) { t = (lane < 6) ? lane : ntiles * 6; stride = ntiles * 6; }
+        else { t = 6 + (tid - 32); stride = kBandThreads - 32; }
+      } else { t = tid; stride = kBandThreads; }
+      (void)first;
+      for (; t < ntiles * 6; t += stride) {
         const int tile = t / 6, i = t - 6 * tile;
         int gu = static_cast<int>((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
         while (gu * (gu + 1) / 2 > tile) --gu;
@@ -156,75 +177,99 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
             if (6 * (gv - nbk) + j < m) tgt[j] -= sd[j];
         }
       }
+      if (tid == kBandThreads - 1) {
+        // inverse of this step's diagonal factor, for the back substitution (off the critical path):
+        // Li[i][j] = -(sum_{p=j}^{i-1} L[i][p] Li[p][j]) / L[i][i],  Li[j][j] = 1 / L[j][j]
+        double* Li = LI + static_cast<size_t>(c) * 48 + 8;
+#pragma unroll
+        for (int jj = 0; jj < 6; ++jj) {
+          Li[jj * 6 + jj] = Lic[jj];
+#pragma unroll
+          for (int ii = jj + 1; ii < 6; ++ii) {
+            double acc = 0.0;
+#pragma unroll
+            for (int pp = jj; pp < ii; ++pp) acc -= Wc[ii * 6 + pp] * Li[pp * 6 + jj];
+            Li[ii * 6 + jj] = acc * Lic[ii];
+          }
+        }
+      }
+      if (look && warp == 0) {
+        __syncwarp();
+        if (lane == 0) {
+          if (!chol6(W + static_cast<size_t>(c + 1) * h * 6, 6, LI + static_cast<size_t>(c + 1) * 48)) s_ok = 0;
+        }
+      }
     }
     __syncthreads();
+    HB_TICK(3);
   }
-  // ---- corner: dense Cholesky of CC (m x m) with the rhs row carried along ----
-  for (int q = 0; q < m; ++q) {
-    if (tid == 0) {
+  // ---- corner (m x m, rhs carried as row m) and the whole back substitution in warp 0 ----
+  if (warp == 0) {
+    // right-looking Cholesky, lanes own rows r = lane, lane + 32, ...
+    for (int q = 0; q < m; ++q) {
       const double d = CC[static_cast<size_t>(q) * m + q];
-      if (!(d > 0.0)) s_ok = 0;
-      CC[static_cast<size_t>(q) * m + q] = sqrt(d);
-    }
-    __syncthreads();
-    const double dq = CC[static_cast<size_t>(q) * m + q];
-    for (int r = q + 1 + tid; r <= m; r += kBandThreads) CC[static_cast<size_t>(r) * m + q] /= dq;
-    __syncthreads();
-    const int rem = m - q;  // rows q+1..m
-    for (int e = tid; e < rem * rem; e += kBandThreads) {
-      const int u = q + 1 + e / rem, v = q + 1 + e % rem;
-      if (v > u || v >= m) continue;
-      CC[static_cast<size_t>(u) * m + v] -= CC[static_cast<size_t>(u) * m + q] * CC[static_cast<size_t>(v) * m + q];
-    }
-    __syncthreads();
-  }
-  // ---- back substitution: corner (warp 0), then block columns K-1 .. 0 ----
-  double* Xa = X + np;
-  if (tid < 32) {
-    // y = row m of CC; lanes own entries r = lane, lane+32, ...
-    for (int q = m - 1; q >= 0; --q) {
-      double xq = 0.0;
-      if ((q & 31) == tid) { xq = CC[static_cast<size_t>(m) * m + q] / CC[static_cast<size_t>(q) * m + q]; Xa[q] = xq; }
-      xq = __shfl_sync(0xffffffffu, xq, q & 31);
-      for (int r = tid; r < q; r += 32) CC[static_cast<size_t>(m) * m + r] -= CC[static_cast<size_t>(q) * m + r] * xq;
+      if (!(d > 0.0) && lane == 0) s_ok = 0;
+      const double iv = rsqrt(d);
+      __syncwarp();
+      for (int r = q + lane; r <= m; r += 32) CC[static_cast<size_t>(r) * m + q] = (r == q) ? d * iv : CC[static_cast<size_t>(r) * m + q] * iv;
+      __syncwarp();
+      for (int r = q + 1 + lane; r <= m; r += 32) {
+        const double lrq = CC[static_cast<size_t>(r) * m + q];
+        const int smax = min(r, m - 1);
+        for (int sidx = q + 1; sidx <= smax; ++sidx) CC[static_cast<size_t>(r) * m + sidx] -= lrq * CC[static_cast<size_t>(sidx) * m + q];
+      }
       __syncwarp();
     }
+    HB_TICK(4);
+    double* Xa = X + np;
+    for (int q = m - 1; q >= 0; --q) {
+      double xq = 0.0;
+      if ((q & 31) == lane) { xq = CC[static_cast<size_t>(m) * m + q] / CC[static_cast<size_t>(q) * m + q]; Xa[q] = xq; }
+      xq = __shfl_sync(0xffffffffu, xq, q & 31);
+      for (int r = lane; r < q; r += 32) CC[static_cast<size_t>(m) * m + r] -= CC[static_cast<size_t>(q) * m + r] * xq;
+      __syncwarp();
+    }
+    HB_TICK(5);
+    // block columns K-1 .. 0: lane = (component j = lane % 6, part p = lane / 6), 5 parts
+    const int j = lane % 6, part = lane / 6;
+    for (int c = K - 1; c >= 0; --c) {
+      const double* Wc = W + static_cast<size_t>(c) * h * 6;
+      const double* Li = LI + static_cast<size_t>(c) * 48 + 8;
+      const int nb = min(h - 6, np - 6 * (c + 1));
+      double s = 0.0, s2 = 0.0;
+      if (part < 5) {
+        int t = part;
+        for (; t + 5 < nb + m; t += 10) {   // two independent accumulators
+          s += (t < nb) ? Wc[static_cast<size_t>(6 + t) * 6 + j] * X[6 * (c + 1) + t] : AR[static_cast<size_t>(t - nb) * np + 6 * c + j] * Xa[t - nb];
+          const int t2 = t + 5;
+          s2 += (t2 < nb) ? Wc[static_cast<size_t>(6 + t2) * 6 + j] * X[6 * (c + 1) + t2] : AR[static_cast<size_t>(t2 - nb) * np + 6 * c + j] * Xa[t2 - nb];
+        }
+        if (t < nb + m) s += (t < nb) ? Wc[static_cast<size_t>(6 + t) * 6 + j] * X[6 * (c + 1) + t] : AR[static_cast<size_t>(t - nb) * np + 6 * c + j] * Xa[t - nb];
+        s += s2;
+      }
+      // sum the 5 parts of each component: lanes j, j+6, j+12, j+18, j+24
+      double tot = s;
+      tot += __shfl_sync(0xffffffffu, s, (lane + 6) & 31);
+      tot += __shfl_sync(0xffffffffu, s, (lane + 12) & 31);
+      tot += __shfl_sync(0xffffffffu, s, (lane + 18) & 31);
+      tot += __shfl_sync(0xffffffffu, s, (lane + 24) & 31);
+      // lanes 0..5 now hold the full sums (their partners are lanes j+6k < 30)
+      double v = (lane < 6) ? AR[static_cast<size_t>(m) * np + 6 * c + lane] - tot : 0.0;
+      // x = L^-T v: lane j sums Li[q][j] v_q over q >= j (six independent broadcasts)
+      double xo = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const double vq = __shfl_sync(0xffffffffu, v, q);
+        if (lane < 6 && q >= lane) xo += Li[q * 6 + lane] * vq;
+      }
+      if (lane < 6) X[6 * c + lane] = xo;
+      __syncwarp();
+    }
+    HB_TICK(6);
   }
   __syncthreads();
-  __shared__ double s_rhs[6];
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int c = K - 1; c >= 0; --c) {
-    const double* Wc = W + static_cast<size_t>(c) * h * 6;
-    const int nb = min(h - 6, np - 6 * (c + 1));
-    if (warp < 6) {
-      const int j = warp;
-      double s = 0.0;
-      for (int t = lane; t < nb + m; t += 32) {
-        if (t < nb) s += Wc[static_cast<size_t>(6 + t) * 6 + j] * X[6 * (c + 1) + t];
-        else s += AR[static_cast<size_t>(t - nb) * np + 6 * c + j] * Xa[t - nb];
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) s_rhs[j] = AR[static_cast<size_t>(m) * np + 6 * c + j] - s;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const double* Lic = LI + static_cast<size_t>(c) * 8;
-      double v[6];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) v[q] = s_rhs[q];
-#pragma unroll
-      for (int j = 5; j >= 0; --j) {  // L^T x = rhs
-        v[j] *= Lic[j];
-#pragma unroll
-        for (int q = 0; q < j; ++q) v[q] -= v[j] * Wc[j * 6 + q];
-      }
-#pragma unroll
-      for (int q = 0; q < 6; ++q) X[6 * c + q] = v[q];
-    }
-    __syncthreads();
-  }
   for (int e = tid; e < n; e += kBandThreads) x_out[e] = X[e];
+  if (dbg && tid == 0) for (int i = 0; i < 8; ++i) dbg[i] = t_acc[i];
   if (tid == 0) *spd_flag = s_ok;
 }
 
