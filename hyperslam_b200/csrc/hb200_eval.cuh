@@ -218,6 +218,12 @@ HB_DI double huber_rho(double s, double delta, double* weight) {
 // ---------------------------------------------------------------------------------------------
 // Pixel factor (a5 + a3 + a7..a10 fused).  T: table origin (row r at T + r*kTabStride).
 // ---------------------------------------------------------------------------------------------
+// 256-bit global store (SASS STG.E.256): p must be 32-byte aligned.  Writes whole 32 B sectors, so a
+// thread-per-factor row store costs one L2 sector write per 32 B instead of two half-filled ones.
+HB_DI void st_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 template <int K, bool WANT_J>
 HB_DI void pixel_factor(const double* __restrict__ T, const Basis& B, int base, double t, double zx, double zy,
                         const double* __restrict__ cam, const double* __restrict__ lmk, double* r, double* __restrict__ Jp,
@@ -311,21 +317,20 @@ HB_DI void pixel_factor(const double* __restrict__ T, const Basis& B, int base, 
         EM[j * 6 + 3 * i + c] = E[3 * i] * M[j * 9 + c] + E[3 * i + 1] * M[j * 9 + 3 + c] + E[3 * i + 2] * M[j * 9 + 6 + c];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    double2* out = reinterpret_cast<double2*>(Jp + i * 6 * K);
+    double row[6 * K];
 #pragma unroll
     for (int m = 0; m < K; ++m) {
-      double v[6];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const double cur = (m == 0) ? E[3 * i + c] : EM[(m - 1) * 6 + 3 * i + c];
         const double nxt = (m + 1 < K) ? EM[m * 6 + 3 * i + c] : 0.0;
-        v[c] = cur - nxt;
-        v[3 + c] = -(lam[m] - lam[m + 1]) * F[3 * i + c];
+        row[6 * m + c] = cur - nxt;
+        row[6 * m + 3 + c] = -(lam[m] - lam[m + 1]) * F[3 * i + c];
       }
-      out[3 * m] = make_double2(v[0], v[1]);
-      out[3 * m + 1] = make_double2(v[2], v[3]);
-      out[3 * m + 2] = make_double2(v[4], v[5]);
     }
+    double* out = Jp + i * 6 * K;   // 32-byte aligned: rows are 192 B (K=4) / 288 B (K=6)
+#pragma unroll
+    for (int g = 0; g < 6 * K / 4; ++g) st_v4(out + 4 * g, row[4 * g], row[4 * g + 1], row[4 * g + 2], row[4 * g + 3]);
   }
 }
 

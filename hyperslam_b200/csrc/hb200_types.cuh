@@ -12,7 +12,7 @@ constexpr int kMaxOrder = 6;
 //   [15..23] G_j = Jr^{-1}(d_j) R_j^T                (row 0: zeros)
 //   [24]    stamp_j ; [25..27] pad  -> 28 doubles = 224 B (16 B multiple for cp.async.bulk)
 constexpr int kTabStride = 28;
-constexpr int kTileRows = 40;       // knot-table rows staged per CTA (8.96 KB)
+constexpr int kTileRows = 16;       // knot-table rows staged per CTA (3.6 KB); wider spans read the table from global/L2
 constexpr int kEvalThreads = 64;    // one factor per thread
 
 constexpr int kCamStride = 20;      // R_sb(9) t_bs(3) intrinsics(4) distortion(4)
