@@ -88,6 +88,7 @@ struct hb200_ctx {
   int num_sms = 0;
   long long launches = 0;
   long long launches_per_iteration = 0;
+  long long iter_total = 0, snap_iter_total = 0;   // host mirror of SolverState.iteration (record ring index)
 
   // window state (index 0 = current, 1 = trial)
   int k = 0, K = 0, kb = 4, Kbg = 0, Kba = 0, C = 0, L = 0;
@@ -237,6 +238,7 @@ int reset_solver_state(hb200_ctx* c) {
   HB_CUDA(c->st.ensure(1));
   HB_CUDA(cudaMemcpyAsync(c->st.p, &s, sizeof(s), cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->iter_total = 0;
   return 0;
 }
 
@@ -369,7 +371,9 @@ int enqueue_scalars(hb200_ctx* c) {
 }
 
 int enqueue_accept(hb200_ctx* c) {
-  accept_kernel<<<1, 256, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records);
+  ScalarArgs sa{c->cp_pix[1].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[1].p, c->Ni ? c->n_imu_blocks : 0, c->lm_part.p, (c->L && c->Nv) ? c->n_lm_blocks : 0};
+  accept_kernel<<<1, 256, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
+                                         c->allreduce ? 0 : 1, sa);
   HB_LAUNCH(c, "accept_kernel");
   CommitArgs a{};
   const size_t counts[5] = {8 * static_cast<size_t>(c->K), 4 * static_cast<size_t>(c->Kbg), 4 * static_cast<size_t>(c->Kba), 3, 3 * static_cast<size_t>(c->L)};
@@ -395,7 +399,7 @@ int enqueue_segment(hb200_ctx* c, int segment) {
     if ((rc = enqueue_solve(c))) return rc;
     if ((rc = enqueue_retract(c))) return rc;
     if ((rc = enqueue_evaluate(c, false, 1))) return rc;
-    if ((rc = enqueue_scalars(c))) return rc;
+    if (c->allreduce && (rc = enqueue_scalars(c))) return rc;
   } else {
     if ((rc = enqueue_accept(c))) return rc;
   }
@@ -915,13 +919,9 @@ int hb200_get_delta(hb200_ctx* c, double* dp, double* dl) {
 }  // extern "C"
 
 namespace {
-__global__ void reset_iteration_kernel(SolverState* st) { st->iteration = 0; }
 
 int iterate_enqueue(hb200_ctx* c, int iterations) {
   int rc = 0;
-  // records[] index = SolverState.iteration: reset the device-side counter first.
-  reset_iteration_kernel<<<1, 1, 0, c->stream>>>(c->st.p);
-  HB_LAUNCH(c, "reset_iteration_kernel");
   const bool graph_ok = c->use_graph && !c->allreduce;
   for (int it = 0; it < iterations; ++it) {
     if (graph_ok) {
@@ -964,6 +964,17 @@ int iterate_enqueue(hb200_ctx* c, int iterations) {
     }
   }
   c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->iter_total += iterations;
+  return 0;
+}
+
+// copies the last `iterations` records out of the device ring buffer (asynchronously)
+int fetch_records(hb200_ctx* c, int iterations, std::vector<SolverState>* rec) {
+  rec->resize(iterations);
+  for (int i = 0; i < iterations; ++i) {
+    const long long idx = (c->iter_total - iterations + i) % c->max_records;
+    HB_CUDA(cudaMemcpyAsync(rec->data() + i, c->records.p + idx, sizeof(SolverState), cudaMemcpyDeviceToHost, c->stream));
+  }
   return 0;
 }
 
@@ -984,8 +995,8 @@ int hb200_iterate(hb200_ctx* c, int iterations, hb200_iteration* records) {
   HB_CUDA(cudaSetDevice(c->device));
   if ((rc = iterate_enqueue(c, iterations))) return rc;
   if (records && iterations) {
-    std::vector<SolverState> rec(iterations);
-    HB_CUDA(cudaMemcpyAsync(rec.data(), c->records.p, sizeof(SolverState) * iterations, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<SolverState> rec;
+    if ((rc = fetch_records(c, iterations, &rec))) return rc;
     HB_CUDA(cudaStreamSynchronize(c->stream));
     convert_records(rec, records);
   }
@@ -1009,8 +1020,8 @@ int hb200_optimize(hb200_ctx* c, int iterations, double* knots, double* gyro, do
   if (accel && c->Kba) HB_CUDA(cudaMemcpyAsync(accel, c->ba[0].p, sizeof(double) * 4 * c->Kba, cudaMemcpyDeviceToHost, c->stream));
   if (gravity) HB_CUDA(cudaMemcpyAsync(gravity, c->grav[0].p, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
   if (landmarks && c->L) HB_CUDA(cudaMemcpyAsync(landmarks, c->lms[0].p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToHost, c->stream));
-  std::vector<SolverState> rec(records ? iterations : 0);
-  if (records && iterations) HB_CUDA(cudaMemcpyAsync(rec.data(), c->records.p, sizeof(SolverState) * iterations, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<SolverState> rec;
+  if (records && iterations && (rc = fetch_records(c, iterations, &rec))) return rc;
   HB_CUDA(cudaStreamSynchronize(c->stream));
   if (records && iterations) convert_records(rec, records);
   return 0;
@@ -1053,6 +1064,7 @@ int hb200_profile_iteration(hb200_ctx* c, int reps, int max_entries, char* names
     if (!rc) rc = enqueue_segment(c, 2);
     c->profiling = false;
     if (rc) return rc;
+    c->iter_total += 1;
     HB_CUDA(cudaStreamSynchronize(c->stream));
     if (rep == 0) { acc.assign(c->prof_used, 0.0); nm.assign(c->prof_names.begin(), c->prof_names.begin() + c->prof_used); }
     for (size_t i = 1; i < c->prof_used && i < acc.size(); ++i) {
@@ -1120,6 +1132,7 @@ int hb200_snapshot(hb200_ctx* c) {
   if (c->L) HB_CUDA(cudaMemcpyAsync(c->snap_lms.p, c->lms[0].p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToDevice, c->stream));
   HB_CUDA(cudaMemcpyAsync(c->snap_st.p, c->st.p, sizeof(SolverState), cudaMemcpyDeviceToDevice, c->stream));
   c->have_snapshot = true;
+  c->snap_iter_total = c->iter_total;
   return 0;
 }
 
@@ -1132,6 +1145,7 @@ int hb200_restore(hb200_ctx* c) {
   HB_CUDA(cudaMemcpyAsync(c->grav[0].p, c->snap_grav.p, sizeof(double) * 3, cudaMemcpyDeviceToDevice, c->stream));
   if (c->L) HB_CUDA(cudaMemcpyAsync(c->lms[0].p, c->snap_lms.p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToDevice, c->stream));
   HB_CUDA(cudaMemcpyAsync(c->st.p, c->snap_st.p, sizeof(SolverState), cudaMemcpyDeviceToDevice, c->stream));
+  c->iter_total = c->snap_iter_total;
   c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
   return 0;
 }

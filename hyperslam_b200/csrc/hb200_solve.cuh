@@ -65,9 +65,11 @@ __global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* 
       const int id = threadIdx.x + e * kHessThreads;
       if (id < NB * NB) {
         const int a = id / NB, b = id - a * NB;
-        double s = 0;
-        for (int ff = 0; ff < cnt; ++ff) s += sJ[ff][0][a] * sJ[ff][0][b] + sJ[ff][1][a] * sJ[ff][1][b];
-        acc[e] += s;
+        if (b <= a) {   // lower triangle only: the solvers read S[row >= col]
+          double s = 0;
+          for (int ff = 0; ff < cnt; ++ff) s += sJ[ff][0][a] * sJ[ff][0][b] + sJ[ff][1][a] * sJ[ff][1][b];
+          acc[e] += s;
+        }
       }
     }
     if (threadIdx.x < NB) {
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* 
     const int id = threadIdx.x + e * kHessThreads;
     if (id < NB * NB) {
       const int a = id / NB, b = id - a * NB;
-      atomicAdd(&v.S[static_cast<size_t>(c0 + a) * n + c0 + b], acc[e]);
+      if (b <= a) atomicAdd(&v.S[static_cast<size_t>(c0 + a) * n + c0 + b], acc[e]);
     }
   }
   if (threadIdx.x < NB) atomicAdd(&v.g[c0 + threadIdx.x], gacc);
@@ -142,11 +144,13 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
       const int id = threadIdx.x + e * kHessThreads;
       if (id < NI * NI) {
         const int a = id / NI, b = id - a * NI;
-        double s = 0;
-        for (int ff = 0; ff < cnt; ++ff)
+        if (b <= a) {   // local column order is monotone in the global dof index
+          double s = 0;
+          for (int ff = 0; ff < cnt; ++ff)
 #pragma unroll
-          for (int row = 0; row < 6; ++row) s += sJ[ff][row][a] * sJ[ff][row][b];
-        acc[e] += s;
+            for (int row = 0; row < 6; ++row) s += sJ[ff][row][a] * sJ[ff][row][b];
+          acc[e] += s;
+        }
       }
     }
     if (threadIdx.x < NI) {
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
     const int id = threadIdx.x + e * kHessThreads;
     if (id < NI * NI) {
       const int a = id / NI, b = id - a * NI;
-      if (acc[e] != 0.0) atomicAdd(&v.S[static_cast<size_t>(scol[a]) * n + scol[b]], acc[e]);
+      if (b <= a && acc[e] != 0.0) atomicAdd(&v.S[static_cast<size_t>(scol[a]) * n + scol[b]], acc[e]);
     }
   }
   if (threadIdx.x < NI) atomicAdd(&v.g[scol[threadIdx.x]], gacc);
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(const int* __restr
   }
   for (int e = threadIdx.x; e < rows * rows; e += kSchurThreads) {
     const int a = e / rows, b = e - a * rows;
+    if (b > a) continue;
     const double val = WV[3 * a] * W[3 * b] + WV[3 * a + 1] * W[3 * b + 1] + WV[3 * a + 2] * W[3 * b + 2];
     if (val != 0.0) atomicAdd(&v.S[static_cast<size_t>(r0g + a) * n + r0g + b], -val);
   }
@@ -310,7 +315,7 @@ __global__ void finalize_kernel(double* sys, int n, const SolverState* __restric
   for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total; e += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int i = static_cast<int>(e / n), j = static_cast<int>(e - static_cast<size_t>(i) * n);
     if (i < n) {
-      double s = v.S[e];
+      double s = (j <= i) ? v.S[e] : v.S[static_cast<size_t>(j) * n + i];   // only the lower triangle was accumulated
       if (i == j) {
         const double d = fmin(fmax(v.diagH[i], 1e-6), 1e32);
         D[i] = d;
@@ -650,10 +655,30 @@ __global__ void scalars_kernel(const double* __restrict__ cp_pix, int n_pix_bloc
 }
 
 // Step acceptance (Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy::StepAccepted/Rejected).
-__global__ void accept_kernel(const double* __restrict__ sys, int n, const double* __restrict__ scal, const double* __restrict__ dp,
+struct ScalarArgs {   // inputs of scalars_kernel, for the fused single-GPU path
+  const double* cp_pix; int n_pix_blocks; const double* cp_imu; int n_imu_blocks; const double* lm_part; int n_lm_blocks;
+};
+
+__global__ void accept_kernel(const double* __restrict__ sys, int n, double* __restrict__ scal, const double* __restrict__ dp,
                               const double* __restrict__ D, const unsigned char* __restrict__ fixed, SolverState* st,
-                              const int* __restrict__ spd_flag, SolverState* __restrict__ record, int max_records) {
+                              const int* __restrict__ spd_flag, SolverState* __restrict__ record, int max_records, int fuse_scalars,
+                              ScalarArgs sa) {
   __shared__ double s[2][256];
+  if (fuse_scalars) {   // == scalars_kernel (no all-reduce between the two on a single GPU)
+    __shared__ double q[3][256];
+    double c = 0, a = 0, b = 0;
+    for (int i = threadIdx.x; i < sa.n_pix_blocks; i += blockDim.x) c += sa.cp_pix[i];
+    for (int i = threadIdx.x; i < sa.n_imu_blocks; i += blockDim.x) c += sa.cp_imu[i];
+    for (int i = threadIdx.x; i < sa.n_lm_blocks; i += blockDim.x) { a += sa.lm_part[2 * i]; b += sa.lm_part[2 * i + 1]; }
+    q[0][threadIdx.x] = c; q[1][threadIdx.x] = a; q[2][threadIdx.x] = b;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) { q[0][threadIdx.x] += q[0][threadIdx.x + o]; q[1][threadIdx.x] += q[1][threadIdx.x + o]; q[2][threadIdx.x] += q[2][threadIdx.x + o]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { scal[0] = q[0][0]; scal[1] = q[1][0]; scal[2] = q[2][0]; scal[3] = 0.0; }
+    __syncthreads();
+  }
   const double* g = sys + static_cast<size_t>(n) * n + 2 * static_cast<size_t>(n);
   double a = 0, b = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
@@ -684,7 +709,7 @@ __global__ void accept_kernel(const double* __restrict__ sys, int n, const doubl
       st->decrease_factor *= 2.0;
     }
     st->iteration += 1;
-    if (record && st->iteration <= max_records) record[st->iteration - 1] = *st;
+    if (record) record[(st->iteration - 1) % max_records] = *st;   // ring buffer, host tracks the index
   }
 }
 
