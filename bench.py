@@ -35,11 +35,12 @@ UNIT = "factor evals/s"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=50)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=300)
+    p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--config", type=int, default=1, help="index into BASELINE.json configs (default 1 = headline)")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-large", action="store_true", help="skip the 1M-factor roofline section")
     return p.parse_args()
 
 
@@ -83,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -319,6 +320,42 @@ def main():
                         dominant_kernel_by_time=dominant, kernel_share_of_step=shares,
                         note="cfg1 moves 7.7 MB per sweep (about 1.2 us at peak): launch/latency-bound by construction (SURVEY.md 8d); see profiles/ for larger windows")
 
+    # ---- roofline of the factor kernels on a window large enough to be bandwidth-relevant (1 M factors) ----
+    large = None
+    if world == 1 and not args.no_large:
+        ctx.close()
+        big = synthetic.make_config(4, constant_knots=2)
+        bctx = runtime.Context(local_rank)
+        bctx.load_window(big)
+        bext = torch.cuda.ExternalStream(bctx.stream, device=torch.device("cuda", local_rank))
+        for _ in range(3):
+            bctx.evaluate(jacobians=True)
+        bctx.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        ev0.record(bext)
+        for _ in range(reps):
+            bctx.evaluate(jacobians=True)
+        ev1.record(bext)
+        bctx.synchronize()
+        sweep = ev0.elapsed_time(ev1) / reps
+        bprof = {}
+        for name, ms in bctx.profile_iteration(reps=3):
+            bprof.setdefault(name, ms)
+        bab = algorithmic_bytes(big)
+        peak, peak_src = load_peaks()
+        large = dict(workload=synthetic.CONFIG_NAMES[4], factors=big.num_factors, evaluate_sweep_ms=sweep,
+                     evaluate_sweep_evals_per_s=big.num_factors / (sweep * 1e-3), peak=peak, unit="GB/s")
+        for kname in ("pixel_eval_kernel", "inertial_eval_kernel"):
+            ach = bab[kname] / (bprof[kname] * 1e-3) / 1e9
+            large[kname] = dict(algorithmic_bytes_per_launch=bab[kname], launch_ms=bprof[kname], achieved=ach, frac=ach / peak)
+        large["iteration_kernel_ms"] = {k_: round(v, 4) for k_, v in bprof.items()}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                large["traffic"] = json.load(f).get("large_window")
+        bctx.close()
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -354,11 +391,14 @@ def main():
                 gpu_launches=int(launches), clocks=clocks, gn_iters_per_s=1e3 / ms_per_step,
                 evaluate_sweep=dict(ms=sweep_ms, evals_per_s=nf_total / (sweep_ms * 1e-3)), kernel_ms={k_: round(v, 5) for k_, v in kernel_ms.items()})
     if roofline:
+        if large:
+            roofline["large_window"] = large
         line["roofline"] = roofline
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
-    ctx.close()
+    if world > 1:
+        ctx.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
