@@ -131,15 +131,17 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       const int G = nbk + ng;
       const int ntiles = G * (G + 1) / 2;
       const bool look = (c + 1 < K);   // then tile 0 is the next diagonal block and belongs to warp 0
-      // warp 0 handles tile 0 only (when looking ahead); the other warps share tiles [first, ntiles)
-      const int first = look ? 1 : 0;
+      // warp 0 handles tile 0 only (when looking ahead) and keeps scheduler 0 to itself: the other
+      // tiles go to the warps of schedulers 1..3 (warp % 4 != 0), so the critical path tile 0 -> chol6
+      // does not compete for issue slots.
       int t;
       int stride;
       if (look) {
+        constexpr int kWorkers = (kBandThreads / 32) * 3 / 4 * 32;   // threads in warps with warp % 4 != 0
         if (warp == 0) { t = (lane < 6) ? lane : ntiles * 6; stride = ntiles * 6; }
-        else { t = 6 + (tid - 32); stride = kBandThreads - 32; }
+        else if ((warp & 3) == 0) { t = ntiles * 6; stride = 1; }
+        else { t = 6 + ((warp - (warp >> 2) - 1) * 32 + lane); stride = kWorkers; }
       } else { t = tid; stride = kBandThreads; }
-      (void)first;
       for (; t < ntiles * 6; t += stride) {
         const int tile = t / 6, i = t - 6 * tile;
         int gu = static_cast<int>((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
@@ -151,16 +153,18 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
         if (!ub && ru > m) continue;
         const double* xu = ub ? (Wc + static_cast<size_t>(6 + 6 * gu + i) * 6) : (AR + static_cast<size_t>(ru) * np + 6 * c);
         double a[6], sd[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) a[q] = xu[q];
+        {
+          const double2* x2 = reinterpret_cast<const double2*>(xu);   // rows are 48 B: 16-byte aligned
+          const double2 a0 = x2[0], a1 = x2[1], a2 = x2[2];
+          a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y;
+        }
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
           const int rv = vb ? 0 : 6 * (gv - nbk) + j;
           const double* xv = vb ? (Wc + static_cast<size_t>(6 + 6 * gv + j) * 6) : (AR + static_cast<size_t>(min(rv, m)) * np + 6 * c);
-          double acc = 0.0;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) acc += a[q] * xv[q];
-          sd[j] = acc;
+          const double2* v2 = reinterpret_cast<const double2*>(xv);
+          const double2 b0 = v2[0], b1 = v2[1], b2 = v2[2];
+          sd[j] = a[0] * b0.x + a[1] * b0.y + a[2] * b1.x + a[3] * b1.y + a[4] * b2.x + a[5] * b2.y;
         }
         if (ub) {  // band x band
           double* tgt = W + (static_cast<size_t>(c + 1 + gv) * h + (6 * (gu - gv) + i)) * 6;
@@ -196,30 +200,36 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       if (look && warp == 0) {
         __syncwarp();
         if (lane == 0) {
+          const long long tc0 = dbg ? clock64() : 0;
           if (!chol6(W + static_cast<size_t>(c + 1) * h * 6, 6, LI + static_cast<size_t>(c + 1) * 48)) s_ok = 0;
+          if (dbg) { const long long tc1 = clock64(); t_acc[7] += tc1 - tc0; t_acc[0] += tc0 - t_mark; }
         }
       }
     }
     __syncthreads();
     HB_TICK(3);
   }
-  // ---- corner (m x m, rhs carried as row m) and the whole back substitution in warp 0 ----
-  if (warp == 0) {
-    // right-looking Cholesky, lanes own rows r = lane, lane + 32, ...
-    for (int q = 0; q < m; ++q) {
-      const double d = CC[static_cast<size_t>(q) * m + q];
-      if (!(d > 0.0) && lane == 0) s_ok = 0;
-      const double iv = rsqrt(d);
-      __syncwarp();
-      for (int r = q + lane; r <= m; r += 32) CC[static_cast<size_t>(r) * m + q] = (r == q) ? d * iv : CC[static_cast<size_t>(r) * m + q] * iv;
-      __syncwarp();
-      for (int r = q + 1 + lane; r <= m; r += 32) {
-        const double lrq = CC[static_cast<size_t>(r) * m + q];
-        const int smax = min(r, m - 1);
-        for (int sidx = q + 1; sidx <= smax; ++sidx) CC[static_cast<size_t>(r) * m + sidx] -= lrq * CC[static_cast<size_t>(sidx) * m + q];
-      }
-      __syncwarp();
+  // ---- corner (m x m, rhs carried as row m): right-looking Cholesky by the whole CTA, two barriers
+  // per column (every thread recomputes the reciprocal square root of the pivot) ----
+  for (int q = 0; q < m; ++q) {
+    const double d = CC[static_cast<size_t>(q) * m + q];
+    if (!(d > 0.0) && tid == 0) s_ok = 0;
+    const double iv = rsqrt(d);
+    __syncthreads();   // everyone has read the pivot before it is overwritten
+    for (int r = q + tid; r <= m; r += kBandThreads) CC[static_cast<size_t>(r) * m + q] = (r == q) ? d * iv : CC[static_cast<size_t>(r) * m + q] * iv;
+    __syncthreads();
+    const int rem = m - q;  // rows q+1 .. m (row m = rhs), columns q+1 .. m-1
+    for (int e = tid; e < rem * rem; e += kBandThreads) {
+      const int u = q + 1 + e / rem, v = q + 1 + e % rem;
+      if (v > u || v >= m) continue;
+      CC[static_cast<size_t>(u) * m + v] -= CC[static_cast<size_t>(u) * m + q] * CC[static_cast<size_t>(v) * m + q];
     }
+    // the next iteration's pivot read is ordered after these updates by its first barrier? no: it reads
+    // CC[q+1][q+1] right away, so synchronise here
+    __syncthreads();
+  }
+  // ---- the whole back substitution in warp 0 ----
+  if (warp == 0) {
     HB_TICK(4);
     double* Xa = X + np;
     for (int q = m - 1; q >= 0; --q) {

@@ -8,6 +8,6 @@ ctx = runtime.Context(0); ctx.load_window(win)
 ctx.iterate(3)
 cyc = (C.c_longlong*8)()
 ctx.lib.hb200_debug_band_timing(ctx.h, cyc)
-names=["gather","potf2","trsm","update","corner","backsub_corner","backsub_blocks","-"]
-tot=sum(cyc)
-for n,c in zip(names,cyc): print(f"{n:16s} {c:9d} cycles {c/1.965e3:8.1f} us {100*c/max(tot,1):5.1f}%")
+names=["warp0 tile0 (part of update)","potf2 prologue","trsm","update (incl. look-ahead potf2)","corner","backsub_corner","backsub_blocks","look-ahead chol6 (part of update)"]
+tot=sum(cyc[1:7])
+for n,c in zip(names,cyc): print(f"{n:40s} {c:9d} cycles {c/1.965e3:8.1f} us {100*c/max(tot,1):5.1f}%")
