@@ -302,8 +302,9 @@ def main():
         ab = algorithmic_bytes(win)
         peak, peak_src = load_peaks()
         # pixel_eval_kernel appears twice per iteration (Jacobian pass, cost-only pass): the first is the one with J.
+        # the factor kernels as hb200_evaluate launches them (residual + materialised Jacobian, no fused J^T J)
         first = {}
-        for name, ms in prof:
+        for name, ms in ctx.profile_iteration(reps=10, evaluate_only=True):
             first.setdefault(name, ms)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -318,7 +319,7 @@ def main():
                         inertial_eval_kernel=dict(algorithmic_bytes_per_launch=ab["inertial_eval_kernel"], launch_ms=first.get("inertial_eval_kernel"),
                                                   achieved=(ab["inertial_eval_kernel"] / (first["inertial_eval_kernel"] * 1e-3) / 1e9) if "inertial_eval_kernel" in first else None),
                         dominant_kernel_by_time=dominant, kernel_share_of_step=shares,
-                        note="cfg1 moves 7.7 MB per sweep (about 1.2 us at peak): launch/latency-bound by construction (SURVEY.md 8d); see profiles/ for larger windows")
+                        kernel_ms_source="hb200_profile_iteration(evaluate sweep): CUDA event after every launch", note="cfg1 moves 7.7 MB per sweep (about 1.2 us at peak): launch/latency-bound by construction (SURVEY.md 8d); see profiles/ for larger windows")
 
     # ---- roofline of the factor kernels on a window large enough to be bandwidth-relevant (1 M factors) ----
     large = None
@@ -340,8 +341,11 @@ def main():
         bctx.synchronize()
         sweep = ev0.elapsed_time(ev1) / reps
         bprof = {}
-        for name, ms in bctx.profile_iteration(reps=3):
+        for name, ms in bctx.profile_iteration(reps=5, evaluate_only=True):
             bprof.setdefault(name, ms)
+        biter = {}
+        for name, ms in bctx.profile_iteration(reps=3):
+            biter[name] = biter.get(name, 0.0) + ms
         bab = algorithmic_bytes(big)
         peak, peak_src = load_peaks()
         large = dict(workload=synthetic.CONFIG_NAMES[4], factors=big.num_factors, evaluate_sweep_ms=sweep,
@@ -349,7 +353,7 @@ def main():
         for kname in ("pixel_eval_kernel", "inertial_eval_kernel"):
             ach = bab[kname] / (bprof[kname] * 1e-3) / 1e9
             large[kname] = dict(algorithmic_bytes_per_launch=bab[kname], launch_ms=bprof[kname], achieved=ach, frac=ach / peak)
-        large["iteration_kernel_ms"] = {k_: round(v, 4) for k_, v in bprof.items()}
+        large["iteration_kernel_ms"] = {k_: round(v, 4) for k_, v in biter.items()}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:

@@ -244,13 +244,15 @@ int reset_solver_state(hb200_ctx* c) {
 
 // ---- kernel dispatch on (order, bias order) -------------------------------------------------
 template <int K, bool J>
-int launch_pixel(hb200_ctx* c, int sel) {
+int launch_pixel(hb200_ctx* c, int sel, bool accumulate = false) {
   if (c->Nv == 0) return 0;
   PixelArgs a{};
+  a.sys = accumulate ? c->sys.p : nullptr; a.n_sys = c->n;
   a.n = c->Nv; a.stamp = c->v_stamp.p; a.pixel = reinterpret_cast<const double2*>(c->v_pixel.p); a.idx = c->v_idx.p;
   a.tab = c->tab[sel].p; a.cam_tab = c->cam_tab.p; a.landmarks = c->lms[sel].p;
   a.r = J ? c->v_r.p : nullptr; a.Jp = c->v_Jp.p; a.Jl = c->v_Jl.p; a.cost_partial = c->cp_pix[J ? 0 : 1].p; a.huber = c->huber; a.K_knots = c->K;
-  pixel_eval_kernel<K, J><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
+  if (J && accumulate) pixel_eval_kernel<K, J, J><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
+  else pixel_eval_kernel<K, J, false><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
   HB_LAUNCH(c, "pixel_eval_kernel");
   return 0;
 }
@@ -267,21 +269,31 @@ int launch_inertial(hb200_ctx* c, int sel) {
   return 0;
 }
 
-int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel) {
+int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false) {
   prep_kernel<<<(c->K + 63) / 64, 64, 0, c->stream>>>(c->K, c->knots[sel].p, c->tab[sel].p);
   HB_LAUNCH(c, "prep_kernel");
   int rc = 0;
+  if (accumulate) {   // fused path: pixel J^T J is accumulated by the factor kernel itself
+    rc = (c->k == 4) ? launch_pixel<4, true>(c, sel, true) : launch_pixel<6, true>(c, sel, true);
+    if (rc) return rc;
+    return (c->k == 4) ? launch_inertial<4, true>(c, sel) : launch_inertial<6, true>(c, sel);
+  }
   if (c->k == 4) { rc = want_J ? launch_pixel<4, true>(c, sel) : launch_pixel<4, false>(c, sel); if (rc) return rc; rc = want_J ? launch_inertial<4, true>(c, sel) : launch_inertial<4, false>(c, sel); }
   else if (c->k == 6) { rc = want_J ? launch_pixel<6, true>(c, sel) : launch_pixel<6, false>(c, sel); if (rc) return rc; rc = want_J ? launch_inertial<6, true>(c, sel) : launch_inertial<6, false>(c, sel); }
   else return fail(-4, "spline order %d not supported (4 or 6)", c->k);
   return rc;
 }
 
-int enqueue_build(hb200_ctx* c) {
+int enqueue_clear_system(hb200_ctx* c) {
   const size_t n = c->n;
   HB_CUDA(cudaMemsetAsync(c->sys.p, 0, (n * n + 3 * n + 2) * sizeof(double), c->stream));
   prof_mark(c, "memset(system)");
-  if (c->Nv) {
+  return 0;
+}
+
+int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
+  if (!pixel_fused) { int rc0 = enqueue_clear_system(c); if (rc0) return rc0; }
+  if (c->Nv && !pixel_fused) {
     if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n, c->pix_splits);
     else pixel_hessian_kernel<6><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n, c->pix_splits);
     HB_LAUNCH(c, "pixel_hessian_kernel");
@@ -392,8 +404,9 @@ int enqueue_accept(hb200_ctx* c) {
 int enqueue_segment(hb200_ctx* c, int segment) {
   int rc = 0;
   if (segment == 0) {
-    if ((rc = enqueue_evaluate(c, true, 0))) return rc;
-    if ((rc = enqueue_build(c))) return rc;
+    if ((rc = enqueue_clear_system(c))) return rc;
+    if ((rc = enqueue_evaluate(c, true, 0, true))) return rc;
+    if ((rc = enqueue_build(c, true))) return rc;
   } else if (segment == 1) {
     if ((rc = enqueue_finalize(c))) return rc;
     if ((rc = enqueue_solve(c))) return rc;
@@ -1049,7 +1062,9 @@ __global__ void hb200_spin_kernel(long long cycles) {
 int hb200_profile_iteration(hb200_ctx* c, int reps, int max_entries, char* names, double* ms, int* count) {
   int rc = check_ready(c);
   if (rc) return rc;
-  if (reps <= 0 || !names || !ms || !count) return fail(-1, "invalid argument");
+  if (reps == 0 || !names || !ms || !count) return fail(-1, "invalid argument");
+  const bool reps_mode_evaluate = reps < 0;   // negative reps: profile the Evaluate sweep only
+  if (reps < 0) reps = -reps;
   HB_CUDA(cudaSetDevice(c->device));
   std::vector<double> acc;
   std::vector<std::string> nm;
@@ -1059,12 +1074,16 @@ int hb200_profile_iteration(hb200_ctx* c, int reps, int max_entries, char* names
     hb200_spin_kernel<<<1, 1, 0, c->stream>>>(600000);
     c->profiling = true;
     prof_mark(c, "start");
-    rc = enqueue_segment(c, 0);
-    if (!rc) rc = enqueue_segment(c, 1);
-    if (!rc) rc = enqueue_segment(c, 2);
+    if (reps_mode_evaluate) {
+      rc = enqueue_evaluate(c, true, 0);          // the plain Evaluate sweep (hb200_evaluate), Jacobians materialised
+    } else {
+      rc = enqueue_segment(c, 0);
+      if (!rc) rc = enqueue_segment(c, 1);
+      if (!rc) rc = enqueue_segment(c, 2);
+    }
     c->profiling = false;
     if (rc) return rc;
-    c->iter_total += 1;
+    if (!reps_mode_evaluate) c->iter_total += 1;
     HB_CUDA(cudaStreamSynchronize(c->stream));
     if (rep == 0) { acc.assign(c->prof_used, 0.0); nm.assign(c->prof_names.begin(), c->prof_names.begin() + c->prof_used); }
     for (size_t i = 1; i < c->prof_used && i < acc.size(); ++i) {

@@ -348,17 +348,86 @@ struct PixelArgs {
   double* cost_partial;   // [gridDim.x]
   double huber;
   int K_knots;
+  double* sys;            // packed reduced system [S | b | diagH | g | ...] to accumulate J^T J / J^T r into, or null
+  int n_sys;              // its dimension n
 };
+
+// J^T J / J^T r of up to 32 consecutive pixel factors [f0, f0 + cnt) of this CTA, accumulated into the
+// lower triangle of S and into g with FP64 atomics.  Called right after the CTA wrote those factors'
+// residuals and Jacobians, so the re-read hits L2.  3x3 register tiles, one (or two) per thread, each
+// thread walks all rows itself: no cross-thread reduction.
+template <int K>
+HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[64][6K+1]*/, double* sr /*[64]*/, int* sb /*[64]*/) {
+  constexpr int NB = 6 * K, LD = NB + 1, NT = NB / 3, NTILES = NT * (NT + 1) / 2;
+  const int tid = threadIdx.x;
+  const int rows = 2 * cnt;
+  __syncthreads();   // previous use of the scratch is complete
+  for (int e = tid; e < rows * NB; e += kEvalThreads) {
+    const int row = e / NB, c = e - row * NB;
+    const int f = f0 + (row >> 1);
+    const double r0 = a.r[2 * static_cast<size_t>(f)], r1 = a.r[2 * static_cast<size_t>(f) + 1];
+    double wgt;
+    huber_rho(r0 * r0 + r1 * r1, a.huber, &wgt);
+    const double sw = sqrt(wgt);
+    sJ[row * LD + c] = sw * a.Jp[static_cast<size_t>(f) * 2 * NB + (row & 1) * NB + c];
+    if (c == 0) { sr[row] = sw * ((row & 1) ? r1 : r0); sb[row] = a.idx[f].x; }
+  }
+  __syncthreads();
+  double* S = a.sys;
+  double* g = a.sys + static_cast<size_t>(a.n_sys) * a.n_sys + 2 * static_cast<size_t>(a.n_sys);
+  const int base_lo = sb[0], base_hi = sb[rows - 1];   // bound order is sorted by base
+  for (int base = base_lo; base <= base_hi; ++base) {
+    // contiguous row range of this base inside the sub-tile
+    int r_lo = 0, r_hi = rows;
+    while (r_lo < rows && sb[r_lo] < base) ++r_lo;
+    r_hi = r_lo;
+    while (r_hi < rows && sb[r_hi] == base) ++r_hi;
+    if (r_hi == r_lo) continue;
+    const int c0 = 6 * base;
+    for (int tile = tid; tile < NTILES; tile += kEvalThreads) {
+      int ti = static_cast<int>((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
+      while (ti * (ti + 1) / 2 > tile) --ti;
+      while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+      const int tj = tile - ti * (ti + 1) / 2;
+      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int row = r_lo; row < r_hi; ++row) {
+        const double* jr = sJ + row * LD;
+        const double u0 = jr[3 * ti], u1 = jr[3 * ti + 1], u2 = jr[3 * ti + 2];
+        const double v0 = jr[3 * tj], v1 = jr[3 * tj + 1], v2 = jr[3 * tj + 2];
+        acc[0] += u0 * v0; acc[1] += u0 * v1; acc[2] += u0 * v2;
+        acc[3] += u1 * v0; acc[4] += u1 * v1; acc[5] += u1 * v2;
+        acc[6] += u2 * v0; acc[7] += u2 * v1; acc[8] += u2 * v2;
+      }
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int rr = 3 * ti + p, cc = 3 * tj + q;
+          if (cc <= rr) atomicAdd(&S[static_cast<size_t>(c0 + rr) * a.n_sys + c0 + cc], acc[3 * p + q]);
+        }
+    }
+    if (tid >= kEvalThreads - NB) {   // gradient: the last NB threads (the first ones carry the tiles)
+      const int c = tid - (kEvalThreads - NB);
+      double gacc = 0.0;
+      for (int row = r_lo; row < r_hi; ++row) gacc += sJ[row * LD + c] * sr[row];
+      atomicAdd(&g[c0 + c], gacc);
+    }
+  }
+}
 
 #ifndef HB_PIX_MINBLOCKS
 #define HB_PIX_MINBLOCKS 1
 #endif
-template <int K, bool WANT_J>
+template <int K, bool WANT_J, bool FUSE = false>
 __global__ void __launch_bounds__(kEvalThreads, HB_PIX_MINBLOCKS) pixel_eval_kernel(PixelArgs a, Basis B) {
   __shared__ __align__(16) double s_tab[kTileRows * kTabStride];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_red[2];
   __shared__ double s_cost[kEvalThreads / 32];
+  // scratch of the fused J^T J accumulation (32 factors = 64 rows at a time)
+  __shared__ double s_J[FUSE ? 64 * (6 * K + 1) : 1];
+  __shared__ double s_r[FUSE ? 64 : 1];
+  __shared__ int s_b[FUSE ? 64 : 1];
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = f < a.n;
   int4 id = make_int4(0, 0, 0, 0);
@@ -392,6 +461,13 @@ __global__ void __launch_bounds__(kEvalThreads, HB_PIX_MINBLOCKS) pixel_eval_ker
     double c = 0;
     for (int w = 0; w < kEvalThreads / 32; ++w) c += s_cost[w];
     a.cost_partial[blockIdx.x] = c;
+  }
+  if (FUSE && a.sys != nullptr) {
+    // fused normal equations: this CTA's factors, two sub-tiles of 32 (residuals / Jacobians were
+    // written above; the barrier in the cost reduction ordered them for the whole CTA)
+    const int f_lo = blockIdx.x * kEvalThreads;
+    const int total = min(kEvalThreads, a.n - f_lo);
+    for (int off = 0; off < total; off += 32) cta_pixel_hessian<K>(a, f_lo + off, min(32, total - off), s_J, s_r, s_b);
   }
 }
 

@@ -250,7 +250,9 @@ class Context:
     def restore(self):
         self._check(self.lib.hb200_restore(self.h))
 
-    def profile_iteration(self, reps=5, max_entries=64):
+    def profile_iteration(self, reps=5, max_entries=64, evaluate_only=False):
+        if evaluate_only:
+            reps = -abs(reps)
         names = C.create_string_buffer(32 * max_entries)
         ms = np.zeros(max_entries)
         cnt = C.c_int(0)

@@ -117,7 +117,8 @@ int hb200_snapshot(hb200_ctx* ctx);
 int hb200_restore(hb200_ctx* ctx);
 /* Runs `reps` LM iterations with a CUDA event after every kernel and returns the average duration of
  * each launch in issue order (names are kernel names, 32 chars each).  Not for timing the step --
- * for attributing it (bench.py roofline / kernel shares). */
+ * for attributing it (bench.py roofline / kernel shares).  A negative `reps` profiles |reps| plain
+ * Evaluate sweeps (what hb200_evaluate(HB200_EVAL_JACOBIANS) launches) instead of full iterations. */
 int hb200_profile_iteration(hb200_ctx* ctx, int reps, int max_entries, char* names /* [max_entries][32] */, double* ms, int* count);
 /* Spline interpolation of the current state at `n` stamps (device kernel): pose [n][7] = [q|p], and
  * optionally (may be NULL) body velocity [n][6] = [omega | R^T pdot] and acceleration [n][6]. Stamps
