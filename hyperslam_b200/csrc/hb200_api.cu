@@ -228,7 +228,7 @@ int ensure_system(hb200_ctx* c) {
   if (getenv("HB200_BAND_TIMING")) HB_CUDA(c->band_dbg.ensure(8));
   // parallelism of the J^T J kernels: aim at ~2 CTAs per SM
   c->pix_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nseg, 1) - 1) / std::max(c->nseg, 1), std::max(1, c->Nv / (16 * std::max(c->nseg, 1)))));
-  c->imu_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nruns, 1) - 1) / std::max(c->nruns, 1), std::max(1, c->Ni / (8 * std::max(c->nruns, 1)))));
+  c->imu_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nruns, 1) - 1) / std::max(c->nruns, 1), std::max(1, c->Ni / (16 * std::max(c->nruns, 1)))));
   return 0;
 }
 

@@ -91,7 +91,12 @@ __global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* 
   if (threadIdx.x < NB) atomicAdd(&v.g[c0 + threadIdx.x], gacc);
 }
 
-// Inertial factors: one CTA per run of identical (pose base, gyro-bias base, accel-bias base).
+// Inertial factors: one CTA per (run of identical (pose base, gyro-bias base, accel-bias base), split).
+// The factor Jacobian is structured -- pose block 6 x 6K dense, bias blocks wg[m] I3 (gyro rows) /
+// wa[m] I3 (accel rows), gravity 6 x 2 -- so J^T J is accumulated block by block instead of as a dense
+// 6 x (6K + 6KB + 2) product: pose-pose (lower), bias-pose, gravity-pose, bias-bias (diagonal 3x3
+// blocks, gyro-accel coupling is identically zero), gravity-bias, gravity-gravity.  Lower triangle of
+// S only (dof order pose < gyro bias < accel bias < gravity).
 template <int K, int KB>
 __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const int* __restrict__ run_off, const int4* __restrict__ idx,
                                                                         const double* __restrict__ r, const double* __restrict__ Jp,
@@ -99,78 +104,190 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
                                                                         const double* __restrict__ Jg, double loss_scale, double* sys,
                                                                         int n, int o_bg, int o_ba, int o_g, int splits) {
   constexpr int NP = 6 * K;
-  constexpr int NI = NP + 6 * KB + 2;
-  constexpr int CH = 8;
-  constexpr int EPT = (NI * NI + kHessThreads - 1) / kHessThreads;
-  __shared__ double sJ[CH][6][NI];
-  __shared__ double sr[CH][6];
-  __shared__ int scol[NI];
+  constexpr int CH = 16;
+  constexpr int NPP = NP * (NP + 1) / 2;          // pose-pose lower entries
+  constexpr int NBP = 3 * KB * NP;                // bias-pose entries (per bias spline)
+  constexpr int NGP = 2 * NP;                     // gravity-pose
+  constexpr int NBB = KB * (KB + 1) / 2;          // bias-bias scalar weights (lower), each lands on 3 diagonal entries
+  constexpr int NGB = 2 * 3 * KB;                 // gravity-bias (per bias spline)
+  constexpr int NMISC = 2 * NBB + 2 * NGB + 3 + NP + 2 * 3 * KB + 2;   // + gravity-gravity (3) + gradients
+  constexpr int E1 = (NPP + kHessThreads - 1) / kHessThreads;
+  constexpr int E2 = (NBP + kHessThreads - 1) / kHessThreads;
+  constexpr int E4 = (NGP + kHessThreads - 1) / kHessThreads;
+  constexpr int E5 = (NMISC + kHessThreads - 1) / kHessThreads;
+  __shared__ double sJ[CH][6][NP + 1];
+  __shared__ double sWg[CH][KB], sWa[CH][KB], sG[CH][12], sR[CH][6];
   const int run = blockIdx.x / splits, part = blockIdx.x - run * splits;
   const int rlo = run_off[run], rhi = run_off[run + 1];
   const int len = (rhi - rlo + splits - 1) / splits;
   const int lo = rlo + part * len, hi = min(rhi, lo + len);
   if (lo >= hi) return;
   const int4 id0 = idx[lo];
-  for (int c = threadIdx.x; c < NI; c += kHessThreads) {
-    int col;
-    if (c < NP) col = 6 * id0.x + c;
-    else if (c < NP + 3 * KB) col = o_bg + 3 * id0.y + (c - NP);
-    else if (c < NP + 6 * KB) col = o_ba + 3 * id0.z + (c - NP - 3 * KB);
-    else col = o_g + (c - NP - 6 * KB);
-    scol[c] = col;
-  }
-  const double sw = sqrt(loss_scale);
-  double acc[EPT], gacc = 0.0;
+  const int tid = threadIdx.x;
+  double a1[E1], a2[E2], a3[E2], a4[E4], a5[E5];
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) acc[e] = 0.0;
+  for (int e = 0; e < E1; ++e) a1[e] = 0.0;
+#pragma unroll
+  for (int e = 0; e < E2; ++e) { a2[e] = 0.0; a3[e] = 0.0; }
+#pragma unroll
+  for (int e = 0; e < E4; ++e) a4[e] = 0.0;
+#pragma unroll
+  for (int e = 0; e < E5; ++e) a5[e] = 0.0;
   for (int f0 = lo; f0 < hi; f0 += CH) {
     const int cnt = min(CH, hi - f0);
     __syncthreads();
-    for (int e = threadIdx.x; e < cnt * 6 * NI; e += kHessThreads) {
-      const int ff = e / (6 * NI), rem = e - ff * 6 * NI;
-      const int row = rem / NI, c = rem - row * NI;
-      const size_t f = f0 + ff;
-      double v;
-      if (c < NP) v = Jp[f * 6 * NP + row * NP + c];
-      else if (c < NP + 3 * KB) { const int m = (c - NP) / 3, a = (c - NP) % 3; v = (row == a) ? wg[f * KB + m] : 0.0; }
-      else if (c < NP + 6 * KB) { const int m = (c - NP - 3 * KB) / 3, a = (c - NP - 3 * KB) % 3; v = (row == 3 + a) ? wa[f * KB + m] : 0.0; }
-      else v = Jg[f * 12 + 2 * row + (c - NP - 6 * KB)];
-      sJ[ff][row][c] = sw * v;
-      if (c == 0) sr[ff][row] = sw * r[f * 6 + row];
+    for (int e = tid; e < cnt * 6 * NP; e += kHessThreads) {   // contiguous in global memory
+      const int ff = e / (6 * NP), rem = e - ff * 6 * NP;
+      sJ[ff][rem / NP][rem % NP] = Jp[static_cast<size_t>(f0) * 6 * NP + e];
     }
+    for (int e = tid; e < cnt * KB; e += kHessThreads) { sWg[e / KB][e % KB] = wg[static_cast<size_t>(f0) * KB + e]; sWa[e / KB][e % KB] = wa[static_cast<size_t>(f0) * KB + e]; }
+    for (int e = tid; e < cnt * 12; e += kHessThreads) sG[e / 12][e % 12] = Jg[static_cast<size_t>(f0) * 12 + e];
+    for (int e = tid; e < cnt * 6; e += kHessThreads) sR[e / 6][e % 6] = r[static_cast<size_t>(f0) * 6 + e];
     __syncthreads();
+    // (1) pose-pose, lower triangle
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      const int id = threadIdx.x + e * kHessThreads;
-      if (id < NI * NI) {
-        const int a = id / NI, b = id - a * NI;
-        if (b <= a) {   // local column order is monotone in the global dof index
-          double s = 0;
-          for (int ff = 0; ff < cnt; ++ff)
+    for (int e = 0; e < E1; ++e) {
+      const int id = tid + e * kHessThreads;
+      if (id < NPP) {
+        int a = static_cast<int>((sqrtf(8.0f * id + 1.0f) - 1.0f) * 0.5f);
+        while (a * (a + 1) / 2 > id) --a;
+        while ((a + 1) * (a + 2) / 2 <= id) ++a;
+        const int b = id - a * (a + 1) / 2;
+        double s = 0;
+        for (int ff = 0; ff < cnt; ++ff)
 #pragma unroll
-            for (int row = 0; row < 6; ++row) s += sJ[ff][row][a] * sJ[ff][row][b];
-          acc[e] += s;
-        }
+          for (int row = 0; row < 6; ++row) s += sJ[ff][row][a] * sJ[ff][row][b];
+        a1[e] += s;
       }
     }
-    if (threadIdx.x < NI) {
-      double s = 0;
-      for (int ff = 0; ff < cnt; ++ff)
+    // (2)/(3) bias-pose: entry (m, c, a) = sum_f w[f][m] * Jp[f][row c (+3)][a]
 #pragma unroll
-        for (int row = 0; row < 6; ++row) s += sJ[ff][row][threadIdx.x] * sr[ff][row];
-      gacc += s;
+    for (int e = 0; e < E2; ++e) {
+      const int id = tid + e * kHessThreads;
+      if (id < NBP) {
+        const int a = id % NP, mc = id / NP, m = mc / 3, c = mc - 3 * m;
+        double s2 = 0, s3 = 0;
+        for (int ff = 0; ff < cnt; ++ff) { s2 += sWg[ff][m] * sJ[ff][c][a]; s3 += sWa[ff][m] * sJ[ff][3 + c][a]; }
+        a2[e] += s2; a3[e] += s3;
+      }
+    }
+    // (4) gravity-pose
+#pragma unroll
+    for (int e = 0; e < E4; ++e) {
+      const int id = tid + e * kHessThreads;
+      if (id < NGP) {
+        const int a = id % NP, gm = id / NP;
+        double s = 0;
+        for (int ff = 0; ff < cnt; ++ff)
+#pragma unroll
+          for (int row = 0; row < 6; ++row) s += sG[ff][2 * row + gm] * sJ[ff][row][a];
+        a4[e] += s;
+      }
+    }
+    // (5) small blocks and gradients
+#pragma unroll
+    for (int e = 0; e < E5; ++e) {
+      int id = tid + e * kHessThreads;
+      if (id < NMISC) {
+        double s = 0;
+        if (id < 2 * NBB) {                       // bias-bias weights
+          const bool acc_b = id >= NBB;
+          const int q = acc_b ? id - NBB : id;
+          int m = static_cast<int>((sqrtf(8.0f * q + 1.0f) - 1.0f) * 0.5f);
+          while (m * (m + 1) / 2 > q) --m;
+          while ((m + 1) * (m + 2) / 2 <= q) ++m;
+          const int m2 = q - m * (m + 1) / 2;
+          for (int ff = 0; ff < cnt; ++ff) s += acc_b ? sWa[ff][m] * sWa[ff][m2] : sWg[ff][m] * sWg[ff][m2];
+        } else if ((id -= 2 * NBB) < 2 * NGB) {  // gravity-bias: (which, gm, m, c)
+          const bool acc_b = id >= NGB;
+          const int q = acc_b ? id - NGB : id;
+          const int gm = q / (3 * KB), mc = q - gm * 3 * KB, m = mc / 3, c = mc - 3 * m;
+          for (int ff = 0; ff < cnt; ++ff) s += sG[ff][2 * (acc_b ? 3 + c : c) + gm] * (acc_b ? sWa[ff][m] : sWg[ff][m]);
+        } else if ((id -= 2 * NGB) < 3) {         // gravity-gravity lower: (0,0) (1,0) (1,1)
+          const int ga = (id == 0) ? 0 : 1, gb = (id == 2) ? 1 : 0;
+          for (int ff = 0; ff < cnt; ++ff)
+#pragma unroll
+            for (int row = 0; row < 6; ++row) s += sG[ff][2 * row + ga] * sG[ff][2 * row + gb];
+        } else if ((id -= 3) < NP) {              // gradient, pose
+          for (int ff = 0; ff < cnt; ++ff)
+#pragma unroll
+            for (int row = 0; row < 6; ++row) s += sJ[ff][row][id] * sR[ff][row];
+        } else if ((id -= NP) < 2 * 3 * KB) {     // gradient, biases
+          const bool acc_b = id >= 3 * KB;
+          const int q = acc_b ? id - 3 * KB : id, m = q / 3, c = q - 3 * m;
+          for (int ff = 0; ff < cnt; ++ff) s += (acc_b ? sWa[ff][m] * sR[ff][3 + c] : sWg[ff][m] * sR[ff][c]);
+        } else {                                  // gradient, gravity
+          id -= 2 * 3 * KB;
+          for (int ff = 0; ff < cnt; ++ff)
+#pragma unroll
+            for (int row = 0; row < 6; ++row) s += sG[ff][2 * row + id] * sR[ff][row];
+        }
+        a5[e] += s;
+      }
     }
   }
+  // ---- flush (loss scaling applied once here: J^T J and J^T r both carry loss_scale) ----
   SysView v = sys_view(sys, n);
+  const int cp = 6 * id0.x, cg = o_bg + 3 * id0.y, ca = o_ba + 3 * id0.z;
+  const double ls = loss_scale;
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-    const int id = threadIdx.x + e * kHessThreads;
-    if (id < NI * NI) {
-      const int a = id / NI, b = id - a * NI;
-      if (b <= a && acc[e] != 0.0) atomicAdd(&v.S[static_cast<size_t>(scol[a]) * n + scol[b]], acc[e]);
+  for (int e = 0; e < E1; ++e) {
+    const int id = tid + e * kHessThreads;
+    if (id < NPP) {
+      int a = static_cast<int>((sqrtf(8.0f * id + 1.0f) - 1.0f) * 0.5f);
+      while (a * (a + 1) / 2 > id) --a;
+      while ((a + 1) * (a + 2) / 2 <= id) ++a;
+      const int b = id - a * (a + 1) / 2;
+      atomicAdd(&v.S[static_cast<size_t>(cp + a) * n + cp + b], ls * a1[e]);
     }
   }
-  if (threadIdx.x < NI) atomicAdd(&v.g[scol[threadIdx.x]], gacc);
+#pragma unroll
+  for (int e = 0; e < E2; ++e) {
+    const int id = tid + e * kHessThreads;
+    if (id < NBP) {
+      const int a = id % NP, mc = id / NP;
+      atomicAdd(&v.S[static_cast<size_t>(cg + mc) * n + cp + a], ls * a2[e]);
+      atomicAdd(&v.S[static_cast<size_t>(ca + mc) * n + cp + a], ls * a3[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E4; ++e) {
+    const int id = tid + e * kHessThreads;
+    if (id < NGP) atomicAdd(&v.S[static_cast<size_t>(o_g + id / NP) * n + cp + id % NP], ls * a4[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < E5; ++e) {
+    int id = tid + e * kHessThreads;
+    if (id < NMISC) {
+      const double val = ls * a5[e];
+      if (id < 2 * NBB) {
+        const bool acc_b = id >= NBB;
+        const int q = acc_b ? id - NBB : id;
+        int m = static_cast<int>((sqrtf(8.0f * q + 1.0f) - 1.0f) * 0.5f);
+        while (m * (m + 1) / 2 > q) --m;
+        while ((m + 1) * (m + 2) / 2 <= q) ++m;
+        const int m2 = q - m * (m + 1) / 2;
+        const int c0 = acc_b ? ca : cg;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(&v.S[static_cast<size_t>(c0 + 3 * m + c) * n + c0 + 3 * m2 + c], val);
+      } else if ((id -= 2 * NBB) < 2 * NGB) {
+        const bool acc_b = id >= NGB;
+        const int q = acc_b ? id - NGB : id;
+        const int gm = q / (3 * KB), mc = q - gm * 3 * KB;
+        atomicAdd(&v.S[static_cast<size_t>(o_g + gm) * n + (acc_b ? ca : cg) + mc], val);
+      } else if ((id -= 2 * NGB) < 3) {
+        const int ga = (id == 0) ? 0 : 1, gb = (id == 2) ? 1 : 0;
+        atomicAdd(&v.S[static_cast<size_t>(o_g + ga) * n + o_g + gb], val);
+      } else if ((id -= 3) < NP) {
+        atomicAdd(&v.g[cp + id], val);
+      } else if ((id -= NP) < 2 * 3 * KB) {
+        const bool acc_b = id >= 3 * KB;
+        atomicAdd(&v.g[(acc_b ? ca : cg) + (acc_b ? id - 3 * KB : id)], val);
+      } else {
+        atomicAdd(&v.g[o_g + id - 2 * 3 * KB], val);
+      }
+    }
+  }
 }
 
 // diagH = diag(H), b = -g, cost = sum of the evaluation kernels' per-block partials (fixed order).
