@@ -89,7 +89,7 @@ if os.path.exists(lst):
 
 tr = {}
 if "cfg1" in traffic:
-    pe = [v for k, v in traffic["cfg1"].items() if k.startswith("pixel_eval_kernel<4, 1>") or k.startswith("pixel_eval_kernel<4,1>")]
+    pe = [v for k, v in traffic["cfg1"].items() if k.startswith("pixel_eval_kernel<4, 1")]
     if pe:
         tr["pixel_eval_kernel_dram_bytes"] = pe[0]["dram_bytes"]
 tr["cfg1"] = traffic.get("cfg1")
