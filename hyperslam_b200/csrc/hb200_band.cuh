@@ -25,14 +25,30 @@ __host__ __device__ inline size_t band_workspace_doubles(int K, int beta, int m)
 }
 
 // Right-looking Cholesky of a 6x6 SPD block (lower, row-major with stride ld), division-free:
-// inv[j] = 1 / L[j][j] comes straight out of rsqrt.
-HB_DI bool chol6(double* A, int ld, double* inv /*6*/) {
+// inv[j] = 1 / L[j][j] comes straight out of rsqrt.  If X != nullptr the block first receives its
+// pending trailing update A -= X X^T (X = the 6 panel rows of this block, row-major 6x6), so the
+// look-ahead thread does not wait for a separate update pass.
+HB_DI bool chol6(double* A, int ld, double* inv /*6*/, const double* X = nullptr) {
   double L[21];  // packed lower: L[i(i+1)/2 + j]
   bool ok = true;
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int j = 0; j <= i; ++j) L[i * (i + 1) / 2 + j] = A[i * ld + j];
+  if (X != nullptr) {
+    double x[36];
+#pragma unroll
+    for (int e = 0; e < 18; ++e) { const double2 t = reinterpret_cast<const double2*>(X)[e]; x[2 * e] = t.x; x[2 * e + 1] = t.y; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc += x[6 * i + q] * x[6 * j + q];
+        L[i * (i + 1) / 2 + j] -= acc;
+      }
+  }
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     const double d = L[j * (j + 1) / 2 + j];
@@ -70,7 +86,8 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   const double* b = sys + static_cast<size_t>(n) * n;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   __shared__ int s_ok;
-  if (tid == 0) s_ok = 1;
+  __shared__ long long s_dbg[2], s_mark;   // look-ahead warp timing (debug)
+  if (tid == 0) { s_ok = 1; s_dbg[0] = 0; s_dbg[1] = 0; }
   // ---- gather the band, the arrow and the corner from the dense system ----
   {
     const int h6 = h * 6;
@@ -124,6 +141,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     }
     __syncthreads();
     HB_TICK(2);
+    if (dbg && tid == 0) s_mark = t_mark;   // (racy by a few cycles with the readers; debug only)
     // trailing update in 6x6 tiles: groups = band blocks below the diagonal, then arrow rows in sixes
     // (the rhs row is the last arrow row).  Thread = (tile, row i of the tile): 6 dots of length 6.
     {
@@ -137,10 +155,14 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       int t;
       int stride;
       if (look) {
-        constexpr int kWorkers = (kBandThreads / 32) * 3 / 4 * 32;   // threads in warps with warp % 4 != 0
-        if (warp == 0) { t = (lane < 6) ? lane : ntiles * 6; stride = ntiles * 6; }
-        else if ((warp & 3) == 0) { t = ntiles * 6; stride = 1; }
-        else { t = 6 + ((warp - (warp >> 2) - 1) * 32 + lane); stride = kWorkers; }
+        // Scheduler 0 (warps 0, 4, 8, 12; the arbiter favours the highest warp id) is reserved for the
+        // latency-critical look-ahead: warp 12 runs it, warp 8 hosts the block-inverse thread (lane 0)
+        // and takes a few left-over items, warps 0 and 4 idle.  The 12 warps of schedulers 1..3 share
+        // tiles 1 .. ntiles-1 (tile 0 = next diagonal block, done by the look-ahead warp).
+        constexpr int kWorkers = 12 * 32 + 31;
+        if ((warp & 3) != 0) { t = 6 + (warp - (warp >> 2) - 1) * 32 + lane; stride = kWorkers; }
+        else if (warp == 8 && lane > 0) { t = 6 + 12 * 32 + lane - 1; stride = kWorkers; }
+        else { t = ntiles * 6; stride = 1; }
       } else { t = tid; stride = kBandThreads; }
       for (; t < ntiles * 6; t += stride) {
         const int tile = t / 6, i = t - 6 * tile;
@@ -181,7 +203,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
             if (6 * (gv - nbk) + j < m) tgt[j] -= sd[j];
         }
       }
-      if (tid == kBandThreads - 1) {
+      if (tid == 8 * 32) {   // lane 0 of warp 8
         // inverse of this step's diagonal factor, for the back substitution (off the critical path):
         // Li[i][j] = -(sum_{p=j}^{i-1} L[i][p] Li[p][j]) / L[i][i],  Li[j][j] = 1 / L[j][j]
         double* Li = LI + static_cast<size_t>(c) * 48 + 8;
@@ -197,12 +219,27 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
           }
         }
       }
-      if (look && warp == 0) {
+      if (look && warp == 12) {
+        // next diagonal block: lanes 0..5 apply row i of its update A -= X X^T from this step's panel
+        // rows (tile 0), then lane 0 factors it
+        double* An = W + static_cast<size_t>(c + 1) * h * 6;
+        if (lane < 6) {
+          const double2* xi = reinterpret_cast<const double2*>(Wc + 36 + 6 * lane);
+          const double2 a0 = xi[0], a1 = xi[1], a2 = xi[2];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            if (j <= lane) {
+              const double2* xj = reinterpret_cast<const double2*>(Wc + 36 + 6 * j);
+              const double2 b0 = xj[0], b1 = xj[1], b2 = xj[2];
+              An[6 * lane + j] -= a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
+            }
+          }
+        }
         __syncwarp();
         if (lane == 0) {
           const long long tc0 = dbg ? clock64() : 0;
-          if (!chol6(W + static_cast<size_t>(c + 1) * h * 6, 6, LI + static_cast<size_t>(c + 1) * 48)) s_ok = 0;
-          if (dbg) { const long long tc1 = clock64(); t_acc[7] += tc1 - tc0; t_acc[0] += tc0 - t_mark; }
+          if (!chol6(An, 6, LI + static_cast<size_t>(c + 1) * 48)) s_ok = 0;
+          if (dbg) { const long long tc1 = clock64(); s_dbg[1] += tc1 - tc0; s_dbg[0] += tc0 - s_mark; }
         }
       }
     }
@@ -240,6 +277,19 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       __syncwarp();
     }
     HB_TICK(5);
+  }
+  __syncthreads();
+  // arrow contribution to every block's right-hand side, all at once: y_p -= AR^T x_a (row m of AR = y)
+  {
+    const double* Xa = X + np;
+    for (int col = tid; col < np; col += kBandThreads) {
+      double s = 0.0;
+      for (int r = 0; r < m; ++r) s += AR[static_cast<size_t>(r) * np + col] * Xa[r];
+      AR[static_cast<size_t>(m) * np + col] -= s;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
     // block columns K-1 .. 0: lane = (component j = lane % 6, part p = lane / 6), 5 parts
     const int j = lane % 6, part = lane / 6;
     for (int c = K - 1; c >= 0; --c) {
@@ -247,14 +297,13 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       const double* Li = LI + static_cast<size_t>(c) * 48 + 8;
       const int nb = min(h - 6, np - 6 * (c + 1));
       double s = 0.0, s2 = 0.0;
-      if (part < 5) {
+      if (part < 5) {   // band rows only; the arrow part was folded into y above
         int t = part;
-        for (; t + 5 < nb + m; t += 10) {   // two independent accumulators
-          s += (t < nb) ? Wc[static_cast<size_t>(6 + t) * 6 + j] * X[6 * (c + 1) + t] : AR[static_cast<size_t>(t - nb) * np + 6 * c + j] * Xa[t - nb];
-          const int t2 = t + 5;
-          s2 += (t2 < nb) ? Wc[static_cast<size_t>(6 + t2) * 6 + j] * X[6 * (c + 1) + t2] : AR[static_cast<size_t>(t2 - nb) * np + 6 * c + j] * Xa[t2 - nb];
+        for (; t + 5 < nb; t += 10) {   // two independent accumulators
+          s += Wc[static_cast<size_t>(6 + t) * 6 + j] * X[6 * (c + 1) + t];
+          s2 += Wc[static_cast<size_t>(6 + t + 5) * 6 + j] * X[6 * (c + 1) + t + 5];
         }
-        if (t < nb + m) s += (t < nb) ? Wc[static_cast<size_t>(6 + t) * 6 + j] * X[6 * (c + 1) + t] : AR[static_cast<size_t>(t - nb) * np + 6 * c + j] * Xa[t - nb];
+        if (t < nb) s += Wc[static_cast<size_t>(6 + t) * 6 + j] * X[6 * (c + 1) + t];
         s += s2;
       }
       // sum the 5 parts of each component: lanes j, j+6, j+12, j+18, j+24
@@ -279,7 +328,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   }
   __syncthreads();
   for (int e = tid; e < n; e += kBandThreads) x_out[e] = X[e];
-  if (dbg && tid == 0) for (int i = 0; i < 8; ++i) dbg[i] = t_acc[i];
+  if (dbg && tid == 0) { t_acc[0] = s_dbg[0]; t_acc[7] = s_dbg[1]; for (int i = 0; i < 8; ++i) dbg[i] = t_acc[i]; }
   if (tid == 0) *spd_flag = s_ok;
 }
 
