@@ -444,28 +444,40 @@ extern "C" {
 
 const char* hb200_last_error_string(void) { return g_error.c_str(); }
 
-int hb200_create(const hb200_options* options, hb200_ctx** out) {
-  if (!out) return fail(-1, "null output pointer");
+namespace {
+int create_impl(const hb200_options* options, hb200_ctx* c) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) return fail(100 + static_cast<int>(e), "no CUDA device: %s (libhyperb200 has no CPU fallback)", cudaGetErrorString(e));
-  hb200_ctx* c = new hb200_ctx();
   c->device = options ? options->device : 0;
-  if (c->device < 0 || c->device >= count) { delete c; return fail(-1, "invalid device %d", c->device); }
+  if (c->device < 0 || c->device >= count) return fail(-1, "invalid device %d", c->device);
   HB_CUDA(cudaSetDevice(c->device));
   cudaDeviceProp prop{};
   HB_CUDA(cudaGetDeviceProperties(&prop, c->device));
-  if (prop.major < 10) { const int maj = prop.major, mnr = prop.minor; delete c; return fail(-5, "device sm_%d%d is not Blackwell (built for sm_100a only)", maj, mnr); }
+  if (prop.major < 10) return fail(-5, "device sm_%d%d is not Blackwell (built for sm_100a only)", prop.major, prop.minor);
   c->num_sms = prop.multiProcessorCount;
   c->use_graph = options ? options->use_graph != 0 : true;
   c->force_dense = options ? (options->reserved & 1) != 0 : false;
   if (options && options->stream) { c->stream = static_cast<cudaStream_t>(options->stream); c->own_stream = false; }
   else { HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   int rc = ensure_placeholders(c);
-  if (rc) { delete c; return rc; }
+  if (rc) return rc;
   HB_CUDA(cudaFuncSetAttribute(cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCholSmem)));
-  rc = reset_solver_state(c);
-  if (rc) { delete c; return rc; }
+  return reset_solver_state(c);
+}
+}  // namespace
+
+int hb200_create(const hb200_options* options, hb200_ctx** out) {
+  if (!out) return fail(-1, "null output pointer");
+  *out = nullptr;
+  hb200_ctx* c = new hb200_ctx();
+  const int rc = create_impl(options, c);
+  if (rc) {
+    const std::string keep = g_error;   // hb200_destroy must not clobber the message
+    hb200_destroy(c);
+    g_error = keep;
+    return rc;
+  }
   *out = c;
   return 0;
 }
@@ -473,7 +485,8 @@ int hb200_create(const hb200_options* options, hb200_ctx** out) {
 void hb200_destroy(hb200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->graph) cudaGraphDestroy(c->graph);
   for (int s = 0; s < 2; ++s) { c->knots[s].release(); c->bg[s].release(); c->ba[s].release(); c->grav[s].release(); c->lms[s].release(); c->tab[s].release(); c->cp_pix[s].release(); c->cp_imu[s].release(); }
@@ -483,7 +496,8 @@ void hb200_destroy(hb200_ctx* c) {
   c->v_r.release(); c->v_Jp.release(); c->v_Jl.release(); c->i_r.release(); c->i_Jp.release(); c->i_wg.release(); c->i_wa.release(); c->i_Jg.release();
   c->sys.release(); c->D.release(); c->Lw.release(); c->Ldiag.release(); c->dp.release(); c->dl.release(); c->Vinv.release(); c->gl.release(); c->Dl.release();
   c->band_ws.release(); c->band_dbg.release(); c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
-  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->snap_knots.release(); c->snap_bg.release(); c->snap_ba.release(); c->snap_grav.release(); c->snap_lms.release(); c->snap_st.release();
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 

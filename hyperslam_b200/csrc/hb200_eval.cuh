@@ -415,11 +415,8 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
   }
 }
 
-#ifndef HB_PIX_MINBLOCKS
-#define HB_PIX_MINBLOCKS 1
-#endif
 template <int K, bool WANT_J, bool FUSE = false>
-__global__ void __launch_bounds__(kEvalThreads, HB_PIX_MINBLOCKS) pixel_eval_kernel(PixelArgs a, Basis B) {
+__global__ void __launch_bounds__(kEvalThreads) pixel_eval_kernel(PixelArgs a, Basis B) {
   __shared__ __align__(16) double s_tab[kTileRows * kTabStride];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_red[2];

@@ -586,7 +586,6 @@ __global__ void __launch_bounds__(kCholThreads) cholesky_kernel(double* __restri
 __global__ void __launch_bounds__(1024) backsolve_kernel(const double* __restrict__ Lw, const double* __restrict__ Ldiag, int n,
                                                          double* __restrict__ x) {
   __shared__ double part[32][kCholNB + 1];
-  __shared__ double sx[kCholNB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = (n + kCholNB - 1) / kCholNB;
   for (int p = T - 1; p >= 0; --p) {
@@ -610,7 +609,6 @@ __global__ void __launch_bounds__(1024) backsolve_kernel(const double* __restric
         if (lane < q) rhs -= Ld[q * kCholNB + lane] * xq;
       }
       if (col < n) x[col] = xv;
-      sx[lane] = xv;
     }
     __syncthreads();
   }
