@@ -102,10 +102,18 @@ struct hb200_ctx {
   double huber = 0.5, imu_scale = 1.6e-5, radius0 = 1e4;
 
   // factors (host copies in user order; device copies in bound order)
-  int Nv = 0, Ni = 0;
-  std::vector<double> h_v_stamp, h_v_pixel, h_i_stamp, h_i_meas;
+  // visual list = pixel factors [0, Np) followed by bearing factors [Np, Np + Nb): both travel through the
+  // same kernels and the same compact layout (kind flag in idx.w); manifold (pose) factors have their own.
+  int Nv = 0, Ni = 0, Np = 0, Nb = 0, Nm = 0, P = 0;
+  std::vector<double> h_p_stamp, h_p_pixel, h_b_stamp, h_b_bearing, h_m_stamp, h_m_meas, h_sensors;
+  std::vector<int> h_p_cam, h_p_lm, h_b_cam, h_b_lm, h_m_sensor;
+  std::vector<double> h_v_stamp, h_v_pixel, h_v_z, h_i_stamp, h_i_meas;
   std::vector<int> h_v_cam, h_v_lm;
-  DevBuf<double> v_stamp, v_pixel, i_stamp, i_meas;
+  DevBuf<double> v_stamp, v_pixel, v_z, v_w, i_stamp, i_meas, m_stamp, m_meas, sensors;
+  DevBuf<int> m_sensor;
+  DevBuf<int2> m_idx;
+  std::vector<int2> h_m_idx;
+  double huber_bearing = 1.6e-3;   // reference optimizer.cpp:204
   DevBuf<int> v_cam, v_lm;
   DevBuf<int4> v_idx, i_idx;
   std::vector<int4> h_v_idx, h_i_idx;       // bound order
@@ -120,13 +128,13 @@ struct hb200_ctx {
   bool bound = false;
 
   // outputs
-  DevBuf<double> v_r, v_Jp, v_Jl, i_r, i_Jp, i_wg, i_wa, i_Jg;
+  DevBuf<double> v_r, v_Jp, v_Jl, i_r, i_Jp, i_wg, i_wa, i_Jg, m_r, m_Jp;
   DevBuf<double> cp_pix[2], cp_imu[2];
-  int n_pix_blocks = 0, n_imu_blocks = 0;
+  int n_pix_blocks = 0, n_imu_blocks = 0, n_man_blocks = 0;   // manifold cost partials follow the inertial ones in cp_imu
   bool evaluated_J = false;
   // host mirror for hb200_factor_evaluate
   bool mirror_valid = false;
-  std::vector<double> m_v_r, m_v_Jp, m_v_Jl, m_i_r, m_i_Jp, m_i_wg, m_i_wa, m_i_Jg, m_grav;
+  std::vector<double> m_v_r, m_v_Jp, m_v_Jl, m_i_r, m_i_Jp, m_i_wg, m_i_wa, m_i_Jg, m_grav, m_b_r, m_b_Jp, m_b_Jl, m_m_r, m_m_Jp;
 
   // system
   int n = 0;
@@ -248,9 +256,9 @@ int launch_pixel(hb200_ctx* c, int sel, bool accumulate = false) {
   if (c->Nv == 0) return 0;
   PixelArgs a{};
   a.sys = accumulate ? c->sys.p : nullptr; a.n_sys = c->n;
-  a.n = c->Nv; a.stamp = c->v_stamp.p; a.pixel = reinterpret_cast<const double2*>(c->v_pixel.p); a.idx = c->v_idx.p;
+  a.n = c->Nv; a.stamp = c->v_stamp.p; a.pixel = reinterpret_cast<const double2*>(c->v_pixel.p); a.meas_z = c->v_z.p; a.idx = c->v_idx.p;
   a.tab = c->tab[sel].p; a.cam_tab = c->cam_tab.p; a.landmarks = c->lms[sel].p;
-  a.r = J ? c->v_r.p : nullptr; a.Jp = c->v_Jp.p; a.Jl = c->v_Jl.p; a.cost_partial = c->cp_pix[J ? 0 : 1].p; a.huber = c->huber; a.K_knots = c->K;
+  a.r = J ? c->v_r.p : nullptr; a.Jp = c->v_Jp.p; a.Jl = c->v_Jl.p; a.w = c->v_w.p; a.cost_partial = c->cp_pix[J ? 0 : 1].p; a.huber = c->huber; a.huber_bearing = c->huber_bearing; a.K_knots = c->K;
   if (J && accumulate) pixel_eval_kernel<K, J, J><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
   else pixel_eval_kernel<K, J, false><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
   HB_LAUNCH(c, "pixel_eval_kernel");
@@ -269,6 +277,21 @@ int launch_inertial(hb200_ctx* c, int sel) {
   return 0;
 }
 
+template <int K, bool J>
+int launch_manifold(hb200_ctx* c, int sel) {
+  if (c->Nm == 0) return 0;
+  ManifoldArgs a{};
+  a.n = c->Nm; a.stamp = c->m_stamp.p; a.meas = c->m_meas.p; a.idx = c->m_idx.p; a.tab = c->tab[sel].p; a.sensors = c->sensors.p;
+  a.r = J ? c->m_r.p : nullptr; a.Jp = c->m_Jp.p; a.cost_partial = c->cp_imu[J ? 0 : 1].p + c->n_imu_blocks;
+  manifold_eval_kernel<K, J><<<c->n_man_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
+  HB_LAUNCH(c, "manifold_eval_kernel");
+  return 0;
+}
+int enqueue_manifold(hb200_ctx* c, bool want_J, int sel) {
+  if (c->k == 4) return want_J ? launch_manifold<4, true>(c, sel) : launch_manifold<4, false>(c, sel);
+  return want_J ? launch_manifold<6, true>(c, sel) : launch_manifold<6, false>(c, sel);
+}
+
 int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false) {
   prep_kernel<<<(c->K + 63) / 64, 64, 0, c->stream>>>(c->K, c->knots[sel].p, c->tab[sel].p);
   HB_LAUNCH(c, "prep_kernel");
@@ -276,12 +299,15 @@ int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false
   if (accumulate) {   // fused path: pixel J^T J is accumulated by the factor kernel itself
     rc = (c->k == 4) ? launch_pixel<4, true>(c, sel, true) : launch_pixel<6, true>(c, sel, true);
     if (rc) return rc;
-    return (c->k == 4) ? launch_inertial<4, true>(c, sel) : launch_inertial<6, true>(c, sel);
+    rc = (c->k == 4) ? launch_inertial<4, true>(c, sel) : launch_inertial<6, true>(c, sel);
+    if (rc) return rc;
+    return enqueue_manifold(c, true, sel);
   }
   if (c->k == 4) { rc = want_J ? launch_pixel<4, true>(c, sel) : launch_pixel<4, false>(c, sel); if (rc) return rc; rc = want_J ? launch_inertial<4, true>(c, sel) : launch_inertial<4, false>(c, sel); }
   else if (c->k == 6) { rc = want_J ? launch_pixel<6, true>(c, sel) : launch_pixel<6, false>(c, sel); if (rc) return rc; rc = want_J ? launch_inertial<6, true>(c, sel) : launch_inertial<6, false>(c, sel); }
   else return fail(-4, "spline order %d not supported (4 or 6)", c->k);
-  return rc;
+  if (rc) return rc;
+  return enqueue_manifold(c, want_J, sel);
 }
 
 int enqueue_clear_system(hb200_ctx* c) {
@@ -294,8 +320,8 @@ int enqueue_clear_system(hb200_ctx* c) {
 int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
   if (!pixel_fused) { int rc0 = enqueue_clear_system(c); if (rc0) return rc0; }
   if (c->Nv && !pixel_fused) {
-    if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n, c->pix_splits);
-    else pixel_hessian_kernel<6><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->huber, c->sys.p, c->n, c->pix_splits);
+    if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->sys.p, c->n, c->pix_splits);
+    else pixel_hessian_kernel<6><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->sys.p, c->n, c->pix_splits);
     HB_LAUNCH(c, "pixel_hessian_kernel");
   }
   if (c->Ni) {
@@ -307,16 +333,22 @@ int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
                                                                              c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     HB_LAUNCH(c, "inertial_hessian_kernel");
   }
+  if (c->Nm) {
+    const int blocks = (c->Nm + kManWarps - 1) / kManWarps;
+    if (c->k == 4) manifold_hessian_kernel<4><<<blocks, kManWarps * 32, 0, c->stream>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->n);
+    else manifold_hessian_kernel<6><<<blocks, kManWarps * 32, 0, c->stream>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->n);
+    HB_LAUNCH(c, "manifold_hessian_kernel");
+  }
   diag_cost_kernel<<<std::max(1, (c->n + 255) / 256), 256, 0, c->stream>>>(c->sys.p, c->n, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p,
-                                                                         c->Ni ? c->n_imu_blocks : 0);
+                                                                         c->n_imu_blocks + c->n_man_blocks);
   HB_LAUNCH(c, "diag_cost_kernel");
   if (c->Nv && c->L) {
     const size_t smem = 2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double);
     if (c->k == 4)
-      schur_kernel<4><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber, c->st.p,
+      schur_kernel<4><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p, c->st.p,
                                                                 c->sys.p, c->n, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
     else
-      schur_kernel<6><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber, c->st.p,
+      schur_kernel<6><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p, c->st.p,
                                                                 c->sys.p, c->n, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
     HB_LAUNCH(c, "schur_kernel");
   }
@@ -353,10 +385,10 @@ int enqueue_solve(hb200_ctx* c) {
   if (c->L) {
     if (c->Nv) {
       if (c->k == 4)
-        lm_backsub_kernel<4><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber,
+        lm_backsub_kernel<4><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
                                                                     c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p);
       else
-        lm_backsub_kernel<6><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->huber,
+        lm_backsub_kernel<6><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
                                                                     c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p);
       HB_LAUNCH(c, "lm_backsub_kernel");
     } else {
@@ -376,14 +408,14 @@ int enqueue_retract(hb200_ctx* c) {
 }
 
 int enqueue_scalars(hb200_ctx* c) {
-  scalars_kernel<<<1, 256, 0, c->stream>>>(c->cp_pix[1].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[1].p, c->Ni ? c->n_imu_blocks : 0, c->lm_part.p,
+  scalars_kernel<<<1, 256, 0, c->stream>>>(c->cp_pix[1].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[1].p, c->n_imu_blocks + c->n_man_blocks, c->lm_part.p,
                                           (c->L && c->Nv) ? c->n_lm_blocks : 0, c->scal.p);
   HB_LAUNCH(c, "scalars_kernel");
   return 0;
 }
 
 int enqueue_accept(hb200_ctx* c) {
-  ScalarArgs sa{c->cp_pix[1].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[1].p, c->Ni ? c->n_imu_blocks : 0, c->lm_part.p, (c->L && c->Nv) ? c->n_lm_blocks : 0};
+  ScalarArgs sa{c->cp_pix[1].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[1].p, c->n_imu_blocks + c->n_man_blocks, c->lm_part.p, (c->L && c->Nv) ? c->n_lm_blocks : 0};
   accept_kernel<<<1, 256, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
                                          c->allreduce ? 0 : 1, sa);
   HB_LAUNCH(c, "accept_kernel");
@@ -424,7 +456,8 @@ int check_ready(hb200_ctx* c) {
   if (c->K == 0) return fail(-2, "spline not set");
   if (!c->bound) return fail(-2, "factors not bound (call hb200_bind)");
   if (c->Ni && (!c->have_imu || !c->have_gravity || c->Kbg == 0 || c->Kba == 0)) return fail(-2, "inertial factors need IMU calibration, bias splines and gravity");
-  if (c->Nv && (c->C == 0 || c->L == 0)) return fail(-2, "pixel factors need cameras and landmarks");
+  if (c->Nv && (c->C == 0 || c->L == 0)) return fail(-2, "pixel / bearing factors need cameras and landmarks");
+  if (c->Nm && c->P == 0) return fail(-2, "manifold factors need pose sensors");
   return 0;
 }
 
@@ -435,6 +468,7 @@ int ensure_placeholders(hb200_ctx* c) {
     HB_CUDA(c->cp_pix[s].ensure(1)); HB_CUDA(c->cp_imu[s].ensure(1));
   }
   HB_CUDA(c->imu_tab.ensure(kImuStride)); HB_CUDA(c->cam_tab.ensure(kCamStride));
+  HB_CUDA(c->v_z.ensure(1)); HB_CUDA(c->v_w.ensure(1)); HB_CUDA(c->sensors.ensure(7)); HB_CUDA(c->m_idx.ensure(1));
   return 0;
 }
 
@@ -492,6 +526,7 @@ void hb200_destroy(hb200_ctx* c) {
   for (int s = 0; s < 2; ++s) { c->knots[s].release(); c->bg[s].release(); c->ba[s].release(); c->grav[s].release(); c->lms[s].release(); c->tab[s].release(); c->cp_pix[s].release(); c->cp_imu[s].release(); }
   c->cams.release(); c->imu.release(); c->cam_tab.release(); c->imu_tab.release(); c->fixed.release();
   c->v_stamp.release(); c->v_pixel.release(); c->i_stamp.release(); c->i_meas.release(); c->v_cam.release(); c->v_lm.release(); c->v_idx.release(); c->i_idx.release();
+  c->v_z.release(); c->v_w.release(); c->m_stamp.release(); c->m_meas.release(); c->sensors.release(); c->m_sensor.release(); c->m_idx.release(); c->m_r.release(); c->m_Jp.release();
   c->seg_off.release(); c->run_off.release(); c->lm_off.release(); c->lm_obs.release(); c->d_invalid.release();
   c->v_r.release(); c->v_Jp.release(); c->v_Jl.release(); c->i_r.release(); c->i_Jp.release(); c->i_wg.release(); c->i_wa.release(); c->i_Jg.release();
   c->sys.release(); c->D.release(); c->Lw.release(); c->Ldiag.release(); c->dp.release(); c->dl.release(); c->Vinv.release(); c->gl.release(); c->Dl.release();
@@ -616,11 +651,69 @@ int hb200_set_options(hb200_ctx* c, double huber_pixel, double imu_loss_scale, d
   return reset_solver_state(c);
 }
 
+namespace {
+// visual list = pixel factors followed by bearing factors
+void rebuild_visual(hb200_ctx* c) {
+  const size_t Np = c->Np, Nb = c->Nb, N = Np + Nb;
+  c->Nv = static_cast<int>(N);
+  c->h_v_stamp.resize(N); c->h_v_cam.resize(N); c->h_v_lm.resize(N); c->h_v_pixel.resize(2 * N); c->h_v_z.assign(N, 0.0);
+  std::copy(c->h_p_stamp.begin(), c->h_p_stamp.end(), c->h_v_stamp.begin());
+  std::copy(c->h_p_cam.begin(), c->h_p_cam.end(), c->h_v_cam.begin());
+  std::copy(c->h_p_lm.begin(), c->h_p_lm.end(), c->h_v_lm.begin());
+  std::copy(c->h_p_pixel.begin(), c->h_p_pixel.end(), c->h_v_pixel.begin());
+  for (size_t f = 0; f < Nb; ++f) {
+    c->h_v_stamp[Np + f] = c->h_b_stamp[f]; c->h_v_cam[Np + f] = c->h_b_cam[f]; c->h_v_lm[Np + f] = c->h_b_lm[f];
+    c->h_v_pixel[2 * (Np + f)] = c->h_b_bearing[3 * f]; c->h_v_pixel[2 * (Np + f) + 1] = c->h_b_bearing[3 * f + 1];
+    c->h_v_z[Np + f] = c->h_b_bearing[3 * f + 2];
+  }
+  c->bound = false; c->invalidate();
+}
+}  // namespace
+
 int hb200_set_pixel_factors(hb200_ctx* c, int n, const double* stamp, const int* camera, const int* landmark, const double* pixel) {
   if (!c || n < 0 || (n > 0 && (!stamp || !camera || !landmark || !pixel))) return fail(-1, "invalid pixel factors");
-  c->Nv = n;
-  c->h_v_stamp.assign(stamp, stamp + n); c->h_v_cam.assign(camera, camera + n); c->h_v_lm.assign(landmark, landmark + n);
-  c->h_v_pixel.assign(pixel, pixel + 2 * static_cast<size_t>(n));
+  c->Np = n;
+  c->h_p_stamp.assign(stamp, stamp + n); c->h_p_cam.assign(camera, camera + n); c->h_p_lm.assign(landmark, landmark + n);
+  c->h_p_pixel.assign(pixel, pixel + 2 * static_cast<size_t>(n));
+  rebuild_visual(c);
+  return 0;
+}
+
+int hb200_set_bearing_factors(hb200_ctx* c, int n, const double* stamp, const int* camera, const int* landmark, const double* bearing) {
+  if (!c || n < 0 || (n > 0 && (!stamp || !camera || !landmark || !bearing))) return fail(-1, "invalid bearing factors");
+  c->Nb = n;
+  c->h_b_stamp.assign(stamp, stamp + n); c->h_b_cam.assign(camera, camera + n); c->h_b_lm.assign(landmark, landmark + n);
+  c->h_b_bearing.assign(bearing, bearing + 3 * static_cast<size_t>(n));
+  rebuild_visual(c);
+  return 0;
+}
+
+int hb200_set_bearing_loss(hb200_ctx* c, double huber_bearing) {
+  if (!c) return fail(-1, "null context");
+  if (!(huber_bearing > 0)) return fail(-1, "options must be positive");
+  if (huber_bearing != c->huber_bearing) c->graph_valid = false;
+  c->huber_bearing = huber_bearing;
+  c->system_built = false; c->evaluated_J = false;
+  return 0;
+}
+
+int hb200_set_pose_sensors(hb200_ctx* c, int n, const double* T_bs) {
+  if (!c || n < 0 || (n > 0 && !T_bs)) return fail(-1, "invalid pose sensors");
+  HB_CUDA(cudaSetDevice(c->device));
+  if (n != c->P) c->bound = false;
+  c->P = n;
+  c->h_sensors.assign(T_bs, T_bs + 7 * static_cast<size_t>(n));
+  HB_CUDA(c->sensors.ensure(7 * static_cast<size_t>(std::max(n, 1))));
+  if (n) HB_CUDA(cudaMemcpyAsync(c->sensors.p, c->h_sensors.data(), sizeof(double) * 7 * n, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->invalidate();
+  return 0;
+}
+
+int hb200_set_manifold_factors(hb200_ctx* c, int n, const double* stamp, const int* sensor, const double* pose) {
+  if (!c || n < 0 || (n > 0 && (!stamp || !sensor || !pose))) return fail(-1, "invalid manifold factors");
+  c->Nm = n;
+  c->h_m_stamp.assign(stamp, stamp + n); c->h_m_sensor.assign(sensor, sensor + n); c->h_m_meas.assign(pose, pose + 7 * static_cast<size_t>(n));
   c->bound = false; c->invalidate();
   return 0;
 }
@@ -638,12 +731,17 @@ int hb200_bind(hb200_ctx* c, int* num_invalid) {
   if (c->K == 0) return fail(-2, "spline not set");
   if (c->Ni && (c->Kbg == 0 || c->Kba == 0)) return fail(-2, "bias splines not set");
   if (c->Nv && (c->C == 0 || c->L == 0)) return fail(-2, "cameras / landmarks not set");
+  if (c->Nm && c->P == 0) return fail(-2, "pose sensors not set");
   HB_CUDA(cudaSetDevice(c->device));
-  const int Nv = c->Nv, Ni = c->Ni;
+  const int Nv = c->Nv, Ni = c->Ni, Nm = c->Nm;
   HB_CUDA(c->d_invalid.ensure(1));
   HB_CUDA(cudaMemsetAsync(c->d_invalid.p, 0, sizeof(int), c->stream));
   HB_CUDA(c->v_stamp.ensure(std::max(Nv, 1))); HB_CUDA(c->v_pixel.ensure(2 * static_cast<size_t>(std::max(Nv, 1))));
   HB_CUDA(c->v_cam.ensure(std::max(Nv, 1))); HB_CUDA(c->v_lm.ensure(std::max(Nv, 1))); HB_CUDA(c->v_idx.ensure(std::max(Nv, 1)));
+  HB_CUDA(c->v_z.ensure(std::max(Nv, 1))); HB_CUDA(c->v_w.ensure(std::max(Nv, 1)));
+  HB_CUDA(c->m_stamp.ensure(std::max(Nm, 1))); HB_CUDA(c->m_meas.ensure(7 * static_cast<size_t>(std::max(Nm, 1)))); HB_CUDA(c->m_sensor.ensure(std::max(Nm, 1)));
+  HB_CUDA(c->m_idx.ensure(std::max(Nm, 1)));
+  c->h_m_idx.assign(Nm, make_int2(0, 0));
   HB_CUDA(c->i_stamp.ensure(std::max(Ni, 1))); HB_CUDA(c->i_meas.ensure(6 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_idx.ensure(std::max(Ni, 1)));
   c->h_v_idx.assign(Nv, make_int4(0, 0, 0, 0)); c->h_i_idx.assign(Ni, make_int4(0, 0, 0, 0));
   // pass 1: index maps in user order (device), a2/a4
@@ -662,11 +760,20 @@ int hb200_bind(hb200_ctx* c, int* num_invalid) {
     HB_LAUNCH(c, "bind_inertial_kernel");
     HB_CUDA(cudaMemcpyAsync(c->h_i_idx.data(), c->i_idx.p, sizeof(int4) * Ni, cudaMemcpyDeviceToHost, c->stream));
   }
+  if (Nm) {
+    HB_CUDA(cudaMemcpyAsync(c->m_stamp.p, c->h_m_stamp.data(), sizeof(double) * Nm, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->m_meas.p, c->h_m_meas.data(), sizeof(double) * 7 * Nm, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->m_sensor.p, c->h_m_sensor.data(), sizeof(int) * Nm, cudaMemcpyHostToDevice, c->stream));
+    bind_manifold_kernel<<<(Nm + 127) / 128, 128, 0, c->stream>>>(Nm, c->m_stamp.p, c->m_sensor.p, c->knots[0].p, c->K, c->k, c->P, c->m_idx.p, c->d_invalid.p);
+    HB_LAUNCH(c, "bind_manifold_kernel");
+    HB_CUDA(cudaMemcpyAsync(c->h_m_idx.data(), c->m_idx.p, sizeof(int2) * Nm, cudaMemcpyDeviceToHost, c->stream));
+  }
   int invalid = 0;
   HB_CUDA(cudaMemcpyAsync(&invalid, c->d_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   if (num_invalid) *num_invalid = invalid;
-  if (invalid) return fail(2, "%d factor(s) reference a stamp outside the spline's valid range or an invalid camera / landmark", invalid);
+  if (invalid) return fail(2, "%d factor(s) reference a stamp outside the spline's valid range or an invalid camera / landmark / sensor", invalid);
+  for (int u = c->Np; u < Nv; ++u) c->h_v_idx[u].w = 1;   // bearing factors
 
   // pass 2: bound order = stable sort by knot base index (pixel) / (base, gyro base, accel base)
   c->v_perm.resize(Nv); std::iota(c->v_perm.begin(), c->v_perm.end(), 0);
@@ -680,13 +787,14 @@ int hb200_bind(hb200_ctx* c, int* num_invalid) {
     if (!std::is_sorted(ii.begin(), ii.end(), key)) std::stable_sort(c->i_perm.begin(), c->i_perm.end(), [&](int a, int b) { return key(ii[a], ii[b]); });
   }
   {
-    std::vector<double> st(Nv), px(2 * static_cast<size_t>(Nv));
+    std::vector<double> st(Nv), px(2 * static_cast<size_t>(Nv)), vz(Nv);
     std::vector<int4> id(Nv);
-    for (int p = 0; p < Nv; ++p) { const int u = c->v_perm[p]; st[p] = c->h_v_stamp[u]; px[2 * p] = c->h_v_pixel[2 * u]; px[2 * p + 1] = c->h_v_pixel[2 * u + 1]; id[p] = c->h_v_idx[u]; }
+    for (int p = 0; p < Nv; ++p) { const int u = c->v_perm[p]; st[p] = c->h_v_stamp[u]; px[2 * p] = c->h_v_pixel[2 * u]; px[2 * p + 1] = c->h_v_pixel[2 * u + 1]; vz[p] = c->h_v_z[u]; id[p] = c->h_v_idx[u]; }
     c->h_v_idx = id;
     if (Nv) {
       HB_CUDA(cudaMemcpyAsync(c->v_stamp.p, st.data(), sizeof(double) * Nv, cudaMemcpyHostToDevice, c->stream));
       HB_CUDA(cudaMemcpyAsync(c->v_pixel.p, px.data(), sizeof(double) * 2 * Nv, cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(c->v_z.p, vz.data(), sizeof(double) * Nv, cudaMemcpyHostToDevice, c->stream));
       HB_CUDA(cudaMemcpyAsync(c->v_idx.p, id.data(), sizeof(int4) * Nv, cudaMemcpyHostToDevice, c->stream));
     }
     std::vector<double> is(Ni), im(6 * static_cast<size_t>(Ni));
@@ -735,7 +843,9 @@ int hb200_bind(hb200_ctx* c, int* num_invalid) {
   HB_CUDA(c->i_wg.ensure(4 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_wa.ensure(4 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_Jg.ensure(12 * static_cast<size_t>(std::max(Ni, 1))));
   c->n_pix_blocks = (Nv + kEvalThreads - 1) / kEvalThreads;
   c->n_imu_blocks = (Ni + kEvalThreads - 1) / kEvalThreads;
-  for (int s = 0; s < 2; ++s) { HB_CUDA(c->cp_pix[s].ensure(std::max(c->n_pix_blocks, 1))); HB_CUDA(c->cp_imu[s].ensure(std::max(c->n_imu_blocks, 1))); }
+  c->n_man_blocks = (Nm + kEvalThreads - 1) / kEvalThreads;
+  HB_CUDA(c->m_r.ensure(6 * static_cast<size_t>(std::max(Nm, 1)))); HB_CUDA(c->m_Jp.ensure(36 * k * std::max(Nm, 1)));
+  for (int s = 0; s < 2; ++s) { HB_CUDA(c->cp_pix[s].ensure(std::max(c->n_pix_blocks, 1))); HB_CUDA(c->cp_imu[s].ensure(std::max(c->n_imu_blocks + c->n_man_blocks, 1))); }
   if (c->max_rows * 6 * sizeof(double) > 48 * 1024) {
     const int smem = static_cast<int>(2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double));
     HB_CUDA(cudaFuncSetAttribute(schur_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -753,7 +863,7 @@ int hb200_bind(hb200_ctx* c, int* num_invalid) {
 
 int hb200_get_index_maps(hb200_ctx* c, int* pixel_base, int* inertial_base, int* gyro_bias_base, int* accel_bias_base) {
   if (!c || !c->bound) return fail(-2, "not bound");
-  for (int p = 0; p < c->Nv; ++p) if (pixel_base) pixel_base[c->v_perm[p]] = c->h_v_idx[p].x;
+  for (int p = 0; p < c->Nv; ++p) if (pixel_base && c->v_perm[p] < c->Np) pixel_base[c->v_perm[p]] = c->h_v_idx[p].x;
   for (int p = 0; p < c->Ni; ++p) {
     const int u = c->i_perm[p];
     if (inertial_base) inertial_base[u] = c->h_i_idx[p].x;
@@ -789,10 +899,42 @@ int hb200_get_pixel_outputs(hb200_ctx* c, double* r, double* Jp, double* Jl) {
   HB_CUDA(cudaStreamSynchronize(c->stream));
   for (size_t p = 0; p < N; ++p) {
     const size_t u = c->v_perm[p];
+    if (u >= static_cast<size_t>(c->Np)) continue;   // bearing factor
     if (r) { r[2 * u] = tr[2 * p]; r[2 * u + 1] = tr[2 * p + 1]; }
     if (Jp) std::memcpy(Jp + w * u, tJ.data() + w * p, sizeof(double) * w);
     if (Jl) std::memcpy(Jl + 6 * u, tl.data() + 6 * p, sizeof(double) * 6);
   }
+  return 0;
+}
+
+int hb200_get_bearing_outputs(hb200_ctx* c, double* r, double* Jp, double* Jl) {
+  if (!c || !c->bound) return fail(-2, "not bound");
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t N = c->Nv, w = 12 * static_cast<size_t>(c->k);
+  if (c->Nb == 0) return 0;
+  std::vector<double> tr(2 * N), tJ(Jp ? w * N : 0), tl(Jl ? 6 * N : 0);
+  HB_CUDA(cudaMemcpyAsync(tr.data(), c->v_r.p, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, c->stream));
+  if (Jp) HB_CUDA(cudaMemcpyAsync(tJ.data(), c->v_Jp.p, sizeof(double) * w * N, cudaMemcpyDeviceToHost, c->stream));
+  if (Jl) HB_CUDA(cudaMemcpyAsync(tl.data(), c->v_Jl.p, sizeof(double) * 6 * N, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t p = 0; p < N; ++p) {
+    if (c->v_perm[p] < c->Np) continue;
+    const size_t u = c->v_perm[p] - c->Np;   // first row of the 2-row slot carries the angular residual
+    if (r) r[u] = tr[2 * p];
+    if (Jp) std::memcpy(Jp + (w / 2) * u, tJ.data() + w * p, sizeof(double) * (w / 2));
+    if (Jl) std::memcpy(Jl + 3 * u, tl.data() + 6 * p, sizeof(double) * 3);
+  }
+  return 0;
+}
+
+int hb200_get_manifold_outputs(hb200_ctx* c, double* r, double* Jp) {
+  if (!c || !c->bound) return fail(-2, "not bound");
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t N = c->Nm, w = 36 * static_cast<size_t>(c->k);
+  if (N == 0) return 0;
+  if (r) HB_CUDA(cudaMemcpyAsync(r, c->m_r.p, sizeof(double) * 6 * N, cudaMemcpyDeviceToHost, c->stream));
+  if (Jp) HB_CUDA(cudaMemcpyAsync(Jp, c->m_Jp.p, sizeof(double) * w * N, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -826,25 +968,34 @@ int hb200_factor_evaluate(hb200_ctx* c, int kind, int index, const double* const
   if (!parameters || !residuals) return fail(-1, "null argument");
   if (!c->mirror_valid) {
     const size_t k = c->k;
-    c->m_v_r.resize(2 * static_cast<size_t>(c->Nv)); c->m_v_Jp.resize(12 * k * c->Nv); c->m_v_Jl.resize(6 * static_cast<size_t>(c->Nv));
+    c->m_v_r.resize(2 * static_cast<size_t>(c->Np)); c->m_v_Jp.resize(12 * k * c->Np); c->m_v_Jl.resize(6 * static_cast<size_t>(c->Np));
+    c->m_b_r.resize(c->Nb); c->m_b_Jp.resize(6 * k * c->Nb); c->m_b_Jl.resize(3 * static_cast<size_t>(c->Nb));
+    c->m_m_r.resize(6 * static_cast<size_t>(c->Nm)); c->m_m_Jp.resize(36 * k * c->Nm);
     c->m_i_r.resize(6 * static_cast<size_t>(c->Ni)); c->m_i_Jp.resize(36 * k * c->Ni); c->m_i_wg.resize(4 * static_cast<size_t>(c->Ni));
     c->m_i_wa.resize(4 * static_cast<size_t>(c->Ni)); c->m_i_Jg.resize(12 * static_cast<size_t>(c->Ni)); c->m_grav.resize(3);
     int rc = hb200_get_pixel_outputs(c, c->m_v_r.data(), c->m_v_Jp.data(), c->m_v_Jl.data());
     if (rc) return rc;
     rc = hb200_get_inertial_outputs(c, c->m_i_r.data(), c->m_i_Jp.data(), c->m_i_wg.data(), c->m_i_wa.data(), c->m_i_Jg.data());
     if (rc) return rc;
+    rc = hb200_get_bearing_outputs(c, c->m_b_r.data(), c->m_b_Jp.data(), c->m_b_Jl.data());
+    if (rc) return rc;
+    rc = hb200_get_manifold_outputs(c, c->m_m_r.data(), c->m_m_Jp.data());
+    if (rc) return rc;
     HB_CUDA(cudaMemcpy(c->m_grav.data(), c->grav[0].p, 3 * sizeof(double), cudaMemcpyDeviceToHost));
     c->mirror_valid = true;
   }
   const int k = c->k, kb = c->kb;
-  const int nr = (kind == HB200_PIXEL) ? 2 : 6;
-  const int N = (kind == HB200_PIXEL) ? c->Nv : c->Ni;
-  if (kind != HB200_PIXEL && kind != HB200_INERTIAL) return fail(-1, "unknown factor kind %d", kind);
+  if (kind < HB200_PIXEL || kind > HB200_MANIFOLD) return fail(-1, "unknown factor kind %d", kind);
+  const int nrs[4] = {2, 6, 1, 6};
+  const int Ns[4] = {c->Np, c->Ni, c->Nb, c->Nm};
+  const int nr = nrs[kind], N = Ns[kind];
   if (index < 0 || index >= N) return fail(-1, "factor index %d out of range", index);
-  const double* r = (kind == HB200_PIXEL) ? &c->m_v_r[2 * static_cast<size_t>(index)] : &c->m_i_r[6 * static_cast<size_t>(index)];
+  const double* rs[4] = {c->m_v_r.data(), c->m_i_r.data(), c->m_b_r.data(), c->m_m_r.data()};
+  const double* Js[4] = {c->m_v_Jp.data(), c->m_i_Jp.data(), c->m_b_Jp.data(), c->m_m_Jp.data()};
+  const double* r = rs[kind] + static_cast<size_t>(nr) * index;
   for (int i = 0; i < nr; ++i) residuals[i] = r[i];
   if (!jacobians) return 0;
-  const double* Jp = (kind == HB200_PIXEL) ? &c->m_v_Jp[12 * static_cast<size_t>(k) * index] : &c->m_i_Jp[36 * static_cast<size_t>(k) * index];
+  const double* Jp = Js[kind] + static_cast<size_t>(nr) * 6 * k * index;
   // state blocks: [J_theta * A_q(q_m) | J_rho | 0]  (ambient 8, row-major nr x 8)
   for (int m = 0; m < k; ++m) {
     if (!jacobians[m]) continue;
@@ -857,14 +1008,17 @@ int hb200_factor_evaluate(hb200_ctx* c, int kind, int index, const double* const
       o[4] = jt[3]; o[5] = jt[4]; o[6] = jt[5]; o[7] = 0.0;
     }
   }
-  if (kind == HB200_PIXEL) {
+  if (kind == HB200_PIXEL || kind == HB200_BEARING) {
     const int sizes[4] = {7, 4, 4, 3};
+    const double* Jl = (kind == HB200_PIXEL) ? &c->m_v_Jl[6 * static_cast<size_t>(index)] : &c->m_b_Jl[3 * static_cast<size_t>(index)];
     for (int b = 0; b < 4; ++b) {
       double* o = jacobians[k + b];
       if (!o) continue;
-      if (b < 3) std::fill(o, o + 2 * sizes[b], 0.0);  // calibration is constant in the live configuration (reference optimizer.cpp:59)
-      else std::memcpy(o, &c->m_v_Jl[6 * static_cast<size_t>(index)], 6 * sizeof(double));
+      if (b < 3) std::fill(o, o + nr * sizes[b], 0.0);  // calibration is constant in the live configuration (reference optimizer.cpp:59)
+      else std::memcpy(o, Jl, 3 * nr * sizeof(double));
     }
+  } else if (kind == HB200_MANIFOLD) {
+    if (jacobians[k]) std::fill(jacobians[k], jacobians[k] + 6 * 7, 0.0);   // sensor extrinsics: constant
   } else {
     const int sizes[5] = {7, 6, 6, 9, 9};
     for (int b = 0; b < 5; ++b) if (jacobians[k + b]) std::fill(jacobians[k + b], jacobians[k + b] + 6 * sizes[b], 0.0);

@@ -224,8 +224,11 @@ HB_DI void st_v4(double* p, double a, double b, double c, double d) {
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
+// kind 0: pixel residual (reference pixel.cpp:16-146 + CartesianMetric); kind 1: bearing residual
+// (reference bearing.cpp:14-79 + AngularMetric): r = [angle(p_s, z), 0], second Jacobian row zero, so a
+// bearing factor travels through the same compact [2][6K] / [2][3] layout and the same J^T J / Schur code.
 template <int K, bool WANT_J>
-HB_DI void pixel_factor(const double* __restrict__ T, const Basis& B, int base, double t, double zx, double zy,
+HB_DI void pixel_factor(const double* __restrict__ T, const Basis& B, int base, double t, double zx, double zy, double zz, int kind,
                         const double* __restrict__ cam, const double* __restrict__ lmk, double* r, double* __restrict__ Jp,
                         double* __restrict__ Jl) {
   constexpr int left = (K - 1) / 2;
@@ -268,27 +271,49 @@ HB_DI void pixel_factor(const double* __restrict__ T, const Basis& B, int base, 
   m3_tvec(P, q, pb);
   const double pbt[3] = {pb[0] - cam[9], pb[1] - cam[10], pb[2] - cam[11]};
   m3_vec(cam, pbt, ps);
-  const double iz = 1.0 / ps[2];
-  const double x = ps[0] * iz, y = ps[1] * iz;
-  const double cx = cam[12], cy = cam[13], fx = cam[14], fy = cam[15];
-  const double k1 = cam[16], k2 = cam[17], p1 = cam[18], p2 = cam[19];
-  const double r2 = x * x + y * y;
-  const double rad = 1.0 + k1 * r2 + k2 * r2 * r2;
-  const double dx = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
-  const double dy = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
-  r[0] = fx * dx + cx - zx;
-  r[1] = fy * dy + cy - zy;
-  if (!WANT_J) return;
-
-  const double g = k1 + 2.0 * k2 * r2;
-  const double drx = 2.0 * x * g, dry = 2.0 * y * g;
-  // J_r_n = diag(fx, fy) * d(distort)/dn
-  const double a00 = fx * (rad + x * drx + 2.0 * p1 * y + 6.0 * p2 * x);
-  const double a01 = fx * (x * dry + 2.0 * p1 * x + 2.0 * p2 * y);
-  const double a10 = fy * (y * drx + 2.0 * p1 * x + 2.0 * p2 * y);
-  const double a11 = fy * (rad + y * dry + 6.0 * p1 * y + 2.0 * p2 * x);
-  // J_n_p = [iz 0 -x iz; 0 iz -y iz]
-  const double Jps[6] = {a00 * iz, a01 * iz, -(a00 * x + a01 * y) * iz, a10 * iz, a11 * iz, -(a10 * x + a11 * y) * iz};
+  double Jps[6];
+  if (kind == 0) {
+    const double iz = 1.0 / ps[2];
+    const double x = ps[0] * iz, y = ps[1] * iz;
+    const double cx = cam[12], cy = cam[13], fx = cam[14], fy = cam[15];
+    const double k1 = cam[16], k2 = cam[17], p1 = cam[18], p2 = cam[19];
+    const double r2 = x * x + y * y;
+    const double rad = 1.0 + k1 * r2 + k2 * r2 * r2;
+    const double dx = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+    const double dy = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+    r[0] = fx * dx + cx - zx;
+    r[1] = fy * dy + cy - zy;
+    if (!WANT_J) return;
+    const double g = k1 + 2.0 * k2 * r2;
+    const double drx = 2.0 * x * g, dry = 2.0 * y * g;
+    // J_r_n = diag(fx, fy) * d(distort)/dn
+    const double a00 = fx * (rad + x * drx + 2.0 * p1 * y + 6.0 * p2 * x);
+    const double a01 = fx * (x * dry + 2.0 * p1 * x + 2.0 * p2 * y);
+    const double a10 = fy * (y * drx + 2.0 * p1 * x + 2.0 * p2 * y);
+    const double a11 = fy * (rad + y * dry + 6.0 * p1 * y + 2.0 * p2 * x);
+    // J_n_p = [iz 0 -x iz; 0 iz -y iz]
+    Jps[0] = a00 * iz; Jps[1] = a01 * iz; Jps[2] = -(a00 * x + a01 * y) * iz;
+    Jps[3] = a10 * iz; Jps[4] = a11 * iz; Jps[5] = -(a10 * x + a11 * y) * iz;
+  } else {
+    // theta = atan2(|p_s x z|, p_s . z);  d theta / d p_s = [c (z x n) - s z]^T / (|p_s|^2 |z|^2), n = (p_s x z)/s
+    const double z[3] = {zx, zy, zz};
+    double cr[3];
+    cross(ps, z, cr);
+    const double s = sqrt((cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2])), c = (ps[0] * z[0] + ps[1] * z[1] + ps[2] * z[2]);
+    r[0] = atan2(s, c);
+    r[1] = 0.0;
+    if (!WANT_J) return;
+    Jps[0] = Jps[1] = Jps[2] = Jps[3] = Jps[4] = Jps[5] = 0.0;
+    if (s > 1e-300) {
+      const double is = 1.0 / s;
+      const double nrm[3] = {cr[0] * is, cr[1] * is, cr[2] * is};
+      double zn[3];
+      cross(z, nrm, zn);
+      const double iden = 1.0 / ((ps[0] * ps[0] + ps[1] * ps[1] + ps[2] * ps[2]) * (z[0] * z[0] + z[1] * z[1] + z[2] * z[2]));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Jps[i] = (c * zn[i] - s * z[i]) * iden;
+    }
+  }
   double Jpb[6], F[6], E[6];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -337,16 +362,19 @@ HB_DI void pixel_factor(const double* __restrict__ T, const Basis& B, int base, 
 struct PixelArgs {
   int n;
   const double* stamp;
-  const double2* pixel;
-  const int4* idx;        // (base, landmark, camera, -)
+  const double2* pixel;    // pixel measurement, or the first two components of a bearing measurement
+  const double* meas_z;    // third component of a bearing measurement (null when there are no bearing factors)
+  const int4* idx;        // (base, landmark, camera, kind: 0 pixel / 1 bearing)
   const double* tab;      // knot table of the evaluated state
   const double* cam_tab;
   const double* landmarks;
   double* r;              // [n][2]
   double* Jp;             // [n][2][6K]
   double* Jl;             // [n][2][3]
+  double* w;              // [n] robust-loss weight rho'(s) of each factor (written with the Jacobians)
   double* cost_partial;   // [gridDim.x]
-  double huber;
+  double huber;           // Huber delta of the pixel factors (reference optimizer.cpp:226)
+  double huber_bearing;   // Huber delta of the bearing factors (reference optimizer.cpp:204)
   int K_knots;
   double* sys;            // packed reduced system [S | b | diagH | g | ...] to accumulate J^T J / J^T r into, or null
   int n_sys;              // its dimension n
@@ -365,12 +393,9 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
   for (int e = tid; e < rows * NB; e += kEvalThreads) {
     const int row = e / NB, c = e - row * NB;
     const int f = f0 + (row >> 1);
-    const double r0 = a.r[2 * static_cast<size_t>(f)], r1 = a.r[2 * static_cast<size_t>(f) + 1];
-    double wgt;
-    huber_rho(r0 * r0 + r1 * r1, a.huber, &wgt);
-    const double sw = sqrt(wgt);
+    const double sw = sqrt(a.w[f]);
     sJ[row * LD + c] = sw * a.Jp[static_cast<size_t>(f) * 2 * NB + (row & 1) * NB + c];
-    if (c == 0) { sr[row] = sw * ((row & 1) ? r1 : r0); sb[row] = a.idx[f].x; }
+    if (c == 0) { sr[row] = sw * a.r[2 * static_cast<size_t>(f) + (row & 1)]; sb[row] = a.idx[f].x; }
   }
   __syncthreads();
   double* S = a.sys;
@@ -443,11 +468,13 @@ __global__ void __launch_bounds__(kEvalThreads) pixel_eval_kernel(PixelArgs a, B
     double r[2];
     double* Jp = WANT_J ? a.Jp + static_cast<size_t>(f) * 12 * K : nullptr;
     double* Jl = WANT_J ? a.Jl + static_cast<size_t>(f) * 6 : nullptr;
-    if (staged) pixel_factor<K, WANT_J>(s_tab - static_cast<ptrdiff_t>(bmin) * kTabStride, B, id.x, t, z.x, z.y, cam, lmk, r, Jp, Jl);
-    else pixel_factor<K, WANT_J>(a.tab, B, id.x, t, z.x, z.y, cam, lmk, r, Jp, Jl);
+    const double zz = (id.w != 0) ? a.meas_z[f] : 0.0;
+    if (staged) pixel_factor<K, WANT_J>(s_tab - static_cast<ptrdiff_t>(bmin) * kTabStride, B, id.x, t, z.x, z.y, zz, id.w, cam, lmk, r, Jp, Jl);
+    else pixel_factor<K, WANT_J>(a.tab, B, id.x, t, z.x, z.y, zz, id.w, cam, lmk, r, Jp, Jl);
     if (a.r) reinterpret_cast<double2*>(a.r)[f] = make_double2(r[0], r[1]);
     double wgt;
-    cost = 0.5 * huber_rho(r[0] * r[0] + r[1] * r[1], a.huber, &wgt);
+    cost = 0.5 * huber_rho(r[0] * r[0] + r[1] * r[1], (id.w != 0) ? a.huber_bearing : a.huber, &wgt);
+    if (WANT_J) a.w[f] = wgt;
   }
   // deterministic block reduction of the cost
 #pragma unroll
@@ -807,6 +834,132 @@ __global__ void __launch_bounds__(kEvalThreads) inertial_eval_kernel(InertialArg
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Manifold (pose) factor: prediction T_ws = T_wb (+) T_bs (reference
+// internal/hyper/optimizers/evaluators/manifold.cpp:12-61), residual = ManifoldMetric<SE3> =
+// [Log(R_ws R_z^T) | p_ws - p_z] (wired at reference optimizer.cpp:237, no loss).  Outputs r[6] and
+// Jp[6][6K] on the control-point tangents.  Pose factors are few (priors, ground-truth poses), so the
+// kernel reads the knot table straight from L2 -- no staging.
+// ---------------------------------------------------------------------------------------------
+struct ManifoldArgs {
+  int n;
+  const double* stamp;
+  const double* meas;      // [n][7] = [q(4) | p(3)]
+  const int2* idx;         // (base, sensor)
+  const double* tab;
+  const double* sensors;   // [P][7] = T_bs of each pose sensor
+  double* r;               // [n][6]
+  double* Jp;              // [n][6][6K]
+  double* cost_partial;    // [gridDim.x]
+};
+
+__global__ void bind_manifold_kernel(int n, const double* __restrict__ stamp, const int* __restrict__ sensor, const double* __restrict__ knots, int K,
+                                     int k, int P, int2* __restrict__ idx, int* __restrict__ num_invalid) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const int base = segment_base(knots, 8, 7, K, k, stamp[f]);
+  const int s = sensor[f];
+  idx[f] = make_int2(base, s);
+  if (base < 0 || s < 0 || s >= P) atomicAdd(num_invalid, 1);
+}
+
+template <int K, bool WANT_J>
+__global__ void __launch_bounds__(kEvalThreads) manifold_eval_kernel(ManifoldArgs a, Basis B) {
+  __shared__ double s_cost[kEvalThreads / 32];
+  constexpr int left = (K - 1) / 2;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double cost = 0.0;
+  if (f < a.n) {
+    const int2 id = a.idx[f];
+    const double* row0 = a.tab + static_cast<size_t>(id.x) * kTabStride;
+    const double t0 = row0[left * kTabStride + 24], t1 = row0[(left + 1) * kTabStride + 24];
+    const double inv_dt = 1.0 / (t1 - t0);
+    const double u = (a.stamp[f] - t0) * inv_dt;
+    double lam[K + 1];
+    basis_eval<K, false>(B, u, inv_dt, lam, nullptr, nullptr);
+    double P[9], p[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) P[i] = row0[i];
+    p[0] = row0[9]; p[1] = row0[10]; p[2] = row0[11];
+    double M[(K - 1) * 9];
+#pragma unroll
+    for (int j = 1; j < K; ++j) {
+      const double* rj = row0 + j * kTabStride;
+      const double w[3] = {lam[j] * rj[12], lam[j] * rj[13], lam[j] * rj[14]};
+      double A[9], Jr[9], Pn[9];
+      so3_exp_and_Jr(w, A, WANT_J ? Jr : nullptr);
+      m3_mul(P, A, Pn);
+      if (WANT_J) {
+        double G[9], JG[9], PJG[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) G[i] = rj[15 + i];
+        m3_mul(Jr, G, JG);
+        m3_mul(Pn, JG, PJG);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) M[(j - 1) * 9 + i] = lam[j] * PJG[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) P[i] = Pn[i];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) p[c] += lam[j] * (rj[9 + c] - rj[9 + c - kTabStride]);
+    }
+    const double* T_bs = a.sensors + 7 * static_cast<size_t>(id.y);
+    const double* z = a.meas + 7 * static_cast<size_t>(f);
+    double Rbs[9], Rz[9], Rws[9], Rerr[9], Rt[3], q[4], th[3];
+    quat_to_rot(T_bs, Rbs);
+    quat_to_rot(z, Rz);
+    m3_vec(P, T_bs + 4, Rt);
+    m3_mul(P, Rbs, Rws);
+    m3_mult(Rws, Rz, Rerr);
+    rot_to_quat(Rerr, q);
+    quat_log(q, th);
+    double r[6] = {th[0], th[1], th[2], p[0] + Rt[0] - z[4], p[1] + Rt[1] - z[5], p[2] + Rt[2] - z[6]};
+    if (a.r) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) a.r[6 * static_cast<size_t>(f) + i] = r[i];
+    }
+    cost = 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3] + r[4] * r[4] + r[5] * r[5]);
+    if (WANT_J) {
+      const double nth[3] = {-th[0], -th[1], -th[2]};
+      double A[9], H[9];
+      so3_Jr_inv(nth, A);   // Jl^{-1}(theta) = Jr^{-1}(-theta)
+      hat(Rt, H);
+      double* out = a.Jp + static_cast<size_t>(f) * 36 * K;
+#pragma unroll
+      for (int m = 0; m < K; ++m) {
+        double D[9], AD[9], HD[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const double cur = (m == 0) ? ((i % 4 == 0) ? 1.0 : 0.0) : M[(m - 1) * 9 + i];
+          const double nxt = (m + 1 < K) ? M[m * 9 + i] : 0.0;
+          D[i] = cur - nxt;   // d theta / d phi_m
+        }
+        m3_mul(A, D, AD);
+        m3_mul(H, D, HD);
+        const double wm = lam[m] - lam[m + 1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            out[i * 6 * K + 6 * m + c] = AD[3 * i + c];
+            out[i * 6 * K + 6 * m + 3 + c] = 0.0;
+            out[(3 + i) * 6 * K + 6 * m + c] = -HD[3 * i + c];
+            out[(3 + i) * 6 * K + 6 * m + 3 + c] = (i == c) ? wm : 0.0;
+          }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+  if ((threadIdx.x & 31) == 0) s_cost[threadIdx.x >> 5] = cost;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0;
+    for (int w = 0; w < kEvalThreads / 32; ++w) c += s_cost[w];
+    a.cost_partial[blockIdx.x] = c;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Plain spline interpolation at arbitrary stamps (no Jacobians): pose [q|p], body velocity

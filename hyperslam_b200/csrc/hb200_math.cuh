@@ -90,6 +90,25 @@ HB_DI void quat_log(const double* q, double* d) {
   else s = 2.0 * atan2(n, w) / n;
   d[0] = s * x; d[1] = s * y; d[2] = s * z;
 }
+// Rotation matrix -> unit quaternion [x y z w] (Shepperd's method: pivot on the largest of w^2, x^2, y^2, z^2).
+HB_DI void rot_to_quat(const double* R, double* q) {
+  const double tr = R[0] + R[4] + R[8];
+  double x, y, z, w;
+  if (tr > 0.0) {
+    const double s = 2.0 * sqrt(1.0 + tr);
+    w = 0.25 * s; x = (R[7] - R[5]) / s; y = (R[2] - R[6]) / s; z = (R[3] - R[1]) / s;
+  } else if (R[0] > R[4] && R[0] > R[8]) {
+    const double s = 2.0 * sqrt(1.0 + R[0] - R[4] - R[8]);
+    w = (R[7] - R[5]) / s; x = 0.25 * s; y = (R[1] + R[3]) / s; z = (R[2] + R[6]) / s;
+  } else if (R[4] > R[8]) {
+    const double s = 2.0 * sqrt(1.0 + R[4] - R[0] - R[8]);
+    w = (R[2] - R[6]) / s; x = (R[1] + R[3]) / s; y = 0.25 * s; z = (R[5] + R[7]) / s;
+  } else {
+    const double s = 2.0 * sqrt(1.0 + R[8] - R[0] - R[4]);
+    w = (R[3] - R[1]) / s; x = (R[2] + R[6]) / s; y = (R[5] + R[7]) / s; z = 0.25 * s;
+  }
+  q[0] = x; q[1] = y; q[2] = z; q[3] = w;
+}
 HB_DI void quat_exp(const double* d, double* q) {
   const double t2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
   const double t = sqrt(t2);

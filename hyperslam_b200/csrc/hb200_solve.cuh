@@ -32,7 +32,7 @@ constexpr int kHessThreads = 128;
 
 template <int K>
 __global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* __restrict__ seg_off, const double* __restrict__ r,
-                                                                     const double* __restrict__ Jp, double huber, double* sys, int n, int splits) {
+                                                                     const double* __restrict__ Jp, const double* __restrict__ wv, double* sys, int n, int splits) {
   constexpr int NB = 6 * K;
   constexpr int CH = 16;
   constexpr int EPT = (NB * NB + kHessThreads - 1) / kHessThreads;
@@ -53,9 +53,7 @@ __global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* 
       const int ff = e / (2 * NB), rem = e - ff * 2 * NB;
       const int f = f0 + ff;
       const double r0 = r[2 * f], r1 = r[2 * f + 1];
-      double wgt;
-      huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
-      const double sw = sqrt(wgt);
+      const double sw = sqrt(wv[f]);
       sJ[ff][rem / NB][rem % NB] = sw * Jp[static_cast<size_t>(f) * 2 * NB + rem];
       if (rem < 2) sr[ff][rem] = sw * (rem == 0 ? r0 : r1);
     }
@@ -290,6 +288,38 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
   }
 }
 
+// J^T J / J^T r of the manifold (pose) factors: one warp per factor, lower triangle of its 6K x 6K block.
+constexpr int kManWarps = 4;
+template <int K>
+__global__ void __launch_bounds__(kManWarps * 32) manifold_hessian_kernel(int nf, const int2* __restrict__ idx, const double* __restrict__ r,
+                                                                         const double* __restrict__ Jp, double* sys, int n) {
+  constexpr int NB = 6 * K;
+  __shared__ double sJ[kManWarps][6][NB];
+  __shared__ double sr[kManWarps][6];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * kManWarps + warp;
+  if (f >= nf) return;
+  for (int e = lane; e < 6 * NB; e += 32) sJ[warp][e / NB][e % NB] = Jp[static_cast<size_t>(f) * 6 * NB + e];
+  if (lane < 6) sr[warp][lane] = r[6 * static_cast<size_t>(f) + lane];
+  __syncwarp();
+  const int c0 = 6 * idx[f].x;
+  double* g = sys + static_cast<size_t>(n) * n + 2 * static_cast<size_t>(n);
+  for (int e = lane; e < NB * NB; e += 32) {
+    const int a = e / NB, b = e - a * NB;
+    if (b > a) continue;
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) s += sJ[warp][q][a] * sJ[warp][q][b];
+    atomicAdd(&sys[static_cast<size_t>(c0 + a) * n + c0 + b], s);
+  }
+  for (int a = lane; a < NB; a += 32) {
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) s += sJ[warp][q][a] * sr[warp][q];
+    atomicAdd(&g[c0 + a], s);
+  }
+}
+
 // diagH = diag(H), b = -g, cost = sum of the evaluation kernels' per-block partials (fixed order).
 __global__ void diag_cost_kernel(double* sys, int n, const double* __restrict__ cp_pix, int n_pix_blocks, const double* __restrict__ cp_imu,
                                  int n_imu_blocks) {
@@ -324,7 +354,7 @@ constexpr int kSchurThreads = 128;
 template <int K>
 __global__ void __launch_bounds__(kSchurThreads) schur_kernel(const int* __restrict__ lm_off, const int* __restrict__ lm_obs,
                                                               const int4* __restrict__ idx, const double* __restrict__ r,
-                                                              const double* __restrict__ Jp, const double* __restrict__ Jl, double huber,
+                                                              const double* __restrict__ Jp, const double* __restrict__ Jl, const double* __restrict__ wv,
                                                               const SolverState* __restrict__ st, double* sys, int n,
                                                               double* __restrict__ Vinv, double* __restrict__ gl, double* __restrict__ Dl,
                                                               int max_rows) {
@@ -350,8 +380,7 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(const int* __restr
     for (int o = o_lo; o < o_hi; ++o) {
       const int f = lm_obs[o];
       const double r0 = r[2 * f], r1 = r[2 * f + 1];
-      double wgt;
-      huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
+      const double wgt = wv[f];
       const double* jl = Jl + 6 * static_cast<size_t>(f);
       if (threadIdx.x < 9) { const int a = threadIdx.x / 3, b = threadIdx.x % 3; s += wgt * (jl[a] * jl[b] + jl[3 + a] * jl[3 + b]); }
       else { const int a = threadIdx.x - 9; s += wgt * (jl[a] * r0 + jl[3 + a] * r1); }
@@ -366,9 +395,7 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(const int* __restr
       const int f = lm_obs[o];
       const int a = row - 6 * (idx[f].x - cp_lo);
       if (a >= 0 && a < NB) {
-        const double r0 = r[2 * f], r1 = r[2 * f + 1];
-        double wgt;
-        huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
+        const double wgt = wv[f];
         const double* jp = Jp + static_cast<size_t>(f) * 2 * NB;
         const double* jl = Jl + 6 * static_cast<size_t>(f);
         s += wgt * (jp[a] * jl[c] + jp[NB + a] * jl[3 + c]);
@@ -621,7 +648,7 @@ constexpr int kLmWarps = 4;
 template <int K>
 __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const int* __restrict__ lm_off, const int* __restrict__ lm_obs,
                                                                   const int4* __restrict__ idx, const double* __restrict__ r,
-                                                                  const double* __restrict__ Jp, const double* __restrict__ Jl, double huber,
+                                                                  const double* __restrict__ Jp, const double* __restrict__ Jl, const double* __restrict__ wv,
                                                                   const double* __restrict__ Vinv, const double* __restrict__ gl,
                                                                   const double* __restrict__ Dl, const double* __restrict__ dp,
                                                                   double* __restrict__ dl, double* __restrict__ part /*[grid][2]*/) {
@@ -639,8 +666,7 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const 
       double t0 = 0, t1 = 0, wgt = 0, jl[6] = {0, 0, 0, 0, 0, 0};
       if (o < o_hi) {
         const int f = lm_obs[o];
-        const double r0 = r[2 * f], r1 = r[2 * f + 1];
-        huber_rho(r0 * r0 + r1 * r1, huber, &wgt);
+        wgt = wv[f];
         const double* jp = Jp + static_cast<size_t>(f) * 2 * NB + cg * CG;
         const double* d = dp + 6 * idx[f].x + cg * CG;
 #pragma unroll

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhyperb200.so")
 
-PIXEL, INERTIAL = 0, 1
+PIXEL, INERTIAL, BEARING, MANIFOLD = 0, 1, 2, 3
 EVAL_JACOBIANS, EVAL_TRIAL = 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -39,7 +39,8 @@ EXPORTS = [
     "hb200_factor_evaluate", "hb200_reduced_size", "hb200_build_system", "hb200_get_system", "hb200_solve",
     "hb200_get_delta", "hb200_iterate", "hb200_cost", "hb200_get_state", "hb200_set_allreduce",
     "hb200_system_device_ptr", "hb200_stream", "hb200_launch_count", "hb200_optimize", "hb200_snapshot", "hb200_restore",
-    "hb200_profile_iteration", "hb200_interpolate",
+    "hb200_profile_iteration", "hb200_interpolate", "hb200_set_bearing_factors", "hb200_set_bearing_loss",
+    "hb200_set_pose_sensors", "hb200_set_manifold_factors", "hb200_get_bearing_outputs", "hb200_get_manifold_outputs",
 ]
 
 _lib = None
@@ -88,7 +89,7 @@ class Context:
         opts = Options(device, stream, int(use_graph), int(force_dense))
         self._check(self.lib.hb200_create(C.byref(opts), C.byref(self.h)))
         self._cb = None
-        self.order = self.K = self.Kbg = self.Kba = self.L = self.Nv = self.Ni = 0
+        self.order = self.K = self.Kbg = self.Kba = self.L = self.Nv = self.Ni = self.Nb = self.Nm = 0
         self.bias_order = 4
 
     def _check(self, rc: int):
@@ -146,6 +147,24 @@ class Context:
         self.Nv = stamp.size
         self._check(self.lib.hb200_set_pixel_factors(self.h, self.Nv, _d(stamp), _i(cam), _i(lm), _d(pixel)))
 
+    def set_bearing_factors(self, stamp, cam, lm, bearing, huber=None):
+        stamp, bearing = _f64(stamp), _f64(bearing)
+        cam, lm = np.ascontiguousarray(cam, dtype=np.int32), np.ascontiguousarray(lm, dtype=np.int32)
+        self.Nb = stamp.size
+        self._check(self.lib.hb200_set_bearing_factors(self.h, self.Nb, _d(stamp), _i(cam), _i(lm), _d(bearing)))
+        if huber is not None:
+            self._check(self.lib.hb200_set_bearing_loss(self.h, C.c_double(huber)))
+
+    def set_pose_sensors(self, T_bs):
+        T_bs = _f64(T_bs)
+        self._check(self.lib.hb200_set_pose_sensors(self.h, T_bs.shape[0], _d(T_bs)))
+
+    def set_manifold_factors(self, stamp, sensor, pose):
+        stamp, pose = _f64(stamp), _f64(pose)
+        sensor = np.ascontiguousarray(sensor, dtype=np.int32)
+        self.Nm = stamp.size
+        self._check(self.lib.hb200_set_manifold_factors(self.h, self.Nm, _d(stamp), _i(sensor), _d(pose)))
+
     def set_inertial_factors(self, stamp, meas):
         stamp, meas = _f64(stamp), _f64(meas)
         self.Ni = stamp.size
@@ -169,6 +188,9 @@ class Context:
         self.set_options(w.huber_pixel, w.imu_loss_scale, radius)
         self.set_pixel_factors(w.v_stamp, w.v_cam, w.v_lm, w.v_pixel)
         self.set_inertial_factors(w.i_stamp, w.i_meas)
+        self.set_bearing_factors(w.b_stamp, w.b_cam, w.b_lm, w.b_bearing, w.huber_bearing)
+        self.set_pose_sensors(w.pose_sensors)
+        self.set_manifold_factors(w.m_stamp, w.m_sensor, w.m_pose)
         self.bind()
         self.set_constant(w.knot_const, w.gravity_const, w.bias_const)
 
@@ -191,13 +213,24 @@ class Context:
         self._check(self.lib.hb200_get_pixel_outputs(self.h, _d(out["v_r"]), _d(out.get("v_Jp")), _d(out.get("v_Jl"))))
         self._check(self.lib.hb200_get_inertial_outputs(self.h, _d(out["i_r"]), _d(out.get("i_Jp")), _d(out.get("i_wg")),
                                                         _d(out.get("i_wa")), _d(out.get("i_Jg"))))
+        Nb, Nm = self.Nb, self.Nm
+        if Nb:
+            out["b_r"] = np.zeros(Nb)
+            if jacobians:
+                out.update(b_Jp=np.zeros((Nb, 6 * k)), b_Jl=np.zeros((Nb, 3)))
+            self._check(self.lib.hb200_get_bearing_outputs(self.h, _d(out["b_r"]), _d(out.get("b_Jp")), _d(out.get("b_Jl"))))
+        if Nm:
+            out["m_r"] = np.zeros((Nm, 6))
+            if jacobians:
+                out["m_Jp"] = np.zeros((Nm, 6, 6 * k))
+            self._check(self.lib.hb200_get_manifold_outputs(self.h, _d(out["m_r"]), _d(out.get("m_Jp"))))
         return out
 
     def factor_evaluate(self, kind, index, blocks, want_jacobians=True):
         """Ceres-shaped copy-out; blocks = list of 1-D parameter-block arrays in ExteroceptiveCost order."""
         blocks = [_f64(b) for b in blocks]
         nb = len(blocks)
-        nr = 2 if kind == PIXEL else 6
+        nr = {PIXEL: 2, INERTIAL: 6, BEARING: 1, MANIFOLD: 6}[kind]
         params = (_dp * nb)(*[_d(b) for b in blocks])
         r = np.zeros(nr)
         if want_jacobians:

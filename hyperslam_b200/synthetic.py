@@ -56,10 +56,21 @@ class Window:
     huber_pixel: float = 0.5          # reference optimizer.cpp:226
     imu_loss_scale: float = 1.6e-5    # reference optimizer.cpp:267
     truth: dict | None = None
+    # bearing factors (VisualBearingObservation, reference optimizer.cpp:189-210): same blocks as a pixel factor
+    b_stamp: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0))
+    b_cam: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+    b_lm: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+    b_bearing: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros((0, 3)))
+    huber_bearing: float = 1.6e-3     # reference optimizer.cpp:204
+    # manifold (pose) factors (ManifoldObservation<SE3>, reference optimizer.cpp:234-251)
+    pose_sensors: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros((0, 7)))   # (P, 7) T_bs
+    m_stamp: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0))
+    m_sensor: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+    m_pose: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros((0, 7)))         # (Nm, 7) measured T_ws
 
     @property
     def num_factors(self) -> int:
-        return int(self.v_stamp.size + self.i_stamp.size)
+        return int(self.v_stamp.size + self.i_stamp.size + self.b_stamp.size + self.m_stamp.size)
 
     def reduced_size(self) -> int:
         return 6 * self.knots.shape[0] + 3 * self.gyro_bias.shape[0] + 3 * self.accel_bias.shape[0] + 2
@@ -74,8 +85,14 @@ class Window:
         vm = (self.v_lm >= owner_lo) & (self.v_lm < owner_hi)
         Ni = self.i_stamp.size
         i_lo, i_hi = (Ni * rank) // world, (Ni * (rank + 1)) // world
+        bm = (self.b_lm >= owner_lo) & (self.b_lm < owner_hi)
+        Nm = self.m_stamp.size
+        m_lo, m_hi = (Nm * rank) // world, (Nm * (rank + 1)) // world
         return dataclasses.replace(
-            self, v_stamp=np.ascontiguousarray(self.v_stamp[vm]), v_cam=np.ascontiguousarray(self.v_cam[vm]),
+            self, b_stamp=np.ascontiguousarray(self.b_stamp[bm]), b_cam=np.ascontiguousarray(self.b_cam[bm]),
+            b_lm=np.ascontiguousarray(self.b_lm[bm]), b_bearing=np.ascontiguousarray(self.b_bearing[bm]),
+            m_stamp=np.ascontiguousarray(self.m_stamp[m_lo:m_hi]), m_sensor=np.ascontiguousarray(self.m_sensor[m_lo:m_hi]),
+            m_pose=np.ascontiguousarray(self.m_pose[m_lo:m_hi]), v_stamp=np.ascontiguousarray(self.v_stamp[vm]), v_cam=np.ascontiguousarray(self.v_cam[vm]),
             v_lm=np.ascontiguousarray(self.v_lm[vm]), v_pixel=np.ascontiguousarray(self.v_pixel[vm]),
             i_stamp=np.ascontiguousarray(self.i_stamp[i_lo:i_hi]), i_meas=np.ascontiguousarray(self.i_meas[i_lo:i_hi]))
 
@@ -380,6 +397,45 @@ def make_window(order=4, num_knots=50, dt=0.1, num_landmarks=1000, frames_per_la
                   v_stamp=np.ascontiguousarray(v_stamp), v_cam=cam_idx.astype(np.int32), v_lm=lm_idx.astype(np.int32),
                   v_pixel=np.ascontiguousarray(v_pixel), i_stamp=np.ascontiguousarray(i_stamp), i_meas=np.ascontiguousarray(i_meas),
                   knot_const=knot_const, truth=truth)
+
+
+def add_bearing_and_pose_factors(win: Window, num_bearing=0, num_pose=0, seed=SEED_BASE + 77, convert=True,
+                                 bearing_sigma=1e-3, pose_sigma=(2e-3, 5e-3), num_pose_sensors=2) -> Window:
+    """Widen a window with the two other factor families the reference optimizer accepts:
+    bearing factors (a random subset of the pixel observations re-expressed as unit directions in the sensor
+    frame, removed from the pixel list when `convert`) and pose factors (noisy T_ws = T_wb (+) T_bs samples
+    of the ground-truth trajectory on `num_pose_sensors` pose sensors)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    truth = win.truth
+    out = {}
+    if num_bearing:
+        Nv = win.v_stamp.size
+        sel = np.sort(rng.choice(Nv, size=min(num_bearing, Nv), replace=False))
+        _, p_s = pixel_model(truth["knots"], win.order, win.cameras, truth["landmarks"], win.v_stamp[sel], win.v_cam[sel], win.v_lm[sel])
+        b = p_s / np.linalg.norm(p_s, axis=1, keepdims=True) + rng.normal(0.0, bearing_sigma, p_s.shape)
+        b *= rng.uniform(0.5, 2.0, (sel.size, 1))     # the angular metric is scale-free in the measurement
+        out.update(b_stamp=np.ascontiguousarray(win.v_stamp[sel]), b_cam=np.ascontiguousarray(win.v_cam[sel]),
+                   b_lm=np.ascontiguousarray(win.v_lm[sel]), b_bearing=np.ascontiguousarray(b))
+        if convert:
+            keep = np.ones(Nv, dtype=bool); keep[sel] = False
+            out.update(v_stamp=np.ascontiguousarray(win.v_stamp[keep]), v_cam=np.ascontiguousarray(win.v_cam[keep]),
+                       v_lm=np.ascontiguousarray(win.v_lm[keep]), v_pixel=np.ascontiguousarray(win.v_pixel[keep]))
+    if num_pose:
+        k, kt = win.order, win.knots[:, 7]
+        left = (k - 1) // 2
+        t_lo, t_hi = kt[left], kt[len(kt) - 1 - (k - 1 - left)]
+        sensors = np.zeros((num_pose_sensors, 7))
+        sensors[:, :4] = rot_to_quat(so3_exp(rng.normal(0, 0.3, (num_pose_sensors, 3))))
+        sensors[:, 4:] = rng.normal(0, 0.1, (num_pose_sensors, 3))
+        stamp = t_lo + (np.arange(num_pose) + 0.5) * (t_hi - t_lo) / num_pose
+        sidx = rng.integers(0, num_pose_sensors, num_pose).astype(np.int32)
+        R, p, *_ = spline_eval(truth["knots"], k, stamp)
+        R_bs = quat_to_rot(sensors[sidx, :4]); t_bs = sensors[sidx, 4:]
+        R_ws = so3_exp(rng.normal(0, pose_sigma[0], (num_pose, 3))) @ R @ R_bs
+        p_ws = p + (R @ t_bs[..., None])[..., 0] + rng.normal(0, pose_sigma[1], (num_pose, 3))
+        pose = np.concatenate([rot_to_quat(R_ws), p_ws], axis=1)
+        out.update(pose_sensors=sensors, m_stamp=np.ascontiguousarray(stamp), m_sensor=sidx, m_pose=np.ascontiguousarray(pose))
+    return dataclasses.replace(win, **out)
 
 
 # BASELINE.json configs (index = position in BASELINE.json "configs").

@@ -39,7 +39,7 @@ typedef struct hb200_iteration {
   int spd;              /* reduced system was positive definite */
 } hb200_iteration;
 
-enum { HB200_PIXEL = 0, HB200_INERTIAL = 1 };
+enum { HB200_PIXEL = 0, HB200_INERTIAL = 1, HB200_BEARING = 2, HB200_MANIFOLD = 3 };
 enum { HB200_EVAL_JACOBIANS = 1, HB200_EVAL_TRIAL = 2 };
 
 int hb200_create(const hb200_options* options, hb200_ctx** out);
@@ -73,6 +73,16 @@ int hb200_set_options(hb200_ctx* ctx, double huber_pixel, double imu_loss_scale,
 /* ---- factor lists: replace problem_.AddResidualBlock (reference optimizer.cpp:212-232,253-274) */
 int hb200_set_pixel_factors(hb200_ctx* ctx, int n, const double* stamp, const int* camera, const int* landmark, const double* pixel);
 int hb200_set_inertial_factors(hb200_ctx* ctx, int n, const double* stamp, const double* measurement /* [n][6] gyro|accel */);
+/* VisualBearingObservation -> AngularMetric residual behind HuberLoss(1.6e-3) (reference
+ * optimizer.cpp:189-210, evaluators/bearing.cpp:14-79); bearing = [n][3] direction in the sensor frame
+ * (any positive length).  Same parameter blocks as a pixel factor. */
+int hb200_set_bearing_factors(hb200_ctx* ctx, int n, const double* stamp, const int* camera, const int* landmark, const double* bearing);
+int hb200_set_bearing_loss(hb200_ctx* ctx, double huber_bearing);
+/* ManifoldObservation<SE3> -> ManifoldMetric residual, no loss (reference optimizer.cpp:234-251,
+ * evaluators/manifold.cpp:12-61).  Pose sensors carry only T_bs [q(4) p(3)] (plain Sensor, reference
+ * manifold.cpp:30); pose = [n][7] measured T_ws. */
+int hb200_set_pose_sensors(hb200_ctx* ctx, int num_sensors, const double* T_bs /* [P][7] */);
+int hb200_set_manifold_factors(hb200_ctx* ctx, int n, const double* stamp, const int* sensor, const double* pose /* [n][7] */);
 /* ExteroceptiveCost::update() for every factor (reference exteroceptive.cpp:25-99): resolves the
  * knot base index of each stamp and the segment / landmark incidence lists.  num_invalid receives
  * the number of factors whose stamp or indices fall outside the window (they are an error). */
@@ -87,6 +97,9 @@ int hb200_get_index_maps(hb200_ctx* ctx, int* pixel_base, int* inertial_base, in
 int hb200_evaluate(hb200_ctx* ctx, int flags);
 int hb200_get_pixel_outputs(hb200_ctx* ctx, double* r, double* Jp, double* Jl);
 int hb200_get_inertial_outputs(hb200_ctx* ctx, double* r, double* Jp, double* wg, double* wa, double* Jg);
+/*   bearing : r[n], Jp[n][6k], Jl[n][3]            manifold: r[n][6], Jp[n][6][6k]             */
+int hb200_get_bearing_outputs(hb200_ctx* ctx, double* r, double* Jp, double* Jl);
+int hb200_get_manifold_outputs(hb200_ctx* ctx, double* r, double* Jp);
 /* Ceres-shaped copy-out of one factor after hb200_evaluate(JACOBIANS): same signature, block order
  * and row-major ambient Jacobians as ExteroceptiveCost::Evaluate (reference exteroceptive.hpp:31,
  * exteroceptive.cpp:149-156).  parameters must be the blocks the window was uploaded from; blocks

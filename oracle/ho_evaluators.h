@@ -150,7 +150,7 @@ inline void imu_align_jacobian(const double* v, double* J /*3x6*/) {
 // ---------------------------------------------------------------------------------------------
 // Factor description + layout (reference EvaluatorLayout, evaluators/forward.hpp:19-39).
 // ---------------------------------------------------------------------------------------------
-enum FactorKind { kPixel = 0, kInertial = 1 };
+enum FactorKind { kPixel = 0, kInertial = 1, kBearing = 2, kManifold = 3 };
 
 // Reference-quirk switches for the inertial evaluator.
 enum Quirks {
@@ -174,13 +174,14 @@ struct Layout {
 struct Factor {
   int kind = kPixel;
   double stamp = 0;
-  double measurement[6] = {0, 0, 0, 0, 0, 0};
+  double measurement[7] = {0, 0, 0, 0, 0, 0, 0};
   int k = 4;     // state spline order (interpolator()->layout().outer.size)
   int k_bg = 4;  // gyroscope bias spline order
   int k_ba = 4;  // accelerometer bias spline order
 };
 
-inline int num_residuals(const Factor& f) { return f.kind == kPixel ? 2 : 6; }
+inline int num_residuals(const Factor& f) { return f.kind == kPixel ? 2 : (f.kind == kBearing ? 1 : 6); }
+inline int measurement_size(const Factor& f) { return f.kind == kPixel ? 2 : (f.kind == kInertial ? 6 : (f.kind == kBearing ? 3 : 7)); }
 
 // ExteroceptiveCost::update (reference exteroceptive.cpp:25-99): block order
 // state (k x 8) | sensor static | sensor dynamic | observation; offsets = exclusive prefix sums.
@@ -189,7 +190,11 @@ inline void layout_update(const Factor& f, Layout* L) {
   L->state_idx = 0;
   for (int i = 0; i < f.k; ++i) L->sizes[n++] = 8;
   L->sensor_static_idx = n;
-  if (f.kind == kPixel) {
+  if (f.kind == kManifold) {
+    L->sizes[n++] = 7;  // T_bs of a plain Sensor (Traits<Sensor>::kTransformationOffset, reference manifold.cpp:30)
+    L->sensor_dynamic_idx = n;
+    L->observation_idx = n;  // ManifoldObservation carries no extra variables
+  } else if (f.kind == kPixel || f.kind == kBearing) {
     L->sizes[n++] = 7;  // T_bs      Traits<Camera>::kTransformationOffset
     L->sizes[n++] = 4;  // intrinsics
     L->sizes[n++] = 4;  // distortion
@@ -492,6 +497,136 @@ inline void inertial_evaluate(const Factor& f, const Layout& L, const Basis& bas
 }
 
 // ---------------------------------------------------------------------------------------------
+// VisualBearingEvaluator<SE3>::evaluate (reference internal/hyper/optimizers/evaluators/bearing.cpp:14-79):
+// prediction = landmark position in the sensor frame p_s (3); J_e 3 x num_parameters.
+// ---------------------------------------------------------------------------------------------
+inline void bearing_evaluate(const Factor& f, const Layout& L, const Basis& basis, const double* const* p_ps, double* J_e,
+                             const double* const* p_js, double* prediction) {
+  const int o_T_bs = L.sensor_static_idx + 0, o_p_w = L.observation_idx + 0;
+  const double* T_bs = p_ps[o_T_bs];
+  const double* p_w = p_ps[o_p_w];
+  StateResult S;
+  if (!J_e) {
+    state_evaluate(basis, p_ps + L.state_idx, f.stamp, 0, false, &S);
+    double T_ws[7], T_sw[7];
+    se3_group_plus(S.value, T_bs, T_ws, nullptr, nullptr);
+    se3_group_inverse(T_ws, T_sw, nullptr);
+    se3_vector_plus(T_sw, p_w, prediction, nullptr);
+    return;
+  }
+  const int np = L.num_parameters;
+  std::memset(J_e, 0, sizeof(double) * 3 * np);
+  bool J_S_wb = false;
+  for (int i = 0; i < f.k; ++i) J_S_wb = J_S_wb || (p_js[L.state_idx + i] != nullptr);
+  state_evaluate(basis, p_ps + L.state_idx, f.stamp, 0, J_S_wb, &S);
+  double T_ws[7], J_T_ws_S_wb[36], J_T_ws_T_bs[36], T_sw[7], J_T_sw_T_ws[36], J_p_s_T_sw[18];
+  se3_group_plus(S.value, T_bs, T_ws, J_T_ws_S_wb, J_T_ws_T_bs);
+  se3_group_inverse(T_ws, T_sw, J_T_sw_T_ws);
+  se3_vector_plus(T_sw, p_w, prediction, J_p_s_T_sw);
+  double J_p_s_T_ws[18];
+  mat_mul(J_p_s_T_sw, J_T_sw_T_ws, J_p_s_T_ws, 3, 6, 6);  // bearing.cpp:71
+  if (J_S_wb) {                                            // :73
+    double t[18];
+    mat_mul(J_p_s_T_ws, J_T_ws_S_wb, t, 3, 6, 6);
+    const int cols = 8 * f.k;
+    std::vector<double> blk(3 * cols);
+    mat_mul(t, S.J[0], blk.data(), 3, 6, cols);
+    put_block(J_e, np, 0, L.offsets[L.state_idx], blk.data(), 3, cols);
+  }
+  if (p_js[o_T_bs]) {  // :74
+    double t[18], Ad[42], blk[21];
+    mat_mul(J_p_s_T_ws, J_T_ws_T_bs, t, 3, 6, 6);
+    se3_adapter(T_bs, Ad);
+    mat_mul(t, Ad, blk, 3, 6, 7);
+    put_block(J_e, np, 0, L.offsets[o_T_bs], blk, 3, 7);
+  }
+  if (p_js[o_p_w]) {  // :75
+    double R_sw[9];
+    quat_to_rot(T_sw, R_sw);
+    put_block(J_e, np, 0, L.offsets[o_p_w], R_sw, 3, 3);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ManifoldEvaluator<SE3>::evaluate (reference internal/hyper/optimizers/evaluators/manifold.cpp:12-61):
+// prediction = T_ws = T_wb (+) T_bs (7); J_e 6 x num_parameters (rows = tangent of the prediction).
+// ---------------------------------------------------------------------------------------------
+inline void manifold_evaluate(const Factor& f, const Layout& L, const Basis& basis, const double* const* p_ps, double* J_e,
+                              const double* const* p_js, double* prediction) {
+  const int o_T_bs = L.sensor_static_idx + 0;
+  const double* T_bs = p_ps[o_T_bs];
+  StateResult S;
+  if (!J_e) {
+    state_evaluate(basis, p_ps + L.state_idx, f.stamp, 0, false, &S);
+    se3_group_plus(S.value, T_bs, prediction, nullptr, nullptr);
+    return;
+  }
+  const int np = L.num_parameters;
+  std::memset(J_e, 0, sizeof(double) * 6 * np);
+  bool J_S_wb = false;
+  for (int i = 0; i < f.k; ++i) J_S_wb = J_S_wb || (p_js[L.state_idx + i] != nullptr);
+  state_evaluate(basis, p_ps + L.state_idx, f.stamp, 0, J_S_wb, &S);
+  double J_r_S_wb[36], J_r_T_bs[36];
+  se3_group_plus(S.value, T_bs, prediction, J_r_S_wb, J_r_T_bs);
+  if (J_S_wb) {  // manifold.cpp:56
+    const int cols = 8 * f.k;
+    std::vector<double> blk(6 * cols);
+    mat_mul(J_r_S_wb, S.J[0], blk.data(), 6, 6, cols);
+    put_block(J_e, np, 0, L.offsets[L.state_idx], blk.data(), 6, cols);
+  }
+  if (p_js[o_T_bs]) {  // :57
+    double Ad[42], blk[42];
+    se3_adapter(T_bs, Ad);
+    mat_mul(J_r_T_bs, Ad, blk, 6, 6, 7);
+    put_block(J_e, np, 0, L.offsets[o_T_bs], blk, 6, 7);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Metrics (HyperVariables, not in the tree -- [INFERRED]):
+//   AngularMetric<Bearing>::distance(lhs, rhs, J_lhs): the angle between the two vectors,
+//     theta = atan2(|lhs x rhs|, lhs . rhs)  (1 residual; wired at reference optimizer.cpp:192),
+//     J_lhs = [c (rhs x n) - s rhs]^T / (|lhs|^2 |rhs|^2), n = (lhs x rhs)/s; zero when s -> 0.
+//   ManifoldMetric<SE3>::distance(lhs, rhs, J_lhs): lhs (-) rhs in the tangent convention of this
+//     repo, [Log(R_lhs R_rhs^T) | p_lhs - p_rhs]  (6 residuals; wired at optimizer.cpp:237),
+//     J_lhs = blockdiag(Jl^{-1}(theta), I) with Jl^{-1}(theta) = Jr^{-1}(-theta).
+// ---------------------------------------------------------------------------------------------
+inline double angular_distance(const double* a, const double* b, double* J_a /*1x3 or null*/) {
+  double cr[3];
+  v3_cross(a, b, cr);
+  const double s = std::sqrt(v3_dot(cr, cr)), c = v3_dot(a, b);
+  const double theta = std::atan2(s, c);
+  if (J_a) {
+    if (s < 1e-300) { J_a[0] = J_a[1] = J_a[2] = 0.0; }
+    else {
+      const double n[3] = {cr[0] / s, cr[1] / s, cr[2] / s};
+      double bn[3];
+      v3_cross(b, n, bn);
+      const double den = v3_dot(a, a) * v3_dot(b, b);
+      for (int i = 0; i < 3; ++i) J_a[i] = (c * bn[i] - s * b[i]) / den;
+    }
+  }
+  return theta;
+}
+inline void manifold_distance(const double* lhs, const double* rhs, double* d /*6*/, double* J_lhs /*6x6 or null*/) {
+  double qc[4], qr[4];
+  quat_conj(rhs, qc);
+  quat_mul(lhs, qc, qr);   // R_lhs R_rhs^T
+  quat_log(qr, d);
+  for (int i = 0; i < 3; ++i) d[3 + i] = lhs[4 + i] - rhs[4 + i];
+  if (J_lhs) {
+    std::memset(J_lhs, 0, 36 * sizeof(double));
+    const double neg[3] = {-d[0], -d[1], -d[2]};
+    double Jli[9];
+    so3_Jr_inv(neg, Jli);
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) J_lhs[6 * i + j] = Jli[3 * i + j];
+      J_lhs[6 * (3 + i) + 3 + i] = 1.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // ExteroceptiveCost<CERES>::Evaluate (reference exteroceptive.cpp:101-160) with
 // CartesianMetric (distance = lhs - rhs, J_lhs = I; wired at optimizer.cpp:215,256) and no weights.
 // jacobians[i] row-major num_residuals x sizes[i], ambient coordinates; may be null.
@@ -499,22 +634,40 @@ inline void inertial_evaluate(const Factor& f, const Layout& L, const Basis& bas
 inline bool cost_evaluate(const Factor& f, const Layout& L, const Basis& basis, const Basis& bias_basis,
                           const double* const* parameters, double* residuals, double** jacobians, int quirks) {
   const int nr = num_residuals(f);
-  double prediction[6];
-  if (!jacobians) {
-    if (f.kind == kPixel) pixel_evaluate(f, L, basis, parameters, nullptr, nullptr, prediction);
-    else inertial_evaluate(f, L, basis, bias_basis, parameters, nullptr, nullptr, prediction, quirks);
-    for (int i = 0; i < nr; ++i) residuals[i] = prediction[i] - f.measurement[i];
-    return true;
+  const int ne = (f.kind == kPixel) ? 2 : (f.kind == kBearing ? 3 : 6);   // rows of the evaluator Jacobian J_e
+  double prediction[7];
+  std::vector<double> J_e;
+  double* pJ = nullptr;
+  if (jacobians) { J_e.resize((size_t)ne * L.num_parameters); pJ = J_e.data(); }
+  switch (f.kind) {
+    case kPixel: pixel_evaluate(f, L, basis, parameters, pJ, jacobians, prediction); break;
+    case kInertial: inertial_evaluate(f, L, basis, bias_basis, parameters, pJ, jacobians, prediction, quirks); break;
+    case kBearing: bearing_evaluate(f, L, basis, parameters, pJ, jacobians, prediction); break;
+    default: manifold_evaluate(f, L, basis, parameters, pJ, jacobians, prediction); break;
   }
-  std::vector<double> J_e((size_t)nr * L.num_parameters);
-  if (f.kind == kPixel) pixel_evaluate(f, L, basis, parameters, J_e.data(), jacobians, prediction);
-  else inertial_evaluate(f, L, basis, bias_basis, parameters, J_e.data(), jacobians, prediction, quirks);
-  for (int i = 0; i < nr; ++i) residuals[i] = prediction[i] - f.measurement[i];
+  // metric: CartesianMetric (pixel, inertial: optimizer.cpp:215,256), AngularMetric (bearing, :192),
+  // ManifoldMetric (manifold, :237); J_w = J_m * J_e (exteroceptive.cpp:136-137)
+  double J_m[36];
+  if (f.kind == kPixel || f.kind == kInertial) {
+    for (int i = 0; i < nr; ++i) residuals[i] = prediction[i] - f.measurement[i];
+  } else if (f.kind == kBearing) {
+    residuals[0] = angular_distance(prediction, f.measurement, jacobians ? J_m : nullptr);
+  } else {
+    manifold_distance(prediction, f.measurement, residuals, jacobians ? J_m : nullptr);
+  }
+  if (!jacobians) return true;
+  std::vector<double> J_w;
+  const double* Jw = J_e.data();
+  if (f.kind == kBearing || f.kind == kManifold) {
+    J_w.resize((size_t)nr * L.num_parameters);
+    mat_mul(J_m, J_e.data(), J_w.data(), nr, ne, L.num_parameters);
+    Jw = J_w.data();
+  }
   for (int b = 0; b < L.num_blocks; ++b) {
     if (!jacobians[b]) continue;
     const int sz = L.sizes[b];
     for (int r = 0; r < nr; ++r)
-      for (int c = 0; c < sz; ++c) jacobians[b][r * sz + c] = J_e[(size_t)r * L.num_parameters + L.offsets[b] + c];
+      for (int c = 0; c < sz; ++c) jacobians[b][r * sz + c] = Jw[(size_t)r * L.num_parameters + L.offsets[b] + c];
   }
   return true;
 }

@@ -11,6 +11,8 @@
 //
 // Compact per-factor output layout (shared with the CUDA path, DESIGN.md "HBM layout"):
 //   pixel   : r[2], Jp[2][6k] (pose control-point tangents [theta|rho] x k), Jl[2][3]
+//   bearing : same slot as a pixel factor, r = [angle, 0], second Jacobian row zero (Huber 1.6e-3, :204)
+//   manifold: r[6], Jp[6][6k] (no loss, :250)
 //   inertial: r[6], Jp[6][6k], wg[k_b], wa[k_b] (bias basis weights), Jg[6][2] (gravity tangent)
 // Tangents: theta GLOBAL rotation vector (R <- Exp(theta) R), rho additive; gravity tangent is the
 // Ceres SphereManifold<3> tangent.
@@ -34,16 +36,22 @@ struct Window {
   double imu[37] = {0};      // T_bs 7, i_g 6, i_a 6, S_g 9, X_a 9
   int L = 0;
   std::vector<double> landmarks;  // L x 3
-  int Nv = 0;
-  std::vector<double> v_stamp, v_pixel;
+  // visual list: pixel factors [0, Np) followed by bearing factors [Np, Nv)
+  int Nv = 0, Np = 0;
+  std::vector<double> v_stamp, v_pixel, v_z;  // v_pixel: pixel, or bearing xy; v_z: bearing z
   std::vector<int> v_cam, v_lm;
+  // manifold (pose) factors
+  int Nm = 0, P = 0;
+  std::vector<double> m_stamp, m_meas, pose_sensors;  // m_meas Nm x 7, pose_sensors P x 7
+  std::vector<int> m_sensor, m_base;
   int Ni = 0;
   std::vector<double> i_stamp, i_meas;
   // index maps (bind)
   std::vector<int> v_base, i_base, i_bg_base, i_ba_base;
   std::vector<uint8_t> knot_const;
   int gravity_const = 0, bias_const = 0;
-  double huber_pixel = 0.5, imu_loss_scale = 1.6e-5;
+  double huber_pixel = 0.5, huber_bearing = 1.6e-3, imu_loss_scale = 1.6e-5;
+  double huber_of(int f) const { return f < Np ? huber_pixel : huber_bearing; }
   int quirks = 0;
   Basis basis, bias_basis;
   // solver state
@@ -83,6 +91,11 @@ inline int window_bind(Window* w) {
     w->i_ba_base[f] = segment_base(w->ba.data(), 4, 3, w->Kba, w->k_b, w->i_stamp[f]);
     if (w->i_base[f] < 0 || w->i_bg_base[f] < 0 || w->i_ba_base[f] < 0) ++bad;
   }
+  w->m_base.resize(w->Nm);
+  for (int f = 0; f < w->Nm; ++f) {
+    w->m_base[f] = segment_base(w->knots.data(), 8, 7, w->K, w->k, w->m_stamp[f]);
+    if (w->m_base[f] < 0 || w->m_sensor[f] < 0 || w->m_sensor[f] >= w->P) ++bad;
+  }
   if ((int)w->knot_const.size() != w->K) w->knot_const.assign(w->K, 0);
   return bad;
 }
@@ -97,8 +110,11 @@ inline void quat_dtheta(const double* q, double* P /*4x3*/) {
 // Reference-shaped Evaluate of pixel factor f + projection to the compact tangent layout.
 inline void window_eval_pixel(const Window& w, int f, bool want_J, double* r, double* Jp, double* Jl) {
   const int k = w.k;
-  Factor fac; fac.kind = kPixel; fac.stamp = w.v_stamp[f]; fac.k = k;
+  const bool bearing = f >= w.Np;
+  Factor fac; fac.kind = bearing ? kBearing : kPixel; fac.stamp = w.v_stamp[f]; fac.k = k;
   fac.measurement[0] = w.v_pixel[2 * f]; fac.measurement[1] = w.v_pixel[2 * f + 1];
+  if (bearing) fac.measurement[2] = w.v_z[f];
+  const int nr = bearing ? 1 : 2;
   Layout L; layout_update(fac, &L);
   const double* ptrs[kMaxBlocks];
   const int base = w.v_base[f];
@@ -106,6 +122,7 @@ inline void window_eval_pixel(const Window& w, int f, bool want_J, double* r, do
   const double* cam = &w.cams[15 * w.v_cam[f]];
   ptrs[k] = cam; ptrs[k + 1] = cam + 7; ptrs[k + 2] = cam + 11;
   ptrs[k + 3] = &w.landmarks[3 * w.v_lm[f]];
+  r[1] = 0.0;
   if (!want_J) { cost_evaluate(fac, L, w.basis, w.bias_basis, ptrs, r, nullptr, w.quirks); return; }
   double jbuf[2 * 8 * kMaxOrder + 6];
   double* jptrs[kMaxBlocks];
@@ -113,17 +130,69 @@ inline void window_eval_pixel(const Window& w, int f, bool want_J, double* r, do
   for (int m = 0; m < k; ++m) jptrs[m] = jbuf + 16 * m;
   jptrs[k + 3] = jbuf + 16 * k;
   cost_evaluate(fac, L, w.basis, w.bias_basis, ptrs, r, jptrs, w.quirks);
+  if (bearing) { for (int i = 0; i < 6 * k; ++i) Jp[6 * k + i] = 0.0; for (int i = 3; i < 6; ++i) Jl[i] = 0.0; }
   for (int m = 0; m < k; ++m) {
     double P[12];
     quat_dtheta(ptrs[m], P);
-    const double* Ja = jptrs[m];  // 2 x 8
-    for (int row = 0; row < 2; ++row) {
+    const double* Ja = jptrs[m];  // nr x 8
+    for (int row = 0; row < nr; ++row) {
       for (int c = 0; c < 3; ++c)
         Jp[row * 6 * k + 6 * m + c] = Ja[8 * row] * P[c] + Ja[8 * row + 1] * P[3 + c] + Ja[8 * row + 2] * P[6 + c] + Ja[8 * row + 3] * P[9 + c];
       for (int c = 0; c < 3; ++c) Jp[row * 6 * k + 6 * m + 3 + c] = Ja[8 * row + 4 + c];
     }
   }
-  for (int i = 0; i < 6; ++i) Jl[i] = jptrs[k + 3][i];
+  for (int i = 0; i < 3 * nr; ++i) Jl[i] = jptrs[k + 3][i];
+}
+
+// Manifold (pose) factor f: r[6], Jp[6][6k].
+inline void window_eval_manifold(const Window& w, int f, bool want_J, double* r, double* Jp) {
+  const int k = w.k;
+  Factor fac; fac.kind = kManifold; fac.stamp = w.m_stamp[f]; fac.k = k;
+  for (int i = 0; i < 7; ++i) fac.measurement[i] = w.m_meas[7 * f + i];
+  Layout L; layout_update(fac, &L);
+  const double* ptrs[kMaxBlocks];
+  const int base = w.m_base[f];
+  for (int m = 0; m < k; ++m) ptrs[m] = &w.knots[8 * (base + m)];
+  ptrs[k] = &w.pose_sensors[7 * w.m_sensor[f]];
+  if (!want_J) { cost_evaluate(fac, L, w.basis, w.bias_basis, ptrs, r, nullptr, w.quirks); return; }
+  double jbuf[6 * 8 * kMaxOrder];
+  double* jptrs[kMaxBlocks];
+  for (int b = 0; b < L.num_blocks; ++b) jptrs[b] = nullptr;
+  for (int m = 0; m < k; ++m) jptrs[m] = jbuf + 48 * m;
+  cost_evaluate(fac, L, w.basis, w.bias_basis, ptrs, r, jptrs, w.quirks);
+  for (int m = 0; m < k; ++m) {
+    double P[12];
+    quat_dtheta(ptrs[m], P);
+    const double* Ja = jptrs[m];  // 6 x 8
+    for (int row = 0; row < 6; ++row) {
+      for (int c = 0; c < 3; ++c)
+        Jp[row * 6 * k + 6 * m + c] = Ja[8 * row] * P[c] + Ja[8 * row + 1] * P[3 + c] + Ja[8 * row + 2] * P[6 + c] + Ja[8 * row + 3] * P[9 + c];
+      for (int c = 0; c < 3; ++c) Jp[row * 6 * k + 6 * m + 3 + c] = Ja[8 * row + 4 + c];
+    }
+  }
+}
+
+// J^T J / J^T r / cost of the manifold factors into a dense n x n (row-major) H and g.
+inline double window_accumulate_manifold(const Window& w, double* H, double* g, int n) {
+  const int nc = 6 * w.k;
+  double cost = 0;
+  for (int f = 0; f < w.Nm; ++f) {
+    double r[6], Jp[6 * 6 * kMaxOrder];
+    window_eval_manifold(w, f, true, r, Jp);
+    const int c0 = 6 * w.m_base[f];
+    for (int i = 0; i < 6; ++i) cost += 0.5 * r[i] * r[i];
+    for (int a = 0; a < nc; ++a) {
+      double ga = 0;
+      for (int q = 0; q < 6; ++q) ga += Jp[q * nc + a] * r[q];
+      g[c0 + a] += ga;
+      for (int b = 0; b < nc; ++b) {
+        double h = 0;
+        for (int q = 0; q < 6; ++q) h += Jp[q * nc + a] * Jp[q * nc + b];
+        H[(size_t)(c0 + a) * n + c0 + b] += h;
+      }
+    }
+  }
+  return cost;
 }
 
 inline void window_eval_inertial(const Window& w, int f, bool want_J, double* r, double* Jp, double* wg, double* wa, double* Jg) {
@@ -191,8 +260,13 @@ inline double window_cost(const Window& w) {
   for (int f = 0; f < w.Nv; ++f) {
     double r[2], rho;
     window_eval_pixel(w, f, false, r, nullptr, nullptr);
-    huber_weight(r[0] * r[0] + r[1] * r[1], w.huber_pixel, &rho);
+    huber_weight(r[0] * r[0] + r[1] * r[1], w.huber_of(f), &rho);
     cost += 0.5 * rho;
+  }
+  for (int f = 0; f < w.Nm; ++f) {
+    double r[6];
+    window_eval_manifold(w, f, false, r, nullptr);
+    for (int i = 0; i < 6; ++i) cost += 0.5 * r[i] * r[i];
   }
 #pragma omp parallel for reduction(+ : cost) schedule(static)
   for (int f = 0; f < w.Ni; ++f) {
@@ -281,7 +355,7 @@ inline void window_iterate(Window* w, IterationOutput* out, int apply) {
     o.lm = w->v_lm[f]; o.base = w->v_base[f];
     window_eval_pixel(*w, f, true, o.r, o.Jp, o.Jl);
     double rho;
-    const double wgt = huber_weight(o.r[0] * o.r[0] + o.r[1] * o.r[1], w->huber_pixel, &rho);
+    const double wgt = huber_weight(o.r[0] * o.r[0] + o.r[1] * o.r[1], w->huber_of(f), &rho);
     cost += 0.5 * rho;
     const double sw = std::sqrt(wgt);
     for (int i = 0; i < 2 * 6 * k; ++i) o.Jp[i] *= sw;
@@ -335,6 +409,7 @@ inline void window_iterate(Window* w, IterationOutput* out, int apply) {
       }
     }
   }
+  cost += window_accumulate_manifold(*w, H.data(), g.data(), n);
   out->cost = cost;
   // Constant dofs (reference optimizer.cpp:322-328 SetParameterBlockConstant; setGravityConstant).
   std::vector<uint8_t> fixed(n, 0);
@@ -454,7 +529,7 @@ inline void window_build_packed(const Window& w, std::vector<double>* packed) {
     o.lm = w.v_lm[f]; o.base = w.v_base[f];
     window_eval_pixel(w, f, true, o.r, o.Jp, o.Jl);
     double rho;
-    const double wgt = huber_weight(o.r[0] * o.r[0] + o.r[1] * o.r[1], w.huber_pixel, &rho);
+    const double wgt = huber_weight(o.r[0] * o.r[0] + o.r[1] * o.r[1], w.huber_of(f), &rho);
     *cost += 0.5 * rho;
     const double sw = std::sqrt(wgt);
     for (int i = 0; i < 2 * nc; ++i) o.Jp[i] *= sw;
@@ -499,6 +574,7 @@ inline void window_build_packed(const Window& w, std::vector<double>* packed) {
       }
     }
   }
+  *cost += window_accumulate_manifold(w, S, g, n);
   for (int a = 0; a < n; ++a) { diagH[a] = S[(size_t)a * n + a]; b[a] = -g[a]; }
   const double mu = 1.0 / w.radius;
   std::vector<std::vector<int>> lm_obs(L);

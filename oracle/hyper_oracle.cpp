@@ -31,8 +31,8 @@ Manifold make_block_manifold(int id, int size) {
 Factor make_factor(int kind, double stamp, const double* meas, int k, int k_bg, int k_ba) {
   Factor f;
   f.kind = kind; f.stamp = stamp; f.k = k; f.k_bg = k_bg; f.k_ba = k_ba;
-  const int nr = num_residuals(f);
-  for (int i = 0; i < nr; ++i) f.measurement[i] = meas[i];
+  const int nm = measurement_size(f);
+  for (int i = 0; i < nm; ++i) f.measurement[i] = meas[i];
   return f;
 }
 

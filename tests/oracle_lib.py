@@ -12,7 +12,8 @@ import numpy as np
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "libhyper_oracle.so")
 
-PIXEL, INERTIAL = 0, 1
+PIXEL, INERTIAL, BEARING, MANIFOLD = 0, 1, 2, 3
+NUM_RESIDUALS = {0: 2, 1: 6, 2: 1, 3: 6}
 M_STATE, M_SE3, M_EUCLIDEAN, M_CONSTANT, M_BIAS, M_SPHERE = range(6)
 QUIRKS_ALL = 15
 
@@ -82,7 +83,7 @@ def layout(kind, k=4, k_bg=4, k_ba=4):
 def cost_evaluate(kind, stamp, meas, params, k=4, k_bg=4, k_ba=4, jac=True, jac_mask=None, quirks=0):
     """Per-factor reference-shaped Evaluate.  Returns (residuals, [per-block row-major jacobians])."""
     L = layout(kind, k, k_bg, k_ba)
-    nr = 2 if kind == PIXEL else 6
+    nr = NUM_RESIDUALS[kind]
     params = np.ascontiguousarray(params, dtype=np.float64)
     assert params.size == L["num_parameters"]
     meas = np.ascontiguousarray(meas, dtype=np.float64)
@@ -154,6 +155,12 @@ class OracleWindow:
         L.ho_window_set_landmarks(self.h, w.landmarks.shape[0], _d(w.landmarks))
         L.ho_window_set_pixel_factors(self.h, w.v_stamp.size, _d(w.v_stamp), _i(w.v_cam), _i(w.v_lm), _d(w.v_pixel))
         L.ho_window_set_inertial_factors(self.h, w.i_stamp.size, _d(w.i_stamp), _d(w.i_meas))
+        if w.b_stamp.size:
+            L.ho_window_set_bearing_factors(self.h, w.b_stamp.size, _d(w.b_stamp), _i(w.b_cam), _i(w.b_lm), _d(w.b_bearing))
+            L.ho_window_set_bearing_loss(self.h, C.c_double(w.huber_bearing))
+        if w.m_stamp.size:
+            L.ho_window_set_pose_sensors(self.h, w.pose_sensors.shape[0], _d(w.pose_sensors))
+            L.ho_window_set_manifold_factors(self.h, w.m_stamp.size, _d(w.m_stamp), _i(w.m_sensor), _d(w.m_pose))
         kc = np.ascontiguousarray(w.knot_const, dtype=np.uint8)
         L.ho_window_set_constant(self.h, kc.ctypes.data_as(C.POINTER(C.c_ubyte)), int(w.gravity_const), int(w.bias_const))
         L.ho_window_set_options(self.h, C.c_double(w.huber_pixel), C.c_double(w.imu_loss_scale), quirks, C.c_double(radius))
@@ -178,7 +185,8 @@ class OracleWindow:
     def evaluate(self, want_J=True, nthreads=0, v_count=-1, i_count=-1, outputs=True):
         w = self.win
         k, kb = w.order, w.bias_order
-        nv, ni = w.v_stamp.size, w.i_stamp.size
+        np_, nb, nm = w.v_stamp.size, w.b_stamp.size, w.m_stamp.size
+        nv, ni = np_ + nb, w.i_stamp.size     # visual list = pixel factors followed by bearing factors
         if not outputs:
             lib().ho_window_evaluate(self.h, int(want_J), None, None, None, None, None, None, None, None, nthreads, v_count, i_count)
             return None
@@ -186,6 +194,13 @@ class OracleWindow:
                    i_Jp=np.zeros((ni, 6, 6 * k)), i_wg=np.zeros((ni, kb)), i_wa=np.zeros((ni, kb)), i_Jg=np.zeros((ni, 6, 2)))
         lib().ho_window_evaluate(self.h, int(want_J), _d(out["v_r"]), _d(out["v_Jp"]), _d(out["v_Jl"]), _d(out["i_r"]), _d(out["i_Jp"]),
                                  _d(out["i_wg"]), _d(out["i_wa"]), _d(out["i_Jg"]), nthreads, v_count, i_count)
+        if nb:
+            assert np.all(out["v_r"][np_:, 1] == 0) and np.all(out["v_Jp"][np_:, 1] == 0) and np.all(out["v_Jl"][np_:, 1] == 0)
+            out.update(b_r=out["v_r"][np_:, 0].copy(), b_Jp=out["v_Jp"][np_:, 0].copy(), b_Jl=out["v_Jl"][np_:, 0].copy())
+            out.update(v_r=out["v_r"][:np_], v_Jp=out["v_Jp"][:np_], v_Jl=out["v_Jl"][:np_])
+        if nm:
+            out.update(m_r=np.zeros((nm, 6)), m_Jp=np.zeros((nm, 6, 6 * k)))
+            lib().ho_window_evaluate_manifold(self.h, int(want_J), _d(out["m_r"]), _d(out["m_Jp"]))
         return out
 
     def cost(self):

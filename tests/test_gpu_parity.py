@@ -253,3 +253,128 @@ def test_interpolate_matches_oracle_state_evaluate(built):
             assert np.abs(vel[i] - ve).max() < 1e-9 * max(1.0, np.abs(ve).max())
             assert np.abs(acc[i] - ac).max() < 1e-8 * max(1.0, np.abs(ac).max())
         ctx.close()
+
+
+# ---- (f) rank 1: bearing + manifold (pose) factors --------------------------------------------------
+def widened_window(order, seed_off=0, **kw):
+    cfg = dict(order=order, num_knots=20, num_landmarks=120, num_imu=400, constant_knots=2)
+    cfg.update(kw)
+    base = synthetic.make_window(seed=synthetic.SEED_BASE + 300 + seed_off, **cfg)
+    return synthetic.add_bearing_and_pose_factors(base, num_bearing=150, num_pose=40, seed=synthetic.SEED_BASE + 310 + seed_off)
+
+
+@pytest.mark.parametrize("order", [4, 6])
+def test_bearing_and_manifold_evaluate_parity(built, order):
+    """VisualBearingEvaluator + AngularMetric and ManifoldEvaluator + ManifoldMetric (reference
+    evaluators/bearing.cpp:14-79, manifold.cpp:12-61) against the oracle, next to the pixel / inertial lists."""
+    win = widened_window(order)
+    ow = ol.OracleWindow(win)
+    assert ow.bad == 0
+    ref = ow.evaluate()
+    ctx = make_ctx(win)
+    ctx.evaluate(jacobians=True)
+    got = ctx.outputs()
+    for key in ("v_r", "i_r", "b_r", "m_r"):
+        assert rel_err(got[key], ref[key]) < R_TOL, key
+    for key in ("v_Jp", "v_Jl", "i_Jp", "i_wg", "i_wa", "i_Jg", "b_Jp", "b_Jl", "m_Jp"):
+        assert rel_err(got[key], ref[key]) < J_TOL, key
+    ctx.evaluate(jacobians=False)
+    assert abs(ctx.cost() - ow.cost()) <= 1e-10 * abs(ow.cost())
+    ctx.close()
+
+
+@pytest.mark.parametrize("force_dense", [False, True])
+@pytest.mark.parametrize("order", [4, 6])
+def test_bearing_and_manifold_system_parity(built, order, force_dense):
+    win = widened_window(order, seed_off=1)
+    ow = ol.OracleWindow(win)
+    o = ow.iterate(apply=False)
+    ctx = make_ctx(win, force_dense=force_dense)
+    ctx.evaluate()
+    ctx.build_system()
+    S, b = ctx.system()
+    assert rel_err(S, o["S"]) < 1e-9
+    assert rel_err(b, o["b"]) < 1e-9
+    ctx.solve()
+    dp, dl = ctx.delta()
+    res = np.abs(o["S"] @ dp - o["b"]).max() / (np.abs(o["b"]).max() + 1e-300)
+    assert res < 1e-7, res
+    assert rel_err(dp, o["delta_p"]) < 1e-5
+    assert rel_err(dl, o["delta_l"]) < 1e-5
+    ctx.close()
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_bearing_and_manifold_iterate_parity(built, use_graph):
+    win = widened_window(4, seed_off=2)
+    ow = ol.OracleWindow(win)
+    ctx = make_ctx(win, use_graph=use_graph)
+    recs = ctx.iterate(5)
+    for it, rec in enumerate(recs):
+        o = ow.iterate(apply=True)
+        assert rec["spd"] == 1 and o["spd"] == 1
+        assert abs(rec["cost"] - o["cost"]) <= 1e-7 * abs(o["cost"]), (it, rec, o["cost"])
+        assert abs(rec["cost_new"] - o["cost_new"]) <= 1e-6 * abs(o["cost_new"]), (it, rec, o["cost_new"])
+        assert rec["accepted"] == o["accepted"], (it, rec, o["rho"])
+    st, so = ctx.state(), ow.state()
+    for key in so:
+        assert rel_err(st[key], so[key]) < 1e-6, key
+    assert recs[-1]["cost"] < recs[0]["cost"]
+    ctx.close()
+
+
+def test_bearing_only_and_pose_only_windows(built):
+    """Windows holding a single factor family: bearing-only (no pixel factors at all) and pose-only
+    (no cameras, landmarks or IMU) bind, evaluate and solve."""
+    base = synthetic.make_window(order=4, num_knots=16, num_landmarks=60, num_imu=0, seed=synthetic.SEED_BASE + 320, constant_knots=2)
+    win = synthetic.add_bearing_and_pose_factors(base, num_bearing=base.v_stamp.size, num_pose=0)
+    assert win.v_stamp.size == 0 and win.b_stamp.size == base.v_stamp.size
+    ow = ol.OracleWindow(win)
+    ctx = make_ctx(win)
+    ctx.evaluate()
+    got, ref = ctx.outputs(), ow.evaluate()
+    assert rel_err(got["b_r"], ref["b_r"]) < R_TOL and rel_err(got["b_Jp"], ref["b_Jp"]) < J_TOL and rel_err(got["b_Jl"], ref["b_Jl"]) < J_TOL
+    rec, o = ctx.iterate(1)[0], ow.iterate()
+    assert abs(rec["cost"] - o["cost"]) <= 1e-8 * o["cost"] and abs(rec["cost_new"] - o["cost_new"]) <= 1e-6 * o["cost_new"]
+    ctx.close()
+    plain = synthetic.make_window(order=6, num_knots=16, num_landmarks=0, num_imu=0, seed=synthetic.SEED_BASE + 321)
+    win = synthetic.add_bearing_and_pose_factors(plain, num_bearing=0, num_pose=64)
+    ow = ol.OracleWindow(win)
+    ctx = make_ctx(win)
+    recs = ctx.iterate(3)
+    for rec in recs:
+        o = ow.iterate()
+        assert abs(rec["cost"] - o["cost"]) <= 1e-7 * o["cost"] and rec["accepted"] == o["accepted"]
+    assert recs[-1]["cost_new"] < 0.2 * recs[0]["cost"]
+    ctx.close()
+
+
+def test_bearing_and_manifold_factor_evaluate_ceres_shape(built):
+    """hb200_factor_evaluate for kinds BEARING / MANIFOLD == oracle ExteroceptiveCost::Evaluate after the
+    manifold projection (calibration blocks are constant in the live configuration: zero)."""
+    win = widened_window(4, seed_off=3)
+    ctx = make_ctx(win)
+    ctx.evaluate()
+    k = win.order
+    left = (k - 1) // 2
+    for f in (0, 17, win.b_stamp.size - 1):
+        base = int(np.searchsorted(win.knots[:, 7], win.b_stamp[f], side="right") - 1 - left)
+        cam = win.cameras[win.b_cam[f]]
+        blocks = [win.knots[base + m] for m in range(k)] + [cam[:7], cam[7:11], cam[11:15], win.landmarks[win.b_lm[f]]]
+        r, jac = ctx.factor_evaluate(runtime.BEARING, f, blocks)
+        r_o, jac_o = ol.cost_evaluate(ol.BEARING, win.b_stamp[f], win.b_bearing[f], np.concatenate(blocks), k=k)
+        assert r.shape == (1,) and abs(r[0] - r_o[0]) < 1e-12
+        for m in range(k):
+            PJ = ol.manifold_plus_jacobian(ol.M_STATE, blocks[m])
+            assert rel_err(jac[m] @ PJ, jac_o[m] @ PJ) < 1e-8
+        assert rel_err(jac[k + 3], jac_o[k + 3]) < 1e-8
+    for f in (0, 9, win.m_stamp.size - 1):
+        base = int(np.searchsorted(win.knots[:, 7], win.m_stamp[f], side="right") - 1 - left)
+        blocks = [win.knots[base + m] for m in range(k)] + [win.pose_sensors[win.m_sensor[f]]]
+        r, jac = ctx.factor_evaluate(runtime.MANIFOLD, f, blocks)
+        r_o, jac_o = ol.cost_evaluate(ol.MANIFOLD, win.m_stamp[f], win.m_pose[f], np.concatenate(blocks), k=k)
+        assert rel_err(r, r_o) < 1e-9
+        for m in range(k):
+            PJ = ol.manifold_plus_jacobian(ol.M_STATE, blocks[m])
+            assert rel_err(jac[m] @ PJ, jac_o[m] @ PJ) < 1e-8
+    ctx.close()

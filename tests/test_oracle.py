@@ -5,6 +5,7 @@ import glob
 import json
 import os
 
+import dataclasses
 import numpy as np
 import pytest
 
@@ -127,6 +128,74 @@ def test_inertial_gradients_reference_protocol(k, general):
         ok, res, per = ol.probe(ol.INERTIAL, stamp, rng.uniform(-1, 1, 6), params, ids, k=k)
         n_fail += not ok
     assert n_fail == 0, n_fail
+
+
+@pytest.mark.parametrize("k", [4, 6])
+def test_bearing_gradients_reference_protocol(k):
+    """BearingEvaluatorTests/Gradients (reference tests/internal/tests/optimizers/evaluators/bearing.cpp:47-98):
+    AngularMetric residual (1 row), blocks k x state | T_bs | intrinsics | distortion | landmark."""
+    rng = np.random.default_rng(300 + k)
+    ids = [ol.M_STATE] * k + [ol.M_SE3, ol.M_EUCLIDEAN, ol.M_EUCLIDEAN, ol.M_EUCLIDEAN]
+    n_fail = 0
+    for _ in range(200):
+        cps, stamp = random_state(rng, k)
+        T_bs = np.concatenate([unit_quat(rng), rng.uniform(-1, 1, 3)])
+        intr = np.array([367.215, 248.375, 458.654, 457.296])
+        dist = np.array([-0.28340811, 0.07395907, 1.76187114e-05, 0.00019359])
+        params = np.concatenate([cps.ravel(), T_bs, intr, dist, sphere_point(rng, 10.0)])
+        bearing = sphere_point(rng, 1.0)                                             # Mock<Bearing>::Random()
+        ok, res, per = ol.probe(ol.BEARING, stamp, bearing, params, ids, k=k, richardson=(k == 6))
+        n_fail += not ok
+        assert np.all(per[k + 1:k + 3] == 0)                                         # intrinsics / distortion: zero columns
+    assert n_fail == 0, n_fail
+
+
+@pytest.mark.parametrize("k", [4, 6])
+def test_manifold_gradients_reference_protocol(k):
+    """ManifoldEvaluatorTests/Gradients (reference tests/internal/tests/optimizers/evaluators/manifold.cpp:43-92):
+    ManifoldMetric<SE3> residual (6 rows), blocks k x state | T_bs of a plain Sensor."""
+    rng = np.random.default_rng(400 + k)
+    ids = [ol.M_STATE] * k + [ol.M_SE3]
+    n_fail = 0
+    for _ in range(200):
+        cps, stamp = random_state(rng, k)
+        T_bs = np.concatenate([unit_quat(rng), rng.uniform(-1, 1, 3)])
+        element = np.concatenate([unit_quat(rng), rng.uniform(-1, 1, 3)])             # Mock<SE3>::Random()
+        params = np.concatenate([cps.ravel(), T_bs])
+        ok, res, per = ol.probe(ol.MANIFOLD, stamp, element, params, ids, k=k, richardson=(k == 6))
+        n_fail += not ok
+    # rotation differences near pi put Log at its branch cut, where h = 1e-6 differences are noisy
+    assert n_fail <= 2, n_fail
+
+
+def test_bearing_and_manifold_metrics_closed_form():
+    """Angle between prediction and bearing is scale-free in both arguments and zero at alignment;
+    the manifold residual vanishes when the measurement equals the prediction and equals
+    [Log(dR) | dp] for a left perturbation of it."""
+    rng = np.random.default_rng(7)
+    k = 4
+    cps, stamp = random_state(rng, k)
+    T_bs = np.concatenate([unit_quat(rng), rng.uniform(-1, 1, 3)])
+    cam = np.concatenate([T_bs, [367.2, 248.4, 458.7, 457.3], [0, 0, 0, 0.0]])
+    lm = sphere_point(rng, 10.0)
+    params = np.concatenate([cps.ravel(), cam, lm])
+    # prediction through the pixel evaluator's intermediate: use a manifold factor to get T_ws
+    r0, _ = ol.cost_evaluate(ol.MANIFOLD, stamp, np.array([0, 0, 0, 1, 0, 0, 0.0]), np.concatenate([cps.ravel(), T_bs]), k=k, jac=False)
+    from hyperslam_b200 import synthetic as syn
+    R_ws = syn.so3_exp(r0[:3]); p_ws = r0[3:]
+    p_s = R_ws.T @ (lm - p_ws)
+    for scale in (0.1, 1.0, 25.0):
+        r, _ = ol.cost_evaluate(ol.BEARING, stamp, scale * p_s, params, k=k, jac=False)
+        assert abs(r[0]) < 1e-7
+    b = sphere_point(rng, 1.0)
+    r, _ = ol.cost_evaluate(ol.BEARING, stamp, b, params, k=k, jac=False)
+    expect = np.arccos(np.clip(p_s @ b / np.linalg.norm(p_s), -1, 1))
+    assert abs(r[0] - expect) < 1e-12
+    # manifold: measurement = Exp(-w) T_ws shifted by -dp  ->  residual [w | dp]
+    w = np.array([0.3, -0.2, 0.1]); dp = np.array([0.5, 0.25, -1.0])
+    meas = np.concatenate([syn.rot_to_quat(syn.so3_exp(-w) @ R_ws), p_ws - dp])
+    r, _ = ol.cost_evaluate(ol.MANIFOLD, stamp, meas, np.concatenate([cps.ravel(), T_bs]), k=k, jac=False)
+    assert np.allclose(r, np.concatenate([w, dp]), atol=1e-12)
 
 
 def test_reference_quirks_agree_on_reference_fixtures():
@@ -305,3 +374,47 @@ def test_sharded_normal_equations_are_additive():
         np.testing.assert_allclose(S, ref["S"], atol=1e-12 * np.abs(ref["S"]).max())
         np.testing.assert_allclose(b, ref["b"], atol=1e-11 * np.abs(ref["b"]).max())
         assert abs(total[-2] - ref["cost"]) < 1e-12 * ref["cost"]
+
+
+def test_window_with_bearing_and_pose_factors():
+    """The widened window (bearing + pose factors next to pixel + inertial): the assembled gradient matches
+    central differences of the window cost through the retraction, LM descends, and the sharded normal
+    equations stay additive."""
+    from hyperslam_b200 import synthetic as syn
+    base = syn.make_config(1, scale=0.04)
+    win = syn.add_bearing_and_pose_factors(base, num_bearing=60, num_pose=24)
+    assert win.b_stamp.size == 60 and win.m_stamp.size == 24 and win.v_stamp.size == base.v_stamp.size - 60
+    ow = ol.OracleWindow(win)
+    assert ow.bad == 0
+    out = ow.evaluate()
+    assert out["b_r"].shape == (60,) and out["m_r"].shape == (24, 6)
+    assert np.abs(out["b_r"]).max() < 0.1 and np.abs(out["m_r"]).max() < 0.2
+    n = ow.n
+    packed = ow.build_packed()
+    g = packed[n * n + 2 * n: n * n + 3 * n]
+    assert abs(packed[n * n + 3 * n] - ow.cost()) < 1e-9 * max(1.0, ow.cost())
+    # gradient of the cost w.r.t. a few pose dofs (theta: R <- Exp(theta) R; rho additive).  The landmark
+    # blocks are eliminated, but g is the un-reduced pose gradient, so plain differences apply.
+    h = 1e-6
+    for j, a in [(3, 0), (10, 2), (20, 4), (31, 5), (40, 1)]:
+        vals = []
+        for sgn in (+1, -1):
+            kn = win.knots.copy()
+            if a < 3:
+                d = np.zeros(3); d[a] = sgn * h
+                kn[j, :4] = syn.rot_to_quat(syn.so3_exp(d) @ syn.quat_to_rot(kn[j, :4]))
+                if np.dot(kn[j, :4], win.knots[j, :4]) < 0:
+                    kn[j, :4] *= -1
+            else:
+                kn[j, 4 + a - 3] += sgn * h
+            vals.append(ol.OracleWindow(dataclasses.replace(win, knots=kn)).cost())
+        num = (vals[0] - vals[1]) / (2 * h)
+        assert abs(num - g[6 * j + a]) < 1e-5 * max(1.0, abs(num)), (j, a, num, g[6 * j + a])
+    # sharded form is additive
+    total = sum(ol.OracleWindow(win.shard(r, 2)).build_packed() for r in range(2))
+    assert np.allclose(total, packed, rtol=1e-9, atol=1e-9 * np.abs(packed).max())
+    costs = []
+    for _ in range(6):
+        it = ow.iterate()
+        costs.append((it["cost"], it["cost_new"], it["accepted"]))
+    assert costs[0][2] == 1 and costs[-1][1] < 0.5 * costs[0][0], costs
