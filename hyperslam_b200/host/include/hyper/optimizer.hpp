@@ -18,6 +18,10 @@ struct Landmark { Position variable; };
 
 struct VisualPixelObservation { Stamp stamp; const Camera* camera; Landmark* landmark; Pixel measurement; };
 struct InertialObservation { Stamp stamp; const IMU* imu; Gravity* gravity; Tangent6 measurement; };
+// Bearing = direction of the landmark in the sensor frame (reference optimizers/evaluators/bearing.cpp:14-79).
+struct VisualBearingObservation { Stamp stamp; const Camera* camera; Landmark* landmark; Position measurement; };
+// ManifoldObservation<SE3>: a measured T_ws of a plain Sensor (reference optimizers/evaluators/manifold.cpp:12-61).
+struct ManifoldObservation { Stamp stamp; const Sensor* sensor; SE3 measurement; };
 
 // Evaluator layout of one cost (reference include/hyper/optimizers/evaluators/forward.hpp:19-39).
 struct EvaluatorLayout {
@@ -44,7 +48,7 @@ class Optimizer;
 // (reference internal/hyper/optimizers/ceres/costs/exteroceptive.cpp:101-160).
 class ExteroceptiveCost final : public CostFunction {
  public:
-  enum Kind { kPixel = 0, kInertial = 1 };
+  enum Kind { kPixel = 0, kInertial = 1, kBearing = 2, kManifold = 3 };
   // Collects the parameter-block pointers in reference order and fills the layout (exteroceptive.cpp:25-99).
   Pointers<Scalar> update();
   bool Evaluate(const double* const* parameters, double* residuals, double** jacobians) const override;
@@ -75,6 +79,8 @@ class Optimizer {   // OptimizerSuite::B200
   void addLandmark(Landmark& landmark) { landmarks_.push_back(&landmark); dirty_ = true; }       // reference optimizer.cpp:347-358
   ExteroceptiveCost* add(VisualPixelObservation& observation);                                   // reference optimizer.cpp:212-232
   ExteroceptiveCost* add(InertialObservation& observation);                                      // reference optimizer.cpp:253-274
+  ExteroceptiveCost* add(VisualBearingObservation& observation);                                 // reference optimizer.cpp:189-210
+  ExteroceptiveCost* add(ManifoldObservation& observation);                                      // reference optimizer.cpp:234-251
   void setStateConstant(const std::vector<bool>& constant) { constant_ = constant; dirty_ = true; }
   void setGravityConstant(bool constant) { gravity_constant_ = constant; dirty_ = true; }          // reference abstract.cpp:57-61
 
@@ -102,6 +108,9 @@ class Optimizer {   // OptimizerSuite::B200
   std::vector<Landmark*> landmarks_;
   std::vector<VisualPixelObservation*> pixel_obs_;
   std::vector<InertialObservation*> inertial_obs_;
+  std::vector<VisualBearingObservation*> bearing_obs_;
+  std::vector<ManifoldObservation*> manifold_obs_;
+  std::vector<const Sensor*> pose_sensors_;   // distinct sensors of the manifold observations, in order of first use
   std::vector<std::unique_ptr<ExteroceptiveCost>> costs_;
   std::vector<bool> constant_;
   bool gravity_constant_ = false;

@@ -226,6 +226,20 @@ ExteroceptiveCost* Optimizer::add(InertialObservation& obs) {
   return costs_.back().get();
 }
 
+ExteroceptiveCost* Optimizer::add(VisualBearingObservation& obs) {
+  bearing_obs_.push_back(&obs);
+  costs_.emplace_back(new ExteroceptiveCost(this, ExteroceptiveCost::kBearing, static_cast<Index>(bearing_obs_.size() - 1)));
+  dirty_ = true;
+  return costs_.back().get();
+}
+ExteroceptiveCost* Optimizer::add(ManifoldObservation& obs) {
+  manifold_obs_.push_back(&obs);
+  if (std::find(pose_sensors_.begin(), pose_sensors_.end(), obs.sensor) == pose_sensors_.end()) pose_sensors_.push_back(obs.sensor);
+  costs_.emplace_back(new ExteroceptiveCost(this, ExteroceptiveCost::kManifold, static_cast<Index>(manifold_obs_.size() - 1)));
+  dirty_ = true;
+  return costs_.back().get();
+}
+
 void Optimizer::upload(bool factors) {
   if (!state_) throw std::logic_error("Optimizer: state not set");
   const auto& el = state_->elements();
@@ -256,6 +270,11 @@ void Optimizer::upload(bool factors) {
   lms_.resize(3 * landmarks_.size());
   for (size_t l = 0; l < landmarks_.size(); ++l) std::copy(landmarks_[l]->variable.v.begin(), landmarks_[l]->variable.v.end(), lms_.begin() + 3 * l);
   check(hb200_set_landmarks(ctx_, static_cast<int>(landmarks_.size()), lms_.data()), "hb200_set_landmarks");
+  if (!pose_sensors_.empty()) {
+    std::vector<double> T(7 * pose_sensors_.size());
+    for (size_t i = 0; i < pose_sensors_.size(); ++i) std::copy(pose_sensors_[i]->transformation().v.begin(), pose_sensors_[i]->transformation().v.end(), T.begin() + 7 * i);
+    check(hb200_set_pose_sensors(ctx_, static_cast<int>(pose_sensors_.size()), T.data()), "hb200_set_pose_sensors");
+  }
   if (factors) {
     std::vector<double> vs, vp, is, im;
     std::vector<int> vc, vl;
@@ -263,6 +282,16 @@ void Optimizer::upload(bool factors) {
     for (auto* o : inertial_obs_) { is.push_back(o->stamp); for (int i = 0; i < 6; ++i) im.push_back(o->measurement[i]); }
     check(hb200_set_pixel_factors(ctx_, static_cast<int>(vs.size()), vs.data(), vc.data(), vl.data(), vp.data()), "hb200_set_pixel_factors");
     check(hb200_set_inertial_factors(ctx_, static_cast<int>(is.size()), is.data(), im.data()), "hb200_set_inertial_factors");
+    std::vector<double> bs, bm, ms, mm;
+    std::vector<int> bc, bl, msens;
+    for (auto* o : bearing_obs_) { bs.push_back(o->stamp); bc.push_back(cameraIndex(o->camera)); bl.push_back(landmarkIndex(o->landmark)); for (int i = 0; i < 3; ++i) bm.push_back(o->measurement[i]); }
+    for (auto* o : manifold_obs_) {
+      ms.push_back(o->stamp);
+      msens.push_back(static_cast<int>(std::find(pose_sensors_.begin(), pose_sensors_.end(), o->sensor) - pose_sensors_.begin()));
+      for (int i = 0; i < 7; ++i) mm.push_back(o->measurement.v[i]);
+    }
+    check(hb200_set_bearing_factors(ctx_, static_cast<int>(bs.size()), bs.data(), bc.data(), bl.data(), bm.data()), "hb200_set_bearing_factors");
+    check(hb200_set_manifold_factors(ctx_, static_cast<int>(ms.size()), ms.data(), msens.data(), mm.data()), "hb200_set_manifold_factors");
     int bad = 0;
     check(hb200_bind(ctx_, &bad), "hb200_bind");                       // == cost->update() for every cost
     std::vector<unsigned char> kc(K, 0);
@@ -308,21 +337,29 @@ Pointers<Scalar> ExteroceptiveCost::update() {
   Optimizer& o = *optimizer_;
   Pointers<Scalar> p;
   layout_ = EvaluatorLayout{};
-  const Stamp stamp = (kind_ == kPixel) ? o.pixel_obs_[index_]->stamp : o.inertial_obs_[index_]->stamp;
+  const Stamp stamp = (kind_ == kPixel) ? o.pixel_obs_[index_]->stamp : (kind_ == kInertial) ? o.inertial_obs_[index_]->stamp
+                    : (kind_ == kBearing) ? o.bearing_obs_[index_]->stamp : o.manifold_obs_[index_]->stamp;
   auto state_blocks = o.state_->parameters(stamp);
   if (state_blocks.empty()) throw std::out_of_range("ExteroceptiveCost::update: stamp outside the state's range");
   for (auto* b : state_blocks) { p.push_back(b); layout_.sizes.push_back(8); }
   layout_.indices.static_state_idx = 0;
   layout_.indices.static_sensor_idx = static_cast<Index>(p.size());
-  if (kind_ == kPixel) {
-    auto* obs = o.pixel_obs_[index_];
-    auto v = const_cast<Camera*>(obs->camera)->variables();
+  if (kind_ == kPixel || kind_ == kBearing) {
+    const Camera* camera = (kind_ == kPixel) ? o.pixel_obs_[index_]->camera : o.bearing_obs_[index_]->camera;
+    Landmark* landmark = (kind_ == kPixel) ? o.pixel_obs_[index_]->landmark : o.bearing_obs_[index_]->landmark;
+    auto v = const_cast<Camera*>(camera)->variables();
     const int sizes[3] = {7, 4, 4};
     for (int b = 0; b < 3; ++b) { p.push_back(v[b]); layout_.sizes.push_back(sizes[b]); }
     layout_.indices.dynamic_sensor_idx = static_cast<Index>(p.size());
     layout_.indices.static_observation_idx = static_cast<Index>(p.size());
-    p.push_back(obs->landmark->variable.data()); layout_.sizes.push_back(3);
-    num_residuals_ = 2;
+    p.push_back(landmark->variable.data()); layout_.sizes.push_back(3);
+    num_residuals_ = (kind_ == kPixel) ? 2 : 1;   // CartesianMetric<Pixel> / AngularMetric<Bearing>
+  } else if (kind_ == kManifold) {
+    auto* obs = o.manifold_obs_[index_];
+    p.push_back(const_cast<Sensor*>(obs->sensor)->transformation().data()); layout_.sizes.push_back(7);
+    layout_.indices.dynamic_sensor_idx = static_cast<Index>(p.size());
+    layout_.indices.static_observation_idx = static_cast<Index>(p.size());   // no observation variables
+    num_residuals_ = 6;                           // ManifoldMetric<SE3>
   } else {
     auto* obs = o.inertial_obs_[index_];
     IMU* imu = const_cast<IMU*>(obs->imu);

@@ -21,8 +21,8 @@ int main(int argc, char** argv) {
   if (argc < 3) { std::fprintf(stderr, "usage: host_test <window.txt> <out.txt>\n"); return 2; }
   std::ifstream in(argv[1]);
   if (!in) { std::fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
-  int order, K, Kb, C, L, Nv, Ni, nconst;
-  in >> order >> K >> Kb >> C >> L >> Nv >> Ni >> nconst;
+  int order, K, Kb, C, L, Nv, Ni, nconst, Nb, Nm, P;
+  in >> order >> K >> Kb >> C >> L >> Nv >> Ni >> nconst >> Nb >> Nm >> P;
   ContinuousState state(std::make_unique<BasisInterpolator>(order - 1, true));
   for (int j = 0; j < K; ++j) { ContinuousState::Element e; for (int i = 0; i < 8; ++i) in >> e.v[i]; state.elements().push_back(e); }
   IMU imu;
@@ -43,6 +43,13 @@ int main(int argc, char** argv) {
   for (int f = 0; f < Nv; ++f) { int c, l; in >> vobs[f].stamp >> c >> l >> vobs[f].measurement[0] >> vobs[f].measurement[1]; if (!in || c < 0 || c >= C || l < 0 || l >= L) { std::fprintf(stderr, "malformed pixel factor %d\n", f); return 2; } vobs[f].camera = cams[c].get(); vobs[f].landmark = &lms[l]; }
   std::vector<InertialObservation> iobs(Ni);
   for (int f = 0; f < Ni; ++f) { in >> iobs[f].stamp; for (int i = 0; i < 6; ++i) in >> iobs[f].measurement[i]; iobs[f].imu = &imu; iobs[f].gravity = &gravity; }
+  std::vector<VisualBearingObservation> bobs(Nb);
+  for (int f = 0; f < Nb; ++f) { int c, l; in >> bobs[f].stamp >> c >> l; for (int i = 0; i < 3; ++i) in >> bobs[f].measurement[i]; bobs[f].camera = cams[c].get(); bobs[f].landmark = &lms[l]; }
+  std::vector<Sensor> pose_sensors(P);
+  for (int p = 0; p < P; ++p) for (int i = 0; i < 7; ++i) in >> pose_sensors[p].transformation().v[i];
+  std::vector<ManifoldObservation> mobs(Nm);
+  for (int f = 0; f < Nm; ++f) { int sidx; in >> mobs[f].stamp >> sidx; for (int i = 0; i < 7; ++i) in >> mobs[f].measurement.v[i]; mobs[f].sensor = &pose_sensors[sidx]; }
+  if (!in) { std::fprintf(stderr, "window file is truncated\n"); return 2; }
 
   if (!in) { std::fprintf(stderr, "malformed window file\n"); return 2; }
   Optimizer optimizer(0);
@@ -52,9 +59,11 @@ int main(int argc, char** argv) {
   optimizer.setIMU(&imu);
   optimizer.setGravity(&gravity);
   for (auto& l : lms) optimizer.addLandmark(l);
-  std::vector<ExteroceptiveCost*> vcosts, icosts;
+  std::vector<ExteroceptiveCost*> vcosts, icosts, bcosts, mcosts;
   for (auto& o : vobs) vcosts.push_back(optimizer.add(o));
   for (auto& o : iobs) icosts.push_back(optimizer.add(o));
+  for (auto& o : bobs) bcosts.push_back(optimizer.add(o));
+  for (auto& o : mobs) mcosts.push_back(optimizer.add(o));
   std::vector<bool> constant(K, false); for (int j = 0; j < nconst; ++j) constant[j] = true;
   optimizer.setStateConstant(constant);
 
@@ -109,6 +118,8 @@ int main(int argc, char** argv) {
   const int k = order;
   if (Nv) for (int f : {0, Nv / 2}) { std::vector<std::pair<int, const Manifold*>> blk; for (int m = 1; m + 1 < k; ++m) blk.push_back({m, &state_manifold}); blk.push_back({k + 3, &landmark_manifold}); probe(vcosts[f], blk); }
   if (Ni) for (int f : {Ni / 3}) { std::vector<std::pair<int, const Manifold*>> blk; for (int m = 1; m + 1 < k; ++m) blk.push_back({m, &state_manifold}); blk.push_back({k + 5 + 1, &bias_manifold}); blk.push_back({k + 5 + 4 + 2, &bias_manifold}); blk.push_back({k + 13, &gravity_manifold}); probe(icosts[f], blk); }
+  if (Nb) for (int f : {0, Nb - 1}) { std::vector<std::pair<int, const Manifold*>> blk; for (int m = 1; m + 1 < k; ++m) blk.push_back({m, &state_manifold}); blk.push_back({k + 3, &landmark_manifold}); probe(bcosts[f], blk); }
+  if (Nm) for (int f : {0, Nm - 1}) { std::vector<std::pair<int, const Manifold*>> blk; for (int m = 1; m + 1 < k; ++m) blk.push_back({m, &state_manifold}); probe(mcosts[f], blk); }
   out << "probe " << probe_blocks << " " << probe_failures << "\n";
 
   // ---- (2) copy-out of a few costs + state interpolation + optimize ----
@@ -131,6 +142,8 @@ int main(int argc, char** argv) {
   };
   if (Nv) { dump_cost(vcosts[0]); dump_cost(vcosts[Nv - 1]); }
   if (Ni) { dump_cost(icosts[0]); dump_cost(icosts[Ni - 1]); }
+  if (Nb) { dump_cost(bcosts[0]); dump_cost(bcosts[Nb - 1]); }
+  if (Nm) { dump_cost(mcosts[0]); dump_cost(mcosts[Nm - 1]); }
   const auto range = state.range();
   std::vector<Stamp> ts; for (int i = 0; i < 5; ++i) ts.push_back(range.lower + (range.upper - range.lower) * (i + 0.5) / 5.0);
   auto sr = state.evaluate(optimizer.context(), ts, 2);

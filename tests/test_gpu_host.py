@@ -18,19 +18,26 @@ def dump_window(win, path, nconst):
     with open(path, "w") as f:
         w = lambda a: f.write(" ".join(repr(float(x)) for x in np.asarray(a).ravel()) + "\n")
         f.write(f"{win.order} {win.knots.shape[0]} {win.gyro_bias.shape[0]} {win.cameras.shape[0]} {win.landmarks.shape[0]} "
-                f"{win.v_stamp.size} {win.i_stamp.size} {nconst}\n")
+                f"{win.v_stamp.size} {win.i_stamp.size} {nconst} {win.b_stamp.size} {win.m_stamp.size} {win.pose_sensors.shape[0]}\n")
         w(win.knots); w(win.gyro_bias); w(win.accel_bias); w(win.gravity); w(win.cameras); w(win.imu); w(win.landmarks)
         for i in range(win.v_stamp.size):
             f.write(f"{float(win.v_stamp[i])!r} {int(win.v_cam[i])} {int(win.v_lm[i])} {float(win.v_pixel[i, 0])!r} {float(win.v_pixel[i, 1])!r}\n")
         for i in range(win.i_stamp.size):
             f.write(f"{float(win.i_stamp[i])!r} " + " ".join(repr(float(x)) for x in win.i_meas[i]) + "\n")
+        for i in range(win.b_stamp.size):
+            f.write(f"{float(win.b_stamp[i])!r} {int(win.b_cam[i])} {int(win.b_lm[i])} " + " ".join(repr(float(x)) for x in win.b_bearing[i]) + "\n")
+        w(win.pose_sensors) if win.pose_sensors.size else None
+        for i in range(win.m_stamp.size):
+            f.write(f"{float(win.m_stamp[i])!r} {int(win.m_sensor[i])} " + " ".join(repr(float(x)) for x in win.m_pose[i]) + "\n")
 
 
-@pytest.mark.parametrize("order", [4, 6])
-def test_cpp_plugin_surface(built, tmp_path, order):
+@pytest.mark.parametrize("order,widened", [(4, False), (6, False), (4, True), (6, True)])
+def test_cpp_plugin_surface(built, tmp_path, order, widened):
     exe = os.path.join(ROOT, "hyperslam_b200", "lib", "host_test")
     assert os.path.exists(exe), "host_test not built (python -c 'import __graft_entry__ as g; g.build()')"
     win = synthetic.make_window(order=order, num_knots=14, num_landmarks=30, num_imu=40, seed=synthetic.SEED_BASE + 500 + order, constant_knots=2)
+    if widened:   # + VisualBearingObservation / ManifoldObservation costs (reference optimizer.cpp:189-251)
+        win = synthetic.add_bearing_and_pose_factors(win, num_bearing=40, num_pose=12, seed=synthetic.SEED_BASE + 520 + order)
     src, dst = tmp_path / "window.txt", tmp_path / "out.txt"
     dump_window(win, src, 2)
     res = subprocess.run([exe, str(src), str(dst)], capture_output=True, text=True, timeout=300)
@@ -38,7 +45,7 @@ def test_cpp_plugin_surface(built, tmp_path, order):
     lines = open(dst).read().split("\n")
     it = iter(lines)
     head = next(it).split()
-    assert head[0] == "probe" and int(head[1]) >= 8 and int(head[2]) == 0          # reference Probe protocol passes
+    assert head[0] == "probe" and int(head[1]) >= (14 if widened else 8) and int(head[2]) == 0          # reference Probe protocol passes
     ow = ol.OracleWindow(win)
     vb, ib, ig, ia = ow.index_maps()
     k, kb = win.order, win.bias_order
@@ -56,6 +63,19 @@ def test_cpp_plugin_surface(built, tmp_path, order):
             r_o, J_o = ol.cost_evaluate(ol.PIXEL, win.v_stamp[index], win.v_pixel[index], np.concatenate(blocks), k=k)
             assert sizes == [8] * k + [7, 4, 4, 3] and int(npar) == 8 * k + 18
             var = list(range(k)) + [k + 3]
+        elif kind == 2:
+            base = int(np.searchsorted(win.knots[:, 7], win.b_stamp[index], side="right") - 1 - (k - 1) // 2)
+            cam = win.cameras[win.b_cam[index]]
+            blocks = [win.knots[base + m] for m in range(k)] + [cam[:7], cam[7:11], cam[11:15], win.landmarks[win.b_lm[index]]]
+            r_o, J_o = ol.cost_evaluate(ol.BEARING, win.b_stamp[index], win.b_bearing[index], np.concatenate(blocks), k=k)
+            assert nr == 1 and sizes == [8] * k + [7, 4, 4, 3]
+            var = list(range(k)) + [k + 3]
+        elif kind == 3:
+            base = int(np.searchsorted(win.knots[:, 7], win.m_stamp[index], side="right") - 1 - (k - 1) // 2)
+            blocks = [win.knots[base + m] for m in range(k)] + [win.pose_sensors[win.m_sensor[index]]]
+            r_o, J_o = ol.cost_evaluate(ol.MANIFOLD, win.m_stamp[index], win.m_pose[index], np.concatenate(blocks), k=k)
+            assert nr == 6 and sizes == [8] * k + [7]
+            var = list(range(k))
         else:
             imu = win.imu
             blocks = ([win.knots[ib[index] + m] for m in range(k)] + [imu[:7], imu[7:13], imu[13:19], imu[19:28], imu[28:37]]
@@ -72,7 +92,7 @@ def test_cpp_plugin_surface(built, tmp_path, order):
             assert np.abs(a - o).max() < 1e-8 * scale, (kind, index, b)
         n_costs += 1
         line = next(it)
-    assert n_costs == 4
+    assert n_costs == (8 if widened else 4)
     assert line.startswith("interp")
     left = (k - 1) // 2
     for _ in range(int(line.split()[1])):
