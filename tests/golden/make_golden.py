@@ -135,6 +135,35 @@ def pixel_residual(st, f):
     return [fx * dx + cx - f["pixel"][0], fy * dy + cy - f["pixel"][1]]
 
 
+def bearing_residual(st, f):
+    """AngularMetric<Bearing>: angle between p_s (reference bearing.cpp:58-60) and the measured direction."""
+    R, p = pose(st["knots"], st["k"], f["stamp"])
+    cam = st["cams"][f["cam"]]
+    R_bs = quat_to_rot(cam[:4]); t_bs = mp.matrix(cam[4:7])
+    p_s = R_bs.T * (R.T * (mp.matrix(st["landmarks"][f["lm"]]) - p) - t_bs)
+    b = mp.matrix(f["bearing"])
+    cr = mp.matrix([p_s[1] * b[2] - p_s[2] * b[1], p_s[2] * b[0] - p_s[0] * b[2], p_s[0] * b[1] - p_s[1] * b[0]])
+    return [mp.atan2(mp.sqrt(cr[0] ** 2 + cr[1] ** 2 + cr[2] ** 2), p_s[0] * b[0] + p_s[1] * b[1] + p_s[2] * b[2])]
+
+
+def rot_log(R):
+    c = (R[0, 0] + R[1, 1] + R[2, 2] - 1) / 2
+    t = mp.acos(c)
+    v = vee(R - R.T)         # vee() averages the two off-diagonal entries: vee(R - R^T) = 2 sin(t) axis
+    return v * (t / (2 * mp.sin(t))) if t != 0 else mp.matrix([0, 0, 0])
+
+
+def pose_residual(st, f):
+    """ManifoldMetric<SE3> of T_ws = T_wb (+) T_bs (reference manifold.cpp:38) against the measured pose."""
+    R, p = pose(st["knots"], st["k"], f["stamp"])
+    T_bs = st["pose_sensors"][f["sensor"]]
+    R_ws = R * quat_to_rot(T_bs[:4])
+    p_ws = p + R * mp.matrix(T_bs[4:7])
+    th = rot_log(R_ws * quat_to_rot(f["pose"][:4]).T)
+    d = p_ws - mp.matrix(f["pose"][4:7])
+    return [th[0], th[1], th[2], d[0], d[1], d[2]]
+
+
 def imu_matrix(c):
     return mp.matrix([[c[0], 0, 0], [c[3], c[1], 0], [c[4], c[5], c[2]]])
 
@@ -268,8 +297,49 @@ def make_case(name, n_pix=3, n_imu=3, **kw):
     print("wrote", out)
 
 
+def make_widened_case(name, n_bearing=3, n_pose=3, **kw):
+    """Bearing + pose factors (the two other residual families of reference optimizer.cpp:189-251)."""
+    w = synthetic.add_bearing_and_pose_factors(synthetic.make_window(**kw), num_bearing=8, num_pose=8, seed=kw["seed"] + 50)
+    st = to_mp_state(w)
+    st["pose_sensors"] = [[mp.mpf(float(x)) for x in row] for row in w.pose_sensors]
+    k = w.order
+    stamps = [kn[7] for kn in st["knots"]]
+    case = dict(name=name, window=dict(order=k, bias_order=w.bias_order, knots=w.knots.tolist(), gyro_bias=w.gyro_bias.tolist(), accel_bias=w.accel_bias.tolist(),
+                                       gravity=w.gravity.tolist(), cameras=w.cameras.tolist(), imu=w.imu.tolist(), landmarks=w.landmarks.tolist(),
+                                       pose_sensors=w.pose_sensors.tolist()),
+                pixel=[], inertial=[], bearing=[], pose=[], digits=mp.mp.dps)
+    fl = lambda v: [float(x) for x in v]
+    for f_ in range(n_bearing):
+        f = dict(stamp=mp.mpf(float(w.b_stamp[f_])), cam=int(w.b_cam[f_]), lm=int(w.b_lm[f_]), bearing=[mp.mpf(float(x)) for x in w.b_bearing[f_]])
+        base, _ = segment(stamps, k, f["stamp"])
+        r = bearing_residual(st, f)
+        Jp = [numdiff(bearing_residual, st, f, "knot", base + m, c) for m in range(k) for c in range(6)]
+        Jl = [numdiff(bearing_residual, st, f, "landmark", f["lm"], c) for c in range(3)]
+        case["bearing"].append(dict(stamp=float(w.b_stamp[f_]), cam=f["cam"], lm=f["lm"], bearing=w.b_bearing[f_].tolist(), base=base, r=fl(r),
+                                    Jp=[float(Jp[c][0]) for c in range(6 * k)], Jl=[float(Jl[c][0]) for c in range(3)]))
+        print(name, "bearing", f_, fl(r))
+    for f_ in range(n_pose):
+        f = dict(stamp=mp.mpf(float(w.m_stamp[f_])), sensor=int(w.m_sensor[f_]), pose=[mp.mpf(float(x)) for x in w.m_pose[f_]])
+        base, _ = segment(stamps, k, f["stamp"])
+        r = pose_residual(st, f)
+        Jp = [numdiff(pose_residual, st, f, "knot", base + m, c) for m in range(k) for c in range(6)]
+        case["pose"].append(dict(stamp=float(w.m_stamp[f_]), sensor=f["sensor"], pose=w.m_pose[f_].tolist(), base=base, r=fl(r),
+                                 Jp=[[float(Jp[c][row]) for c in range(6 * k)] for row in range(6)]))
+        print(name, "pose", f_, fl(r)[:3])
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), f"{name}.json")
+    with open(out, "w") as fh:
+        json.dump(case, fh)
+    print("wrote", out)
+
+
 if __name__ == "__main__":
+    if "--widened-only" in sys.argv:
+        make_widened_case("k4_bearing_pose", order=4, num_knots=10, num_landmarks=12, num_imu=0, seed=synthetic.SEED_BASE + 905)
+        make_widened_case("k6_bearing_pose", order=6, num_knots=12, num_landmarks=12, num_imu=0, seed=synthetic.SEED_BASE + 906, n_bearing=2, n_pose=2)
+        sys.exit(0)
     make_case("k4_euroc", order=4, num_knots=10, num_landmarks=12, num_imu=20, seed=synthetic.SEED_BASE + 901)
     make_case("k6_euroc", order=6, num_knots=12, num_landmarks=12, num_imu=20, seed=synthetic.SEED_BASE + 902)
     make_case("k4_generic_calibration", order=4, num_knots=10, num_landmarks=12, num_imu=20, generic_calibration=True, seed=synthetic.SEED_BASE + 903)
     make_case("k6_generic_calibration", order=6, num_knots=12, num_landmarks=12, num_imu=20, generic_calibration=True, seed=synthetic.SEED_BASE + 904, n_pix=2, n_imu=2)
+    make_widened_case("k4_bearing_pose", order=4, num_knots=10, num_landmarks=12, num_imu=0, seed=synthetic.SEED_BASE + 905)
+    make_widened_case("k6_bearing_pose", order=6, num_knots=12, num_landmarks=12, num_imu=0, seed=synthetic.SEED_BASE + 906, n_bearing=2, n_pose=2)

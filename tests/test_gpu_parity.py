@@ -225,7 +225,7 @@ def test_gpu_matches_mpmath_golden(built):
     import os
     from test_oracle import check_against_golden, window_from_golden
     paths = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.json")))
-    assert len(paths) >= 4
+    assert len(paths) >= 6
     for path in paths:
         with open(path) as f:
             case = json.load(f)

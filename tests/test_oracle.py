@@ -17,7 +17,7 @@ GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)
 
 def window_from_golden(case):
     w = case["window"]
-    pix, imu = case["pixel"], case["inertial"]
+    pix, imu, brg, pos = case["pixel"], case["inertial"], case.get("bearing", []), case.get("pose", [])
     K = len(w["knots"])
     return synthetic.Window(
         order=w["order"], knots=np.array(w["knots"]), bias_order=w["bias_order"], gyro_bias=np.array(w["gyro_bias"]),
@@ -26,7 +26,11 @@ def window_from_golden(case):
         v_stamp=np.array([p["stamp"] for p in pix]), v_cam=np.array([p["cam"] for p in pix], dtype=np.int32),
         v_lm=np.array([p["lm"] for p in pix], dtype=np.int32), v_pixel=np.array([p["pixel"] for p in pix]).reshape(-1, 2),
         i_stamp=np.array([p["stamp"] for p in imu]), i_meas=np.array([p["meas"] for p in imu]).reshape(-1, 6),
-        knot_const=np.zeros(K, dtype=np.uint8))
+        knot_const=np.zeros(K, dtype=np.uint8),
+        b_stamp=np.array([p["stamp"] for p in brg]), b_cam=np.array([p["cam"] for p in brg], dtype=np.int32),
+        b_lm=np.array([p["lm"] for p in brg], dtype=np.int32), b_bearing=np.array([p["bearing"] for p in brg]).reshape(-1, 3),
+        pose_sensors=np.array(w.get("pose_sensors", [])).reshape(-1, 7), m_stamp=np.array([p["stamp"] for p in pos]),
+        m_sensor=np.array([p["sensor"] for p in pos], dtype=np.int32), m_pose=np.array([p["pose"] for p in pos]).reshape(-1, 7))
 
 
 def check_against_golden(case, out, maps, r_tol=1e-9, j_tol=1e-8):
@@ -46,6 +50,14 @@ def check_against_golden(case, out, maps, r_tol=1e-9, j_tol=1e-8):
         np.testing.assert_allclose(out["i_wa"][f], p["wa"], rtol=0, atol=1e-12)
         Jg = np.array(p["Jg"])
         np.testing.assert_allclose(out["i_Jg"][f], Jg, rtol=0, atol=j_tol * np.abs(Jg).max())
+    for f, p in enumerate(case.get("bearing", [])):
+        np.testing.assert_allclose(out["b_r"][f], p["r"][0], rtol=0, atol=r_tol)
+        np.testing.assert_allclose(out["b_Jp"][f], p["Jp"], rtol=0, atol=j_tol * np.abs(p["Jp"]).max())
+        np.testing.assert_allclose(out["b_Jl"][f], p["Jl"], rtol=0, atol=j_tol * np.abs(p["Jl"]).max())
+    for f, p in enumerate(case.get("pose", [])):
+        np.testing.assert_allclose(out["m_r"][f], p["r"], rtol=0, atol=r_tol)
+        Jp = np.array(p["Jp"])
+        np.testing.assert_allclose(out["m_Jp"][f], Jp, rtol=0, atol=j_tol * np.abs(Jp).max())
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
