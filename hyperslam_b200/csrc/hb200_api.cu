@@ -233,7 +233,7 @@ int ensure_system(hb200_ctx* c) {
     else HB_CUDA(c->band_ws.ensure(ws / sizeof(double)));
   }
   HB_CUDA(c->band_ws.ensure(1));
-  if (getenv("HB200_BAND_TIMING")) HB_CUDA(c->band_dbg.ensure(8));
+  if (getenv("HB200_BAND_TIMING")) HB_CUDA(c->band_dbg.ensure(72));
   // parallelism of the J^T J kernels: aim at ~2 CTAs per SM
   c->pix_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nseg, 1) - 1) / std::max(c->nseg, 1), std::max(1, c->Nv / (16 * std::max(c->nseg, 1)))));
   c->imu_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nruns, 1) - 1) / std::max(c->nruns, 1), std::max(1, c->Ni / (16 * std::max(c->nruns, 1)))));
@@ -1300,9 +1300,9 @@ int hb200_interpolate(hb200_ctx* c, int n, const double* stamps, double* pose, d
   return 0;
 }
 
-int hb200_debug_band_timing(hb200_ctx* c, long long* cycles /*[8]*/) {
+int hb200_debug_band_timing(hb200_ctx* c, long long* cycles /*[72]: 8 phase totals + 8 steps x 8 raw stamps*/) {
   if (!c || !c->band_dbg.p) return fail(-2, "set HB200_BAND_TIMING=1 before hb200_bind");
-  HB_CUDA(cudaMemcpy(cycles, c->band_dbg.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  HB_CUDA(cudaMemcpy(cycles, c->band_dbg.p, 72 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 
