@@ -49,7 +49,7 @@ __host__ __device__ inline size_t band_workspace_doubles(int K, int beta, int m)
   d += static_cast<size_t>(m + 1) * 6 * (n0 + n1);  // AR
   d += (n0 + n1) * 48;                           // LI
   d += 6 * (n0 + n1);                            // X
-  d += static_cast<size_t>(m + 1) * m + m;       // CC, XA
+  d += static_cast<size_t>(m + 1) * (m | 1) + m; // CC (odd row stride: conflict-free column access), XA
   return d + 8;
 }
 
@@ -107,6 +107,10 @@ HB_DI long long clock_after(double dep) {
   return t;
 }
 
+// Named barriers (ids 1..15; id 0 is __syncthreads): only the warps of one chain's pipeline take part.
+HB_DI void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+HB_DI void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 struct BandChain {
   double *W, *AR, *LI, *X;
   int Ke;     // block columns this chain eliminates in the two-sided phase
@@ -116,12 +120,12 @@ struct BandChain {
 
 // Panel of block column s: solve x L^T = a for every row below the diagonal block (band rows, arrow rows,
 // rhs row), one row per thread lt, lt += nthreads.
-HB_DI void band_panel(const BandChain& C, int s, int h, int m, int lt, int nthreads) {
+HB_DI void band_panel(const BandChain& C, int s, int h, int m, int lt, int nthreads, int row0 = 0) {
   double* Wc = C.W + static_cast<size_t>(s) * h * 6;
   const double* Lic = C.LI + static_cast<size_t>(s) * 48;
   const int nb = min(h - 6, C.npc - 6 * (s + 1));  // band rows below the diagonal block
   const int R = nb + m + 1;                          // + arrow rows + rhs row
-  for (int t = lt; t < R; t += nthreads) {
+  for (int t = row0 + lt; t < R; t += nthreads) {
     double* a = (t < nb) ? (Wc + static_cast<size_t>(6 + t) * 6) : (C.AR + static_cast<size_t>(t - nb) * C.npc + 6 * s);
     double v[6];
 #pragma unroll
@@ -138,19 +142,23 @@ HB_DI void band_panel(const BandChain& C, int s, int h, int m, int lt, int nthre
 }
 
 // Trailing update of block column s in 6x6 tiles (band x band lower triangle, then arrow x band; the
-// arrow x arrow part is deferred).  Worker = (tile, row i of the tile): 6 dots of length 6.  With `look`
-// tile 0 (the next diagonal block) is left to the look-ahead warp.
-HB_DI void band_update(const BandChain& C, int s, int h, int m, bool look, int worker, int nworkers) {
+// arrow x arrow part is deferred).  Worker = (tile, row i of the tile): 6 dots of length 6.  Items start at
+// `first` (6 = tile 0, the next diagonal block, is left to the look-ahead warp).  tile_uv: optional lookup
+// table tile -> (gu, gv) valid for full-band steps (nbk == beta): the decode then costs two byte loads.
+HB_DI void band_update(const BandChain& C, int s, int h, int m, int first, int worker, int nworkers, const unsigned char* tile_uv, int beta) {
   double* Wc = C.W + static_cast<size_t>(s) * h * 6;
   const int nb = min(h - 6, C.npc - 6 * (s + 1));
   const int nbk = nb / 6;
   const int ng = (m + 1 + 5) / 6;
   const int ntri = nbk * (nbk + 1) / 2;
   const int ntiles = ntri + ng * nbk;
-  for (int t = (look ? 6 : 0) + worker; t < ntiles * 6; t += nworkers) {
+  const bool table = tile_uv != nullptr && nbk == beta;
+  for (int t = first + worker; t < ntiles * 6; t += nworkers) {
     const int tile = t / 6, i = t - 6 * tile;
     int gu, gv;
-    if (tile < ntri) {
+    if (table) {
+      gu = tile_uv[2 * tile]; gv = tile_uv[2 * tile + 1];
+    } else if (tile < ntri) {
       gu = static_cast<int>((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
       while (gu * (gu + 1) / 2 > tile) --gu;
       while ((gu + 1) * (gu + 2) / 2 <= tile) ++gu;
@@ -164,22 +172,24 @@ HB_DI void band_update(const BandChain& C, int s, int h, int m, bool look, int w
     const int ru = ub ? 0 : 6 * (gu - nbk) + i;   // arrow row index of u
     if (!ub && ru > m) continue;
     const double* xu = ub ? (Wc + static_cast<size_t>(6 + 6 * gu + i) * 6) : (C.AR + static_cast<size_t>(ru) * C.npc + 6 * s);
+    double* tgt = ub ? (C.W + (static_cast<size_t>(s + 1 + gv) * h + (6 * (gu - gv) + i)) * 6)   // band x band
+                     : (C.AR + static_cast<size_t>(ru) * C.npc + 6 * (s + 1 + gv));              // arrow x band
     double a[6], sd[6];
     {
       const double2* x2 = reinterpret_cast<const double2*>(xu);   // rows are 48 B: 16-byte aligned
       const double2 a0 = x2[0], a1 = x2[1], a2 = x2[2];
       a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y;
     }
+    double2* t2 = reinterpret_cast<double2*>(tgt);
+    double2 o0 = t2[0], o1 = t2[1], o2 = t2[2];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       const double2* v2 = reinterpret_cast<const double2*>(Wc + static_cast<size_t>(6 + 6 * gv + j) * 6);
       const double2 b0 = v2[0], b1 = v2[1], b2 = v2[2];
       sd[j] = a[0] * b0.x + a[1] * b0.y + a[2] * b1.x + a[3] * b1.y + a[4] * b2.x + a[5] * b2.y;
     }
-    double* tgt = ub ? (C.W + (static_cast<size_t>(s + 1 + gv) * h + (6 * (gu - gv) + i)) * 6)   // band x band
-                     : (C.AR + static_cast<size_t>(ru) * C.npc + 6 * (s + 1 + gv));              // arrow x band
-#pragma unroll
-    for (int j = 0; j < 6; ++j) tgt[j] -= sd[j];
+    o0.x -= sd[0]; o0.y -= sd[1]; o1.x -= sd[2]; o1.y -= sd[3]; o2.x -= sd[4]; o2.y -= sd[5];
+    t2[0] = o0; t2[1] = o1; t2[2] = o2;
   }
 }
 
@@ -213,26 +223,58 @@ HB_DI void band_block_inverse(const BandChain& C, int s, int h) {
   for (int e = 0; e < 36; ++e) Lo[e] = Li[e];
 }
 
-// Look-ahead (one warp): the next diagonal block receives row i of its update A -= X X^T from this step's
-// panel rows (tile 0) in lanes 0..5, then lane 0 factors it.
-HB_DI bool band_lookahead(const BandChain& C, int s, int h, int lane) {
-  const double* Wc = C.W + static_cast<size_t>(s) * h * 6;
-  double* An = C.W + static_cast<size_t>(s + 1) * h * 6;
-  if (lane < 6) {
-    const double2* xi = reinterpret_cast<const double2*>(Wc + 36 + 6 * lane);
-    const double2 a0 = xi[0], a1 = xi[1], a2 = xi[2];
+// Look-ahead warp, one step: lanes 0..5 solve the panel rows of the first band block (the only rows the next
+// diagonal block depends on) and publish them (arrive on barrier A, which the update warps wait on); lane 0
+// then applies the pending update A -= X X^T to the next diagonal block in registers and factors it.  The
+// critical chain potf2 -> first panel block -> potf2 never waits for the rest of the panel or the update.
+HB_DI bool band_la_step(const BandChain& C, int s, int h, int lane, bool do_chol, int barA, int countA) {
+  double* Wc = C.W + static_cast<size_t>(s) * h * 6;
+  const double* Lic = C.LI + static_cast<size_t>(s) * 48;
+  const int nb = min(h - 6, C.npc - 6 * (s + 1));
+  bool ok = true;
+  if (nb >= 6 && lane < 6) {
+    double* a = Wc + static_cast<size_t>(6 + lane) * 6;
+    double v[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) v[q] = a[q];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-      if (j <= lane) {
-        const double2* xj = reinterpret_cast<const double2*>(Wc + 36 + 6 * j);
-        const double2 b0 = xj[0], b1 = xj[1], b2 = xj[2];
-        An[6 * lane + j] -= a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
-      }
+      v[j] *= Lic[j];
+#pragma unroll
+      for (int q = j + 1; q < 6; ++q) v[q] -= v[j] * Wc[q * 6 + j];
     }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) a[q] = v[q];
   }
   __syncwarp();
-  bool ok = true;
-  if (lane == 0) ok = chol6(An, 6, C.LI + static_cast<size_t>(s + 1) * 48);
+  __threadfence_block();
+  nbar_arrive(barA, countA);
+  if (nb >= 6) {
+    // next diagonal block: lane i < 6 subtracts row i of X X^T (X = the 6 panel rows just solved), everything
+    // loaded before anything is stored (no store->load serialisation); lane 0 then factors the block
+    double* An = C.W + static_cast<size_t>(s + 1) * h * 6;
+    if (lane < 6) {
+      double x[36], xi[6], an[6];
+#pragma unroll
+      for (int e = 0; e < 18; ++e) { const double2 t = reinterpret_cast<const double2*>(Wc + 36)[e]; x[2 * e] = t.x; x[2 * e + 1] = t.y; }
+#pragma unroll
+      for (int e = 0; e < 3; ++e) { const double2 t = reinterpret_cast<const double2*>(Wc + 36 + 6 * lane)[e]; xi[2 * e] = t.x; xi[2 * e + 1] = t.y; }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) an[j] = An[6 * lane + j];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc += xi[q] * x[6 * j + q];
+        an[j] -= acc;
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j <= lane) An[6 * lane + j] = an[j];
+    }
+    __syncwarp();
+    if (do_chol && lane == 0) ok = chol6(An, 6, C.LI + static_cast<size_t>(s + 1) * 48);
+  }
   return ok;
 }
 
@@ -272,6 +314,67 @@ HB_DI void band_backsub_column(const BandChain& C, int c, int h, int m, int lane
   __syncwarp();
 }
 
+// Back substitution of block columns c_hi .. c_lo of one chain (one warp) AFTER the row transform
+// B <- B Li, y <- Li^T y (band_transform_row): x_c = y~_c - sum_r N_{c,r}^T x_{c+r} needs no triangular solve
+// and no cross-lane reduction.  Lane j < 6 owns component j and keeps the BETA following solution blocks
+// in registers; the only cross-lane traffic on the chain is the broadcast of the 6 new components.
+template <int BETA>
+HB_DI void band_backsub_chain(const BandChain& C, int c_hi, int c_lo, int h, int m, int lane, long long* ts = nullptr) {
+  const int j = lane % 6;
+  double xh[BETA][6];
+#pragma unroll
+  for (int r = 0; r < BETA; ++r)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) xh[r][q] = (c_hi + 1 + r < C.ncol) ? C.X[6 * (c_hi + 1 + r) + q] : 0.0;
+  for (int c = c_hi; c >= c_lo; --c) {
+    const double* Wc = C.W + static_cast<size_t>(c) * h * 6;
+    const int nbk = min(h - 6, C.npc - 6 * (c + 1)) / 6;
+    double nv[BETA][6];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int t = 0; t < 6; ++t) nv[r][t] = (r < nbk) ? Wc[static_cast<size_t>(6 + 6 * r + t) * 6 + j] : 0.0;
+    const double y = C.AR[static_cast<size_t>(m) * C.npc + 6 * c + j];
+    double acc[BETA];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r) {
+      acc[r] = 0.0;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) acc[r] += nv[r][t] * xh[r][t];
+    }
+    double tot = acc[0];
+#pragma unroll
+    for (int r = 1; r < BETA; ++r) tot += acc[r];
+    const double xo = y - tot;
+#pragma unroll
+    for (int r = BETA - 1; r > 0; --r)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) xh[r][q] = xh[r - 1][q];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) xh[0][q] = __shfl_sync(0xffffffffu, xo, q);
+    if (lane < 6) C.X[6 * c + lane] = xo;
+    if (ts && lane == 0 && c_hi - c < 16) ts[c_hi - c] = clock_after(xo);
+  }
+  __syncwarp();
+}
+
+// Row transform v <- v Li (Li = inverse of the column's diagonal Cholesky block, lower triangular):
+// v'[j] = sum_{q >= j} v[q] Li[q][j].  Applied to every panel row below the diagonal and to the rhs row.
+HB_DI void band_transform_row(double* v, const double* Li) {
+  double x[6], o[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) x[q] = v[q];
+#pragma unroll
+  for (int jj = 0; jj < 6; ++jj) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = jj; q < 6; ++q) acc += x[q] * Li[q * 6 + jj];
+    o[jj] = acc;
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) v[q] = o[q];
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* __restrict__ sys, int n, int K, int beta,
                                                                   double* __restrict__ ws_global, double* __restrict__ x_out,
@@ -304,13 +407,15 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     ws = p;
   }
   double* CC = ws;
-  double* XA = CC + static_cast<size_t>(m + 1) * m;
+  const int LDc = m | 1;
+  double* XA = CC + static_cast<size_t>(m + 1) * LDc;
   const BandChain C = my_chain ? C1 : C0;           // this thread's chain in the update phase (registers)
   const BandChain CP = (tid >> 8) ? C1 : C0;        // ... and in the panel phase (threads 0..255 / 256..511)
   const double* S = sys;
   const double* b = sys + static_cast<size_t>(n) * n;
   __shared__ int s_ok;
   if (tid == 0) s_ok = 1;
+  const int dmode = dbg ? static_cast<int>(dbg[71]) : 0;   // timing experiments only (HB200_BAND_DBGMODE): results are wrong when != 0
   // ---- gather: chain 0 reads P top-down, chain 1 reads J P J (index reversal) and starts its copy of the
   // separator and of the separator's arrow columns at zero (they only accumulate updates) ----
   {
@@ -340,11 +445,12 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     }
     for (int e = tid; e < (m + 1) * m; e += kBandThreads) {
       const int r = e / m, q = e - r * m;
-      CC[e] = (r < m) ? S[static_cast<size_t>(np + r) * n + np + q] : b[np + q];
+      CC[static_cast<size_t>(r) * LDc + q] = (r < m) ? S[static_cast<size_t>(np + r) * n + np + q] : b[np + q];
     }
   }
   __syncthreads();
   long long t_mark = clock64(), t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define HB_TICKD(i, addr) do { if (dbg && tid == 0) { const long long now = clock_after(*reinterpret_cast<const volatile double*>(addr)); t_acc[i] += now - t_mark; t_mark = now; } } while (0)
 #define HB_TICK(i) do { if (dbg && tid == 0) { const long long now = clock64(); t_acc[i] += now - t_mark; t_mark = now; } } while (0)
   // ---- two-sided factorisation + forward substitution: step s eliminates block column s of BOTH chains.
   // The 6x6 Cholesky of a chain's NEXT diagonal block is done by its look-ahead warp inside the
@@ -353,29 +459,110 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   if (tid == 32 && C1.Ke > 0) { if (!chol6(C1.W, 6, C1.LI)) s_ok = 0; }
   __syncthreads();
   HB_TICK(0);
-  const int steps = max(C0.Ke, C1.Ke);
-  const int urank = ((warp >> 2) & 1) * 2 + (sched - 2);   // update warps: 0..3 within their chain
-  __shared__ long long s_ts[8][8];
-  for (int s = 0; s < steps; ++s) {
-    const bool rec = dbg && s >= 4 && s < 12;
-    if (rec && tid == 0) s_ts[s - 4][0] = clock_after(C0.LI[static_cast<size_t>(s) * 48]);      // panel may start (chol(s) visible)
-    if (s < CP.Ke) band_panel(CP, s, h, m, tid & 255, 256);
-    if (rec && tid == 0) s_ts[s - 4][1] = clock_after(C0.W[static_cast<size_t>(s) * h6 + 36]);  // own panel row written
-    __syncthreads();
-    if (rec && tid == 2 * 32) s_ts[s - 4][2] = clock_after(C0.W[static_cast<size_t>(s) * h6 + 36]);   // update warp released
-    if (rec && tid == 12 * 32) s_ts[s - 4][4] = clock_after(C0.W[static_cast<size_t>(s) * h6 + 36]);  // look-ahead warp released
-    if (s < C.Ke) {
-      const bool look = s + 1 < C.Ke;
-      if (sched >= 2) band_update(C, s, h, m, look, urank * 32 + lane, 4 * 32);
-      else if ((warp >> 2) == 3 && look) { if (!band_lookahead(C, s, h, lane)) s_ok = 0; }
+  // Pipeline of one chain: 4 update warps (128 threads: panel rows, then trailing-update tiles) + its
+  // look-ahead warp.  Barrier A: panel of step s complete (update warps sync, look-ahead warp arrives after
+  // its first panel block); barrier B: step s complete.  The chains never synchronise with each other.
+  __shared__ unsigned char s_tile[2 * 192];
+  const int ng_full = (m + 1 + 5) / 6;
+  const int ntiles_full = beta * (beta + 1) / 2 + ng_full * beta;
+  const bool have_table = ntiles_full <= 192;
+  if (have_table) {
+    for (int tile = tid; tile < ntiles_full; tile += kBandThreads) {
+      int gu, gv;
+      const int ntri = beta * (beta + 1) / 2;
+      if (tile < ntri) {
+        gu = 0;
+        while ((gu + 1) * (gu + 2) / 2 <= tile) ++gu;
+        gv = tile - gu * (gu + 1) / 2;
+      } else { gu = beta + (tile - ntri) / beta; gv = (tile - ntri) % beta; }
+      s_tile[2 * tile] = static_cast<unsigned char>(gu);
+      s_tile[2 * tile + 1] = static_cast<unsigned char>(gv);
     }
-    if (rec && tid == 2 * 32) s_ts[s - 4][3] = clock_after(C0.W[static_cast<size_t>(s + 1) * h6 + 6 * 6]);   // update warp done (approx)
-    if (rec && tid == 12 * 32) s_ts[s - 4][5] = clock_after(C0.LI[static_cast<size_t>(s + 1) * 48]);        // chol(s+1) done
-    __syncthreads();
   }
+  __syncthreads();
+  const bool is_la = (sched < 2) && (warp >> 2) == 3;
+  const bool is_worker = sched >= 2;
+  const int wid = (((warp >> 2) & 1) * 2 + (sched - 2)) * 32 + lane;   // 0..127 within the chain's update warps
+  const int barA = 1 + 2 * my_chain, barB = 2 + 2 * my_chain;
+  __shared__ long long s_ts[8][8];
+  // Two-sided phase: every step has the full band below it (the separator follows the last eliminated
+  // column), so a worker's items are the same every step and their addresses are affine in s: decode once.
+  constexpr int kMaxRounds = 3;
+  const int nitems_full = ntiles_full * 6 - 6;   // tile 0 belongs to the look-ahead warp
+  const bool fast = have_table && pl.Kb > 0 && nitems_full <= kMaxRounds * 128;
+  const double* f_u[kMaxRounds]; const double* f_v[kMaxRounds]; double* f_t[kMaxRounds]; int f_su[kMaxRounds]; bool f_ok[kMaxRounds];
+#pragma unroll
+  for (int r = 0; r < kMaxRounds; ++r) {
+    const int t = 6 + wid + 128 * r;
+    f_ok[r] = fast && is_worker && t < ntiles_full * 6;
+    f_u[r] = C.W; f_v[r] = C.W; f_t[r] = C.W; f_su[r] = 0;
+    if (f_ok[r]) {
+      const int tile = t / 6, i = t - 6 * tile;
+      const int gu = s_tile[2 * tile], gv = s_tile[2 * tile + 1];
+      const bool ub = gu < beta;
+      const int ru = ub ? 0 : 6 * (gu - beta) + i;
+      if (!ub && ru > m) f_ok[r] = false;
+      else {
+        f_u[r] = ub ? (C.W + static_cast<size_t>(6 + 6 * gu + i) * 6) : (C.AR + static_cast<size_t>(ru) * C.npc);
+        f_su[r] = ub ? h6 : 6;
+        f_v[r] = C.W + static_cast<size_t>(6 + 6 * gv) * 6;
+        f_t[r] = ub ? (C.W + (static_cast<size_t>(1 + gv) * h + (6 * (gu - gv) + i)) * 6) : (C.AR + static_cast<size_t>(ru) * C.npc + 6 * (1 + gv));
+      }
+    }
+  }
+  auto fast_update = [&](int s) {
+#pragma unroll
+    for (int r = 0; r < kMaxRounds; ++r) {
+      if (!f_ok[r]) continue;
+      const double2* x2 = reinterpret_cast<const double2*>(f_u[r] + static_cast<size_t>(s) * f_su[r]);
+      const double2* v2 = reinterpret_cast<const double2*>(f_v[r] + static_cast<size_t>(s) * h6);
+      double2* t2 = reinterpret_cast<double2*>(f_t[r] + static_cast<size_t>(s) * f_su[r]);
+      const double2 a0 = x2[0], a1 = x2[1], a2 = x2[2];
+      double2 o0 = t2[0], o1 = t2[1], o2 = t2[2];
+      double sd[6];
+      if (dmode & 4) {   // no v loads, no FMAs
+#pragma unroll
+        for (int j = 0; j < 6; ++j) sd[j] = a0.x;
+      } else if (dmode & 1) {   // v loads, no FMAs
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { const double2 b0 = v2[3 * j], b1 = v2[3 * j + 1], b2 = v2[3 * j + 2]; sd[j] = b0.x + b1.y + b2.x; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const double2 b0 = v2[3 * j], b1 = v2[3 * j + 1], b2 = v2[3 * j + 2];
+          sd[j] = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
+        }
+      }
+      o0.x -= sd[0]; o0.y -= sd[1]; o1.x -= sd[2]; o1.y -= sd[3]; o2.x -= sd[4]; o2.y -= sd[5];
+      if (!(dmode & 2)) { t2[0] = o0; t2[1] = o1; t2[2] = o2; }
+    }
+  };
+  auto run_steps = [&](const BandChain& Q, int s0, int s1, bool use_fast) {
+    for (int s = s0; s < s1; ++s) {
+      const bool rec = dbg && my_chain == 0 && s >= 4 && s < 12 && lane == 0 && (warp == 2 || warp == 12);
+      if (rec) s_ts[s - 4][warp == 2 ? 0 : 4] = clock_after(Q.LI[static_cast<size_t>(s) * 48]);   // released (chol(s) visible)
+      if (is_worker) {
+        const int nb = min(h - 6, Q.npc - 6 * (s + 1));
+        if (!(dmode & 16)) band_panel(Q, s, h, m, wid, 128, nb >= 6 ? 6 : 0);
+        if (rec) s_ts[s - 4][1] = clock_after(Q.AR[6 * s]);           // own panel row (arrow row 0... wid 0 -> band row 6) done
+        nbar_sync(barA, 160);
+        if (rec) s_ts[s - 4][2] = clock_after(Q.W[static_cast<size_t>(s) * h6 + 36]);   // A released
+        if (dmode & 32) {} else if (use_fast) fast_update(s);
+        else band_update(Q, s, h, m, 6, wid, 128, have_table ? s_tile : nullptr, beta);
+        if (rec) s_ts[s - 4][3] = clock_after(Q.W[static_cast<size_t>(s + 1) * h6 + 36]);  // update done (approx)
+      } else {
+        if (!band_la_step(Q, s, h, lane, (s + 1 < s1) && !(dmode & 8), barA, 160)) s_ok = 0;
+        if (rec) s_ts[s - 4][5] = clock_after(Q.LI[static_cast<size_t>(s + 1) * 48]);      // chol(s+1) done
+      }
+      nbar_sync(barB, 160);
+    }
+  };
+  if (is_la || is_worker) run_steps(C, 0, C.Ke, fast);
+  __syncthreads();
   if (dbg && tid < 64) dbg[8 + tid] = s_ts[tid >> 3][tid & 7];
+  HB_TICKD(1, C0.W);
   // ---- merge chain 1's copy of the separator (index-reversed) and of its arrow columns into chain 0,
-  // then chain 0 eliminates the separator columns with all 8 update warps ----
+  // then chain 0's pipeline eliminates the separator columns ----
   if (pl.Kb) {
     const int nsep = 6 * pl.bs, N1 = C1.npc;
     for (int e = tid; e < nsep * nsep; e += kBandThreads) {
@@ -392,17 +579,10 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     __syncthreads();
     if (tid == 0 && !chol6(C0.W + static_cast<size_t>(C0.Ke) * h6, 6, C0.LI + static_cast<size_t>(C0.Ke) * 48)) s_ok = 0;
     __syncthreads();
-    const int urank8 = (warp >> 2) * 2 + (sched - 2);
-    for (int s = C0.Ke; s < C0.ncol; ++s) {
-      band_panel(C0, s, h, m, tid, kBandThreads);
-      __syncthreads();
-      const bool look = s + 1 < C0.ncol;
-      if (sched >= 2) band_update(C0, s, h, m, look, urank8 * 32 + lane, 8 * 32);
-      else if (warp == 12 && look) { if (!band_lookahead(C0, s, h, lane)) s_ok = 0; }
-      __syncthreads();
-    }
+    if ((is_la || is_worker) && my_chain == 0) run_steps(C0, C0.Ke, C0.ncol, false);
+    __syncthreads();
   }
-  HB_TICK(2);
+  HB_TICKD(2, C0.W);
   // ---- block inverses of every eliminated column (one thread each), and the deferred corner update
   // C -= sum over all eliminated columns of (arrow panel)(arrow panel)^T, rhs row included (row m):
   // one (u, v) pair per warp pass, lanes stride the columns (conflict-free), butterfly reduction ----
@@ -411,57 +591,111 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     else band_block_inverse(C1, c - C0.ncol, h);
   }
   {
-    const int n0 = C0.npc, n1 = 6 * C1.Ke;
-    const int npairs = (m + 1) * m;   // (u, v) with v <= u are used
-    for (int e = warp; e < npairs; e += kBandThreads / 32) {
-      const int u = e / m, v = e - u * m;
-      if (v > u) continue;
-      const double* au = C0.AR + static_cast<size_t>(u) * C0.npc;
-      const double* av = C0.AR + static_cast<size_t>(v) * C0.npc;
-      double a0 = 0.0, a1 = 0.0;
-      int col = lane;
-      for (; col + 32 < n0; col += 64) { a0 += au[col] * av[col]; a1 += au[col + 32] * av[col + 32]; }
-      if (col < n0) a0 += au[col] * av[col];
-      au = C1.AR + static_cast<size_t>(u) * C1.npc;
-      av = C1.AR + static_cast<size_t>(v) * C1.npc;
-      for (col = lane; col + 32 < n1; col += 64) { a0 += au[col] * av[col]; a1 += au[col + 32] * av[col + 32]; }
-      if (col < n1) a0 += au[col] * av[col];
-      a0 += a1;
+    // 3x3 register tiles of the lower triangle (rows u in [0, m], columns v in [0, m)); one tile per warp
+    // pass, lanes stride the eliminated columns of both chains, butterfly reduction of the 9 sums
+    const int nrt = (m + 3) / 3, nct = (m + 2) / 3;
+    for (int e = warp; e < nrt * nct; e += kBandThreads / 32) {
+      const int tu = e / nct, tv = e - tu * nct;
+      if (tv > tu) continue;
+      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      if (lane == 0) CC[e] -= a0;
+      for (int ci = 0; ci < 2; ++ci) {
+        const BandChain& Q = ci ? C1 : C0;
+        const int nused = ci ? 6 * C1.Ke : C0.npc;
+        const double* ru0 = Q.AR + static_cast<size_t>(min(3 * tu, m)) * Q.npc;
+        const double* ru1 = Q.AR + static_cast<size_t>(min(3 * tu + 1, m)) * Q.npc;
+        const double* ru2 = Q.AR + static_cast<size_t>(min(3 * tu + 2, m)) * Q.npc;
+        const double* rv0 = Q.AR + static_cast<size_t>(min(3 * tv, m - 1)) * Q.npc;
+        const double* rv1 = Q.AR + static_cast<size_t>(min(3 * tv + 1, m - 1)) * Q.npc;
+        const double* rv2 = Q.AR + static_cast<size_t>(min(3 * tv + 2, m - 1)) * Q.npc;
+        for (int col = lane; col < nused; col += 32) {
+          const double u0 = ru0[col], u1 = ru1[col], u2 = ru2[col];
+          const double v0 = rv0[col], v1 = rv1[col], v2 = rv2[col];
+          acc[0] += u0 * v0; acc[1] += u0 * v1; acc[2] += u0 * v2;
+          acc[3] += u1 * v0; acc[4] += u1 * v1; acc[5] += u1 * v2;
+          acc[6] += u2 * v0; acc[7] += u2 * v1; acc[8] += u2 * v2;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const int u = 3 * tu + q / 3, v = 3 * tv + q % 3;
+          if (u <= m && v < m && v <= u) CC[static_cast<size_t>(u) * LDc + v] -= acc[q];
+        }
+      }
     }
   }
   __syncthreads();
-  HB_TICK(3);
-  // ---- corner (m x m, rhs carried as row m): right-looking Cholesky by the whole CTA ----
-  for (int q = 0; q < m; ++q) {
-    const double d = CC[static_cast<size_t>(q) * m + q];
-    if (!(d > 0.0) && tid == 0) s_ok = 0;
-    const double iv = rsqrt(d);
-    __syncthreads();   // everyone has read the pivot before it is overwritten
-    for (int r = q + tid; r <= m; r += kBandThreads) CC[static_cast<size_t>(r) * m + q] = (r == q) ? d * iv : CC[static_cast<size_t>(r) * m + q] * iv;
-    __syncthreads();
-    const int rem = m - q;  // rows q+1 .. m (row m = rhs), columns q+1 .. m-1
-    for (int e = tid; e < rem * rem; e += kBandThreads) {
-      const int u = q + 1 + e / rem, v = q + 1 + e % rem;
-      if (v > u || v >= m) continue;
-      CC[static_cast<size_t>(u) * m + v] -= CC[static_cast<size_t>(u) * m + q] * CC[static_cast<size_t>(v) * m + q];
+  HB_TICKD(3, CC);
+  // ---- corner (m x m, rhs carried as row m).  m < 32: one warp, lane r owns row r, no CTA barriers (the
+  // CTA-wide version spent its time in 3 barriers per column); otherwise the whole CTA ----
+  if (m < 32 && !(dmode & 128)) {
+    if (warp == 0) {
+      const int r = lane;
+      for (int q = 0; q < m; ++q) {
+        const double d = CC[static_cast<size_t>(q) * LDc + q];
+        if (!(d > 0.0) && lane == 0) s_ok = 0;
+        const double iv = rsqrt(d);
+        double lr = 0.0;
+        if (r >= q && r <= m) {
+          lr = (r == q) ? d * iv : CC[static_cast<size_t>(r) * LDc + q] * iv;
+          CC[static_cast<size_t>(r) * LDc + q] = lr;
+        }
+        __syncwarp();
+        if (r > q && r <= m) {
+          const int vmax = min(r, m - 1);
+          double* row = CC + static_cast<size_t>(r) * LDc;
+          for (int v = q + 1; v <= vmax; ++v) row[v] -= lr * CC[static_cast<size_t>(v) * LDc + q];
+        }
+        __syncwarp();
+      }
+      HB_TICK(4);
+      // back substitution with the rhs in registers: lane r holds y_r; x_q = y_q / L_qq is broadcast, then
+      // y_r -= L_qr x_q for r < q (row q of L is contiguous: conflict-free)
+      double y = (lane < m) ? CC[static_cast<size_t>(m) * LDc + lane] : 0.0;
+      const double dinv = (lane < m) ? 1.0 / CC[static_cast<size_t>(lane) * LDc + lane] : 0.0;
+#pragma unroll 4
+      for (int q = m - 1; q >= 0; --q) {
+        const double lq = (lane < q) ? CC[static_cast<size_t>(q) * LDc + lane] : 0.0;
+        const double xq = __shfl_sync(0xffffffffu, y * dinv, q);
+        if (lane == q) XA[q] = xq;
+        y -= lq * xq;
+      }
     }
-    __syncthreads();
-  }
-  HB_TICK(4);
-  if (warp == 0) {   // back substitution of the corner
-    for (int q = m - 1; q >= 0; --q) {
-      double xq = 0.0;
-      if ((q & 31) == lane) { xq = CC[static_cast<size_t>(m) * m + q] / CC[static_cast<size_t>(q) * m + q]; XA[q] = xq; }
-      xq = __shfl_sync(0xffffffffu, xq, q & 31);
-      for (int r = lane; r < q; r += 32) CC[static_cast<size_t>(m) * m + r] -= CC[static_cast<size_t>(q) * m + r] * xq;
-      __syncwarp();
+  } else {
+    for (int q = 0; q < m; ++q) {
+      const double d = CC[static_cast<size_t>(q) * LDc + q];
+      if (!(d > 0.0) && tid == 0) s_ok = 0;
+      const double iv = rsqrt(d);
+      __syncthreads();   // everyone has read the pivot before it is overwritten
+      for (int r = q + tid; r <= m; r += kBandThreads) CC[static_cast<size_t>(r) * LDc + q] = (r == q) ? d * iv : CC[static_cast<size_t>(r) * LDc + q] * iv;
+      __syncthreads();
+      const int rem = m - q;  // rows q+1 .. m (row m = rhs), columns q+1 .. m-1
+      for (int e = tid; e < rem * rem; e += kBandThreads) {
+        const int u = q + 1 + e / rem, v = q + 1 + e % rem;
+        if (v > u || v >= m) continue;
+        CC[static_cast<size_t>(u) * LDc + v] -= CC[static_cast<size_t>(u) * LDc + q] * CC[static_cast<size_t>(v) * LDc + q];
+      }
+      __syncthreads();
+    }
+    HB_TICK(4);
+    if (warp == 0) {
+      for (int q = m - 1; q >= 0; --q) {
+        double xq = 0.0;
+        if ((q & 31) == lane) { xq = CC[static_cast<size_t>(m) * LDc + q] / CC[static_cast<size_t>(q) * LDc + q]; XA[q] = xq; }
+        xq = __shfl_sync(0xffffffffu, xq, q & 31);
+        for (int r = lane; r < q; r += 32) CC[static_cast<size_t>(m) * LDc + r] -= CC[static_cast<size_t>(q) * LDc + r] * xq;
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
-  HB_TICK(5);
+  HB_TICKD(5, XA);
   // arrow contribution to every eliminated block's right-hand side, all at once: y_p -= AR^T x_a (row m of AR = y)
   {
     const int n0 = C0.npc, n1 = 6 * C1.Ke;
@@ -474,22 +708,42 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     }
   }
   __syncthreads();
+  const bool fast_bs = (beta == 3 || beta == 5) && !(dmode & 64);
+  if (fast_bs) {
+    // row transform of every eliminated column: panel rows B <- B Li and rhs y <- Li^T y (one row per thread)
+    const int rows_per_col = (h - 6) + 1;
+    const int ncols = C0.ncol + C1.Ke;
+    for (int e = tid; e < ncols * rows_per_col; e += kBandThreads) {
+      const int cc = e / rows_per_col, t = e - cc * rows_per_col;
+      const BandChain& Q = cc < C0.ncol ? C0 : C1;
+      const int c = cc < C0.ncol ? cc : cc - C0.ncol;
+      const int nb = min(h - 6, Q.npc - 6 * (c + 1));
+      const double* Li = Q.LI + static_cast<size_t>(c) * 48 + 8;
+      if (t < nb) band_transform_row(Q.W + (static_cast<size_t>(c) * h + 6 + t) * 6, Li);
+      else if (t == h - 6) band_transform_row(Q.AR + static_cast<size_t>(m) * Q.npc + 6 * c, Li);
+    }
+    __syncthreads();
+  }
+  HB_TICKD(7, C0.AR);
   // separator columns first (chain 0, warp 0), then outwards: chain 0 in warp 0, chain 1 in warp 1
-  if (warp == 0) {
-    for (int c = C0.ncol - 1; c >= C0.Ke; --c) band_backsub_column(C0, c, h, m, lane);
+  if (warp == 0 && C0.ncol > C0.Ke) {
+    if (beta == 3 && fast_bs) band_backsub_chain<3>(C0, C0.ncol - 1, C0.Ke, h, m, lane);
+    else if (beta == 5 && fast_bs) band_backsub_chain<5>(C0, C0.ncol - 1, C0.Ke, h, m, lane);
+    else for (int c = C0.ncol - 1; c >= C0.Ke; --c) band_backsub_column(C0, c, h, m, lane);
   }
   __syncthreads();
   if (pl.Kb) {
     for (int v = tid; v < 6 * pl.bs; v += kBandThreads) C1.X[C1.npc - 1 - v] = C0.X[6 * C0.Ke + v];
     __syncthreads();
   }
-  if (warp == 0) {
-    for (int c = C0.Ke - 1; c >= 0; --c) band_backsub_column(C0, c, h, m, lane);
-  } else if (warp == 1) {
-    for (int c = C1.Ke - 1; c >= 0; --c) band_backsub_column(C1, c, h, m, lane);
+  if (warp < 2) {
+    const BandChain& Q = warp ? C1 : C0;
+    if (beta == 3 && fast_bs) band_backsub_chain<3>(Q, Q.Ke - 1, 0, h, m, lane);
+    else if (beta == 5 && fast_bs) band_backsub_chain<5>(Q, Q.Ke - 1, 0, h, m, lane);
+    else for (int c = Q.Ke - 1; c >= 0; --c) band_backsub_column(Q, c, h, m, lane);
   }
   __syncthreads();
-  HB_TICK(6);
+  HB_TICKD(6, C0.X);
   for (int e = tid; e < C0.npc; e += kBandThreads) x_out[e] = C0.X[e];
   for (int e = tid; e < 6 * C1.Ke; e += kBandThreads) x_out[np - 1 - e] = C1.X[e];
   for (int e = tid; e < m; e += kBandThreads) x_out[np + e] = XA[e];

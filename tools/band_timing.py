@@ -5,17 +5,20 @@ import numpy as np
 from hyperslam_b200 import runtime, synthetic
 win = synthetic.make_config(1, constant_knots=2)
 ctx = runtime.Context(0); ctx.load_window(win)
-ctx.iterate(3)
+ctx.iterate(1)
 cyc = (C.c_longlong*72)()
 ctx.lib.hb200_debug_band_timing(ctx.h, cyc)
-names=["potf2 prologue","two-sided: panel phases","merge + separator columns","deferred corner update","corner Cholesky","corner back substitution","arrow pre-pass + outward back substitution","two-sided: update/look-ahead phases"]
+names=["potf2 prologue","two-sided factorisation","merge + separator columns","block inverses + deferred corner update","corner Cholesky","corner back substitution","outward back substitution","arrow pre-pass + row transform"]
 tot=sum(cyc[0:8])
 for n,c in zip(names,cyc): print(f"{n:40s} {c:9d} cycles {c/1.965e3:8.1f} us {100*c/max(tot,1):5.1f}%")
 
-print("raw stamps, steps 4..11 of chain 0 (cycles relative to the step's panel start):")
-print("step  panel_end  upd_start  upd_end  la_start  la_end   next_panel_start")
+
+print("chain 0, steps 4..11: cycles relative to the update warp's release (B of the previous step)")
+print("step  panel_end  A_release  upd_end | la_release  la_end | next_release")
 for i in range(8):
     r = cyc[8+8*i:8+8*i+6]
     nxt = cyc[8+8*(i+1)] if i < 7 else 0
     b = r[0]
-    print(f"{i+4:4d} {r[1]-b:9d} {r[2]-b:9d} {r[3]-b:8d} {r[4]-b:9d} {r[5]-b:8d} {(nxt-b) if nxt else 0:9d}")
+    print(f"{i+4:4d} {r[1]-b:9d} {r[2]-b:9d} {r[3]-b:8d} | {r[4]-b:9d} {r[5]-b:8d} | {(nxt-b) if nxt else 0:9d}")
+
+print("TOTAL cycles", tot, "us", tot/1.965e3)
