@@ -49,7 +49,7 @@ __host__ __device__ inline size_t band_workspace_doubles(int K, int beta, int m)
   d += static_cast<size_t>(m + 1) * 6 * (n0 + n1);  // AR
   d += (n0 + n1) * 48;                           // LI
   d += 6 * (n0 + n1);                            // X
-  d += static_cast<size_t>(m + 1) * (m | 1) + m; // CC (odd row stride: conflict-free column access), XA
+  d += static_cast<size_t>(m + 1) * (m | 1) + 2 * static_cast<size_t>(m); // CC (odd row stride: conflict-free column access), XA, DG
   return d + 8;
 }
 
@@ -193,36 +193,6 @@ HB_DI void band_update(const BandChain& C, int s, int h, int m, int first, int w
   }
 }
 
-// Inverse of block column s's diagonal factor, for the back substitution (one thread per block column, all
-// columns at once after the factorisation -- it used to sit in the per-step loop, where its long
-// store->load dependent chain, not the look-ahead potf2, bounded the step):
-// Li[i][j] = -(sum_{p=j}^{i-1} L[i][p] Li[p][j]) / L[i][i],  Li[j][j] = 1 / L[j][j]
-HB_DI void band_block_inverse(const BandChain& C, int s, int h) {
-  const double* Wc = C.W + static_cast<size_t>(s) * h * 6;
-  const double* Lic = C.LI + static_cast<size_t>(s) * 48;
-  double* Lo = C.LI + static_cast<size_t>(s) * 48 + 8;
-  double L[36], Li[36], rd[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    rd[i] = Lic[i];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) { L[6 * i + j] = (j < i) ? Wc[i * 6 + j] : 0.0; Li[6 * i + j] = 0.0; }
-  }
-#pragma unroll
-  for (int jj = 0; jj < 6; ++jj) {
-    Li[jj * 6 + jj] = rd[jj];
-#pragma unroll
-    for (int ii = jj + 1; ii < 6; ++ii) {
-      double acc = 0.0;
-#pragma unroll
-      for (int pp = jj; pp < ii; ++pp) acc -= L[ii * 6 + pp] * Li[pp * 6 + jj];
-      Li[ii * 6 + jj] = acc * rd[ii];
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 36; ++e) Lo[e] = Li[e];
-}
-
 // Look-ahead warp, one step: lanes 0..5 solve the panel rows of the first band block (the only rows the next
 // diagonal block depends on) and publish them (arrive on barrier A, which the update warps wait on); lane 0
 // then applies the pending update A -= X X^T to the next diagonal block in registers and factors it.  The
@@ -278,101 +248,51 @@ HB_DI bool band_la_step(const BandChain& C, int s, int h, int lane, bool do_chol
   return ok;
 }
 
-// One block column of the back substitution (one warp): x_c = L_cc^-T (y_c - sum_band L_rc^T x_r); the arrow
-// part was folded into y beforehand.  lane = (component j = lane % 6, part p = lane / 6), 5 parts.
-HB_DI void band_backsub_column(const BandChain& C, int c, int h, int m, int lane) {
-  const int j = lane % 6, part = lane / 6;
-  const double* Wc = C.W + static_cast<size_t>(c) * h * 6;
-  const double* Li = C.LI + static_cast<size_t>(c) * 48 + 8;
-  const int nb = min(h - 6, C.npc - 6 * (c + 1));
-  double sa = 0.0, s2 = 0.0;
-  if (part < 5) {
-    int t = part;
-    for (; t + 5 < nb; t += 10) {   // two independent accumulators
-      sa += Wc[static_cast<size_t>(6 + t) * 6 + j] * C.X[6 * (c + 1) + t];
-      s2 += Wc[static_cast<size_t>(6 + t + 5) * 6 + j] * C.X[6 * (c + 1) + t + 5];
-    }
-    if (t < nb) sa += Wc[static_cast<size_t>(6 + t) * 6 + j] * C.X[6 * (c + 1) + t];
-    sa += s2;
-  }
-  // sum the 5 parts of each component: lanes j, j+6, j+12, j+18, j+24
-  double tot = sa;
-  tot += __shfl_sync(0xffffffffu, sa, (lane + 6) & 31);
-  tot += __shfl_sync(0xffffffffu, sa, (lane + 12) & 31);
-  tot += __shfl_sync(0xffffffffu, sa, (lane + 18) & 31);
-  tot += __shfl_sync(0xffffffffu, sa, (lane + 24) & 31);
-  // lanes 0..5 now hold the full sums (their partners are lanes j+6k < 30)
-  const double v = (lane < 6) ? C.AR[static_cast<size_t>(m) * C.npc + 6 * c + lane] - tot : 0.0;
-  // x = L^-T v: lane j sums Li[q][j] v_q over q >= j (six independent broadcasts)
-  double xo = 0.0;
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    const double vq = __shfl_sync(0xffffffffu, v, q);
-    if (lane < 6 && q >= lane) xo += Li[q * 6 + lane] * vq;
-  }
-  if (lane < 6) C.X[6 * c + lane] = xo;
-  __syncwarp();
-}
-
 // Back substitution of block columns c_hi .. c_lo of one chain (one warp) AFTER the row transform
-// B <- B Li, y <- Li^T y (band_transform_row): x_c = y~_c - sum_r N_{c,r}^T x_{c+r} needs no triangular solve
-// and no cross-lane reduction.  Lane j < 6 owns component j and keeps the BETA following solution blocks
-// in registers; the only cross-lane traffic on the chain is the broadcast of the 6 new components.
-template <int BETA>
-HB_DI void band_backsub_chain(const BandChain& C, int c_hi, int c_lo, int h, int m, int lane, long long* ts = nullptr) {
-  const int j = lane % 6;
-  double xh[BETA][6];
-#pragma unroll
-  for (int r = 0; r < BETA; ++r)
-#pragma unroll
-    for (int q = 0; q < 6; ++q) xh[r][q] = (c_hi + 1 + r < C.ncol) ? C.X[6 * (c_hi + 1 + r) + q] : 0.0;
+// B <- B L_cc^-1, y <- y L_cc^-1 (band_transform_row): x_c = y~_c - sum_r N_{c,r}^T x_{c+r} -- no triangular
+// solve on the chain.  Lane = (component j = lane % 6, band block r = lane / 6): one 6-term dot per lane,
+// a five-way shuffle reduction, lanes 0..5 publish x_c.  The loop body is kept small on purpose: this code
+// runs once per solve, and one-shot code is bound by instruction fetch, not by issue (tools/microbench).
+HB_DI void band_backsub_chain(const BandChain& C, int c_hi, int c_lo, int h, int m, int lane) {
+  const int j = lane % 6, g = lane / 6;
   for (int c = c_hi; c >= c_lo; --c) {
-    const double* Wc = C.W + static_cast<size_t>(c) * h * 6;
+    const double* Wc = C.W + static_cast<size_t>(c) * h * 6 + 36 + j;
     const int nbk = min(h - 6, C.npc - 6 * (c + 1)) / 6;
-    double nv[BETA][6];
+    double acc = 0.0;
+    if (g < 5) {
+      for (int r = g; r < nbk; r += 5) {
+        const double* nr = Wc + 36 * r;
+        const double* xr = C.X + 6 * (c + 1 + r);
 #pragma unroll
-    for (int r = 0; r < BETA; ++r)
-#pragma unroll
-      for (int t = 0; t < 6; ++t) nv[r][t] = (r < nbk) ? Wc[static_cast<size_t>(6 + 6 * r + t) * 6 + j] : 0.0;
-    const double y = C.AR[static_cast<size_t>(m) * C.npc + 6 * c + j];
-    double acc[BETA];
-#pragma unroll
-    for (int r = 0; r < BETA; ++r) {
-      acc[r] = 0.0;
-#pragma unroll
-      for (int t = 0; t < 6; ++t) acc[r] += nv[r][t] * xh[r][t];
+        for (int t = 0; t < 6; ++t) acc += nr[6 * t] * xr[t];
+      }
     }
-    double tot = acc[0];
-#pragma unroll
-    for (int r = 1; r < BETA; ++r) tot += acc[r];
-    const double xo = y - tot;
-#pragma unroll
-    for (int r = BETA - 1; r > 0; --r)
-#pragma unroll
-      for (int q = 0; q < 6; ++q) xh[r][q] = xh[r - 1][q];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) xh[0][q] = __shfl_sync(0xffffffffu, xo, q);
-    if (lane < 6) C.X[6 * c + lane] = xo;
-    if (ts && lane == 0 && c_hi - c < 16) ts[c_hi - c] = clock_after(xo);
+    double tot = acc;
+    tot += __shfl_sync(0xffffffffu, acc, (lane + 6) & 31);
+    tot += __shfl_sync(0xffffffffu, acc, (lane + 12) & 31);
+    tot += __shfl_sync(0xffffffffu, acc, (lane + 18) & 31);
+    tot += __shfl_sync(0xffffffffu, acc, (lane + 24) & 31);
+    if (lane < 6) C.X[6 * c + lane] = C.AR[static_cast<size_t>(m) * C.npc + 6 * c + lane] - tot;
+    __syncwarp();
   }
-  __syncwarp();
 }
 
-// Row transform v <- v Li (Li = inverse of the column's diagonal Cholesky block, lower triangular):
-// v'[j] = sum_{q >= j} v[q] Li[q][j].  Applied to every panel row below the diagonal and to the rhs row.
-HB_DI void band_transform_row(double* v, const double* Li) {
-  double x[6], o[6];
+// Row transform v <- v L^-1 (L = the column's diagonal Cholesky block, row-major 6x6, rd = reciprocal
+// diagonal): solve x L = v from the last component down.  Applied to every panel row below the diagonal
+// and to the rhs row, it turns the back substitution into plain dot products.
+HB_DI void band_transform_row(double* v, const double* L, const double* rd) {
+  double x[6];
 #pragma unroll
   for (int q = 0; q < 6; ++q) x[q] = v[q];
 #pragma unroll
-  for (int jj = 0; jj < 6; ++jj) {
-    double acc = 0.0;
+  for (int jj = 5; jj >= 0; --jj) {
+    double acc = x[jj];
 #pragma unroll
-    for (int q = jj; q < 6; ++q) acc += x[q] * Li[q * 6 + jj];
-    o[jj] = acc;
+    for (int q = jj + 1; q < 6; ++q) acc -= x[q] * L[q * 6 + jj];
+    x[jj] = acc * rd[jj];
   }
 #pragma unroll
-  for (int q = 0; q < 6; ++q) v[q] = o[q];
+  for (int q = 0; q < 6; ++q) v[q] = x[q];
 }
 
 template <bool SMEM>
@@ -415,7 +335,6 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   const double* b = sys + static_cast<size_t>(n) * n;
   __shared__ int s_ok;
   if (tid == 0) s_ok = 1;
-  const int dmode = dbg ? static_cast<int>(dbg[71]) : 0;   // timing experiments only (HB200_BAND_DBGMODE): results are wrong when != 0
   // ---- gather: chain 0 reads P top-down, chain 1 reads J P J (index reversal) and starts its copy of the
   // separator and of the separator's arrow columns at zero (they only accumulate updates) ----
   {
@@ -520,21 +439,13 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       const double2 a0 = x2[0], a1 = x2[1], a2 = x2[2];
       double2 o0 = t2[0], o1 = t2[1], o2 = t2[2];
       double sd[6];
-      if (dmode & 4) {   // no v loads, no FMAs
 #pragma unroll
-        for (int j = 0; j < 6; ++j) sd[j] = a0.x;
-      } else if (dmode & 1) {   // v loads, no FMAs
-#pragma unroll
-        for (int j = 0; j < 6; ++j) { const double2 b0 = v2[3 * j], b1 = v2[3 * j + 1], b2 = v2[3 * j + 2]; sd[j] = b0.x + b1.y + b2.x; }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const double2 b0 = v2[3 * j], b1 = v2[3 * j + 1], b2 = v2[3 * j + 2];
-          sd[j] = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
-        }
+      for (int j = 0; j < 6; ++j) {
+        const double2 b0 = v2[3 * j], b1 = v2[3 * j + 1], b2 = v2[3 * j + 2];
+        sd[j] = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
       }
       o0.x -= sd[0]; o0.y -= sd[1]; o1.x -= sd[2]; o1.y -= sd[3]; o2.x -= sd[4]; o2.y -= sd[5];
-      if (!(dmode & 2)) { t2[0] = o0; t2[1] = o1; t2[2] = o2; }
+      t2[0] = o0; t2[1] = o1; t2[2] = o2;
     }
   };
   auto run_steps = [&](const BandChain& Q, int s0, int s1, bool use_fast) {
@@ -543,15 +454,15 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       if (rec) s_ts[s - 4][warp == 2 ? 0 : 4] = clock_after(Q.LI[static_cast<size_t>(s) * 48]);   // released (chol(s) visible)
       if (is_worker) {
         const int nb = min(h - 6, Q.npc - 6 * (s + 1));
-        if (!(dmode & 16)) band_panel(Q, s, h, m, wid, 128, nb >= 6 ? 6 : 0);
+        band_panel(Q, s, h, m, wid, 128, nb >= 6 ? 6 : 0);
         if (rec) s_ts[s - 4][1] = clock_after(Q.AR[6 * s]);           // own panel row (arrow row 0... wid 0 -> band row 6) done
         nbar_sync(barA, 160);
         if (rec) s_ts[s - 4][2] = clock_after(Q.W[static_cast<size_t>(s) * h6 + 36]);   // A released
-        if (dmode & 32) {} else if (use_fast) fast_update(s);
+        if (use_fast) fast_update(s);
         else band_update(Q, s, h, m, 6, wid, 128, have_table ? s_tile : nullptr, beta);
         if (rec) s_ts[s - 4][3] = clock_after(Q.W[static_cast<size_t>(s + 1) * h6 + 36]);  // update done (approx)
       } else {
-        if (!band_la_step(Q, s, h, lane, (s + 1 < s1) && !(dmode & 8), barA, 160)) s_ok = 0;
+        if (!band_la_step(Q, s, h, lane, s + 1 < s1, barA, 160)) s_ok = 0;
         if (rec) s_ts[s - 4][5] = clock_after(Q.LI[static_cast<size_t>(s + 1) * 48]);      // chol(s+1) done
       }
       nbar_sync(barB, 160);
@@ -586,110 +497,83 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   // ---- block inverses of every eliminated column (one thread each), and the deferred corner update
   // C -= sum over all eliminated columns of (arrow panel)(arrow panel)^T, rhs row included (row m):
   // one (u, v) pair per warp pass, lanes stride the columns (conflict-free), butterfly reduction ----
-  for (int c = tid; c < C0.ncol + C1.Ke; c += kBandThreads) {
-    if (c < C0.ncol) band_block_inverse(C0, c, h);
-    else band_block_inverse(C1, c - C0.ncol, h);
-  }
   {
-    // 3x3 register tiles of the lower triangle (rows u in [0, m], columns v in [0, m)); one tile per warp
-    // pass, lanes stride the eliminated columns of both chains, butterfly reduction of the 9 sums
-    const int nrt = (m + 3) / 3, nct = (m + 2) / 3;
-    for (int e = warp; e < nrt * nct; e += kBandThreads / 32) {
-      const int tu = e / nct, tv = e - tu * nct;
-      if (tv > tu) continue;
-      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // FP64 tensor-core tiles (mma.sync m8n8k4 -> SASS DMMA.8x8x4): output tile (ub, vb) of 8 x 8 corner entries,
+    // K = the eliminated columns of both chains in steps of 4.  Operand fragments: lane l holds
+    // A[row l/4][k l%4] and B[k l%4][col l/4] -- both are AR[row][col0 + l%4] -- and C[row l/4][col 2(l%4)+{0,1}].
+    const int nrb = (m + 1 + 7) / 8, ncb = (m + 7) / 8;
+    const int lr = lane >> 2, lk = lane & 3;
+    for (int e = warp; e < nrb * ncb; e += kBandThreads / 32) {
+      const int ub = e / ncb, vb = e - ub * ncb;
+      if (vb > ub) continue;
+      double c0 = 0.0, c1 = 0.0;
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         const BandChain& Q = ci ? C1 : C0;
         const int nused = ci ? 6 * C1.Ke : C0.npc;
-        const double* ru0 = Q.AR + static_cast<size_t>(min(3 * tu, m)) * Q.npc;
-        const double* ru1 = Q.AR + static_cast<size_t>(min(3 * tu + 1, m)) * Q.npc;
-        const double* ru2 = Q.AR + static_cast<size_t>(min(3 * tu + 2, m)) * Q.npc;
-        const double* rv0 = Q.AR + static_cast<size_t>(min(3 * tv, m - 1)) * Q.npc;
-        const double* rv1 = Q.AR + static_cast<size_t>(min(3 * tv + 1, m - 1)) * Q.npc;
-        const double* rv2 = Q.AR + static_cast<size_t>(min(3 * tv + 2, m - 1)) * Q.npc;
-        for (int col = lane; col < nused; col += 32) {
-          const double u0 = ru0[col], u1 = ru1[col], u2 = ru2[col];
-          const double v0 = rv0[col], v1 = rv1[col], v2 = rv2[col];
-          acc[0] += u0 * v0; acc[1] += u0 * v1; acc[2] += u0 * v2;
-          acc[3] += u1 * v0; acc[4] += u1 * v1; acc[5] += u1 * v2;
-          acc[6] += u2 * v0; acc[7] += u2 * v1; acc[8] += u2 * v2;
+        const double* pa = Q.AR + static_cast<size_t>(min(8 * ub + lr, m)) * Q.npc + lk;
+        const double* pb = Q.AR + static_cast<size_t>(min(8 * vb + lr, m)) * Q.npc + lk;
+        for (int col = 0; col < nused; col += 4) {
+          const bool in = col + lk < nused;
+          const double av = in ? pa[col] : 0.0, bv = in ? pb[col] : 0.0;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
         }
       }
-#pragma unroll
-      for (int q = 0; q < 9; ++q) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < 9; ++q) {
-          const int u = 3 * tu + q / 3, v = 3 * tv + q % 3;
-          if (u <= m && v < m && v <= u) CC[static_cast<size_t>(u) * LDc + v] -= acc[q];
-        }
-      }
+      const int u = 8 * ub + lr, v = 8 * vb + 2 * lk;
+      if (u <= m && v < m && v <= u) CC[static_cast<size_t>(u) * LDc + v] -= c0;
+      if (u <= m && v + 1 < m && v + 1 <= u) CC[static_cast<size_t>(u) * LDc + v + 1] -= c1;
     }
   }
   __syncthreads();
   HB_TICKD(3, CC);
-  // ---- corner (m x m, rhs carried as row m).  m < 32: one warp, lane r owns row r, no CTA barriers (the
-  // CTA-wide version spent its time in 3 barriers per column); otherwise the whole CTA ----
-  if (m < 32 && !(dmode & 128)) {
-    if (warp == 0) {
-      const int r = lane;
-      for (int q = 0; q < m; ++q) {
-        const double d = CC[static_cast<size_t>(q) * LDc + q];
-        if (!(d > 0.0) && lane == 0) s_ok = 0;
-        const double iv = rsqrt(d);
-        double lr = 0.0;
-        if (r >= q && r <= m) {
-          lr = (r == q) ? d * iv : CC[static_cast<size_t>(r) * LDc + q] * iv;
-          CC[static_cast<size_t>(r) * LDc + q] = lr;
-        }
-        __syncwarp();
-        if (r > q && r <= m) {
-          const int vmax = min(r, m - 1);
-          double* row = CC + static_cast<size_t>(r) * LDc;
-          for (int v = q + 1; v <= vmax; ++v) row[v] -= lr * CC[static_cast<size_t>(v) * LDc + q];
-        }
-        __syncwarp();
-      }
-      HB_TICK(4);
-      // back substitution with the rhs in registers: lane r holds y_r; x_q = y_q / L_qq is broadcast, then
-      // y_r -= L_qr x_q for r < q (row q of L is contiguous: conflict-free)
-      double y = (lane < m) ? CC[static_cast<size_t>(m) * LDc + lane] : 0.0;
-      const double dinv = (lane < m) ? 1.0 / CC[static_cast<size_t>(lane) * LDc + lane] : 0.0;
-#pragma unroll 4
-      for (int q = m - 1; q >= 0; --q) {
-        const double lq = (lane < q) ? CC[static_cast<size_t>(q) * LDc + lane] : 0.0;
-        const double xq = __shfl_sync(0xffffffffu, y * dinv, q);
-        if (lane == q) XA[q] = xq;
-        y -= lq * xq;
-      }
-    }
-  } else {
+  // ---- corner (m x m, rhs carried as row m): right-looking Cholesky by the whole CTA with FIXED element
+  // ownership (element (u, v), v <= min(u, m-1), decoded once), two barriers per column and no
+  // division / modulo in the column loop.  The pivot's square root goes to XA's neighbour array DG so
+  // that nobody overwrites CC[q][q] while others still read it. ----
+  {
+    double* DG = XA + m;   // diagonal of the corner factor
+    const int ntri = m * (m + 1) / 2, nel = ntri + m;
+    auto decode = [&](int e, int* pu, int* pv) {
+      if (e < ntri) {
+        int u = static_cast<int>((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+        while (u * (u + 1) / 2 > e) --u;
+        while ((u + 1) * (u + 2) / 2 <= e) ++u;
+        *pu = u; *pv = e - u * (u + 1) / 2;
+      } else { *pu = m; *pv = e - ntri; }
+    };
+    int u0 = 0, v0 = m;   // this thread's first element (v0 = m: none)
+    if (tid < nel) decode(tid, &u0, &v0);
+    double* own0 = CC + static_cast<size_t>(u0) * LDc + v0;
     for (int q = 0; q < m; ++q) {
       const double d = CC[static_cast<size_t>(q) * LDc + q];
-      if (!(d > 0.0) && tid == 0) s_ok = 0;
       const double iv = rsqrt(d);
-      __syncthreads();   // everyone has read the pivot before it is overwritten
-      for (int r = q + tid; r <= m; r += kBandThreads) CC[static_cast<size_t>(r) * LDc + q] = (r == q) ? d * iv : CC[static_cast<size_t>(r) * LDc + q] * iv;
+      if (tid == 0) { if (!(d > 0.0)) s_ok = 0; DG[q] = d * iv; }
+      for (int r = q + 1 + tid; r <= m; r += kBandThreads) CC[static_cast<size_t>(r) * LDc + q] *= iv;
       __syncthreads();
-      const int rem = m - q;  // rows q+1 .. m (row m = rhs), columns q+1 .. m-1
-      for (int e = tid; e < rem * rem; e += kBandThreads) {
-        const int u = q + 1 + e / rem, v = q + 1 + e % rem;
-        if (v > u || v >= m) continue;
-        CC[static_cast<size_t>(u) * LDc + v] -= CC[static_cast<size_t>(u) * LDc + q] * CC[static_cast<size_t>(v) * LDc + q];
+      if (v0 > q && v0 < m) *own0 -= CC[static_cast<size_t>(u0) * LDc + q] * CC[static_cast<size_t>(v0) * LDc + q];
+      for (int e = tid + kBandThreads; e < nel; e += kBandThreads) {   // only for m > 30
+        int u, v;
+        decode(e, &u, &v);
+        if (v > q) CC[static_cast<size_t>(u) * LDc + v] -= CC[static_cast<size_t>(u) * LDc + q] * CC[static_cast<size_t>(v) * LDc + q];
       }
       __syncthreads();
     }
     HB_TICK(4);
     if (warp == 0) {
-      for (int q = m - 1; q >= 0; --q) {
-        double xq = 0.0;
-        if ((q & 31) == lane) { xq = CC[static_cast<size_t>(m) * LDc + q] / CC[static_cast<size_t>(q) * LDc + q]; XA[q] = xq; }
-        xq = __shfl_sync(0xffffffffu, xq, q & 31);
-        for (int r = lane; r < q; r += 32) CC[static_cast<size_t>(m) * LDc + r] -= CC[static_cast<size_t>(q) * LDc + r] * xq;
+      // back substitution with the rhs in registers: lane r holds y_r; x_q = y_q / L_qq is broadcast, then
+      // y_r -= L_qr x_q for r < q (row q of L is contiguous: conflict-free)
+      for (int base = ((m - 1) / 32) * 32; base >= 0; base -= 32) {   // m <= 32: one pass
+        const int r = base + lane;
+        double y = (r < m) ? CC[static_cast<size_t>(m) * LDc + r] : 0.0;
+        const double dinv = (r < m) ? 1.0 / DG[r] : 0.0;
+        // contributions of already solved x (rows above this 32-block)
+        for (int q = m - 1; q >= base + 32; --q) if (r < m) y -= CC[static_cast<size_t>(q) * LDc + r] * XA[q];
+        for (int q = min(m, base + 32) - 1; q >= base; --q) {
+          const double lq = (r < q) ? CC[static_cast<size_t>(q) * LDc + r] : 0.0;
+          const double xq = __shfl_sync(0xffffffffu, y * dinv, q - base);
+          if (r == q) XA[q] = xq;
+          y -= lq * xq;
+        }
         __syncwarp();
       }
     }
@@ -708,9 +592,8 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     }
   }
   __syncthreads();
-  const bool fast_bs = (beta == 3 || beta == 5) && !(dmode & 64);
-  if (fast_bs) {
-    // row transform of every eliminated column: panel rows B <- B Li and rhs y <- Li^T y (one row per thread)
+  {
+    // row transform of every eliminated column: panel rows B <- B L^-1 and rhs y <- y L^-1 (one row per thread)
     const int rows_per_col = (h - 6) + 1;
     const int ncols = C0.ncol + C1.Ke;
     for (int e = tid; e < ncols * rows_per_col; e += kBandThreads) {
@@ -718,19 +601,16 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       const BandChain& Q = cc < C0.ncol ? C0 : C1;
       const int c = cc < C0.ncol ? cc : cc - C0.ncol;
       const int nb = min(h - 6, Q.npc - 6 * (c + 1));
-      const double* Li = Q.LI + static_cast<size_t>(c) * 48 + 8;
-      if (t < nb) band_transform_row(Q.W + (static_cast<size_t>(c) * h + 6 + t) * 6, Li);
-      else if (t == h - 6) band_transform_row(Q.AR + static_cast<size_t>(m) * Q.npc + 6 * c, Li);
+      const double* L = Q.W + static_cast<size_t>(c) * h6;
+      const double* rd = Q.LI + static_cast<size_t>(c) * 48;
+      if (t < nb) band_transform_row(Q.W + (static_cast<size_t>(c) * h + 6 + t) * 6, L, rd);
+      else if (t == h - 6) band_transform_row(Q.AR + static_cast<size_t>(m) * Q.npc + 6 * c, L, rd);
     }
     __syncthreads();
   }
   HB_TICKD(7, C0.AR);
   // separator columns first (chain 0, warp 0), then outwards: chain 0 in warp 0, chain 1 in warp 1
-  if (warp == 0 && C0.ncol > C0.Ke) {
-    if (beta == 3 && fast_bs) band_backsub_chain<3>(C0, C0.ncol - 1, C0.Ke, h, m, lane);
-    else if (beta == 5 && fast_bs) band_backsub_chain<5>(C0, C0.ncol - 1, C0.Ke, h, m, lane);
-    else for (int c = C0.ncol - 1; c >= C0.Ke; --c) band_backsub_column(C0, c, h, m, lane);
-  }
+  if (warp == 0 && C0.ncol > C0.Ke) band_backsub_chain(C0, C0.ncol - 1, C0.Ke, h, m, lane);
   __syncthreads();
   if (pl.Kb) {
     for (int v = tid; v < 6 * pl.bs; v += kBandThreads) C1.X[C1.npc - 1 - v] = C0.X[6 * C0.Ke + v];
@@ -738,9 +618,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   }
   if (warp < 2) {
     const BandChain& Q = warp ? C1 : C0;
-    if (beta == 3 && fast_bs) band_backsub_chain<3>(Q, Q.Ke - 1, 0, h, m, lane);
-    else if (beta == 5 && fast_bs) band_backsub_chain<5>(Q, Q.Ke - 1, 0, h, m, lane);
-    else for (int c = Q.Ke - 1; c >= 0; --c) band_backsub_column(Q, c, h, m, lane);
+    band_backsub_chain(Q, Q.Ke - 1, 0, h, m, lane);
   }
   __syncthreads();
   HB_TICKD(6, C0.X);
