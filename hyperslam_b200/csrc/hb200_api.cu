@@ -83,6 +83,11 @@ void compute_basis(Basis* b, int k) {
 struct hb200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // side stream: the inertial / manifold factor kernels (and their J^T J) are independent of the visual ones and
+  // run concurrently with them -- a fork / join inside the iteration (and inside its CUDA graph)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool forked = false;
   bool own_stream = false;
   bool use_graph = true;
   int num_sms = 0;
@@ -192,6 +197,23 @@ int check_launch(hb200_ctx* c, const char* what) {
     if (rc__) return rc__;                         \
   } while (0)
 
+cudaStream_t side(hb200_ctx* c) { return c->forked ? c->stream2 : c->stream; }
+int fork_side(hb200_ctx* c) {
+  static const bool no_fork = getenv("HB200_NO_FORK") != nullptr;   // A/B switch for measurements
+  if (c->profiling || c->forked || !c->stream2 || no_fork) return 0;   // the per-launch profile wants a serial timeline
+  HB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  HB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  c->forked = true;
+  return 0;
+}
+int join_side(hb200_ctx* c) {
+  if (!c->forked) return 0;
+  HB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+  HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  c->forked = false;
+  return 0;
+}
+
 int update_fixed(hb200_ctx* c) {
   c->n = 6 * c->K + 3 * c->Kbg + 3 * c->Kba + 2;
   std::vector<unsigned char> f(c->n, 0);
@@ -276,7 +298,7 @@ int launch_inertial(hb200_ctx* c, int sel) {
   a.bg = c->bg[sel].p; a.ba = c->ba[sel].p; a.gravity = c->grav[sel].p;
   a.r = J ? c->i_r.p : nullptr; a.Jp = c->i_Jp.p; a.wg = c->i_wg.p; a.wa = c->i_wa.p; a.Jg = c->i_Jg.p;
   a.cost_partial = c->cp_imu[J ? 0 : 1].p; a.loss_scale = c->imu_scale;
-  inertial_eval_kernel<K, 4, J><<<c->n_imu_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis, c->bias_basis);
+  inertial_eval_kernel<K, 4, J><<<c->n_imu_blocks, kEvalThreads, 0, side(c)>>>(a, c->basis, c->bias_basis);
   HB_LAUNCH(c, "inertial_eval_kernel");
   return 0;
 }
@@ -287,7 +309,7 @@ int launch_manifold(hb200_ctx* c, int sel) {
   ManifoldArgs a{};
   a.n = c->Nm; a.stamp = c->m_stamp.p; a.meas = c->m_meas.p; a.idx = c->m_idx.p; a.tab = c->tab[sel].p; a.sensors = c->sensors.p;
   a.r = J ? c->m_r.p : nullptr; a.Jp = c->m_Jp.p; a.cost_partial = c->cp_imu[J ? 0 : 1].p + c->n_imu_blocks;
-  manifold_eval_kernel<K, J><<<c->n_man_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
+  manifold_eval_kernel<K, J><<<c->n_man_blocks, kEvalThreads, 0, side(c)>>>(a, c->basis);
   HB_LAUNCH(c, "manifold_eval_kernel");
   return 0;
 }
@@ -296,22 +318,32 @@ int enqueue_manifold(hb200_ctx* c, bool want_J, int sel) {
   return want_J ? launch_manifold<6, true>(c, sel) : launch_manifold<6, false>(c, sel);
 }
 
-int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false) {
-  prep_kernel<<<(c->K + 63) / 64, 64, 0, c->stream>>>(c->K, c->knots[sel].p, c->tab[sel].p);
-  HB_LAUNCH(c, "prep_kernel");
+// keep_fork: leave the side stream forked on return (the caller enqueues more side-stream work and joins).
+// clear_system: zero the packed reduced system in the knot-table launch; skip_prep: the table of state `sel` is
+// already up to date (retract_kernel built the trial table).
+int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false, bool keep_fork = false, bool clear_system = false,
+                     bool skip_prep = false) {
+  if (c->k != 4 && c->k != 6) return fail(-4, "spline order %d not supported (4 or 6)", c->k);
+  if (!skip_prep) {
+    const size_t nclear = clear_system ? static_cast<size_t>(c->n) * c->n + 3 * static_cast<size_t>(c->n) + 2 : 0;
+    const int blocks = clear_system ? static_cast<int>(std::min<size_t>((nclear / 4 + 255) / 256, static_cast<size_t>(c->num_sms) * 4)) : (c->K + 255) / 256;
+    prep_kernel<<<std::max(blocks, (c->K + 255) / 256), 256, 0, c->stream>>>(c->K, c->knots[sel].p, c->tab[sel].p, clear_system ? c->sys.p : nullptr, nclear);
+    HB_LAUNCH(c, "prep_kernel");
+  }
   int rc = 0;
+  // visual factors on the main stream, inertial + manifold factors concurrently on the side stream
+  if (c->Nv && (c->Ni || c->Nm) && (rc = fork_side(c))) return rc;
   if (accumulate) {   // fused path: pixel J^T J is accumulated by the factor kernel itself
     rc = (c->k == 4) ? launch_pixel<4, true>(c, sel, true) : launch_pixel<6, true>(c, sel, true);
-    if (rc) return rc;
-    rc = (c->k == 4) ? launch_inertial<4, true>(c, sel) : launch_inertial<6, true>(c, sel);
-    if (rc) return rc;
-    return enqueue_manifold(c, true, sel);
+    if (!rc) rc = (c->k == 4) ? launch_inertial<4, true>(c, sel) : launch_inertial<6, true>(c, sel);
+    if (!rc) rc = enqueue_manifold(c, true, sel);
+  } else {
+    if (c->k == 4) { rc = want_J ? launch_pixel<4, true>(c, sel) : launch_pixel<4, false>(c, sel); if (!rc) rc = want_J ? launch_inertial<4, true>(c, sel) : launch_inertial<4, false>(c, sel); }
+    else { rc = want_J ? launch_pixel<6, true>(c, sel) : launch_pixel<6, false>(c, sel); if (!rc) rc = want_J ? launch_inertial<6, true>(c, sel) : launch_inertial<6, false>(c, sel); }
+    if (!rc) rc = enqueue_manifold(c, want_J, sel);
   }
-  if (c->k == 4) { rc = want_J ? launch_pixel<4, true>(c, sel) : launch_pixel<4, false>(c, sel); if (rc) return rc; rc = want_J ? launch_inertial<4, true>(c, sel) : launch_inertial<4, false>(c, sel); }
-  else if (c->k == 6) { rc = want_J ? launch_pixel<6, true>(c, sel) : launch_pixel<6, false>(c, sel); if (rc) return rc; rc = want_J ? launch_inertial<6, true>(c, sel) : launch_inertial<6, false>(c, sel); }
-  else return fail(-4, "spline order %d not supported (4 or 6)", c->k);
-  if (rc) return rc;
-  return enqueue_manifold(c, want_J, sel);
+  if (rc || !keep_fork) { const int rj = join_side(c); if (!rc) rc = rj; }
+  return rc;
 }
 
 int enqueue_clear_system(hb200_ctx* c) {
@@ -330,19 +362,20 @@ int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
   }
   if (c->Ni) {
     if (c->k == 4)
-      inertial_hessian_kernel<4, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, c->stream>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+      inertial_hessian_kernel<4, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
                                                                              c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     else
-      inertial_hessian_kernel<6, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, c->stream>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+      inertial_hessian_kernel<6, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
                                                                              c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     HB_LAUNCH(c, "inertial_hessian_kernel");
   }
   if (c->Nm) {
     const int blocks = (c->Nm + kManWarps - 1) / kManWarps;
-    if (c->k == 4) manifold_hessian_kernel<4><<<blocks, kManWarps * 32, 0, c->stream>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->n);
-    else manifold_hessian_kernel<6><<<blocks, kManWarps * 32, 0, c->stream>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->n);
+    if (c->k == 4) manifold_hessian_kernel<4><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->n);
+    else manifold_hessian_kernel<6><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->n);
     HB_LAUNCH(c, "manifold_hessian_kernel");
   }
+  { const int rj = join_side(c); if (rj) return rj; }
   diag_cost_kernel<<<std::max(1, (c->n + 255) / 256), 256, 0, c->stream>>>(c->sys.p, c->n, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p,
                                                                          c->n_imu_blocks + c->n_man_blocks);
   HB_LAUNCH(c, "diag_cost_kernel");
@@ -367,11 +400,15 @@ int enqueue_finalize(hb200_ctx* c) {
   return 0;
 }
 
-int enqueue_solve(hb200_ctx* c) {
+// damp_in_solver: the band solver applies LM damping + the constant-dof mask itself (finalize_kernel skipped)
+int enqueue_solve(hb200_ctx* c, bool damp_in_solver = false) {
   if (c->band_solver) {
+    const SolverState* st = damp_in_solver ? c->st.p : nullptr;
+    const unsigned char* fx = damp_in_solver ? c->fixed.p : nullptr;
+    double* Dout = damp_in_solver ? c->D.p : nullptr;
     const size_t smem = c->band_smem ? band_workspace_doubles(c->K, c->beta, c->n - 6 * c->K) * sizeof(double) : 0;
-    if (c->band_smem) band_solve_kernel<true><<<1, kBandThreads, smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p);
-    else band_solve_kernel<false><<<1, kBandThreads, 0, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p);
+    if (c->band_smem) band_solve_kernel<true><<<1, kBandThreads, smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout);
+    else band_solve_kernel<false><<<1, kBandThreads, 0, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout);
     HB_LAUNCH(c, "band_solve_kernel");
   } else {
     int n = c->n;
@@ -390,10 +427,10 @@ int enqueue_solve(hb200_ctx* c) {
     if (c->Nv) {
       if (c->k == 4)
         lm_backsub_kernel<4><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
-                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p);
+                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p);
       else
         lm_backsub_kernel<6><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
-                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p);
+                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p);
       HB_LAUNCH(c, "lm_backsub_kernel");
     } else {
       HB_CUDA(cudaMemsetAsync(c->dl.p, 0, 3 * static_cast<size_t>(c->L) * sizeof(double), c->stream));
@@ -406,7 +443,7 @@ int enqueue_solve(hb200_ctx* c) {
 int enqueue_retract(hb200_ctx* c) {
   const int m = std::max(std::max(c->K, c->L), std::max(std::max(c->Kbg, c->Kba), 1));
   retract_kernel<<<(m + 127) / 128, 128, 0, c->stream>>>(c->K, c->Kbg, c->Kba, c->L, c->dp.p, c->dl.p, c->knots[0].p, c->bg[0].p, c->ba[0].p, c->grav[0].p,
-                                                        c->lms[0].p, c->knots[1].p, c->bg[1].p, c->ba[1].p, c->grav[1].p, c->lms[1].p);
+                                                        c->lms[0].p, c->knots[1].p, c->bg[1].p, c->ba[1].p, c->grav[1].p, c->lms[1].p, c->tab[1].p, (c->L && !c->Nv) ? 1 : 0);
   HB_LAUNCH(c, "retract_kernel");
   return 0;
 }
@@ -420,18 +457,21 @@ int enqueue_scalars(hb200_ctx* c) {
 
 int enqueue_accept(hb200_ctx* c) {
   ScalarArgs sa{c->cp_pix[1].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[1].p, c->n_imu_blocks + c->n_man_blocks, c->lm_part.p, (c->L && c->Nv) ? c->n_lm_blocks : 0};
-  accept_kernel<<<1, 256, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
-                                         c->allreduce ? 0 : 1, sa);
-  HB_LAUNCH(c, "accept_kernel");
   CommitArgs a{};
   const size_t counts[5] = {8 * static_cast<size_t>(c->K), 4 * static_cast<size_t>(c->Kbg), 4 * static_cast<size_t>(c->Kba), 3, 3 * static_cast<size_t>(c->L)};
   const double* srcs[5] = {c->knots[1].p, c->bg[1].p, c->ba[1].p, c->grav[1].p, c->lms[1].p};
   double* dsts[5] = {c->knots[0].p, c->bg[0].p, c->ba[0].p, c->grav[0].p, c->lms[0].p};
-  size_t mx = 1;
-  for (int i = 0; i < 5; ++i) { a.count[i] = counts[i]; a.src[i] = srcs[i]; a.dst[i] = dsts[i]; mx = std::max(mx, counts[i]); }
-  const int blocks = static_cast<int>(std::min<size_t>((mx + 255) / 256, static_cast<size_t>(c->num_sms) * 4));
-  commit_kernel<<<blocks, 256, 0, c->stream>>>(c->st.p, a);
-  HB_LAUNCH(c, "commit_kernel");
+  size_t mx = 1, total = 0;
+  for (int i = 0; i < 5; ++i) { a.count[i] = counts[i]; a.src[i] = srcs[i]; a.dst[i] = dsts[i]; mx = std::max(mx, counts[i]); total += counts[i]; }
+  const bool fuse_commit = total <= 16384;   // small windows: one CTA commits the accepted state right away
+  accept_kernel<<<1, 256, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
+                                         c->allreduce ? 0 : 1, sa, fuse_commit ? 1 : 0, a);
+  HB_LAUNCH(c, "accept_kernel");
+  if (!fuse_commit) {
+    const int blocks = static_cast<int>(std::min<size_t>((mx + 255) / 256, static_cast<size_t>(c->num_sms) * 4));
+    commit_kernel<<<blocks, 256, 0, c->stream>>>(c->st.p, a);
+    HB_LAUNCH(c, "commit_kernel");
+  }
   return 0;
 }
 
@@ -440,14 +480,14 @@ int enqueue_accept(hb200_ctx* c) {
 int enqueue_segment(hb200_ctx* c, int segment) {
   int rc = 0;
   if (segment == 0) {
-    if ((rc = enqueue_clear_system(c))) return rc;
-    if ((rc = enqueue_evaluate(c, true, 0, true))) return rc;
+    if ((rc = enqueue_evaluate(c, true, 0, true, /*keep_fork=*/true, /*clear_system=*/true))) return rc;
     if ((rc = enqueue_build(c, true))) return rc;
   } else if (segment == 1) {
-    if ((rc = enqueue_finalize(c))) return rc;
-    if ((rc = enqueue_solve(c))) return rc;
-    if ((rc = enqueue_retract(c))) return rc;
-    if ((rc = enqueue_evaluate(c, false, 1))) return rc;
+    // band solver: damping + constant-dof mask are applied while it gathers the band (no finalize pass)
+    if (!c->band_solver && (rc = enqueue_finalize(c))) return rc;
+    if ((rc = enqueue_solve(c, /*damp_in_solver=*/c->band_solver))) return rc;
+    if ((rc = enqueue_retract(c))) return rc;   // also builds the trial knot table
+    if ((rc = enqueue_evaluate(c, false, 1, false, false, false, /*skip_prep=*/true))) return rc;
     if (c->allreduce && (rc = enqueue_scalars(c))) return rc;
   } else {
     if ((rc = enqueue_accept(c))) return rc;
@@ -498,6 +538,9 @@ int create_impl(const hb200_options* options, hb200_ctx* c) {
   c->force_dense = options ? (options->reserved & 1) != 0 : false;
   if (options && options->stream) { c->stream = static_cast<cudaStream_t>(options->stream); c->own_stream = false; }
   else { HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  HB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  HB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  HB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   int rc = ensure_placeholders(c);
   if (rc) return rc;
   HB_CUDA(cudaFuncSetAttribute(cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCholSmem)));
@@ -524,6 +567,7 @@ void hb200_destroy(hb200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->graph) cudaGraphDestroy(c->graph);
@@ -536,6 +580,9 @@ void hb200_destroy(hb200_ctx* c) {
   c->sys.release(); c->D.release(); c->Lw.release(); c->Ldiag.release(); c->dp.release(); c->dl.release(); c->Vinv.release(); c->gl.release(); c->Dl.release();
   c->band_ws.release(); c->band_dbg.release(); c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
   c->snap_knots.release(); c->snap_bg.release(); c->snap_ba.release(); c->snap_grav.release(); c->snap_lms.release(); c->snap_st.release();
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1131,6 +1178,11 @@ int iterate_enqueue(hb200_ctx* c, int iterations) {
         HB_CUDA(cudaGraphGetNodes(c->graph, nd, &nodes));
         for (size_t i = 0; i < nodes; ++i) { cudaGraphNodeType t; if (cudaGraphNodeGetType(nd[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) c->launches_per_iteration += 1; }
         delete[] nd;
+        if (getenv("HB200_GRAPH_DEBUG")) {
+          size_t edges = 0;
+          cudaGraphGetEdges(c->graph, nullptr, nullptr, &edges);
+          std::fprintf(stderr, "[hb200] iteration graph: %zu nodes (%lld kernels), %zu edges\n", nodes, c->launches_per_iteration, edges);
+        }
       }
       HB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
       c->launches += c->launches_per_iteration;
@@ -1287,7 +1339,7 @@ int hb200_interpolate(hb200_ctx* c, int n, const double* stamps, double* pose, d
   HB_CUDA(c->d_invalid.ensure(1));
   HB_CUDA(cudaMemsetAsync(c->d_invalid.p, 0, sizeof(int), c->stream));
   HB_CUDA(cudaMemcpyAsync(d_t.p, stamps, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-  prep_kernel<<<(c->K + 63) / 64, 64, 0, c->stream>>>(c->K, c->knots[0].p, c->tab[0].p);
+  prep_kernel<<<(c->K + 63) / 64, 64, 0, c->stream>>>(c->K, c->knots[0].p, c->tab[0].p, nullptr, 0);
   HB_LAUNCH(c, "prep_kernel");
   if (c->k == 4) interpolate_kernel<4><<<(n + 127) / 128, 128, 0, c->stream>>>(n, d_t.p, c->knots[0].p, c->tab[0].p, c->K, c->basis, d_p.p, d_v.p, d_a.p, c->d_invalid.p);
   else interpolate_kernel<6><<<(n + 127) / 128, 128, 0, c->stream>>>(n, d_t.p, c->knots[0].p, c->tab[0].p, c->K, c->basis, d_p.p, d_v.p, d_a.p, c->d_invalid.p);

@@ -298,7 +298,9 @@ HB_DI void band_transform_row(double* v, const double* L, const double* rd) {
 template <bool SMEM>
 __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* __restrict__ sys, int n, int K, int beta,
                                                                   double* __restrict__ ws_global, double* __restrict__ x_out,
-                                                                  int* __restrict__ spd_flag, long long* __restrict__ dbg) {
+                                                                  int* __restrict__ spd_flag, long long* __restrict__ dbg,
+                                                                  const SolverState* __restrict__ st, const unsigned char* __restrict__ fixed,
+                                                                  double* __restrict__ Dout) {
   extern __shared__ double s_band[];
   double* ws = SMEM ? s_band : ws_global;
   const int np = 6 * K, m = n - np, h = 6 + 6 * beta, h6 = h * 6;
@@ -333,6 +335,22 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   const BandChain CP = (tid >> 8) ? C1 : C0;        // ... and in the panel phase (threads 0..255 / 256..511)
   const double* S = sys;
   const double* b = sys + static_cast<size_t>(n) * n;
+  // Dout != null: the system is the raw accumulation (lower triangle of H with the Schur complement applied,
+  // b = -g + ...); LM damping mu * clamp(diag H) and the constant-dof mask are applied while gathering
+  // (== finalize_kernel, which then need not run), and D = clamp(diag H) is written out for accept_kernel.
+  const bool damp = Dout != nullptr;
+  const double* diagH = b + n;
+  const double mu = damp ? 1.0 / st->radius : 0.0;
+  auto Sval = [&](int row, int col) -> double {   // row >= col
+    double v = S[static_cast<size_t>(row) * n + col];
+    if (damp) {
+      if (row == col) v += mu * fmin(fmax(diagH[row], 1e-6), 1e32);
+      if (fixed[row] || fixed[col]) v = (row == col) ? 1.0 : 0.0;
+    }
+    return v;
+  };
+  auto bval = [&](int col) -> double { return (damp && fixed[col]) ? 0.0 : b[col]; };
+  if (damp) for (int a = threadIdx.x; a < n; a += kBandThreads) Dout[a] = fmin(fmax(diagH[a], 1e-6), 1e32);
   __shared__ int s_ok;
   if (tid == 0) s_ok = 1;
   // ---- gather: chain 0 reads P top-down, chain 1 reads J P J (index reversal) and starts its copy of the
@@ -343,28 +361,28 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       const int c = e / h6, rem = e - c * h6;
       const int i = rem / 6, j = rem - 6 * i;
       const int row = 6 * c + i, col = 6 * c + j;
-      C0.W[e] = (row < C0.npc && row >= col) ? S[static_cast<size_t>(row) * n + col] : 0.0;
+      C0.W[e] = (row < C0.npc && row >= col) ? Sval(row, col) : 0.0;
     }
     for (int e = tid; e < C1.ncol * h6; e += kBandThreads) {
       const int c = e / h6, rem = e - c * h6;
       const int i = rem / 6, j = rem - 6 * i;
       const int rr = 6 * c + i, rc = 6 * c + j;          // reversed (chain-local) row / column
       double v = 0.0;
-      if (c < C1.Ke && rr < N1 && rr >= rc) v = S[static_cast<size_t>(np - 1 - rc) * n + (np - 1 - rr)];
+      if (c < C1.Ke && rr < N1 && rr >= rc) v = Sval(np - 1 - rc, np - 1 - rr);
       C1.W[e] = v;
     }
     for (int e = tid; e < (m + 1) * C0.npc; e += kBandThreads) {
       const int r = e / C0.npc, col = e - r * C0.npc;
-      C0.AR[e] = (r < m) ? S[static_cast<size_t>(np + r) * n + col] : b[col];
+      C0.AR[e] = (r < m) ? Sval(np + r, col) : bval(col);
     }
     for (int e = tid; e < (m + 1) * N1; e += kBandThreads) {
       const int r = e / N1, rc = e - r * N1;
       const int col = np - 1 - rc;
-      C1.AR[e] = (rc < 6 * C1.Ke) ? ((r < m) ? S[static_cast<size_t>(np + r) * n + col] : b[col]) : 0.0;
+      C1.AR[e] = (rc < 6 * C1.Ke) ? ((r < m) ? Sval(np + r, col) : bval(col)) : 0.0;
     }
     for (int e = tid; e < (m + 1) * m; e += kBandThreads) {
       const int r = e / m, q = e - r * m;
-      CC[static_cast<size_t>(r) * LDc + q] = (r < m) ? S[static_cast<size_t>(np + r) * n + np + q] : b[np + q];
+      CC[static_cast<size_t>(r) * LDc + q] = (r < m) ? ((q <= r) ? Sval(np + r, np + q) : 0.0) : bval(np + q);
     }
   }
   __syncthreads();

@@ -117,21 +117,17 @@ __global__ void bind_inertial_kernel(int n, const double* __restrict__ stamp, co
 // ---------------------------------------------------------------------------------------------
 // Knot table: one thread per control point (a3, per-segment part shared by all factors).
 // ---------------------------------------------------------------------------------------------
-__global__ void prep_kernel(int K, const double* __restrict__ knots, double* __restrict__ tab) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= K) return;
-  const double* kn = knots + 8 * static_cast<size_t>(j);
-  double* row = tab + static_cast<size_t>(j) * kTabStride;
-  double q[4] = {kn[0], kn[1], kn[2], kn[3]};
+// One knot-table row from the control point's quaternion q, position p, stamp and the previous control
+// point's quaternion qp (have_prev = false for row 0).
+HB_DI void knot_table_row(const double* q, const double* p, double stamp, const double* qp, bool have_prev, double* __restrict__ row) {
   double R[9];
   quat_to_rot(q, R);
 #pragma unroll
   for (int i = 0; i < 9; ++i) row[i] = R[i];
-  row[9] = kn[4]; row[10] = kn[5]; row[11] = kn[6];
+  row[9] = p[0]; row[10] = p[1]; row[11] = p[2];
   double d[3] = {0, 0, 0}, G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (j > 0) {
-    const double* kp = kn - 8;
-    const double qc[4] = {-kp[0], -kp[1], -kp[2], kp[3]};
+  if (have_prev) {
+    const double qc[4] = {-qp[0], -qp[1], -qp[2], qp[3]};
     double qr[4], Ji[9];
     quat_mul(qc, q, qr);
     quat_log(qr, d);
@@ -141,7 +137,21 @@ __global__ void prep_kernel(int K, const double* __restrict__ knots, double* __r
   row[12] = d[0]; row[13] = d[1]; row[14] = d[2];
 #pragma unroll
   for (int i = 0; i < 9; ++i) row[15 + i] = G[i];
-  row[24] = kn[7]; row[25] = 0; row[26] = 0; row[27] = 0;
+  row[24] = stamp; row[25] = 0; row[26] = 0; row[27] = 0;
+}
+
+// clear / nclear: optional buffer zeroed by the same launch (the packed reduced system at the start of an
+// iteration -- saves the separate memset node).
+__global__ void prep_kernel(int K, const double* __restrict__ knots, double* __restrict__ tab, double* __restrict__ clear, size_t nclear) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  for (size_t e = gid; e < nclear; e += static_cast<size_t>(gridDim.x) * blockDim.x) clear[e] = 0.0;
+  const int j = static_cast<int>(gid);
+  if (gid >= static_cast<size_t>(K)) return;
+  const double* kn = knots + 8 * static_cast<size_t>(j);
+  const double q[4] = {kn[0], kn[1], kn[2], kn[3]};
+  double qp[4] = {0, 0, 0, 1};
+  if (j > 0) { qp[0] = kn[-8]; qp[1] = kn[-7]; qp[2] = kn[-6]; qp[3] = kn[-5]; }
+  knot_table_row(q, kn + 4, kn[7], qp, j > 0, tab + static_cast<size_t>(j) * kTabStride);
 }
 
 // Calibration tables (once per set_cameras / set_imu).

@@ -651,7 +651,8 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const 
                                                                   const double* __restrict__ Jp, const double* __restrict__ Jl, const double* __restrict__ wv,
                                                                   const double* __restrict__ Vinv, const double* __restrict__ gl,
                                                                   const double* __restrict__ Dl, const double* __restrict__ dp,
-                                                                  double* __restrict__ dl, double* __restrict__ part /*[grid][2]*/) {
+                                                                  double* __restrict__ dl, double* __restrict__ part /*[grid][2]*/,
+                                                                  const double* __restrict__ lms, double* __restrict__ lms_t) {
   constexpr int NB = 6 * K;
   constexpr int CG = NB / 4;  // columns per lane group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -698,6 +699,7 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const 
       for (int c = 0; c < 3; ++c) {
         const double v = Vi[3 * c] * rhs[0] + Vi[3 * c + 1] * rhs[1] + Vi[3 * c + 2] * rhs[2];
         dl[3 * static_cast<size_t>(l) + c] = v;
+        if (lms_t) lms_t[3 * static_cast<size_t>(l) + c] = lms[3 * static_cast<size_t>(l) + c] + v;   // Manifold::Plus of the landmark block
         s_g += v * g[c];
         s_d += v * v * Dl[3 * static_cast<size_t>(l) + c];
       }
@@ -741,7 +743,8 @@ HB_DI void sphere_plus(const double* x, const double* delta, double* out) {
 __global__ void retract_kernel(int K, int Kbg, int Kba, int L, const double* __restrict__ dp, const double* __restrict__ dl,
                                const double* __restrict__ knots, const double* __restrict__ bg, const double* __restrict__ ba,
                                const double* __restrict__ grav, const double* __restrict__ lms, double* __restrict__ knots_t,
-                               double* __restrict__ bg_t, double* __restrict__ ba_t, double* __restrict__ grav_t, double* __restrict__ lms_t) {
+                               double* __restrict__ bg_t, double* __restrict__ ba_t, double* __restrict__ grav_t, double* __restrict__ lms_t,
+                               double* __restrict__ tab_t /* trial knot table, or null */, int retract_landmarks) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < K) {
     const double* kn = knots + 8 * static_cast<size_t>(i);
@@ -754,6 +757,19 @@ __global__ void retract_kernel(int K, int Kbg, int Kba, int L, const double* __r
     double* o = knots_t + 8 * static_cast<size_t>(i);
     o[0] = qn[0]; o[1] = qn[1]; o[2] = qn[2]; o[3] = qn[3];
     o[4] = kn[4] + d[3]; o[5] = kn[5] + d[4]; o[6] = kn[6] + d[5]; o[7] = kn[7];
+    if (tab_t) {
+      // the trial state's knot-table row (same arithmetic as prep_kernel): this thread retracts knot i-1 again
+      // for the relative rotation instead of waiting for its neighbour
+      double qp[4] = {0, 0, 0, 1};
+      if (i > 0) {
+        const double thp[3] = {d[-6], d[-5], d[-4]};
+        const double qo[4] = {kn[-8], kn[-7], kn[-6], kn[-5]};
+        double qep[4];
+        quat_exp(thp, qep);
+        quat_mul(qep, qo, qp);
+      }
+      knot_table_row(qn, o + 4, o[7], qp, i > 0, tab_t + static_cast<size_t>(i) * kTabStride);
+    }
   }
   if (i < Kbg) {
     const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(i);
@@ -773,7 +789,7 @@ __global__ void retract_kernel(int K, int Kbg, int Kba, int L, const double* __r
     sphere_plus(x, dd, o);
     grav_t[0] = o[0]; grav_t[1] = o[1]; grav_t[2] = o[2];
   }
-  if (i < L) {
+  if (retract_landmarks && i < L) {   // otherwise lm_backsub_kernel has written the trial landmarks already
     for (int c = 0; c < 3; ++c) lms_t[3 * static_cast<size_t>(i) + c] = lms[3 * static_cast<size_t>(i) + c] + dl[3 * static_cast<size_t>(i) + c];
   }
 }
@@ -796,6 +812,12 @@ __global__ void scalars_kernel(const double* __restrict__ cp_pix, int n_pix_bloc
 }
 
 // Step acceptance (Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy::StepAccepted/Rejected).
+struct CommitArgs {
+  size_t count[5];
+  const double* src[5];
+  double* dst[5];
+};
+
 struct ScalarArgs {   // inputs of scalars_kernel, for the fused single-GPU path
   const double* cp_pix; int n_pix_blocks; const double* cp_imu; int n_imu_blocks; const double* lm_part; int n_lm_blocks;
 };
@@ -803,7 +825,7 @@ struct ScalarArgs {   // inputs of scalars_kernel, for the fused single-GPU path
 __global__ void accept_kernel(const double* __restrict__ sys, int n, double* __restrict__ scal, const double* __restrict__ dp,
                               const double* __restrict__ D, const unsigned char* __restrict__ fixed, SolverState* st,
                               const int* __restrict__ spd_flag, SolverState* __restrict__ record, int max_records, int fuse_scalars,
-                              ScalarArgs sa) {
+                              ScalarArgs sa, int fuse_commit, CommitArgs ca) {
   __shared__ double s[2][256];
   if (fuse_scalars) {   // == scalars_kernel (no all-reduce between the two on a single GPU)
     __shared__ double q[3][256];
@@ -852,13 +874,16 @@ __global__ void accept_kernel(const double* __restrict__ sys, int n, double* __r
     st->iteration += 1;
     if (record) record[(st->iteration - 1) % max_records] = *st;   // ring buffer, host tracks the index
   }
+  if (fuse_commit) {   // small windows: the accepted trial state is committed by this CTA (== commit_kernel)
+    __syncthreads();
+    if (st->accepted) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        for (size_t i = threadIdx.x; i < ca.count[q]; i += blockDim.x) ca.dst[q][i] = ca.src[q][i];
+    }
+  }
 }
 
-struct CommitArgs {
-  size_t count[5];
-  const double* src[5];
-  double* dst[5];
-};
 __global__ void commit_kernel(const SolverState* __restrict__ st, CommitArgs a) {
   if (!st->accepted) return;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
