@@ -392,56 +392,64 @@ struct PixelArgs {
 
 // J^T J / J^T r of up to 32 consecutive pixel factors [f0, f0 + cnt) of this CTA, accumulated into the
 // lower triangle of S and into g with FP64 atomics.  Called right after the CTA wrote those factors'
-// residuals and Jacobians, so the re-read hits L2.  3x3 register tiles, one (or two) per thread, each
-// thread walks all rows itself: no cross-thread reduction.
+// residuals and Jacobians, so the re-read hits L2.
+//   * staging: thread = one Jacobian row (2 per factor), copied with 128-bit loads and scaled by sqrt(w);
+//   * J^T J on the FP64 tensor cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4): the 6K x 6K block is cut into 8 x 8
+//     tiles (lower triangle only), the contraction runs over the rows of one knot base in steps of 4, rows
+//     of other bases inside the sub-tile are masked to zero.  Fragments: lane l holds A[m = l/4][k = l%4] =
+//     J[k][m] and B[k = l%4][n = l/4] = J[k][n] -- the same shared-memory access pattern -- and
+//     C[m = l/4][n = 2 (l%4) + {0,1}].  This replaced a scalar 3x3-register-tile loop that executed ~9 000
+//     instructions per warp (ncu smsp__inst_executed, profiles/) against ~1 400 for the factor evaluation itself.
 template <int K>
 HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[64][6K+1]*/, double* sr /*[64]*/, int* sb /*[64]*/) {
-  constexpr int NB = 6 * K, LD = NB + 1, NT = NB / 3, NTILES = NT * (NT + 1) / 2;
-  const int tid = threadIdx.x;
+  constexpr int NB = 6 * K, LD = NB + 1, NT = (NB + 7) / 8, NTILES = NT * (NT + 1) / 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = 2 * cnt;
   __syncthreads();   // previous use of the scratch is complete
-  for (int e = tid; e < rows * NB; e += kEvalThreads) {
-    const int row = e / NB, c = e - row * NB;
-    const int f = f0 + (row >> 1);
+  if (tid < rows) {
+    const int f = f0 + (tid >> 1);
     const double sw = sqrt(a.w[f]);
-    sJ[row * LD + c] = sw * a.Jp[static_cast<size_t>(f) * 2 * NB + (row & 1) * NB + c];
-    if (c == 0) { sr[row] = sw * a.r[2 * static_cast<size_t>(f) + (row & 1)]; sb[row] = a.idx[f].x; }
+    const double2* src = reinterpret_cast<const double2*>(a.Jp + static_cast<size_t>(f) * 2 * NB + (tid & 1) * NB);   // rows are 16 B aligned
+    double* dst = sJ + tid * LD;
+#pragma unroll
+    for (int e = 0; e < NB / 2; ++e) { const double2 v = src[e]; dst[2 * e] = sw * v.x; dst[2 * e + 1] = sw * v.y; }
+    sr[tid] = sw * a.r[2 * static_cast<size_t>(f) + (tid & 1)];
+    sb[tid] = a.idx[f].x;
   }
   __syncthreads();
   double* S = a.sys;
   double* g = a.sys + static_cast<size_t>(a.n_sys) * a.n_sys + 2 * static_cast<size_t>(a.n_sys);
   const int base_lo = sb[0], base_hi = sb[rows - 1];   // bound order is sorted by base
+  const int lm = lane >> 2, lk = lane & 3;
   for (int base = base_lo; base <= base_hi; ++base) {
     // contiguous row range of this base inside the sub-tile
-    int r_lo = 0, r_hi = rows;
+    int r_lo = 0, r_hi;
     while (r_lo < rows && sb[r_lo] < base) ++r_lo;
     r_hi = r_lo;
     while (r_hi < rows && sb[r_hi] == base) ++r_hi;
     if (r_hi == r_lo) continue;
     const int c0 = 6 * base;
-    for (int tile = tid; tile < NTILES; tile += kEvalThreads) {
-      int ti = static_cast<int>((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
-      while (ti * (ti + 1) / 2 > tile) --ti;
+    for (int tile = warp; tile < NTILES; tile += kEvalThreads / 32) {
+      int ti = 0;
       while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
       const int tj = tile - ti * (ti + 1) / 2;
-      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int row = r_lo; row < r_hi; ++row) {
-        const double* jr = sJ + row * LD;
-        const double u0 = jr[3 * ti], u1 = jr[3 * ti + 1], u2 = jr[3 * ti + 2];
-        const double v0 = jr[3 * tj], v1 = jr[3 * tj + 1], v2 = jr[3 * tj + 2];
-        acc[0] += u0 * v0; acc[1] += u0 * v1; acc[2] += u0 * v2;
-        acc[3] += u1 * v0; acc[4] += u1 * v1; acc[5] += u1 * v2;
-        acc[6] += u2 * v0; acc[7] += u2 * v1; acc[8] += u2 * v2;
+      const int ma = 8 * ti + lm, nb_ = 8 * tj + lm;   // this lane's m (A) and n (B) column of J
+      const bool va = ma < NB, vb = nb_ < NB;
+      double c0v = 0.0, c1v = 0.0;
+      for (int k0 = r_lo & ~3; k0 < r_hi; k0 += 4) {
+        const int row = k0 + lk;
+        const bool in = row >= r_lo && row < r_hi;
+        const double av = (in && va) ? sJ[row * LD + ma] : 0.0;
+        const double bv = (in && vb) ? sJ[row * LD + nb_] : 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0v), "+d"(c1v) : "d"(av), "d"(bv));
       }
-#pragma unroll
-      for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const int rr = 3 * ti + p, cc = 3 * tj + q;
-          if (cc <= rr) atomicAdd(&S[static_cast<size_t>(c0 + rr) * a.n_sys + c0 + cc], acc[3 * p + q]);
-        }
+      const int rr = 8 * ti + lm, cc = 8 * tj + 2 * lk;
+      if (rr < NB) {
+        if (cc < NB && cc <= rr) atomicAdd(&S[static_cast<size_t>(c0 + rr) * a.n_sys + c0 + cc], c0v);
+        if (cc + 1 < NB && cc + 1 <= rr) atomicAdd(&S[static_cast<size_t>(c0 + rr) * a.n_sys + c0 + cc + 1], c1v);
+      }
     }
-    if (tid >= kEvalThreads - NB) {   // gradient: the last NB threads (the first ones carry the tiles)
+    if (tid >= kEvalThreads - NB) {   // gradient: the last NB threads
       const int c = tid - (kEvalThreads - NB);
       double gacc = 0.0;
       for (int row = r_lo; row < r_hi; ++row) gacc += sJ[row * LD + c] * sr[row];
