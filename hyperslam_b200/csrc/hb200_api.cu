@@ -464,7 +464,7 @@ int enqueue_accept(hb200_ctx* c) {
   size_t mx = 1, total = 0;
   for (int i = 0; i < 5; ++i) { a.count[i] = counts[i]; a.src[i] = srcs[i]; a.dst[i] = dsts[i]; mx = std::max(mx, counts[i]); total += counts[i]; }
   const bool fuse_commit = total <= 16384;   // small windows: one CTA commits the accepted state right away
-  accept_kernel<<<1, 256, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
+  accept_kernel<<<1, kAcceptThreads, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
                                          c->allreduce ? 0 : 1, sa, fuse_commit ? 1 : 0, a);
   HB_LAUNCH(c, "accept_kernel");
   if (!fuse_commit) {

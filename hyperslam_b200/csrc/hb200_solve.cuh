@@ -822,13 +822,14 @@ struct ScalarArgs {   // inputs of scalars_kernel, for the fused single-GPU path
   const double* cp_pix; int n_pix_blocks; const double* cp_imu; int n_imu_blocks; const double* lm_part; int n_lm_blocks;
 };
 
-__global__ void accept_kernel(const double* __restrict__ sys, int n, double* __restrict__ scal, const double* __restrict__ dp,
+constexpr int kAcceptThreads = 1024;   // one CTA; wide so that the fused commit copies the state in a few passes
+__global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __restrict__ sys, int n, double* __restrict__ scal, const double* __restrict__ dp,
                               const double* __restrict__ D, const unsigned char* __restrict__ fixed, SolverState* st,
                               const int* __restrict__ spd_flag, SolverState* __restrict__ record, int max_records, int fuse_scalars,
                               ScalarArgs sa, int fuse_commit, CommitArgs ca) {
-  __shared__ double s[2][256];
+  __shared__ double s[2][kAcceptThreads];
   if (fuse_scalars) {   // == scalars_kernel (no all-reduce between the two on a single GPU)
-    __shared__ double q[3][256];
+    __shared__ double q[3][kAcceptThreads];
     double c = 0, a = 0, b = 0;
     for (int i = threadIdx.x; i < sa.n_pix_blocks; i += blockDim.x) c += sa.cp_pix[i];
     for (int i = threadIdx.x; i < sa.n_imu_blocks; i += blockDim.x) c += sa.cp_imu[i];
