@@ -88,6 +88,10 @@ struct hb200_ctx {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool forked = false;
+  // hb200_optimize on small windows: the five variable blocks travel as ONE pinned staging buffer each way
+  double* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  DevBuf<double> d_stage;
   bool own_stream = false;
   bool use_graph = true;
   int num_sms = 0;
@@ -580,6 +584,8 @@ void hb200_destroy(hb200_ctx* c) {
   c->sys.release(); c->D.release(); c->Lw.release(); c->Ldiag.release(); c->dp.release(); c->dl.release(); c->Vinv.release(); c->gl.release(); c->Dl.release();
   c->band_ws.release(); c->band_dbg.release(); c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
   c->snap_knots.release(); c->snap_bg.release(); c->snap_ba.release(); c->snap_grav.release(); c->snap_lms.release(); c->snap_st.release();
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->d_stage.release();
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -1206,11 +1212,12 @@ int iterate_enqueue(hb200_ctx* c, int iterations) {
 }
 
 // copies the last `iterations` records out of the device ring buffer (asynchronously)
-int fetch_records(hb200_ctx* c, int iterations, std::vector<SolverState>* rec) {
+int fetch_records(hb200_ctx* c, int iterations, std::vector<SolverState>* rec, SolverState* pinned = nullptr) {
   rec->resize(iterations);
+  SolverState* dst = pinned ? pinned : rec->data();   // pinned destination: the copies are truly asynchronous
   for (int i = 0; i < iterations; ++i) {
     const long long idx = (c->iter_total - iterations + i) % c->max_records;
-    HB_CUDA(cudaMemcpyAsync(rec->data() + i, c->records.p + idx, sizeof(SolverState), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(dst + i, c->records.p + idx, sizeof(SolverState), cudaMemcpyDeviceToHost, c->stream));
   }
   return 0;
 }
@@ -1246,20 +1253,55 @@ int hb200_optimize(hb200_ctx* c, int iterations, double* knots, double* gyro, do
   if (rc) return rc;
   if (iterations < 0 || iterations > c->max_records) return fail(-1, "iterations must be in [0, %d]", c->max_records);
   HB_CUDA(cudaSetDevice(c->device));
-  if (knots) HB_CUDA(cudaMemcpyAsync(c->knots[0].p, knots, sizeof(double) * 8 * c->K, cudaMemcpyHostToDevice, c->stream));
-  if (gyro && c->Kbg) HB_CUDA(cudaMemcpyAsync(c->bg[0].p, gyro, sizeof(double) * 4 * c->Kbg, cudaMemcpyHostToDevice, c->stream));
-  if (accel && c->Kba) HB_CUDA(cudaMemcpyAsync(c->ba[0].p, accel, sizeof(double) * 4 * c->Kba, cudaMemcpyHostToDevice, c->stream));
-  if (gravity) { HB_CUDA(cudaMemcpyAsync(c->grav[0].p, gravity, sizeof(double) * 3, cudaMemcpyHostToDevice, c->stream)); c->have_gravity = true; }
-  if (landmarks && c->L) HB_CUDA(cudaMemcpyAsync(c->lms[0].p, landmarks, sizeof(double) * 3 * c->L, cudaMemcpyHostToDevice, c->stream));
+  double* host[5] = {knots, (gyro && c->Kbg) ? gyro : nullptr, (accel && c->Kba) ? accel : nullptr, gravity, (landmarks && c->L) ? landmarks : nullptr};
+  double* dev[5] = {c->knots[0].p, c->bg[0].p, c->ba[0].p, c->grav[0].p, c->lms[0].p};
+  const size_t cnt[5] = {8 * static_cast<size_t>(c->K), 4 * static_cast<size_t>(c->Kbg), 4 * static_cast<size_t>(c->Kba), 3, 3 * static_cast<size_t>(c->L)};
+  size_t off[5], total = 0;
+  for (int i = 0; i < 5; ++i) { off[i] = total; if (host[i]) total += cnt[i]; }
+  if (gravity) c->have_gravity = true;
+  // Small windows: 11 small copies cost more than the iteration's kernels save; pack the blocks into one pinned
+  // staging buffer (host memcpy, a few KB), one H2D, one segmented device copy -- and the mirror image back.
+  const bool staged = total > 0 && total <= 8192;
+  CommitArgs in{}, out{};
+  if (staged) {
+    if (c->h_stage_cap < total) {
+      if (c->h_stage) cudaFreeHost(c->h_stage);
+      c->h_stage = nullptr; c->h_stage_cap = 0;
+      HB_CUDA(cudaMallocHost(&c->h_stage, sizeof(double) * 8192 + sizeof(SolverState) * c->max_records));
+      c->h_stage_cap = 8192;
+    }
+    HB_CUDA(c->d_stage.ensure(8192));
+    for (int i = 0; i < 5; ++i) {
+      const size_t n_i = host[i] ? cnt[i] : 0;
+      if (n_i) std::memcpy(c->h_stage + off[i], host[i], sizeof(double) * n_i);
+      in.count[i] = n_i; in.src[i] = c->d_stage.p + off[i]; in.dst[i] = dev[i];
+      out.count[i] = n_i; out.src[i] = dev[i]; out.dst[i] = c->d_stage.p + off[i];
+    }
+    HB_CUDA(cudaMemcpyAsync(c->d_stage.p, c->h_stage, sizeof(double) * total, cudaMemcpyHostToDevice, c->stream));
+    copy_segments_kernel<<<4, 256, 0, c->stream>>>(in);
+    HB_LAUNCH(c, "copy_segments_kernel");
+  } else {
+    for (int i = 0; i < 5; ++i)
+      if (host[i]) HB_CUDA(cudaMemcpyAsync(dev[i], host[i], sizeof(double) * cnt[i], cudaMemcpyHostToDevice, c->stream));
+  }
   if ((rc = iterate_enqueue(c, iterations))) return rc;
-  if (knots) HB_CUDA(cudaMemcpyAsync(knots, c->knots[0].p, sizeof(double) * 8 * c->K, cudaMemcpyDeviceToHost, c->stream));
-  if (gyro && c->Kbg) HB_CUDA(cudaMemcpyAsync(gyro, c->bg[0].p, sizeof(double) * 4 * c->Kbg, cudaMemcpyDeviceToHost, c->stream));
-  if (accel && c->Kba) HB_CUDA(cudaMemcpyAsync(accel, c->ba[0].p, sizeof(double) * 4 * c->Kba, cudaMemcpyDeviceToHost, c->stream));
-  if (gravity) HB_CUDA(cudaMemcpyAsync(gravity, c->grav[0].p, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
-  if (landmarks && c->L) HB_CUDA(cudaMemcpyAsync(landmarks, c->lms[0].p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToHost, c->stream));
+  if (staged) {
+    copy_segments_kernel<<<4, 256, 0, c->stream>>>(out);
+    HB_LAUNCH(c, "copy_segments_kernel");
+    HB_CUDA(cudaMemcpyAsync(c->h_stage, c->d_stage.p, sizeof(double) * total, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    for (int i = 0; i < 5; ++i)
+      if (host[i]) HB_CUDA(cudaMemcpyAsync(host[i], dev[i], sizeof(double) * cnt[i], cudaMemcpyDeviceToHost, c->stream));
+  }
   std::vector<SolverState> rec;
-  if (records && iterations && (rc = fetch_records(c, iterations, &rec))) return rc;
+  SolverState* rec_pinned = staged ? reinterpret_cast<SolverState*>(c->h_stage + 8192) : nullptr;
+  if (records && iterations && (rc = fetch_records(c, iterations, &rec, rec_pinned))) return rc;
   HB_CUDA(cudaStreamSynchronize(c->stream));
+  if (staged) {
+    for (int i = 0; i < 5; ++i)
+      if (host[i]) std::memcpy(host[i], c->h_stage + off[i], sizeof(double) * cnt[i]);
+    if (records && iterations) std::copy(rec_pinned, rec_pinned + iterations, rec.begin());
+  }
   if (records && iterations) convert_records(rec, records);
   return 0;
 }

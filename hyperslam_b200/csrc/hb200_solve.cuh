@@ -885,6 +885,14 @@ __global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __
   }
 }
 
+// unconditional segmented copy (host staging buffer <-> variable blocks in hb200_optimize)
+__global__ void copy_segments_kernel(CommitArgs a) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+#pragma unroll
+  for (int s = 0; s < 5; ++s)
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < a.count[s]; i += stride) a.dst[s][i] = a.src[s][i];
+}
+
 __global__ void commit_kernel(const SolverState* __restrict__ st, CommitArgs a) {
   if (!st->accepted) return;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
