@@ -50,6 +50,7 @@ __host__ __device__ inline size_t band_workspace_doubles(int K, int beta, int m)
   d += (n0 + n1) * 48;                           // LI
   d += 6 * (n0 + n1);                            // X
   d += static_cast<size_t>(m + 1) * (m | 1) + 2 * static_cast<size_t>(m); // CC (odd row stride: conflict-free column access), XA, DG
+  d += 6 * static_cast<size_t>(K) + m + (6 * static_cast<size_t>(K) + m) / 8 + 1;   // per-dof damping term and constant-dof mask, staged for the gather
   return d + 8;
 }
 
@@ -340,17 +341,26 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   // (== finalize_kernel, which then need not run), and D = clamp(diag H) is written out for accept_kernel.
   const bool damp = Dout != nullptr;
   const double* diagH = b + n;
-  const double mu = damp ? 1.0 / st->radius : 0.0;
+  // stage the per-dof damping term and the mask once (the gather would otherwise chase them through L2 per element)
+  double* s_dmp = XA + 2 * m;
+  unsigned char* s_fix = reinterpret_cast<unsigned char*>(s_dmp + n);
+  {
+    const double mu = damp ? 1.0 / st->radius : 0.0;
+    for (int a = threadIdx.x; a < n; a += kBandThreads) {
+      const double dcl = damp ? fmin(fmax(diagH[a], 1e-6), 1e32) : 0.0;
+      s_dmp[a] = mu * dcl;
+      s_fix[a] = damp ? fixed[a] : 0;
+      if (damp) Dout[a] = dcl;
+    }
+  }
+  __syncthreads();
   auto Sval = [&](int row, int col) -> double {   // row >= col
     double v = S[static_cast<size_t>(row) * n + col];
-    if (damp) {
-      if (row == col) v += mu * fmin(fmax(diagH[row], 1e-6), 1e32);
-      if (fixed[row] || fixed[col]) v = (row == col) ? 1.0 : 0.0;
-    }
+    if (row == col) v += s_dmp[row];
+    if (s_fix[row] | s_fix[col]) v = (row == col) ? 1.0 : 0.0;
     return v;
   };
-  auto bval = [&](int col) -> double { return (damp && fixed[col]) ? 0.0 : b[col]; };
-  if (damp) for (int a = threadIdx.x; a < n; a += kBandThreads) Dout[a] = fmin(fmax(diagH[a], 1e-6), 1e32);
+  auto bval = [&](int col) -> double { return s_fix[col] ? 0.0 : b[col]; };
   __shared__ int s_ok;
   if (tid == 0) s_ok = 1;
   // ---- gather: chain 0 reads P top-down, chain 1 reads J P J (index reversal) and starts its copy of the
