@@ -133,6 +133,8 @@ struct hb200_ctx {
   int beta = 3;
   bool band_solver = true, band_smem = true, force_dense = false;
   DevBuf<double> band_ws;
+  int band_chunk_cols = 0;       // !band_smem: block columns per shared-memory chunk view (per chain)
+  size_t band_chunk_smem = 0;
   DevBuf<long long> band_dbg;   // optional phase timings of band_solve_kernel (HB200_BAND_TIMING=1)
   bool bound = false;
 
@@ -256,7 +258,16 @@ int ensure_system(hb200_ctx* c) {
   c->band_smem = ws <= 220 * 1024;
   if (c->band_solver) {
     if (c->band_smem) HB_CUDA(cudaFuncSetAttribute(band_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ws)));
-    else HB_CUDA(c->band_ws.ensure(ws / sizeof(double)));
+    else {
+      HB_CUDA(c->band_ws.ensure(ws / sizeof(double)));
+      // chunked factorisation: two shared-memory views of band_chunk_cols block columns (band + arrow + LI)
+      const size_t colbytes = (static_cast<size_t>(6 + 6 * c->beta) * 6 + 6 * static_cast<size_t>(c->n - 6 * c->K + 1) + 48) * sizeof(double);
+      const int fit = static_cast<int>((200 * 1024) / (2 * colbytes));
+      c->band_chunk_cols = std::max(c->beta + 2, std::min(fit, c->K + c->beta));
+      c->band_chunk_smem = 2 * colbytes * c->band_chunk_cols;
+      if (c->band_chunk_smem > 220 * 1024) return fail(-6, "band solver: a chunk of %d block columns does not fit shared memory (arrow too wide)", c->band_chunk_cols);
+      HB_CUDA(cudaFuncSetAttribute(band_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->band_chunk_smem)));
+    }
   }
   HB_CUDA(c->band_ws.ensure(1));
   if (getenv("HB200_BAND_TIMING")) {
@@ -411,8 +422,8 @@ int enqueue_solve(hb200_ctx* c, bool damp_in_solver = false) {
     const unsigned char* fx = damp_in_solver ? c->fixed.p : nullptr;
     double* Dout = damp_in_solver ? c->D.p : nullptr;
     const size_t smem = c->band_smem ? band_workspace_doubles(c->K, c->beta, c->n - 6 * c->K) * sizeof(double) : 0;
-    if (c->band_smem) band_solve_kernel<true><<<1, kBandThreads, smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout);
-    else band_solve_kernel<false><<<1, kBandThreads, 0, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout);
+    if (c->band_smem) band_solve_kernel<true><<<1, kBandThreads, smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout, 0);
+    else band_solve_kernel<false><<<1, kBandThreads, c->band_chunk_smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout, c->band_chunk_cols);
     HB_LAUNCH(c, "band_solve_kernel");
   } else {
     int n = c->n;

@@ -117,6 +117,7 @@ struct BandChain {
   int Ke;     // block columns this chain eliminates in the two-sided phase
   int ncol;   // block columns it stores (Ke + separator)
   int npc;    // 6 * ncol
+  int ars;    // row stride of AR in doubles (= npc for a whole chain; the chunk capacity for a shared-memory view)
 };
 
 // Panel of block column s: solve x L^T = a for every row below the diagonal block (band rows, arrow rows,
@@ -127,7 +128,7 @@ HB_DI void band_panel(const BandChain& C, int s, int h, int m, int lt, int nthre
   const int nb = min(h - 6, C.npc - 6 * (s + 1));  // band rows below the diagonal block
   const int R = nb + m + 1;                          // + arrow rows + rhs row
   for (int t = row0 + lt; t < R; t += nthreads) {
-    double* a = (t < nb) ? (Wc + static_cast<size_t>(6 + t) * 6) : (C.AR + static_cast<size_t>(t - nb) * C.npc + 6 * s);
+    double* a = (t < nb) ? (Wc + static_cast<size_t>(6 + t) * 6) : (C.AR + static_cast<size_t>(t - nb) * C.ars + 6 * s);
     double v[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) v[q] = a[q];
@@ -172,9 +173,9 @@ HB_DI void band_update(const BandChain& C, int s, int h, int m, int first, int w
     const bool ub = gu < nbk;
     const int ru = ub ? 0 : 6 * (gu - nbk) + i;   // arrow row index of u
     if (!ub && ru > m) continue;
-    const double* xu = ub ? (Wc + static_cast<size_t>(6 + 6 * gu + i) * 6) : (C.AR + static_cast<size_t>(ru) * C.npc + 6 * s);
+    const double* xu = ub ? (Wc + static_cast<size_t>(6 + 6 * gu + i) * 6) : (C.AR + static_cast<size_t>(ru) * C.ars + 6 * s);
     double* tgt = ub ? (C.W + (static_cast<size_t>(s + 1 + gv) * h + (6 * (gu - gv) + i)) * 6)   // band x band
-                     : (C.AR + static_cast<size_t>(ru) * C.npc + 6 * (s + 1 + gv));              // arrow x band
+                     : (C.AR + static_cast<size_t>(ru) * C.ars + 6 * (s + 1 + gv));              // arrow x band
     double a[6], sd[6];
     {
       const double2* x2 = reinterpret_cast<const double2*>(xu);   // rows are 48 B: 16-byte aligned
@@ -256,16 +257,31 @@ HB_DI bool band_la_step(const BandChain& C, int s, int h, int lane, bool do_chol
 // runs once per solve, and one-shot code is bound by instruction fetch, not by issue (tools/microbench).
 HB_DI void band_backsub_chain(const BandChain& C, int c_hi, int c_lo, int h, int m, int lane) {
   const int j = lane % 6, g = lane / 6;
-  for (int c = c_hi; c >= c_lo; --c) {
+  // the panel operands of a column do not depend on the solution: they are fetched one column ahead, so that
+  // a workspace in global memory costs no L2 round trip on the sequential chain
+  auto fetch = [&](int c, double* nv, double* y) {
     const double* Wc = C.W + static_cast<size_t>(c) * h * 6 + 36 + j;
     const int nbk = min(h - 6, C.npc - 6 * (c + 1)) / 6;
-    double acc = 0.0;
-    if (g < 5) {
-      for (int r = g; r < nbk; r += 5) {
-        const double* nr = Wc + 36 * r;
-        const double* xr = C.X + 6 * (c + 1 + r);
 #pragma unroll
-        for (int t = 0; t < 6; ++t) acc += nr[6 * t] * xr[t];
+    for (int t = 0; t < 6; ++t) nv[t] = (g < 5 && g < nbk) ? Wc[36 * g + 6 * t] : 0.0;
+    *y = (lane < 6) ? C.AR[static_cast<size_t>(m) * C.npc + 6 * c + lane] : 0.0;
+  };
+  double nv[6], yv;
+  if (c_hi >= c_lo) fetch(c_hi, nv, &yv);
+  for (int c = c_hi; c >= c_lo; --c) {
+    double nn[6] = {0, 0, 0, 0, 0, 0}, yn = 0.0;
+    if (c - 1 >= c_lo) fetch(c - 1, nn, &yn);
+    const int nbk = min(h - 6, C.npc - 6 * (c + 1)) / 6;
+    double acc = 0.0;
+    if (g < 5 && g < nbk) {
+      const double* xr = C.X + 6 * (c + 1 + g);
+#pragma unroll
+      for (int t = 0; t < 6; ++t) acc += nv[t] * xr[t];
+      for (int r = g + 5; r < nbk; r += 5) {   // half-bandwidths above 5 blocks
+        const double* nr = C.W + static_cast<size_t>(c) * h * 6 + 36 + j + 36 * r;
+        const double* xq = C.X + 6 * (c + 1 + r);
+#pragma unroll
+        for (int t = 0; t < 6; ++t) acc += nr[6 * t] * xq[t];
       }
     }
     double tot = acc;
@@ -273,8 +289,11 @@ HB_DI void band_backsub_chain(const BandChain& C, int c_hi, int c_lo, int h, int
     tot += __shfl_sync(0xffffffffu, acc, (lane + 12) & 31);
     tot += __shfl_sync(0xffffffffu, acc, (lane + 18) & 31);
     tot += __shfl_sync(0xffffffffu, acc, (lane + 24) & 31);
-    if (lane < 6) C.X[6 * c + lane] = C.AR[static_cast<size_t>(m) * C.npc + 6 * c + lane] - tot;
+    if (lane < 6) C.X[6 * c + lane] = yv - tot;
     __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 6; ++t) nv[t] = nn[t];
+    yv = yn;
   }
 }
 
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
                                                                   double* __restrict__ ws_global, double* __restrict__ x_out,
                                                                   int* __restrict__ spd_flag, long long* __restrict__ dbg,
                                                                   const SolverState* __restrict__ st, const unsigned char* __restrict__ fixed,
-                                                                  double* __restrict__ Dout) {
+                                                                  double* __restrict__ Dout, int chunk_cols) {
   extern __shared__ double s_band[];
   double* ws = SMEM ? s_band : ws_global;
   const int np = 6 * K, m = n - np, h = 6 + 6 * beta, h6 = h * 6;
@@ -322,6 +341,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       C.Ke = i ? pl.Kb : pl.Kt;
       C.ncol = (i && pl.Kb == 0) ? 0 : C.Ke + pl.bs;
       C.npc = 6 * C.ncol;
+      C.ars = C.npc;
       C.W = p; p += static_cast<size_t>(C.ncol) * h6;
       C.AR = p; p += static_cast<size_t>(m + 1) * C.npc;
       C.LI = p; p += static_cast<size_t>(C.ncol) * 48;
@@ -331,7 +351,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   }
   double* CC = ws;
   const int LDc = m | 1;
-  double* XA = CC + static_cast<size_t>(m + 1) * LDc;
+  double* XA = CC + static_cast<size_t>(m + 1) * LDc;   // (both move to shared memory after the factorisation when !SMEM)
   const BandChain C = my_chain ? C1 : C0;           // this thread's chain in the update phase (registers)
   const BandChain CP = (tid >> 8) ? C1 : C0;        // ... and in the panel phase (threads 0..255 / 256..511)
   const double* S = sys;
@@ -366,30 +386,110 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   // ---- gather: chain 0 reads P top-down, chain 1 reads J P J (index reversal) and starts its copy of the
   // separator and of the separator's arrow columns at zero (they only accumulate updates) ----
   {
+    // Each element is one dependent L2 access; four per thread are kept in flight (values first, stores after):
+    // a one-load-at-a-time loop spent 250 us here at K = 500.
     const int N1 = C1.npc;
-    for (int e = tid; e < C0.ncol * h6; e += kBandThreads) {
+    auto gather4 = [&](int total, auto value, auto store) {
+      for (int e0 = tid; e0 < total; e0 += 4 * kBandThreads) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = e0 + u * kBandThreads; v[u] = (e < total) ? value(e) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = e0 + u * kBandThreads; if (e < total) store(e, v[u]); }
+      }
+    };
+    // band blocks: one unit = 6 contiguous doubles of a row of S (three 128-bit loads), two units in flight
+    auto fix6 = [&](int row, int col0, double* v) {   // damping / mask / lower-triangle cut of S[row][col0 .. col0+5]
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+        const int col = col0 + t;
+        double x = v[t];
+        if (col > row) x = 0.0;
+        else {
+          if (col == row) x += s_dmp[row];
+          if (s_fix[row] | s_fix[col]) x = (col == row) ? 1.0 : 0.0;
+        }
+        v[t] = x;
+      }
+    };
+    auto load6 = [&](int row, int col0, double* v) {
+      const double2* p2 = reinterpret_cast<const double2*>(S + static_cast<size_t>(row) * n + col0);   // n and col0 are even
+      const double2 a0 = p2[0], a1 = p2[1], a2 = p2[2];
+      v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = a2.x; v[5] = a2.y;
+    };
+    const bool vec = (n % 2) == 0;   // (always: n = 6K + 3Kbg + 3Kba + 2 with Kbg == Kba; kept as a guard)
+    if (vec) {
+      const int nu0 = C0.ncol * h;
+      for (int u0 = tid; u0 < nu0; u0 += 2 * kBandThreads) {
+        double v[2][6];
+        int rowv[2], cv[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int u = u0 + w * kBandThreads;
+          const int c = u / h, i = u - c * h;
+          rowv[w] = 6 * c + i; cv[w] = c;
+          if (u < nu0 && rowv[w] < C0.npc) load6(rowv[w], 6 * c, v[w]);
+          else { for (int t = 0; t < 6; ++t) v[w][t] = 0.0; rowv[w] = -1; }
+        }
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int u = u0 + w * kBandThreads;
+          if (u >= nu0) continue;
+          if (rowv[w] >= 0) fix6(rowv[w], 6 * cv[w], v[w]);
+          double* dst = C0.W + static_cast<size_t>(u) * 6;
+#pragma unroll
+          for (int t = 0; t < 6; ++t) dst[t] = v[w][t];
+        }
+      }
+      // chain 1 = J P J: unit (c, q, j) = column j of the 6-row group q of block column c of the reversed band; its six
+      // entries are S[a][b0 .. b0+5] (a = np-1-(6c+j), b descending with the row), contiguous in S
+      const int hq = h / 6, nu1 = C1.Ke * hq * 6;
+      for (int e = tid; e < (C1.ncol - C1.Ke) * h6; e += kBandThreads) C1.W[static_cast<size_t>(C1.Ke) * h6 + e] = 0.0;   // separator copy
+      for (int u0 = tid; u0 < nu1; u0 += 2 * kBandThreads) {
+        double v[2][6];
+        int av[2], b0v[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int u = u0 + w * kBandThreads;
+          const int c = u / (hq * 6), rem = u - c * hq * 6, q = rem / 6, j = rem - 6 * q;
+          av[w] = np - 1 - (6 * c + j);
+          b0v[w] = np - 6 * (c + q) - 6;
+          if (u < nu1 && b0v[w] >= 0) load6(av[w], b0v[w], v[w]);
+          else { for (int t = 0; t < 6; ++t) v[w][t] = 0.0; av[w] = -1; }
+        }
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int u = u0 + w * kBandThreads;
+          if (u >= nu1) continue;
+          const int c = u / (hq * 6), rem = u - c * hq * 6, q = rem / 6, j = rem - 6 * q;
+          if (av[w] >= 0) fix6(av[w], b0v[w], v[w]);
+#pragma unroll
+          for (int t = 0; t < 6; ++t) C1.W[(static_cast<size_t>(c) * h + 6 * q + t) * 6 + j] = v[w][5 - t];   // row 6q+t <-> b = b0 + 5 - t
+        }
+      }
+    } else {
+    gather4(C0.ncol * h6, [&](int e) {
       const int c = e / h6, rem = e - c * h6;
       const int i = rem / 6, j = rem - 6 * i;
       const int row = 6 * c + i, col = 6 * c + j;
-      C0.W[e] = (row < C0.npc && row >= col) ? Sval(row, col) : 0.0;
-    }
-    for (int e = tid; e < C1.ncol * h6; e += kBandThreads) {
+      return (row < C0.npc && row >= col) ? Sval(row, col) : 0.0;
+    }, [&](int e, double v) { C0.W[e] = v; });
+    gather4(C1.ncol * h6, [&](int e) {
       const int c = e / h6, rem = e - c * h6;
       const int i = rem / 6, j = rem - 6 * i;
       const int rr = 6 * c + i, rc = 6 * c + j;          // reversed (chain-local) row / column
-      double v = 0.0;
-      if (c < C1.Ke && rr < N1 && rr >= rc) v = Sval(np - 1 - rc, np - 1 - rr);
-      C1.W[e] = v;
+      return (c < C1.Ke && rr < N1 && rr >= rc) ? Sval(np - 1 - rc, np - 1 - rr) : 0.0;
+    }, [&](int e, double v) { C1.W[e] = v; });
     }
-    for (int e = tid; e < (m + 1) * C0.npc; e += kBandThreads) {
+    gather4((m + 1) * C0.npc, [&](int e) {
       const int r = e / C0.npc, col = e - r * C0.npc;
-      C0.AR[e] = (r < m) ? Sval(np + r, col) : bval(col);
-    }
-    for (int e = tid; e < (m + 1) * N1; e += kBandThreads) {
+      return (r < m) ? Sval(np + r, col) : bval(col);
+    }, [&](int e, double v) { C0.AR[e] = v; });
+    gather4((m + 1) * N1, [&](int e) {
       const int r = e / N1, rc = e - r * N1;
       const int col = np - 1 - rc;
-      C1.AR[e] = (rc < 6 * C1.Ke) ? ((r < m) ? Sval(np + r, col) : bval(col)) : 0.0;
-    }
+      return (rc < 6 * C1.Ke) ? ((r < m) ? Sval(np + r, col) : bval(col)) : 0.0;
+    }, [&](int e, double v) { C1.AR[e] = v; });
     for (int e = tid; e < (m + 1) * m; e += kBandThreads) {
       const int r = e / m, q = e - r * m;
       CC[static_cast<size_t>(r) * LDc + q] = (r < m) ? ((q <= r) ? Sval(np + r, np + q) : 0.0) : bval(np + q);
@@ -437,12 +537,30 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   constexpr int kMaxRounds = 3;
   const int nitems_full = ntiles_full * 6 - 6;   // tile 0 belongs to the look-ahead warp
   const bool fast = have_table && pl.Kb > 0 && nitems_full <= kMaxRounds * 128;
+  // !SMEM: the workspace lives in global memory (it does not fit); the factorisation then runs chunk by chunk
+  // on shared-memory VIEWS of chunk_cols block columns per chain (loaded, eliminated, written back), so its
+  // steps see shared-memory latency instead of L2 latency.  V0 / V1 are the views, F the chain structure the
+  // step loop works on (the resident chain itself when SMEM).
+  BandChain V0 = C0, V1 = C1;
+  if (!SMEM) {
+    double* p = s_band;
+    BandChain* vv[2] = {&V0, &V1};
+    for (int i = 0; i < 2; ++i) {
+      BandChain& V = *vv[i];
+      V.ars = 6 * chunk_cols;
+      V.W = p; p += static_cast<size_t>(chunk_cols) * h6;
+      V.AR = p; p += static_cast<size_t>(m + 1) * V.ars;
+      V.LI = p; p += static_cast<size_t>(chunk_cols) * 48;
+      V.X = nullptr;
+    }
+  }
+  const BandChain F = SMEM ? C : (my_chain ? V1 : V0);
   const double* f_u[kMaxRounds]; const double* f_v[kMaxRounds]; double* f_t[kMaxRounds]; int f_su[kMaxRounds]; bool f_ok[kMaxRounds];
 #pragma unroll
   for (int r = 0; r < kMaxRounds; ++r) {
     const int t = 6 + wid + 128 * r;
     f_ok[r] = fast && is_worker && t < ntiles_full * 6;
-    f_u[r] = C.W; f_v[r] = C.W; f_t[r] = C.W; f_su[r] = 0;
+    f_u[r] = F.W; f_v[r] = F.W; f_t[r] = F.W; f_su[r] = 0;
     if (f_ok[r]) {
       const int tile = t / 6, i = t - 6 * tile;
       const int gu = s_tile[2 * tile], gv = s_tile[2 * tile + 1];
@@ -450,10 +568,10 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       const int ru = ub ? 0 : 6 * (gu - beta) + i;
       if (!ub && ru > m) f_ok[r] = false;
       else {
-        f_u[r] = ub ? (C.W + static_cast<size_t>(6 + 6 * gu + i) * 6) : (C.AR + static_cast<size_t>(ru) * C.npc);
+        f_u[r] = ub ? (F.W + static_cast<size_t>(6 + 6 * gu + i) * 6) : (F.AR + static_cast<size_t>(ru) * F.ars);
         f_su[r] = ub ? h6 : 6;
-        f_v[r] = C.W + static_cast<size_t>(6 + 6 * gv) * 6;
-        f_t[r] = ub ? (C.W + (static_cast<size_t>(1 + gv) * h + (6 * (gu - gv) + i)) * 6) : (C.AR + static_cast<size_t>(ru) * C.npc + 6 * (1 + gv));
+        f_v[r] = F.W + static_cast<size_t>(6 + 6 * gv) * 6;
+        f_t[r] = ub ? (F.W + (static_cast<size_t>(1 + gv) * h + (6 * (gu - gv) + i)) * 6) : (F.AR + static_cast<size_t>(ru) * F.ars + 6 * (1 + gv));
       }
     }
   }
@@ -476,7 +594,8 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       t2[0] = o0; t2[1] = o1; t2[2] = o2;
     }
   };
-  auto run_steps = [&](const BandChain& Q, int s0, int s1, bool use_fast) {
+  // chol_last: the look-ahead of the last step also factors the next diagonal block (more columns follow)
+  auto run_steps = [&](const BandChain& Q, int s0, int s1, bool use_fast, bool chol_last) {
     for (int s = s0; s < s1; ++s) {
       const bool rec = dbg && my_chain == 0 && s >= 4 && s < 12 && lane == 0 && (warp == 2 || warp == 12);
       if (rec) s_ts[s - 4][warp == 2 ? 0 : 4] = clock_after(Q.LI[static_cast<size_t>(s) * 48]);   // released (chol(s) visible)
@@ -490,13 +609,53 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
         else band_update(Q, s, h, m, 6, wid, 128, have_table ? s_tile : nullptr, beta);
         if (rec) s_ts[s - 4][3] = clock_after(Q.W[static_cast<size_t>(s + 1) * h6 + 36]);  // update done (approx)
       } else {
-        if (!band_la_step(Q, s, h, lane, s + 1 < s1, barA, 160)) s_ok = 0;
+        if (!band_la_step(Q, s, h, lane, s + 1 < s1 || chol_last, barA, 160)) s_ok = 0;
         if (rec) s_ts[s - 4][5] = clock_after(Q.LI[static_cast<size_t>(s + 1) * 48]);      // chol(s+1) done
       }
       nbar_sync(barB, 160);
     }
   };
-  if (is_la || is_worker) run_steps(C, 0, C.Ke, fast);
+  // chunk transfer between a chain's global workspace G (columns c0 .. c0 + nview) and its view V, by the
+  // 256 threads of the chain's half of the CTA
+  auto chunk_copy = [&](const BandChain& G, const BandChain& V, int c0, int nview, bool to_view) {
+    const int lt = tid & 255;
+    double* gw = G.W + static_cast<size_t>(c0) * h6;
+    for (int e = lt; e < nview * h6; e += 256) { if (to_view) V.W[e] = gw[e]; else gw[e] = V.W[e]; }
+    double* gl = G.LI + static_cast<size_t>(c0) * 48;
+    for (int e = lt; e < nview * 48; e += 256) { if (to_view) V.LI[e] = gl[e]; else gl[e] = V.LI[e]; }
+    const int w6 = 6 * nview;
+    for (int e = lt; e < (m + 1) * w6; e += 256) {
+      const int r = e / w6, j = e - r * w6;
+      double* g = G.AR + static_cast<size_t>(r) * G.ars + 6 * c0 + j;
+      double* v = V.AR + static_cast<size_t>(r) * V.ars + j;
+      if (to_view) *v = *g; else *g = *v;
+    }
+  };
+  // chunked elimination of columns [c_begin, c_end) of both chains (lim0 / lim1: their end columns)
+  auto run_chunked = [&](int c_begin, int lim0, int lim1, bool use_fast) {
+    const int CH = chunk_cols - beta;
+    for (int c0 = c_begin; c0 < max(lim0, lim1); c0 += CH) {
+      const BandChain& Gh = (tid >> 8) ? C1 : C0;          // chain of this half of the CTA (copies)
+      const BandChain& Vh = (tid >> 8) ? V1 : V0;
+      const int limh = (tid >> 8) ? lim1 : lim0;
+      const int ncur_h = min(max(limh - c0, 0), CH);
+      const int nview_h = ncur_h ? min(ncur_h + beta, Gh.ncol - c0) : 0;
+      if (nview_h) chunk_copy(Gh, Vh, c0, nview_h, true);
+      __syncthreads();
+      const int lim = my_chain ? lim1 : lim0;
+      const int ncur = min(max(lim - c0, 0), CH);
+      if ((is_la || is_worker) && ncur) {
+        BandChain Q = F;
+        Q.Ke = ncur; Q.ncol = min(ncur + beta, C.ncol - c0); Q.npc = 6 * Q.ncol;
+        run_steps(Q, 0, ncur, use_fast, c0 + ncur < lim);
+      }
+      __syncthreads();
+      if (nview_h) chunk_copy(Gh, Vh, c0, nview_h, false);
+      __syncthreads();
+    }
+  };
+  if (SMEM) { if (is_la || is_worker) run_steps(C, 0, C.Ke, fast, false); }
+  else run_chunked(0, C0.Ke, C1.Ke, fast);
   __syncthreads();
   if (dbg && tid < 64) dbg[8 + tid] = s_ts[tid >> 3][tid & 7];
   HB_TICKD(1, C0.W);
@@ -518,10 +677,24 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     __syncthreads();
     if (tid == 0 && !chol6(C0.W + static_cast<size_t>(C0.Ke) * h6, 6, C0.LI + static_cast<size_t>(C0.Ke) * 48)) s_ok = 0;
     __syncthreads();
-    if ((is_la || is_worker) && my_chain == 0) run_steps(C0, C0.Ke, C0.ncol, false);
+    if (SMEM) { if ((is_la || is_worker) && my_chain == 0) run_steps(C0, C0.Ke, C0.ncol, false, false); }
+    else run_chunked(C0.Ke, C0.ncol, 0, false);
     __syncthreads();
   }
   HB_TICKD(2, C0.W);
+  if (!SMEM) {
+    // the chunk views are dead: the corner system, its solution and (if they fit) both chains' solution vectors
+    // move into that shared memory for the latency-bound tail phases
+    __syncthreads();
+    double* p = s_band;
+    const size_t ncc = static_cast<size_t>(m + 1) * LDc + 2 * static_cast<size_t>(m);
+    for (size_t e = tid; e < ncc; e += kBandThreads) p[e] = CC[e];
+    CC = p; XA = CC + static_cast<size_t>(m + 1) * LDc;
+    p += ncc;
+    const size_t avail = 2 * static_cast<size_t>(chunk_cols) * (h6 + 6 * static_cast<size_t>(m + 1) + 48);
+    if (ncc + C0.npc + C1.npc <= avail) { C0.X = p; C1.X = p + C0.npc; }
+    __syncthreads();
+  }
   // ---- block inverses of every eliminated column (one thread each), and the deferred corner update
   // C -= sum over all eliminated columns of (arrow panel)(arrow panel)^T, rhs row included (row m):
   // one (u, v) pair per warp pass, lanes stride the columns (conflict-free), butterfly reduction ----
@@ -531,25 +704,36 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     // A[row l/4][k l%4] and B[k l%4][col l/4] -- both are AR[row][col0 + l%4] -- and C[row l/4][col 2(l%4)+{0,1}].
     const int nrb = (m + 1 + 7) / 8, ncb = (m + 7) / 8;
     const int lr = lane >> 2, lk = lane & 3;
-    for (int e = warp; e < nrb * ncb; e += kBandThreads / 32) {
-      const int ub = e / ncb, vb = e - ub * ncb;
+    const int nks = SMEM ? 1 : 4;   // split the contraction when the panels stream from global memory (more warps, more loads in flight)
+    for (int e = warp; e < nrb * ncb * nks; e += kBandThreads / 32) {
+      const int part = e % nks, tile = e / nks;
+      const int ub = tile / ncb, vb = tile - ub * ncb;
       if (vb > ub) continue;
       double c0 = 0.0, c1 = 0.0;
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         const BandChain& Q = ci ? C1 : C0;
         const int nused = ci ? 6 * C1.Ke : C0.npc;
+        const int per = ((nused + 4 * nks - 1) / (4 * nks)) * 4;          // columns of this part (multiple of 4)
+        const int lo = part * per, hi = min(nused, lo + per);
         const double* pa = Q.AR + static_cast<size_t>(min(8 * ub + lr, m)) * Q.npc + lk;
         const double* pb = Q.AR + static_cast<size_t>(min(8 * vb + lr, m)) * Q.npc + lk;
-        for (int col = 0; col < nused; col += 4) {
-          const bool in = col + lk < nused;
-          const double av = in ? pa[col] : 0.0, bv = in ? pb[col] : 0.0;
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+        for (int col = lo; col < hi; col += 16) {
+          double av[4], bv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool in = col + 4 * u + lk < hi;
+            av[u] = in ? pa[col + 4 * u] : 0.0;
+            bv[u] = in ? pb[col + 4 * u] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(av[u]), "d"(bv[u]));
         }
       }
       const int u = 8 * ub + lr, v = 8 * vb + 2 * lk;
-      if (u <= m && v < m && v <= u) CC[static_cast<size_t>(u) * LDc + v] -= c0;
-      if (u <= m && v + 1 < m && v + 1 <= u) CC[static_cast<size_t>(u) * LDc + v + 1] -= c1;
+      if (u <= m && v < m && v <= u) atomicAdd(&CC[static_cast<size_t>(u) * LDc + v], -c0);
+      if (u <= m && v + 1 < m && v + 1 <= u) atomicAdd(&CC[static_cast<size_t>(u) * LDc + v + 1], -c1);
     }
   }
   __syncthreads();

@@ -378,3 +378,34 @@ def test_bearing_and_manifold_factor_evaluate_ceres_shape(built):
             PJ = ol.manifold_plus_jacobian(ol.M_STATE, blocks[m])
             assert rel_err(jac[m] @ PJ, jac_o[m] @ PJ) < 1e-8
     ctx.close()
+
+
+@pytest.mark.parametrize("order,knots", [(4, 140), (6, 96), (4, 64)])
+def test_long_windows_band_solver_out_of_shared_memory(built, order, knots):
+    """Windows whose band + arrow workspace exceeds shared memory: the two-sided factorisation then runs chunk
+    by chunk on shared-memory views of a global workspace.  Compared with the dense cooperative Cholesky on
+    the same system and with the oracle's step; also through full LM iterations."""
+    win = synthetic.make_window(order=order, num_knots=knots, num_landmarks=300, num_imu=600, seed=synthetic.SEED_BASE + 600 + knots,
+                                constant_knots=2)
+    ow = ol.OracleWindow(win)
+    o = ow.iterate(apply=False)
+    deltas = []
+    for force_dense in (False, True):
+        ctx = make_ctx(win, force_dense=force_dense)
+        ctx.evaluate()
+        ctx.build_system()
+        ctx.solve()
+        dp, dl = ctx.delta()
+        res = np.abs(o["S"] @ dp - o["b"]).max() / (np.abs(o["b"]).max() + 1e-300)
+        assert res < 1e-7, (force_dense, res)
+        assert rel_err(dp, o["delta_p"]) < 1e-5
+        assert rel_err(dl, o["delta_l"]) < 1e-5
+        deltas.append(dp)
+        ctx.close()
+    assert rel_err(deltas[0], deltas[1]) < 1e-6
+    ctx = make_ctx(win)
+    recs = ctx.iterate(3)
+    for rec in recs:
+        oo = ow.iterate(apply=True)
+        assert rec["spd"] == 1 and abs(rec["cost"] - oo["cost"]) <= 1e-7 * oo["cost"] and rec["accepted"] == oo["accepted"]
+    ctx.close()

@@ -3,7 +3,7 @@ os.environ["HB200_BAND_TIMING"]="1"
 sys.path.insert(0,"/root/repo")
 import numpy as np
 from hyperslam_b200 import runtime, synthetic
-win = synthetic.make_config(1, constant_knots=2)
+win = synthetic.make_config(int(os.environ.get("HB200_CFG", "1")), constant_knots=2)
 ctx = runtime.Context(0); ctx.load_window(win)
 ctx.iterate(1)
 cyc = (C.c_longlong*72)()
