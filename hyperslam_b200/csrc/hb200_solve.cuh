@@ -103,13 +103,13 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
                                                                         int n, int o_bg, int o_ba, int o_g, int splits) {
   constexpr int NP = 6 * K;
   constexpr int CH = 16;
-  constexpr int NPP = NP * (NP + 1) / 2;          // pose-pose lower entries
   constexpr int NBP = 3 * KB * NP;                // bias-pose entries (per bias spline)
   constexpr int NGP = 2 * NP;                     // gravity-pose
   constexpr int NBB = KB * (KB + 1) / 2;          // bias-bias scalar weights (lower), each lands on 3 diagonal entries
   constexpr int NGB = 2 * 3 * KB;                 // gravity-bias (per bias spline)
   constexpr int NMISC = 2 * NBB + 2 * NGB + 3 + NP + 2 * 3 * KB + 2;   // + gravity-gravity (3) + gradients
-  constexpr int E1 = (NPP + kHessThreads - 1) / kHessThreads;
+  constexpr int NT = (NP + 7) / 8, NTL = NT * (NT + 1) / 2;     // pose-pose 8 x 8 tiles (lower) for the FP64 tensor cores
+  constexpr int TPW = (NTL + kHessThreads / 32 - 1) / (kHessThreads / 32);   // tiles per warp
   constexpr int E2 = (NBP + kHessThreads - 1) / kHessThreads;
   constexpr int E4 = (NGP + kHessThreads - 1) / kHessThreads;
   constexpr int E5 = (NMISC + kHessThreads - 1) / kHessThreads;
@@ -122,9 +122,10 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
   if (lo >= hi) return;
   const int4 id0 = idx[lo];
   const int tid = threadIdx.x;
-  double a1[E1], a2[E2], a3[E2], a4[E4], a5[E5];
+  double a1[2 * TPW], a2[E2], a3[E2], a4[E4], a5[E5];
 #pragma unroll
-  for (int e = 0; e < E1; ++e) a1[e] = 0.0;
+  for (int e = 0; e < 2 * TPW; ++e) a1[e] = 0.0;
+  const int warp = tid >> 5, lm = (tid & 31) >> 2, lk = tid & 3;
 #pragma unroll
   for (int e = 0; e < E2; ++e) { a2[e] = 0.0; a3[e] = 0.0; }
 #pragma unroll
@@ -142,20 +143,28 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
     for (int e = tid; e < cnt * 12; e += kHessThreads) sG[e / 12][e % 12] = Jg[static_cast<size_t>(f0) * 12 + e];
     for (int e = tid; e < cnt * 6; e += kHessThreads) sR[e / 6][e % 6] = r[static_cast<size_t>(f0) * 6 + e];
     __syncthreads();
-    // (1) pose-pose, lower triangle
+    // (1) pose-pose, lower triangle, on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA.8x8x4): the contraction
+    // index is (factor, residual row) = the rows of sJ; lane l holds A[m = l/4][k = l%4] = J[k][m] and
+    // B[k = l%4][n = l/4] = J[k][n].  (The scalar loop here issued ~290 instructions per entry-triple.)
+    {
+      const double* Jf = &sJ[0][0][0];
+      const int krows = 6 * cnt;
 #pragma unroll
-    for (int e = 0; e < E1; ++e) {
-      const int id = tid + e * kHessThreads;
-      if (id < NPP) {
-        int a = static_cast<int>((sqrtf(8.0f * id + 1.0f) - 1.0f) * 0.5f);
-        while (a * (a + 1) / 2 > id) --a;
-        while ((a + 1) * (a + 2) / 2 <= id) ++a;
-        const int b = id - a * (a + 1) / 2;
-        double s = 0;
-        for (int ff = 0; ff < cnt; ++ff)
-#pragma unroll
-          for (int row = 0; row < 6; ++row) s += sJ[ff][row][a] * sJ[ff][row][b];
-        a1[e] += s;
+      for (int q = 0; q < TPW; ++q) {
+        const int tile = warp + q * (kHessThreads / 32);
+        if (tile < NTL) {
+          int ti = 0;
+          while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+          const int tj = tile - ti * (ti + 1) / 2;
+          const int ma = 8 * ti + lm, nb = 8 * tj + lm;
+          const bool va = ma < NP, vb = nb < NP;
+          for (int k0 = 0; k0 < krows; k0 += 4) {
+            const bool in = k0 + lk < krows;
+            const double av = (in && va) ? Jf[(k0 + lk) * (NP + 1) + ma] : 0.0;
+            const double bv = (in && vb) ? Jf[(k0 + lk) * (NP + 1) + nb] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(a1[2 * q]), "+d"(a1[2 * q + 1]) : "d"(av), "d"(bv));
+          }
+        }
       }
     }
     // (2)/(3) bias-pose: entry (m, c, a) = sum_f w[f][m] * Jp[f][row c (+3)][a]
@@ -229,14 +238,17 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
   const int cp = 6 * id0.x, cg = o_bg + 3 * id0.y, ca = o_ba + 3 * id0.z;
   const double ls = loss_scale;
 #pragma unroll
-  for (int e = 0; e < E1; ++e) {
-    const int id = tid + e * kHessThreads;
-    if (id < NPP) {
-      int a = static_cast<int>((sqrtf(8.0f * id + 1.0f) - 1.0f) * 0.5f);
-      while (a * (a + 1) / 2 > id) --a;
-      while ((a + 1) * (a + 2) / 2 <= id) ++a;
-      const int b = id - a * (a + 1) / 2;
-      atomicAdd(&v.S[static_cast<size_t>(cp + a) * n + cp + b], ls * a1[e]);
+  for (int q = 0; q < TPW; ++q) {
+    const int tile = warp + q * (kHessThreads / 32);
+    if (tile < NTL) {
+      int ti = 0;
+      while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+      const int tj = tile - ti * (ti + 1) / 2;
+      const int a = 8 * ti + lm, b = 8 * tj + 2 * lk;
+      if (a < NP) {
+        if (b < NP && b <= a) atomicAdd(&v.S[static_cast<size_t>(cp + a) * n + cp + b], ls * a1[2 * q]);
+        if (b + 1 < NP && b + 1 <= a) atomicAdd(&v.S[static_cast<size_t>(cp + a) * n + cp + b + 1], ls * a1[2 * q + 1]);
+      }
     }
   }
 #pragma unroll

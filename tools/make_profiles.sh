@@ -14,6 +14,9 @@ ncu --set full --clock-control none --import-source on -k regex:eval_kernel -s 4
 # (3) full capture of the dominant kernel by time at cfg1
 ncu --set full --clock-control none --import-source on -k regex:band_solve -s 3 -c 1 -o gpurun_out/${R}_band_cfg1 \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-large > /dev/null 2> gpurun_out/${R}_ncu_band.err
+# (3b) the J^T J / Schur kernels of the same workload (next-round targets)
+ncu --set full --clock-control none --import-source on -k regex:'inertial_hessian|schur_kernel' -s 4 -c 2 -o gpurun_out/${R}_jtj_cfg1 \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-large > /dev/null 2> gpurun_out/${R}_ncu_jtj.err
 # (4) the real numbers (never taken under a profiler)
 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/${R}_bench_reference.json 2>> gpurun_out/${R}_bench.err

@@ -45,7 +45,8 @@ traffic = {}
 md = [f"# {R}: ncu --set full captures (clock-control none)\n"]
 for tag, title in (("eval_cfg1", "factor kernels on BASELINE config 1 (bench.py workload: 10k pixel + 2k IMU factors)"),
                    ("eval_cfg4", "factor kernels on the 1M-factor window (833k pixel + 167k IMU)"),
-                   ("band_cfg1", "band_solve_kernel on config 1 (dominant kernel of the step by time)")):
+                   ("band_cfg1", "band_solve_kernel on config 1 (dominant kernel of the step by time)"),
+                   ("jtj_cfg1", "inertial J^T J and landmark Schur complement on config 1")):
     rep = os.path.join(G, f"{R}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
