@@ -51,6 +51,10 @@ struct DevBuf {
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }   // scratch buffers of the API calls do not leak on early error returns
 };
 
 void compute_basis(Basis* b, int k) {
@@ -1443,6 +1447,43 @@ int hb200_restore(hb200_ctx* c) {
   HB_CUDA(cudaMemcpyAsync(c->st.p, c->snap_st.p, sizeof(SolverState), cudaMemcpyDeviceToDevice, c->stream));
   c->iter_total = c->snap_iter_total;
   c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  return 0;
+}
+
+int hb200_ingest_stereo(hb200_ctx* c, int n, const double* stamp, const int* camera0, const int* camera1, const double* pixel0,
+                        const double* pixel1, double* bearing0, double* bearing1, double* landmark, int* num_invalid) {
+  if (!c || n < 0) return fail(-1, "invalid arguments");
+  if (c->K == 0 || c->C == 0) return fail(-2, "spline / cameras not set");
+  if (c->k != 4 && c->k != 6) return fail(-4, "spline order %d not supported (4 or 6)", c->k);
+  if (n > 0 && (!stamp || !camera0 || !camera1 || !pixel0 || !pixel1 || !bearing0 || !bearing1 || !landmark)) return fail(-1, "null argument");
+  if (num_invalid) *num_invalid = 0;
+  if (n == 0) return 0;
+  HB_CUDA(cudaSetDevice(c->device));
+  DevBuf<double> d_t, d_p0, d_p1, d_b0, d_b1, d_lm;
+  DevBuf<int> d_c0, d_c1;
+  const size_t N = static_cast<size_t>(n);
+  HB_CUDA(d_t.ensure(N)); HB_CUDA(d_p0.ensure(2 * N)); HB_CUDA(d_p1.ensure(2 * N)); HB_CUDA(d_b0.ensure(3 * N)); HB_CUDA(d_b1.ensure(3 * N));
+  HB_CUDA(d_lm.ensure(3 * N)); HB_CUDA(d_c0.ensure(N)); HB_CUDA(d_c1.ensure(N));
+  HB_CUDA(c->d_invalid.ensure(1));
+  HB_CUDA(cudaMemsetAsync(c->d_invalid.p, 0, sizeof(int), c->stream));
+  HB_CUDA(cudaMemcpyAsync(d_t.p, stamp, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(d_c0.p, camera0, sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(d_c1.p, camera1, sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(d_p0.p, pixel0, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(d_p1.p, pixel1, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, c->stream));
+  prep_kernel<<<(c->K + 63) / 64, 64, 0, c->stream>>>(c->K, c->knots[0].p, c->tab[0].p, nullptr, 0);
+  HB_LAUNCH(c, "prep_kernel");
+  if (c->k == 4) ingest_stereo_kernel<4><<<(n + 127) / 128, 128, 0, c->stream>>>(n, d_t.p, d_c0.p, d_c1.p, d_p0.p, d_p1.p, c->knots[0].p, c->tab[0].p, c->K, c->basis, c->cams.p, c->C, d_b0.p, d_b1.p, d_lm.p, c->d_invalid.p);
+  else ingest_stereo_kernel<6><<<(n + 127) / 128, 128, 0, c->stream>>>(n, d_t.p, d_c0.p, d_c1.p, d_p0.p, d_p1.p, c->knots[0].p, c->tab[0].p, c->K, c->basis, c->cams.p, c->C, d_b0.p, d_b1.p, d_lm.p, c->d_invalid.p);
+  HB_LAUNCH(c, "ingest_stereo_kernel");
+  int bad = 0;
+  HB_CUDA(cudaMemcpyAsync(bearing0, d_b0.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaMemcpyAsync(bearing1, d_b1.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaMemcpyAsync(landmark, d_lm.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaMemcpyAsync(&bad, c->d_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  d_t.release(); d_p0.release(); d_p1.release(); d_b0.release(); d_b1.release(); d_lm.release(); d_c0.release(); d_c1.release();
+  if (num_invalid) *num_invalid = bad;
   return 0;
 }
 

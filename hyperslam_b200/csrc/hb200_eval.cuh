@@ -1045,4 +1045,111 @@ __global__ void interpolate_kernel(int n, const double* __restrict__ stamps, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ingest step in front of the hot path (reference
+// internal/hyper/optimizers/abstract.cpp:186-264): per stereo track, the bearings of both views
+// (C.convertPixelsToBearings, :221-223) and the triangulated landmark in the world frame
+// (Camera::Triangulate(T_01, b0, b1), :252; T_w0.vectorPlus, :253) at the CURRENT state.  The two
+// camera functions live in HyperSensors (not in the tree): pixel -> bearing inverts the
+// radial-tangential model with Newton iterations on the evaluator's own forward model; Triangulate is
+// the midpoint of the common perpendicular [INFERRED].  One track per thread.
+// ---------------------------------------------------------------------------------------------
+HB_DI void pixel_to_bearing(const double* __restrict__ cam /* raw [T_bs 7 | cx cy fx fy | k1 k2 p1 p2] */, double px, double py, double* b) {
+  const double cx = cam[7], cy = cam[8], fx = cam[9], fy = cam[10];
+  const double k1 = cam[11], k2 = cam[12], p1 = cam[13], p2 = cam[14];
+  const double dx = (px - cx) / fx, dy = (py - cy) / fy;
+  double x = dx, y = dy;
+#pragma unroll 1
+  for (int it = 0; it < 10; ++it) {
+    const double r2 = x * x + y * y;
+    const double rad = 1.0 + k1 * r2 + k2 * r2 * r2;
+    const double ox = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+    const double oy = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+    const double g = k1 + 2.0 * k2 * r2;
+    const double drx = 2.0 * x * g, dry = 2.0 * y * g;
+    const double j00 = rad + x * drx + 2.0 * p1 * y + 6.0 * p2 * x;
+    const double j01 = x * dry + 2.0 * p1 * x + 2.0 * p2 * y;
+    const double j10 = y * drx + 2.0 * p1 * x + 2.0 * p2 * y;
+    const double j11 = rad + y * dry + 6.0 * p1 * y + 2.0 * p2 * x;
+    const double e0 = ox - dx, e1 = oy - dy;
+    const double idet = 1.0 / (j00 * j11 - j01 * j10);
+    x -= (j11 * e0 - j01 * e1) * idet;
+    y -= (-j10 * e0 + j00 * e1) * idet;
+  }
+  const double inv = rsqrt(x * x + y * y + 1.0);
+  b[0] = x * inv; b[1] = y * inv; b[2] = inv;
+}
+
+template <int K>
+__global__ void ingest_stereo_kernel(int n, const double* __restrict__ stamps, const int* __restrict__ cam0, const int* __restrict__ cam1,
+                                     const double* __restrict__ px0, const double* __restrict__ px1, const double* __restrict__ knots,
+                                     const double* __restrict__ tab, int Kn, Basis B, const double* __restrict__ cams, int C,
+                                     double* __restrict__ b0_out, double* __restrict__ b1_out, double* __restrict__ lm_out,
+                                     int* __restrict__ num_invalid) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const double t = stamps[f];
+  const int base = segment_base(knots, 8, 7, Kn, K, t);
+  const int c0 = cam0[f], c1 = cam1[f];
+  if (base < 0 || c0 < 0 || c0 >= C || c1 < 0 || c1 >= C) {
+    atomicAdd(num_invalid, 1);
+    for (int i = 0; i < 3; ++i) { b0_out[3 * static_cast<size_t>(f) + i] = 0.0; b1_out[3 * static_cast<size_t>(f) + i] = 0.0; lm_out[3 * static_cast<size_t>(f) + i] = 0.0; }
+    return;
+  }
+  // pose of the body at the stamp (value only)
+  constexpr int left = (K - 1) / 2;
+  const double* row0 = tab + static_cast<size_t>(base) * kTabStride;
+  const double t0 = row0[left * kTabStride + 24], t1 = row0[(left + 1) * kTabStride + 24];
+  const double inv_dt = 1.0 / (t1 - t0);
+  double lam[K + 1];
+  basis_eval<K, false>(B, (t - t0) * inv_dt, inv_dt, lam, nullptr, nullptr);
+  double R[9], p[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = row0[i];
+  p[0] = row0[9]; p[1] = row0[10]; p[2] = row0[11];
+#pragma unroll
+  for (int j = 1; j < K; ++j) {
+    const double* rj = row0 + j * kTabStride;
+    const double w[3] = {lam[j] * rj[12], lam[j] * rj[13], lam[j] * rj[14]};
+    double A[9], Rn[9];
+    so3_exp_and_Jr(w, A, nullptr);
+    m3_mul(R, A, Rn);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] += lam[j] * (rj[9 + c] - rj[9 + c - kTabStride]);
+  }
+  const double* ca = cams + 15 * static_cast<size_t>(c0);
+  const double* cb = cams + 15 * static_cast<size_t>(c1);
+  double b0[3], b1[3];
+  pixel_to_bearing(ca, px0[2 * static_cast<size_t>(f)], px0[2 * static_cast<size_t>(f) + 1], b0);
+  pixel_to_bearing(cb, px1[2 * static_cast<size_t>(f)], px1[2 * static_cast<size_t>(f) + 1], b1);
+  // T_01 = T_b0^-1 (+) T_b1: R_01 = R_b0^T R_b1, t_01 = R_b0^T (t_b1 - t_b0)
+  double Ra[9], Rb[9], R01[9], d1[3], t01[3];
+  quat_to_rot(ca, Ra);
+  quat_to_rot(cb, Rb);
+  m3_tmul(Ra, Rb, R01);
+  const double dt[3] = {cb[4] - ca[4], cb[5] - ca[5], cb[6] - ca[6]};
+  m3_tvec(Ra, dt, t01);
+  m3_vec(R01, b1, d1);
+  const double aa = b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2], bb = b0[0] * d1[0] + b0[1] * d1[1] + b0[2] * d1[2];
+  const double cc = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2];
+  const double ee = b0[0] * t01[0] + b0[1] * t01[1] + b0[2] * t01[2], ff = d1[0] * t01[0] + d1[1] * t01[1] + d1[2] * t01[2];
+  const double idet = 1.0 / (aa * cc - bb * bb);
+  const double sa = (ee * cc - bb * ff) * idet, ub = (bb * ee - aa * ff) * idet;
+  double p0[3], pb[3], pw[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) p0[i] = 0.5 * (sa * b0[i] + t01[i] + ub * d1[i]);
+  // world point: p_w = R (R_b0 p_0 + t_b0) + p
+  m3_vec(Ra, p0, pb);
+  pb[0] += ca[4]; pb[1] += ca[5]; pb[2] += ca[6];
+  m3_vec(R, pb, pw);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    b0_out[3 * static_cast<size_t>(f) + i] = b0[i];
+    b1_out[3 * static_cast<size_t>(f) + i] = b1[i];
+    lm_out[3 * static_cast<size_t>(f) + i] = pw[i] + p[i];
+  }
+}
+
 }  // namespace hb

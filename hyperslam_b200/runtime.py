@@ -41,6 +41,7 @@ EXPORTS = [
     "hb200_system_device_ptr", "hb200_stream", "hb200_launch_count", "hb200_optimize", "hb200_snapshot", "hb200_restore",
     "hb200_profile_iteration", "hb200_interpolate", "hb200_set_bearing_factors", "hb200_set_bearing_loss",
     "hb200_set_pose_sensors", "hb200_set_manifold_factors", "hb200_get_bearing_outputs", "hb200_get_manifold_outputs",
+    "hb200_ingest_stereo",
 ]
 
 _lib = None
@@ -316,6 +317,16 @@ class Context:
         bad = C.c_int(0)
         self._check(self.lib.hb200_interpolate(self.h, n, _d(stamps), _d(pose), _d(vel), _d(acc), C.byref(bad)))
         return pose, vel, acc, bad.value
+
+    def ingest_stereo(self, stamp, cam0, cam1, px0, px1):
+        """Stereo-track ingest (pixels -> bearings + triangulated world landmark at the current state)."""
+        stamp, px0, px1 = _f64(stamp), _f64(px0), _f64(px1)
+        cam0, cam1 = np.ascontiguousarray(cam0, dtype=np.int32), np.ascontiguousarray(cam1, dtype=np.int32)
+        n = stamp.size
+        b0, b1, lm = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+        bad = C.c_int(0)
+        self._check(self.lib.hb200_ingest_stereo(self.h, n, _d(stamp), _i(cam0), _i(cam1), _d(px0), _d(px1), _d(b0), _d(b1), _d(lm), C.byref(bad)))
+        return b0, b1, lm, bad.value
 
     def synchronize(self):
         self._check(self.lib.hb200_synchronize(self.h))

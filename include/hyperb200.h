@@ -139,6 +139,14 @@ int hb200_profile_iteration(hb200_ctx* ctx, int reps, int max_entries, char* nam
  * state->evaluate(StateQuery{stamp, derivative}) for trajectory dumps (reference apps/hyperslam/main.cpp:69-80). */
 int hb200_interpolate(hb200_ctx* ctx, int n, const double* stamps, double* pose, double* velocity, double* acceleration, int* num_invalid);
 int hb200_get_state(hb200_ctx* ctx, double* knots, double* gyro, double* accel, double* gravity, double* landmarks);
+/* Ingest of stereo tracks in front of the factor lists (reference internal/hyper/optimizers/abstract.cpp:186-264):
+ * per track i the unit bearings of both views (C.convertPixelsToBearings, :221-223) and the landmark
+ * triangulated from them and moved to the world frame with the CURRENT state's pose at stamp[i]
+ * (Camera::Triangulate(T_01, b0, b1) :252, T_w0.vectorPlus :253).  Outputs may not be NULL.  Tracks whose stamp
+ * or camera index is invalid are zero-filled and counted. */
+int hb200_ingest_stereo(hb200_ctx* ctx, int n, const double* stamp, const int* camera0, const int* camera1, const double* pixel0 /* [n][2] */,
+                        const double* pixel1 /* [n][2] */, double* bearing0 /* [n][3] */, double* bearing1 /* [n][3] */,
+                        double* landmark /* [n][3] */, int* num_invalid);
 
 /* ---- multi-GPU hook -------------------------------------------------------------------------
  * The packed reduced system [S (n*n) | b (n) | cost (1) | pad (1)] lives in one device buffer;

@@ -7,6 +7,7 @@
 
 #include "ho_evaluators.h"
 #include "ho_manifolds.h"
+#include "ho_ingest.h"
 #include "ho_window.h"
 
 using namespace ho;
@@ -200,6 +201,18 @@ int ho_manifold_minus(int id, int size, const double* y, const double* x, double
   return 0;
 }
 
+}  // extern "C"
+
+extern "C" {
+// Stereo-frame ingest (ho_ingest.h): cps = the k control points around `stamp` ([k][8]).
+int ho_ingest_stereo_frame(int k, const double* cps, double stamp, const double* cam0, const double* cam1, int n, const double* px0,
+                           const double* px1, double* B0, double* B1, double* landmarks) {
+  Basis b; basis_init(&b, k);
+  const double* ptrs[kMaxOrder];
+  for (int i = 0; i < k; ++i) ptrs[i] = cps + 8 * i;
+  ingest_stereo_frame(b, ptrs, stamp, cam0, cam1, n, px0, px1, B0, B1, landmarks);
+  return 0;
+}
 }  // extern "C"
 
 #include "ho_window_api.inc"

@@ -237,5 +237,17 @@ class OracleWindow:
         return dict(knots=knots, gyro_bias=bg, accel_bias=ba, gravity=g, landmarks=lm)
 
 
+def ingest_stereo_frame(cps, stamp, cam0, cam1, px0, px1):
+    """Oracle restatement of the stereo-frame ingest (oracle/ho_ingest.h): returns (B0, B1, landmarks)."""
+    cps = np.ascontiguousarray(cps, dtype=np.float64)
+    px0 = np.ascontiguousarray(px0, dtype=np.float64); px1 = np.ascontiguousarray(px1, dtype=np.float64)
+    n = px0.shape[0]
+    B0, B1, L = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+    rc = lib().ho_ingest_stereo_frame(cps.shape[0], _d(cps), C.c_double(stamp), _d(np.ascontiguousarray(cam0, dtype=np.float64)),
+                                      _d(np.ascontiguousarray(cam1, dtype=np.float64)), n, _d(px0), _d(px1), _d(B0), _d(B1), _d(L))
+    assert rc == 0
+    return B0, B1, L
+
+
 def num_threads():
     return lib().ho_num_threads()
