@@ -419,8 +419,10 @@ int enqueue_finalize(hb200_ctx* c) {
   return 0;
 }
 
-// damp_in_solver: the band solver applies LM damping + the constant-dof mask itself (finalize_kernel skipped)
-int enqueue_solve(hb200_ctx* c, bool damp_in_solver = false) {
+RetractArgs retract_args(hb200_ctx* c);
+// damp_in_solver: the band solver applies LM damping + the constant-dof mask itself (finalize_kernel skipped);
+// fuse_retract: the landmark back-substitution launch also retracts knots / biases / gravity (returns *fused)
+int enqueue_solve(hb200_ctx* c, bool damp_in_solver = false, bool fuse_retract = false, bool* fused = nullptr) {
   if (c->band_solver) {
     const SolverState* st = damp_in_solver ? c->st.p : nullptr;
     const unsigned char* fx = damp_in_solver ? c->fixed.p : nullptr;
@@ -444,12 +446,19 @@ int enqueue_solve(hb200_ctx* c, bool damp_in_solver = false) {
   }
   if (c->L) {
     if (c->Nv) {
+      RetractArgs ra{};
+      int extra = 0;
+      if (fuse_retract) {
+        ra = retract_args(c);
+        extra = (std::max(std::max(c->K, 1), std::max(c->Kbg, c->Kba)) + kLmWarps * 32 - 1) / (kLmWarps * 32);
+        if (fused) *fused = true;
+      }
       if (c->k == 4)
-        lm_backsub_kernel<4><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
-                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p);
+        lm_backsub_kernel<4><<<c->n_lm_blocks + extra, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
+                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p, c->n_lm_blocks, ra);
       else
-        lm_backsub_kernel<6><<<c->n_lm_blocks, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
-                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p);
+        lm_backsub_kernel<6><<<c->n_lm_blocks + extra, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
+                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p, c->n_lm_blocks, ra);
       HB_LAUNCH(c, "lm_backsub_kernel");
     } else {
       HB_CUDA(cudaMemsetAsync(c->dl.p, 0, 3 * static_cast<size_t>(c->L) * sizeof(double), c->stream));
@@ -459,10 +468,17 @@ int enqueue_solve(hb200_ctx* c, bool damp_in_solver = false) {
   return 0;
 }
 
+RetractArgs retract_args(hb200_ctx* c) {
+  RetractArgs ra{};
+  ra.K = c->K; ra.Kbg = c->Kbg; ra.Kba = c->Kba; ra.L = c->L;
+  ra.dp = c->dp.p; ra.dl = c->dl.p; ra.knots = c->knots[0].p; ra.bg = c->bg[0].p; ra.ba = c->ba[0].p; ra.grav = c->grav[0].p; ra.lms = c->lms[0].p;
+  ra.knots_t = c->knots[1].p; ra.bg_t = c->bg[1].p; ra.ba_t = c->ba[1].p; ra.grav_t = c->grav[1].p; ra.lms_t = c->lms[1].p; ra.tab_t = c->tab[1].p;
+  ra.retract_landmarks = (c->L && !c->Nv) ? 1 : 0;
+  return ra;
+}
 int enqueue_retract(hb200_ctx* c) {
   const int m = std::max(std::max(c->K, c->L), std::max(std::max(c->Kbg, c->Kba), 1));
-  retract_kernel<<<(m + 127) / 128, 128, 0, c->stream>>>(c->K, c->Kbg, c->Kba, c->L, c->dp.p, c->dl.p, c->knots[0].p, c->bg[0].p, c->ba[0].p, c->grav[0].p,
-                                                        c->lms[0].p, c->knots[1].p, c->bg[1].p, c->ba[1].p, c->grav[1].p, c->lms[1].p, c->tab[1].p, (c->L && !c->Nv) ? 1 : 0);
+  retract_kernel<<<(m + 127) / 128, 128, 0, c->stream>>>(retract_args(c));
   HB_LAUNCH(c, "retract_kernel");
   return 0;
 }
@@ -504,8 +520,9 @@ int enqueue_segment(hb200_ctx* c, int segment) {
   } else if (segment == 1) {
     // band solver: damping + constant-dof mask are applied while it gathers the band (no finalize pass)
     if (!c->band_solver && (rc = enqueue_finalize(c))) return rc;
-    if ((rc = enqueue_solve(c, /*damp_in_solver=*/c->band_solver))) return rc;
-    if ((rc = enqueue_retract(c))) return rc;   // also builds the trial knot table
+    bool retracted = false;
+    if ((rc = enqueue_solve(c, /*damp_in_solver=*/c->band_solver, /*fuse_retract=*/true, &retracted))) return rc;
+    if (!retracted && (rc = enqueue_retract(c))) return rc;   // (also builds the trial knot table)
     if ((rc = enqueue_evaluate(c, false, 1, false, false, false, /*skip_prep=*/true))) return rc;
     if (c->allreduce && (rc = enqueue_scalars(c))) return rc;
   } else {

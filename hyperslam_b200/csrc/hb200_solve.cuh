@@ -653,6 +653,93 @@ __global__ void __launch_bounds__(1024) backsolve_kernel(const double* __restric
   }
 }
 
+// Ceres SphereManifold<3>::Plus.
+HB_DI void sphere_plus(const double* x, const double* delta, double* out) {
+  const double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1]);
+  if (nd == 0.0) { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; return; }
+  const double sigma = x[0] * x[0] + x[1] * x[1];
+  double v[3] = {x[0], x[1], 1.0};
+  double beta = 0.0;
+  const double xp = x[2];
+  if (sigma <= 2.220446049250313e-16) {
+    if (xp < 0.0) beta = 2.0;
+  } else {
+    const double mu = sqrt(xp * xp + sigma);
+    const double vp = (xp <= 0.0) ? (xp - mu) : (-sigma / (xp + mu));
+    beta = 2.0 * vp * vp / (sigma + vp * vp);
+    v[0] /= vp; v[1] /= vp;
+  }
+  const double nx = sqrt(sigma + xp * xp);
+  const double s = sin(nd) / nd;
+  const double y[3] = {s * delta[0], s * delta[1], cos(nd)};
+  const double vy = v[0] * y[0] + v[1] * y[1] + v[2] * y[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) out[i] = nx * (y[i] - v[i] * beta * vy);
+}
+
+// Manifold::Plus on every variable block: trial = current (+) delta (and the trial state's knot table).
+struct RetractArgs {
+  int K, Kbg, Kba, L;
+  const double *dp, *dl, *knots, *bg, *ba, *grav, *lms;
+  double *knots_t, *bg_t, *ba_t, *grav_t, *lms_t, *tab_t /* or null */;
+  int retract_landmarks;
+};
+HB_DI void retract_body(const RetractArgs& ra, int i) {
+  const int K = ra.K, Kbg = ra.Kbg, Kba = ra.Kba, L = ra.L, retract_landmarks = ra.retract_landmarks;
+  const double* __restrict__ dp = ra.dp; const double* __restrict__ dl = ra.dl; const double* __restrict__ knots = ra.knots;
+  const double* __restrict__ bg = ra.bg; const double* __restrict__ ba = ra.ba; const double* __restrict__ grav = ra.grav;
+  const double* __restrict__ lms = ra.lms;
+  double* __restrict__ knots_t = ra.knots_t; double* __restrict__ bg_t = ra.bg_t; double* __restrict__ ba_t = ra.ba_t;
+  double* __restrict__ grav_t = ra.grav_t; double* __restrict__ lms_t = ra.lms_t; double* __restrict__ tab_t = ra.tab_t;
+  if (i < K) {
+    const double* kn = knots + 8 * static_cast<size_t>(i);
+    const double* d = dp + 6 * static_cast<size_t>(i);
+    double qe[4], qn[4];
+    const double th[3] = {d[0], d[1], d[2]};
+    const double q[4] = {kn[0], kn[1], kn[2], kn[3]};
+    quat_exp(th, qe);
+    quat_mul(qe, q, qn);
+    double* o = knots_t + 8 * static_cast<size_t>(i);
+    o[0] = qn[0]; o[1] = qn[1]; o[2] = qn[2]; o[3] = qn[3];
+    o[4] = kn[4] + d[3]; o[5] = kn[5] + d[4]; o[6] = kn[6] + d[5]; o[7] = kn[7];
+    if (tab_t) {
+      // the trial state's knot-table row (same arithmetic as prep_kernel): this thread retracts knot i-1 again
+      // for the relative rotation instead of waiting for its neighbour
+      double qp[4] = {0, 0, 0, 1};
+      if (i > 0) {
+        const double thp[3] = {d[-6], d[-5], d[-4]};
+        const double qo[4] = {kn[-8], kn[-7], kn[-6], kn[-5]};
+        double qep[4];
+        quat_exp(thp, qep);
+        quat_mul(qep, qo, qp);
+      }
+      knot_table_row(qn, o + 4, o[7], qp, i > 0, tab_t + static_cast<size_t>(i) * kTabStride);
+    }
+  }
+  if (i < Kbg) {
+    const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(i);
+    for (int c = 0; c < 3; ++c) bg_t[4 * i + c] = bg[4 * i + c] + d[c];
+    bg_t[4 * i + 3] = bg[4 * i + 3];
+  }
+  if (i < Kba) {
+    const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(Kbg) + 3 * static_cast<size_t>(i);
+    for (int c = 0; c < 3; ++c) ba_t[4 * i + c] = ba[4 * i + c] + d[c];
+    ba_t[4 * i + 3] = ba[4 * i + 3];
+  }
+  if (i == 0) {
+    const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(Kbg) + 3 * static_cast<size_t>(Kba);
+    const double x[3] = {grav[0], grav[1], grav[2]};
+    const double dd[2] = {d[0], d[1]};
+    double o[3];
+    sphere_plus(x, dd, o);
+    grav_t[0] = o[0]; grav_t[1] = o[1]; grav_t[2] = o[2];
+  }
+  if (retract_landmarks && i < L) {   // otherwise lm_backsub_kernel has written the trial landmarks already
+    for (int c = 0; c < 3; ++c) lms_t[3 * static_cast<size_t>(i) + c] = lms[3 * static_cast<size_t>(i) + c] + dl[3 * static_cast<size_t>(i) + c];
+  }
+}
+__global__ void retract_kernel(RetractArgs ra) { retract_body(ra, blockIdx.x * blockDim.x + threadIdx.x); }
+
 // Landmark back-substitution: dl = V^-1 (-g_l - W^T dp); also partial sums of dl.g_l and dl.D_l.dl.
 // One warp per landmark: 8 observations x 4 column groups in flight per pass.
 constexpr int kLmWarps = 4;
@@ -663,8 +750,11 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const 
                                                                   const double* __restrict__ Jp, const double* __restrict__ Jl, const double* __restrict__ wv,
                                                                   const double* __restrict__ Vinv, const double* __restrict__ gl,
                                                                   const double* __restrict__ Dl, const double* __restrict__ dp,
-                                                                  double* __restrict__ dl, double* __restrict__ part /*[grid][2]*/,
-                                                                  const double* __restrict__ lms, double* __restrict__ lms_t) {
+                                                                  double* __restrict__ dl, double* __restrict__ part /*[n_lm_blocks][2]*/,
+                                                                  const double* __restrict__ lms, double* __restrict__ lms_t,
+                                                                  int n_lm_blocks, RetractArgs ra) {
+  // blocks past the landmark range retract the knots / biases / gravity in the same launch (they only need dp)
+  if (static_cast<int>(blockIdx.x) >= n_lm_blocks) { retract_body(ra, (blockIdx.x - n_lm_blocks) * blockDim.x + threadIdx.x); return; }
   constexpr int NB = 6 * K;
   constexpr int CG = NB / 4;  // columns per lane group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -727,84 +817,6 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const 
   }
 }
 
-// Ceres SphereManifold<3>::Plus.
-HB_DI void sphere_plus(const double* x, const double* delta, double* out) {
-  const double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1]);
-  if (nd == 0.0) { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; return; }
-  const double sigma = x[0] * x[0] + x[1] * x[1];
-  double v[3] = {x[0], x[1], 1.0};
-  double beta = 0.0;
-  const double xp = x[2];
-  if (sigma <= 2.220446049250313e-16) {
-    if (xp < 0.0) beta = 2.0;
-  } else {
-    const double mu = sqrt(xp * xp + sigma);
-    const double vp = (xp <= 0.0) ? (xp - mu) : (-sigma / (xp + mu));
-    beta = 2.0 * vp * vp / (sigma + vp * vp);
-    v[0] /= vp; v[1] /= vp;
-  }
-  const double nx = sqrt(sigma + xp * xp);
-  const double s = sin(nd) / nd;
-  const double y[3] = {s * delta[0], s * delta[1], cos(nd)};
-  const double vy = v[0] * y[0] + v[1] * y[1] + v[2] * y[2];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) out[i] = nx * (y[i] - v[i] * beta * vy);
-}
-
-// Manifold::Plus on every variable block: trial = current (+) delta.
-__global__ void retract_kernel(int K, int Kbg, int Kba, int L, const double* __restrict__ dp, const double* __restrict__ dl,
-                               const double* __restrict__ knots, const double* __restrict__ bg, const double* __restrict__ ba,
-                               const double* __restrict__ grav, const double* __restrict__ lms, double* __restrict__ knots_t,
-                               double* __restrict__ bg_t, double* __restrict__ ba_t, double* __restrict__ grav_t, double* __restrict__ lms_t,
-                               double* __restrict__ tab_t /* trial knot table, or null */, int retract_landmarks) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < K) {
-    const double* kn = knots + 8 * static_cast<size_t>(i);
-    const double* d = dp + 6 * static_cast<size_t>(i);
-    double qe[4], qn[4];
-    const double th[3] = {d[0], d[1], d[2]};
-    const double q[4] = {kn[0], kn[1], kn[2], kn[3]};
-    quat_exp(th, qe);
-    quat_mul(qe, q, qn);
-    double* o = knots_t + 8 * static_cast<size_t>(i);
-    o[0] = qn[0]; o[1] = qn[1]; o[2] = qn[2]; o[3] = qn[3];
-    o[4] = kn[4] + d[3]; o[5] = kn[5] + d[4]; o[6] = kn[6] + d[5]; o[7] = kn[7];
-    if (tab_t) {
-      // the trial state's knot-table row (same arithmetic as prep_kernel): this thread retracts knot i-1 again
-      // for the relative rotation instead of waiting for its neighbour
-      double qp[4] = {0, 0, 0, 1};
-      if (i > 0) {
-        const double thp[3] = {d[-6], d[-5], d[-4]};
-        const double qo[4] = {kn[-8], kn[-7], kn[-6], kn[-5]};
-        double qep[4];
-        quat_exp(thp, qep);
-        quat_mul(qep, qo, qp);
-      }
-      knot_table_row(qn, o + 4, o[7], qp, i > 0, tab_t + static_cast<size_t>(i) * kTabStride);
-    }
-  }
-  if (i < Kbg) {
-    const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(i);
-    for (int c = 0; c < 3; ++c) bg_t[4 * i + c] = bg[4 * i + c] + d[c];
-    bg_t[4 * i + 3] = bg[4 * i + 3];
-  }
-  if (i < Kba) {
-    const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(Kbg) + 3 * static_cast<size_t>(i);
-    for (int c = 0; c < 3; ++c) ba_t[4 * i + c] = ba[4 * i + c] + d[c];
-    ba_t[4 * i + 3] = ba[4 * i + 3];
-  }
-  if (i == 0) {
-    const double* d = dp + 6 * static_cast<size_t>(K) + 3 * static_cast<size_t>(Kbg) + 3 * static_cast<size_t>(Kba);
-    const double x[3] = {grav[0], grav[1], grav[2]};
-    const double dd[2] = {d[0], d[1]};
-    double o[3];
-    sphere_plus(x, dd, o);
-    grav_t[0] = o[0]; grav_t[1] = o[1]; grav_t[2] = o[2];
-  }
-  if (retract_landmarks && i < L) {   // otherwise lm_backsub_kernel has written the trial landmarks already
-    for (int c = 0; c < 3; ++c) lms_t[3 * static_cast<size_t>(i) + c] = lms[3 * static_cast<size_t>(i) + c] + dl[3 * static_cast<size_t>(i) + c];
-  }
-}
 
 // scal = [cost_new, dl.g_l, dl.D_l.dl, 0] (rank-local partial sums, fixed order).
 __global__ void scalars_kernel(const double* __restrict__ cp_pix, int n_pix_blocks, const double* __restrict__ cp_imu, int n_imu_blocks,
@@ -839,37 +851,39 @@ __global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __
                               const double* __restrict__ D, const unsigned char* __restrict__ fixed, SolverState* st,
                               const int* __restrict__ spd_flag, SolverState* __restrict__ record, int max_records, int fuse_scalars,
                               ScalarArgs sa, int fuse_commit, CommitArgs ca) {
-  __shared__ double s[2][kAcceptThreads];
+  // block sums: shuffle within the warp, one partial per warp, fixed order across warps (two barriers in total)
+  __shared__ double s[5][kAcceptThreads / 32];
+  const int wl = threadIdx.x & 31, ww = threadIdx.x >> 5;
+  double v5[5] = {0, 0, 0, 0, 0};   // cost_new, dl.g_l, dl.D_l.dl, dp.g, dp.D.dp
   if (fuse_scalars) {   // == scalars_kernel (no all-reduce between the two on a single GPU)
-    __shared__ double q[3][kAcceptThreads];
-    double c = 0, a = 0, b = 0;
-    for (int i = threadIdx.x; i < sa.n_pix_blocks; i += blockDim.x) c += sa.cp_pix[i];
-    for (int i = threadIdx.x; i < sa.n_imu_blocks; i += blockDim.x) c += sa.cp_imu[i];
-    for (int i = threadIdx.x; i < sa.n_lm_blocks; i += blockDim.x) { a += sa.lm_part[2 * i]; b += sa.lm_part[2 * i + 1]; }
-    q[0][threadIdx.x] = c; q[1][threadIdx.x] = a; q[2][threadIdx.x] = b;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-      if (threadIdx.x < o) { q[0][threadIdx.x] += q[0][threadIdx.x + o]; q[1][threadIdx.x] += q[1][threadIdx.x + o]; q[2][threadIdx.x] += q[2][threadIdx.x + o]; }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) { scal[0] = q[0][0]; scal[1] = q[1][0]; scal[2] = q[2][0]; scal[3] = 0.0; }
-    __syncthreads();
+    for (int i = threadIdx.x; i < sa.n_pix_blocks; i += blockDim.x) v5[0] += sa.cp_pix[i];
+    for (int i = threadIdx.x; i < sa.n_imu_blocks; i += blockDim.x) v5[0] += sa.cp_imu[i];
+    for (int i = threadIdx.x; i < sa.n_lm_blocks; i += blockDim.x) { v5[1] += sa.lm_part[2 * i]; v5[2] += sa.lm_part[2 * i + 1]; }
   }
   const double* g = sys + static_cast<size_t>(n) * n + 2 * static_cast<size_t>(n);
-  double a = 0, b = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
-    if (!fixed[i]) { a += dp[i] * g[i]; b += dp[i] * dp[i] * D[i]; }
-  s[0][threadIdx.x] = a; s[1][threadIdx.x] = b;
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { s[0][threadIdx.x] += s[0][threadIdx.x + o]; s[1][threadIdx.x] += s[1][threadIdx.x + o]; }
-    __syncthreads();
+    if (!fixed[i]) { v5[3] += dp[i] * g[i]; v5[4] += dp[i] * dp[i] * D[i]; }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v5[q] += __shfl_xor_sync(0xffffffffu, v5[q], o);
+    if (wl == 0) s[q][ww] = v5[q];
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t5[5] = {0, 0, 0, 0, 0};
+    for (int w = 0; w < kAcceptThreads / 32; ++w)
+#pragma unroll
+      for (int q = 0; q < 5; ++q) t5[q] += s[q][w];
+    if (fuse_scalars) { scal[0] = t5[0]; scal[1] = t5[1]; scal[2] = t5[2]; scal[3] = 0.0; }
+    s[3][0] = t5[3]; s[4][0] = t5[4];
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     const double mu = 1.0 / st->radius;
     const double cost = sys[static_cast<size_t>(n) * n + 3 * static_cast<size_t>(n)];
     const double cost_new = scal[0];
-    const double dg = s[0][0] + scal[1], dDd = s[1][0] + scal[2];
+    const double dg = s[3][0] + scal[1], dDd = s[4][0] + scal[2];
     const double model = 0.5 * (-dg + mu * dDd);
     const double rho = (cost - cost_new) / model;
     const int spd = *spd_flag;
