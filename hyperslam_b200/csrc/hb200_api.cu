@@ -296,14 +296,28 @@ int reset_solver_state(hb200_ctx* c) {
 }
 
 // ---- kernel dispatch on (order, bias order) -------------------------------------------------
-template <int K, bool J>
-int launch_pixel(hb200_ctx* c, int sel, bool accumulate = false) {
-  if (c->Nv == 0) return 0;
+template <bool J>
+PixelArgs pixel_args(hb200_ctx* c, int sel, bool accumulate) {
   PixelArgs a{};
   a.sys = accumulate ? c->sys.p : nullptr; a.n_sys = c->n;
   a.n = c->Nv; a.stamp = c->v_stamp.p; a.pixel = reinterpret_cast<const double2*>(c->v_pixel.p); a.meas_z = c->v_z.p; a.idx = c->v_idx.p;
   a.tab = c->tab[sel].p; a.cam_tab = c->cam_tab.p; a.landmarks = c->lms[sel].p;
   a.r = J ? c->v_r.p : nullptr; a.Jp = c->v_Jp.p; a.Jl = c->v_Jl.p; a.w = c->v_w.p; a.cost_partial = c->cp_pix[J ? 0 : 1].p; a.huber = c->huber; a.huber_bearing = c->huber_bearing; a.K_knots = c->K;
+  return a;
+}
+template <bool J>
+InertialArgs inertial_args(hb200_ctx* c, int sel) {
+  InertialArgs a{};
+  a.n = c->Ni; a.stamp = c->i_stamp.p; a.meas = c->i_meas.p; a.idx = c->i_idx.p; a.tab = c->tab[sel].p; a.imu_tab = c->imu_tab.p;
+  a.bg = c->bg[sel].p; a.ba = c->ba[sel].p; a.gravity = c->grav[sel].p;
+  a.r = J ? c->i_r.p : nullptr; a.Jp = c->i_Jp.p; a.wg = c->i_wg.p; a.wa = c->i_wa.p; a.Jg = c->i_Jg.p;
+  a.cost_partial = c->cp_imu[J ? 0 : 1].p; a.loss_scale = c->imu_scale;
+  return a;
+}
+template <int K, bool J>
+int launch_pixel(hb200_ctx* c, int sel, bool accumulate = false) {
+  if (c->Nv == 0) return 0;
+  const PixelArgs a = pixel_args<J>(c, sel, accumulate);
   if (J && accumulate) pixel_eval_kernel<K, J, J><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
   else pixel_eval_kernel<K, J, false><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
   HB_LAUNCH(c, "pixel_eval_kernel");
@@ -312,16 +326,22 @@ int launch_pixel(hb200_ctx* c, int sel, bool accumulate = false) {
 template <int K, bool J>
 int launch_inertial(hb200_ctx* c, int sel) {
   if (c->Ni == 0) return 0;
-  InertialArgs a{};
-  a.n = c->Ni; a.stamp = c->i_stamp.p; a.meas = c->i_meas.p; a.idx = c->i_idx.p; a.tab = c->tab[sel].p; a.imu_tab = c->imu_tab.p;
-  a.bg = c->bg[sel].p; a.ba = c->ba[sel].p; a.gravity = c->grav[sel].p;
-  a.r = J ? c->i_r.p : nullptr; a.Jp = c->i_Jp.p; a.wg = c->i_wg.p; a.wa = c->i_wa.p; a.Jg = c->i_Jg.p;
-  a.cost_partial = c->cp_imu[J ? 0 : 1].p; a.loss_scale = c->imu_scale;
+  const InertialArgs a = inertial_args<J>(c, sel);
   inertial_eval_kernel<K, 4, J><<<c->n_imu_blocks, kEvalThreads, 0, side(c)>>>(a, c->basis, c->bias_basis);
   HB_LAUNCH(c, "inertial_eval_kernel");
   return 0;
 }
-
+// visual + inertial factors in one launch (both lists non-empty; separate launches while profiling per kernel)
+template <int K, bool J>
+int launch_factors_merged(hb200_ctx* c, int sel, bool accumulate) {
+  const PixelArgs pa = pixel_args<J>(c, sel, accumulate);
+  const InertialArgs ia = inertial_args<J>(c, sel);
+  const int blocks = c->n_pix_blocks + c->n_imu_blocks;
+  if (J && accumulate) factor_eval_kernel<K, 4, J, J><<<blocks, kEvalThreads, 0, c->stream>>>(pa, ia, c->basis, c->bias_basis, c->n_pix_blocks);
+  else factor_eval_kernel<K, 4, J, false><<<blocks, kEvalThreads, 0, c->stream>>>(pa, ia, c->basis, c->bias_basis, c->n_pix_blocks);
+  HB_LAUNCH(c, "factor_eval_kernel");
+  return 0;
+}
 template <int K, bool J>
 int launch_manifold(hb200_ctx* c, int sel) {
   if (c->Nm == 0) return 0;
@@ -350,6 +370,20 @@ int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false
     HB_LAUNCH(c, "prep_kernel");
   }
   int rc = 0;
+  const bool J_any = want_J || accumulate;
+  // Small windows are latency-bound: one launch for both factor families.  Large windows are throughput-bound: the
+  // merged kernel would run the pixel CTAs at the inertial body's 255 registers, so the families stay separate.
+  if (c->Nv && c->Ni && !c->profiling && c->n_pix_blocks + c->n_imu_blocks <= 4 * c->num_sms) {
+    // visual and inertial factors side by side in one launch; pose factors (if any) on the side stream
+    if (c->Nm && (rc = fork_side(c))) return rc;
+    if (c->k == 4) rc = J_any ? launch_factors_merged<4, true>(c, sel, accumulate) : launch_factors_merged<4, false>(c, sel, false);
+    else rc = J_any ? launch_factors_merged<6, true>(c, sel, accumulate) : launch_factors_merged<6, false>(c, sel, false);
+    if (!rc) rc = enqueue_manifold(c, J_any, sel);
+    // always join here: the inertial Jacobians were produced on the MAIN stream, so the J^T J kernels that follow
+    // (enqueue_build) must not run on a still-forked side stream
+    { const int rj = join_side(c); if (!rc) rc = rj; }
+    return rc;
+  }
   // visual factors on the main stream, inertial + manifold factors concurrently on the side stream
   if (c->Nv && (c->Ni || c->Nm) && (rc = fork_side(c))) return rc;
   if (accumulate) {   // fused path: pixel J^T J is accumulated by the factor kernel itself

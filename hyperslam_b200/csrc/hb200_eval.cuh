@@ -458,8 +458,9 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
   }
 }
 
-template <int K, bool WANT_J, bool FUSE = false>
-__global__ void __launch_bounds__(kEvalThreads) pixel_eval_kernel(PixelArgs a, Basis B) {
+// bid: the CTA's index within the pixel grid (the merged factor kernel offsets it)
+template <int K, bool WANT_J, bool FUSE>
+HB_DI void pixel_eval_body(const PixelArgs& a, const Basis& B, int bid) {
   __shared__ __align__(16) double s_tab[kTileRows * kTabStride];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_red[2];
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(kEvalThreads) pixel_eval_kernel(PixelArgs a, B
   __shared__ double s_J[FUSE ? 64 * (6 * K + 1) : 1];
   __shared__ double s_r[FUSE ? 64 : 1];
   __shared__ int s_b[FUSE ? 64 : 1];
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = bid * kEvalThreads + threadIdx.x;
   const bool active = f < a.n;
   int4 id = make_int4(0, 0, 0, 0);
   if (active) id = a.idx[f];
@@ -502,16 +503,19 @@ __global__ void __launch_bounds__(kEvalThreads) pixel_eval_kernel(PixelArgs a, B
   if (threadIdx.x == 0) {
     double c = 0;
     for (int w = 0; w < kEvalThreads / 32; ++w) c += s_cost[w];
-    a.cost_partial[blockIdx.x] = c;
+    a.cost_partial[bid] = c;
   }
   if (FUSE && a.sys != nullptr) {
     // fused normal equations: this CTA's factors, two sub-tiles of 32 (residuals / Jacobians were
     // written above; the barrier in the cost reduction ordered them for the whole CTA)
-    const int f_lo = blockIdx.x * kEvalThreads;
+    const int f_lo = bid * kEvalThreads;
     const int total = min(kEvalThreads, a.n - f_lo);
     for (int off = 0; off < total; off += 32) cta_pixel_hessian<K>(a, f_lo + off, min(32, total - off), s_J, s_r, s_b);
   }
 }
+
+template <int K, bool WANT_J, bool FUSE = false>
+__global__ void __launch_bounds__(kEvalThreads) pixel_eval_kernel(PixelArgs a, Basis B) { pixel_eval_body<K, WANT_J, FUSE>(a, B, blockIdx.x); }
 
 // ---------------------------------------------------------------------------------------------
 // Inertial factor (a6 + a3 with value/velocity/acceleration Jacobian stacks fused).
@@ -795,7 +799,7 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
 }
 
 template <int K, int KB, bool WANT_J>
-__global__ void __launch_bounds__(kEvalThreads) inertial_eval_kernel(InertialArgs a, Basis B, Basis BB) {
+HB_DI void inertial_eval_body(const InertialArgs& a, const Basis& B, const Basis& BB, int bid) {
   __shared__ __align__(16) double s_tab[kTileRows * kTabStride];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_red[2];
@@ -804,7 +808,7 @@ __global__ void __launch_bounds__(kEvalThreads) inertial_eval_kernel(InertialArg
   __shared__ double s_grav[3];
   if (threadIdx.x < kImuStride) s_imu[threadIdx.x] = a.imu_tab[threadIdx.x];
   if (threadIdx.x < 3) s_grav[threadIdx.x] = a.gravity[threadIdx.x];
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = bid * kEvalThreads + threadIdx.x;
   const bool active = f < a.n;
   int4 id = make_int4(0, 0, 0, 0);
   if (active) id = a.idx[f];
@@ -848,8 +852,19 @@ __global__ void __launch_bounds__(kEvalThreads) inertial_eval_kernel(InertialArg
   if (threadIdx.x == 0) {
     double c = 0;
     for (int w = 0; w < kEvalThreads / 32; ++w) c += s_cost[w];
-    a.cost_partial[blockIdx.x] = c;
+    a.cost_partial[bid] = c;
   }
+}
+template <int K, int KB, bool WANT_J>
+__global__ void __launch_bounds__(kEvalThreads) inertial_eval_kernel(InertialArgs a, Basis B, Basis BB) { inertial_eval_body<K, KB, WANT_J>(a, B, BB, blockIdx.x); }
+
+// Visual and inertial factors in ONE launch (they are independent): CTAs [0, n_pix_blocks) run the pixel / bearing
+// body, the rest the inertial body.  At 12 k factors each of these kernels is a ~20 us latency-bound launch; side by
+// side they cost the longer of the two.
+template <int K, int KB, bool WANT_J, bool FUSE>
+__global__ void __launch_bounds__(kEvalThreads) factor_eval_kernel(PixelArgs pa, InertialArgs ia, Basis B, Basis BB, int n_pix_blocks) {
+  if (static_cast<int>(blockIdx.x) < n_pix_blocks) pixel_eval_body<K, WANT_J, FUSE>(pa, B, blockIdx.x);
+  else inertial_eval_body<K, KB, WANT_J>(ia, B, BB, blockIdx.x - n_pix_blocks);
 }
 
 
