@@ -373,7 +373,8 @@ int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false
   const bool J_any = want_J || accumulate;
   // Small windows are latency-bound: one launch for both factor families.  Large windows are throughput-bound: the
   // merged kernel would run the pixel CTAs at the inertial body's 255 registers, so the families stay separate.
-  if (c->Nv && c->Ni && !c->profiling && c->n_pix_blocks + c->n_imu_blocks <= 4 * c->num_sms) {
+  static const bool no_merge = getenv("HB200_NO_MERGE") != nullptr;   // profiling aid: one kernel per factor family
+  if (c->Nv && c->Ni && !c->profiling && !no_merge && c->n_pix_blocks + c->n_imu_blocks <= 4 * c->num_sms) {
     // visual and inertial factors side by side in one launch; pose factors (if any) on the side stream
     if (c->Nm && (rc = fork_side(c))) return rc;
     if (c->k == 4) rc = J_any ? launch_factors_merged<4, true>(c, sel, accumulate) : launch_factors_merged<4, false>(c, sel, false);
