@@ -276,8 +276,6 @@ int ensure_system(hb200_ctx* c) {
   HB_CUDA(c->band_ws.ensure(1));
   if (getenv("HB200_BAND_TIMING")) {
     HB_CUDA(c->band_dbg.ensure(72));
-    long long mode = getenv("HB200_BAND_DBGMODE") ? atoll(getenv("HB200_BAND_DBGMODE")) : 0;
-    HB_CUDA(cudaMemcpy(c->band_dbg.p + 71, &mode, sizeof(mode), cudaMemcpyHostToDevice));
   }
   // parallelism of the J^T J kernels: aim at ~2 CTAs per SM
   c->pix_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nseg, 1) - 1) / std::max(c->nseg, 1), std::max(1, c->Nv / (16 * std::max(c->nseg, 1)))));
