@@ -21,13 +21,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, widened):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     from hyperslam_b200 import synthetic
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     win = synthetic.make_window(order=4, num_knots=16, num_landmarks=64, num_imu=96, seed=33, constant_knots=2)
+    if widened:   # + bearing factors (sharded by landmark owner like the pixel factors) and pose factors (by index)
+        win = synthetic.add_bearing_and_pose_factors(win, num_bearing=80, num_pose=17, seed=35)
     shard = win.shard(rank, world)
     packed = torch.from_numpy(ol.OracleWindow(shard).build_packed())
     dist.all_reduce(packed)                                  # the one system collective per iteration
@@ -45,9 +47,10 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_allreduce_reproduces_single_rank_system(tmp_path):
+@pytest.mark.parametrize("widened", [False, True])
+def test_two_rank_allreduce_reproduces_single_rank_system(tmp_path, widened):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), widened), nprocs=world, join=True)
     for r in range(world):
         err_S, err_b, err_c, nf, nf_ref = np.load(tmp_path / f"rank{r}.npy")
         assert err_S < 1e-12 and err_b < 1e-10 and err_c < 1e-12
