@@ -191,6 +191,7 @@ def main():
 
     ctx = runtime.Context(local_rank, use_graph=(world == 1))
     ctx.load_window(win)
+    n_reduced = ctx.reduced_size()   # (the context is closed before the large-window section)
     ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
     tensors = {}
@@ -387,7 +388,7 @@ def main():
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=synthetic.CONFIG_NAMES[args.config], factors_per_step=nf_total, factors_per_gpu=nf_local,
-                            reduced_system_size=ctx.reduced_size(), spline_order=win.order, knots=int(win.knots.shape[0]),
+                            reduced_system_size=n_reduced, spline_order=win.order, knots=int(win.knots.shape[0]),
                             landmarks=int(gwin.landmarks.shape[0]), parallelism=f"factor-sharded x{world}" if world > 1 else "single GPU",
                             l2="flushed between timed steps (256 MiB device write)", step="one LM iteration (evaluate r+J, JtJ, Schur, Cholesky, retract, cost, accept) in one CUDA graph" if world == 1 else "one LM iteration, direct launches + 2 NCCL all-reduces"),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_t * 1e3,
