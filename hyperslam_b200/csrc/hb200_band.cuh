@@ -19,7 +19,7 @@
 // eliminates the beta separator columns, and the back substitution runs outwards from the separator
 // in both directions at once.  Sequential depth: ~K/2 + beta steps instead of K.
 // The arrow x arrow (corner) part of every step's trailing update is deferred: the corner receives
-// C -= sum_c A_c A_c^T in one parallel pass after the last column, which takes 15 of 36 tiles out of
+// C -= sum_c A_c A_c^T in one parallel pass after the last column, which takes 15 of 55 tiles (beta = 5, m = 26) out of
 // every step.
 //
 // Per-chain workspace (doubles): W[ncol][h][6] band block-columns (h = 6 + 6 beta rows each: diagonal
