@@ -12,6 +12,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include "../../include/hyperb200.h"
 #include "hb200_band.cuh"
@@ -82,6 +83,44 @@ void compute_basis(Basis* b, int k) {
     }
 }
 
+// ---- NCCL, bound at run time ----------------------------------------------------------------------
+// libnccl.so.2 is resolved with dlopen when the first communicator call is made: inside a torch process this is
+// the copy torch already loaded (same SONAME), in a plain C++ host the system library.  Only the five entry
+// points below are used; their prototypes are those of nccl.h 2.x (ncclUniqueId = 128 bytes by value,
+// ncclDouble = 8, ncclSum = 0).
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int load_nccl() {
+  if (g_nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+  if (!h) return fail(300, "libnccl.so.2 not found: %s", dlerror());
+  NcclApi a;
+  a.lib = h;
+  a.GetUniqueId = reinterpret_cast<int (*)(NcclUid*)>(dlsym(h, "ncclGetUniqueId"));
+  a.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclUid, int)>(dlsym(h, "ncclCommInitRank"));
+  a.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+  a.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+  a.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString) return fail(300, "libnccl.so.2 lacks an expected symbol");
+  g_nccl = a;
+  return 0;
+}
+#define HB_NCCL(expr)                                                                                              \
+  do {                                                                                                             \
+    const int r__ = (expr);                                                                                        \
+    if (r__ != 0) return fail(300 + r__, "%s: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error"); \
+  } while (0)
+
 }  // namespace
 
 struct hb200_ctx {
@@ -134,7 +173,7 @@ struct hb200_ctx {
   DevBuf<int> seg_off, run_off, lm_off, lm_obs, d_invalid;
   int nseg = 0, nruns = 0, max_rows = 6;
   int pix_splits = 1, imu_splits = 1;
-  int beta = 3;
+  int beta = 3, min_beta = 0;   // min_beta: lower bound agreed across ranks (the packed layout must be identical everywhere)
   bool band_solver = true, band_smem = true, force_dense = false;
   DevBuf<double> band_ws;
   int band_chunk_cols = 0;       // !band_smem: block columns per shared-memory chunk view (per chain)
@@ -151,8 +190,9 @@ struct hb200_ctx {
   bool mirror_valid = false;
   std::vector<double> m_v_r, m_v_Jp, m_v_Jl, m_i_r, m_i_Jp, m_i_wg, m_i_wa, m_i_Jg, m_grav, m_b_r, m_b_Jp, m_b_Jl, m_m_r, m_m_Jp;
 
-  // system
+  // system (band-only packed storage, see SysLayout)
   int n = 0;
+  SysLayout lay{};
   DevBuf<double> sys, D, Lw, Ldiag, dp, dl, Vinv, gl, Dl, lm_part, scal;
   DevBuf<int> spd;
   DevBuf<SolverState> st, records;
@@ -162,6 +202,19 @@ struct hb200_ctx {
 
   hb200_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  // multi-GPU: one NCCL all-reduce of the packed system per iteration, enqueued from C on the context's stream
+  // (graph-capturable); the step-acceptance scalars travel through peer memory inside accept_kernel
+  void* nccl = nullptr;
+  bool own_nccl = false;
+  long long nccl_calls = 0, nccl_calls_per_iteration = 0;
+  int nranks = 1, rank = 0;
+  bool comm_warm = false;        // one eager all-reduce has run (NCCL's lazy setup is done: safe to capture)
+  DevBuf<double> mbox;           // [2][kMaxRanks][4]
+  DevBuf<unsigned long long> mbox_seq;
+  DevBuf<double*> d_peers;
+  std::vector<void*> peer_ptrs;  // cudaIpcOpenMemHandle mappings (own entry = mbox.p)
+  bool peers_open = false;
+  bool multi() const { return nccl != nullptr || allreduce != nullptr; }
 
   // profiling (hb200_profile_iteration)
   bool profiling = false;
@@ -237,13 +290,23 @@ int update_fixed(hb200_ctx* c) {
   return 0;
 }
 
-int ensure_system(hb200_ctx* c) {
+// dense work copy of the reduced system: only the dense fallback solver and hb200_get_system need it
+int ensure_dense(hb200_ctx* c) {
   const size_t n = c->n;
   const size_t T = (n + kCholNB - 1) / kCholNB;
-  HB_CUDA(c->sys.ensure(n * n + 3 * n + 2));
-  HB_CUDA(c->D.ensure(n));
   HB_CUDA(c->Lw.ensure((T * kCholNB + 1) * n));
   HB_CUDA(c->Ldiag.ensure(T * kCholNB * kCholNB));
+  return 0;
+}
+
+int ensure_system(hb200_ctx* c) {
+  const size_t n = c->n;
+  // block half-bandwidth of the reduced pose system = longest landmark track in control points (>= k - 1)
+  c->beta = std::max(std::max(c->k - 1, c->max_rows / 6 - 1), c->min_beta);
+  c->beta = std::min(c->beta, std::max(c->K - 1, 0));
+  c->lay = sys_layout(c->K, c->beta, c->n - 6 * c->K);
+  HB_CUDA(c->sys.ensure(static_cast<size_t>(c->lay.total)));
+  HB_CUDA(c->D.ensure(n));
   HB_CUDA(c->dp.ensure(n));
   HB_CUDA(c->dl.ensure(3 * static_cast<size_t>(std::max(c->L, 1))));
   HB_CUDA(c->Vinv.ensure(9 * static_cast<size_t>(std::max(c->L, 1))));
@@ -254,9 +317,7 @@ int ensure_system(hb200_ctx* c) {
   HB_CUDA(c->scal.ensure(4));
   HB_CUDA(c->spd.ensure(1));
   HB_CUDA(c->records.ensure(c->max_records));
-  // solver selection: block-banded + arrowhead (one CTA) unless the band is wide on a large system
-  c->beta = std::max(c->k - 1, c->max_rows / 6 - 1);
-  c->beta = std::min(c->beta, std::max(c->K - 1, 0));
+  // solver selection: block-banded + arrowhead unless the band is wide on a large system
   const size_t ws = band_workspace_doubles(c->K, c->beta, c->n - 6 * c->K) * sizeof(double);
   c->band_solver = !c->force_dense && ((c->n <= 512) || (12 * (c->beta + 1) <= 6 * c->K));
   c->band_smem = ws <= 220 * 1024;
@@ -274,6 +335,7 @@ int ensure_system(hb200_ctx* c) {
     }
   }
   HB_CUDA(c->band_ws.ensure(1));
+  if (!c->band_solver) { int rc = ensure_dense(c); if (rc) return rc; }
   if (getenv("HB200_BAND_TIMING")) {
     HB_CUDA(c->band_dbg.ensure(72));
   }
@@ -297,7 +359,7 @@ int reset_solver_state(hb200_ctx* c) {
 template <bool J>
 PixelArgs pixel_args(hb200_ctx* c, int sel, bool accumulate) {
   PixelArgs a{};
-  a.sys = accumulate ? c->sys.p : nullptr; a.n_sys = c->n;
+  a.sys = accumulate ? c->sys.p : nullptr; a.lay = c->lay;
   a.n = c->Nv; a.stamp = c->v_stamp.p; a.pixel = reinterpret_cast<const double2*>(c->v_pixel.p); a.meas_z = c->v_z.p; a.idx = c->v_idx.p;
   a.tab = c->tab[sel].p; a.cam_tab = c->cam_tab.p; a.landmarks = c->lms[sel].p;
   a.r = J ? c->v_r.p : nullptr; a.Jp = c->v_Jp.p; a.Jl = c->v_Jl.p; a.w = c->v_w.p; a.cost_partial = c->cp_pix[J ? 0 : 1].p; a.huber = c->huber; a.huber_bearing = c->huber_bearing; a.K_knots = c->K;
@@ -362,7 +424,7 @@ int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false
                      bool skip_prep = false) {
   if (c->k != 4 && c->k != 6) return fail(-4, "spline order %d not supported (4 or 6)", c->k);
   if (!skip_prep) {
-    const size_t nclear = clear_system ? static_cast<size_t>(c->n) * c->n + 3 * static_cast<size_t>(c->n) + 2 : 0;
+    const size_t nclear = clear_system ? static_cast<size_t>(c->lay.total) : 0;
     const int blocks = clear_system ? static_cast<int>(std::min<size_t>((nclear / 4 + 255) / 256, static_cast<size_t>(c->num_sms) * 4)) : (c->K + 255) / 256;
     prep_kernel<<<std::max(blocks, (c->K + 255) / 256), 256, 0, c->stream>>>(c->K, c->knots[sel].p, c->tab[sel].p, clear_system ? c->sys.p : nullptr, nclear);
     HB_LAUNCH(c, "prep_kernel");
@@ -399,8 +461,7 @@ int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false
 }
 
 int enqueue_clear_system(hb200_ctx* c) {
-  const size_t n = c->n;
-  HB_CUDA(cudaMemsetAsync(c->sys.p, 0, (n * n + 3 * n + 2) * sizeof(double), c->stream));
+  HB_CUDA(cudaMemsetAsync(c->sys.p, 0, static_cast<size_t>(c->lay.total) * sizeof(double), c->stream));
   prof_mark(c, "memset(system)");
   return 0;
 }
@@ -408,63 +469,68 @@ int enqueue_clear_system(hb200_ctx* c) {
 int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
   if (!pixel_fused) { int rc0 = enqueue_clear_system(c); if (rc0) return rc0; }
   if (c->Nv && !pixel_fused) {
-    if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->sys.p, c->n, c->pix_splits);
-    else pixel_hessian_kernel<6><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->sys.p, c->n, c->pix_splits);
+    if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->sys.p, c->lay, c->pix_splits);
+    else pixel_hessian_kernel<6><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->sys.p, c->lay, c->pix_splits);
     HB_LAUNCH(c, "pixel_hessian_kernel");
   }
   if (c->Ni) {
     if (c->k == 4)
       inertial_hessian_kernel<4, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     else
       inertial_hessian_kernel<6, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->n, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     HB_LAUNCH(c, "inertial_hessian_kernel");
   }
   if (c->Nm) {
     const int blocks = (c->Nm + kManWarps - 1) / kManWarps;
-    if (c->k == 4) manifold_hessian_kernel<4><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->n);
-    else manifold_hessian_kernel<6><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->n);
+    if (c->k == 4) manifold_hessian_kernel<4><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->lay);
+    else manifold_hessian_kernel<6><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->lay);
     HB_LAUNCH(c, "manifold_hessian_kernel");
   }
   { const int rj = join_side(c); if (rj) return rj; }
-  diag_cost_kernel<<<std::max(1, (c->n + 255) / 256), 256, 0, c->stream>>>(c->sys.p, c->n, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p,
+   diag_cost_kernel<<<std::max(1, (c->n + 255) / 256), 256, 0, c->stream>>>(c->sys.p, c->lay, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p,
                                                                          c->n_imu_blocks + c->n_man_blocks);
   HB_LAUNCH(c, "diag_cost_kernel");
   if (c->Nv && c->L) {
     const size_t smem = 2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double);
     if (c->k == 4)
       schur_kernel<4><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p, c->st.p,
-                                                                c->sys.p, c->n, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
+                                                                c->sys.p, c->lay, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
     else
       schur_kernel<6><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p, c->st.p,
-                                                                c->sys.p, c->n, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
+                                                                c->sys.p, c->lay, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
     HB_LAUNCH(c, "schur_kernel");
   }
   return 0;
 }
 
-int enqueue_finalize(hb200_ctx* c) {
+// band-only raw system -> dense damped work copy Lw (dense fallback solver, hb200_get_system)
+int enqueue_densify(hb200_ctx* c) {
+  int rc = ensure_dense(c);
+  if (rc) return rc;
   const size_t total = static_cast<size_t>(c->n + 1) * c->n;
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(c->num_sms) * 8));
-  finalize_kernel<<<blocks, 256, 0, c->stream>>>(c->sys.p, c->n, c->st.p, c->fixed.p, c->D.p, c->Lw.p, c->spd.p);
-  HB_LAUNCH(c, "finalize_kernel");
+  densify_kernel<<<blocks, 256, 0, c->stream>>>(c->sys.p, c->lay, c->st.p, c->fixed.p, c->D.p, c->Lw.p, c->spd.p);
+  HB_LAUNCH(c, "densify_kernel");
   return 0;
 }
 
 RetractArgs retract_args(hb200_ctx* c);
-// damp_in_solver: the band solver applies LM damping + the constant-dof mask itself (finalize_kernel skipped);
+// Both solvers read the raw band-only system and apply LM damping + the constant-dof mask themselves (the band
+// solver while it gathers, the dense fallback in densify_kernel);
 // fuse_retract: the landmark back-substitution launch also retracts knots / biases / gravity (returns *fused)
-int enqueue_solve(hb200_ctx* c, bool damp_in_solver = false, bool fuse_retract = false, bool* fused = nullptr) {
+int enqueue_solve(hb200_ctx* c, bool fuse_retract = false, bool* fused = nullptr) {
   if (c->band_solver) {
-    const SolverState* st = damp_in_solver ? c->st.p : nullptr;
-    const unsigned char* fx = damp_in_solver ? c->fixed.p : nullptr;
-    double* Dout = damp_in_solver ? c->D.p : nullptr;
+    const SolverState* st = c->st.p;
+    const unsigned char* fx = c->fixed.p;
+    double* Dout = c->D.p;
     const size_t smem = c->band_smem ? band_workspace_doubles(c->K, c->beta, c->n - 6 * c->K) * sizeof(double) : 0;
-    if (c->band_smem) band_solve_kernel<true><<<1, kBandThreads, smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout, 0);
-    else band_solve_kernel<false><<<1, kBandThreads, c->band_chunk_smem, c->stream>>>(c->sys.p, c->n, c->K, c->beta, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout, c->band_chunk_cols);
+    if (c->band_smem) band_solve_kernel<true><<<1, kBandThreads, smem, c->stream>>>(c->sys.p, c->lay, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout, 0);
+    else band_solve_kernel<false><<<1, kBandThreads, c->band_chunk_smem, c->stream>>>(c->sys.p, c->lay, c->band_ws.p, c->dp.p, c->spd.p, c->band_dbg.p, st, fx, Dout, c->band_chunk_cols);
     HB_LAUNCH(c, "band_solve_kernel");
   } else {
+    { const int rd = enqueue_densify(c); if (rd) return rd; }
     int n = c->n;
     double* Lw = c->Lw.p; double* Ld = c->Ldiag.p; int* spd = c->spd.p;
     void* args[] = {&Lw, &Ld, &n, &spd};
@@ -532,8 +598,13 @@ int enqueue_accept(hb200_ctx* c) {
   size_t mx = 1, total = 0;
   for (int i = 0; i < 5; ++i) { a.count[i] = counts[i]; a.src[i] = srcs[i]; a.dst[i] = dsts[i]; mx = std::max(mx, counts[i]); total += counts[i]; }
   const bool fuse_commit = total <= 16384;   // small windows: one CTA commits the accepted state right away
-  accept_kernel<<<1, kAcceptThreads, 0, c->stream>>>(c->sys.p, c->n, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
-                                         c->allreduce ? 0 : 1, sa, fuse_commit ? 1 : 0, a);
+  // scalars: summed inside this kernel on one GPU and, across GPUs, exchanged by it through peer memory; only the
+  // fallbacks (callback hook, no peer mapping) run scalars_kernel + a second reduction before it
+  const bool mailbox = c->nccl && c->peers_open;
+  MailboxArgs mb{};
+  mb.nranks = mailbox ? c->nranks : 1; mb.rank = c->rank; mb.peers = c->d_peers.p; mb.local = c->mbox.p; mb.seq = c->mbox_seq.p;
+  accept_kernel<<<1, kAcceptThreads, 0, c->stream>>>(c->sys.p, c->lay, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
+                                         (!c->multi() || mailbox) ? 1 : 0, sa, fuse_commit ? 1 : 0, a, mb);
   HB_LAUNCH(c, "accept_kernel");
   if (!fuse_commit) {
     const int blocks = static_cast<int>(std::min<size_t>((mx + 255) / 256, static_cast<size_t>(c->num_sms) * 4));
@@ -543,23 +614,69 @@ int enqueue_accept(hb200_ctx* c) {
   return 0;
 }
 
-// One LM iteration enqueued on the stream; the two optional all-reduce callbacks split it in three
-// graph-capturable segments.
-int enqueue_segment(hb200_ctx* c, int segment) {
-  int rc = 0;
-  if (segment == 0) {
-    if ((rc = enqueue_evaluate(c, true, 0, true, /*keep_fork=*/true, /*clear_system=*/true))) return rc;
-    if ((rc = enqueue_build(c, true))) return rc;
-  } else if (segment == 1) {
-    // band solver: damping + constant-dof mask are applied while it gathers the band (no finalize pass)
-    if (!c->band_solver && (rc = enqueue_finalize(c))) return rc;
-    bool retracted = false;
-    if ((rc = enqueue_solve(c, /*damp_in_solver=*/c->band_solver, /*fuse_retract=*/true, &retracted))) return rc;
-    if (!retracted && (rc = enqueue_retract(c))) return rc;   // (also builds the trial knot table)
-    if ((rc = enqueue_evaluate(c, false, 1, false, false, false, /*skip_prep=*/true))) return rc;
-    if (c->allreduce && (rc = enqueue_scalars(c))) return rc;
+// Sum of the packed partial systems over the ranks: ONE ncclAllReduce on the context's stream (capturable).
+int enqueue_reduce_system(hb200_ctx* c) {
+  if (c->nccl) {
+    HB_NCCL(g_nccl.AllReduce(c->sys.p, c->sys.p, static_cast<size_t>(c->lay.total), /*ncclDouble*/ 8, /*ncclSum*/ 0, c->nccl, c->stream));
+    c->nccl_calls += 1;
+    prof_mark(c, "ncclAllReduce(system)");
+  } else if (c->allreduce) {
+    const int rc = c->allreduce(c->allreduce_user, c->sys.p, c->lay.total, c->stream);
+    if (rc) return fail(200 + rc, "all-reduce callback failed (%d)", rc);
+    prof_mark(c, "allreduce_callback(system)");
+  }
+  return 0;
+}
+
+// Trial-cost / model-decrease partials: fused into accept_kernel (one GPU: plain sums; NCCL + peer mapping: the
+// mailbox exchange).  Fallbacks only: scalars_kernel + a 4-double reduction.
+int enqueue_reduce_scalars(hb200_ctx* c) {
+  if (!c->multi() || (c->nccl && c->peers_open)) return 0;
+  int rc = enqueue_scalars(c);
+  if (rc) return rc;
+  if (c->nccl) {
+    HB_NCCL(g_nccl.AllReduce(c->scal.p, c->scal.p, 4, 8, 0, c->nccl, c->stream));
+    c->nccl_calls += 1;
+    prof_mark(c, "ncclAllReduce(scalars)");
   } else {
-    if ((rc = enqueue_accept(c))) return rc;
+    rc = c->allreduce(c->allreduce_user, c->scal.p, 4, c->stream);
+    if (rc) return fail(200 + rc, "all-reduce callback failed (%d)", rc);
+    prof_mark(c, "allreduce_callback(scalars)");
+  }
+  return 0;
+}
+
+// One LM iteration enqueued on the stream (graph-capturable unless the callback hook is in use).
+int enqueue_iteration(hb200_ctx* c) {
+  int rc = 0;
+  if ((rc = enqueue_evaluate(c, true, 0, true, /*keep_fork=*/true, /*clear_system=*/true))) return rc;
+  if ((rc = enqueue_build(c, true))) return rc;
+  if ((rc = enqueue_reduce_system(c))) return rc;
+  bool retracted = false;
+  if ((rc = enqueue_solve(c, /*fuse_retract=*/true, &retracted))) return rc;
+  if (!retracted && (rc = enqueue_retract(c))) return rc;   // (also builds the trial knot table)
+  if ((rc = enqueue_evaluate(c, false, 1, false, false, false, /*skip_prep=*/true))) return rc;
+  if ((rc = enqueue_reduce_scalars(c))) return rc;
+  return enqueue_accept(c);
+}
+
+// The band layout depends on the longest landmark track of the LOCAL shard; the ranks agree on the maximum
+// (one 4-byte ncclAllReduce(max) at bind / attach time, never on the iteration path).
+int sync_layout(hb200_ctx* c) {
+  if (!c->nccl || !c->bound) return 0;
+  DevBuf<int> d;
+  HB_CUDA(d.ensure(1));
+  int v = c->beta;
+  HB_CUDA(cudaMemcpyAsync(d.p, &v, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  HB_NCCL(g_nccl.AllReduce(d.p, d.p, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, c->nccl, c->stream));
+  HB_CUDA(cudaMemcpyAsync(&v, d.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->comm_warm = true;
+  if (v != c->beta) {
+    c->min_beta = v;
+    const int rc = ensure_system(c);
+    if (rc) return rc;
+    c->invalidate();
   }
   return 0;
 }
@@ -612,6 +729,7 @@ int create_impl(const hb200_options* options, hb200_ctx* c) {
   HB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   int rc = ensure_placeholders(c);
   if (rc) return rc;
+  if (options && options->nccl_comm && (rc = hb200_set_nccl_comm(c, options->nccl_comm, options->nranks, options->rank))) return rc;
   HB_CUDA(cudaFuncSetAttribute(cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCholSmem)));
   return reset_solver_state(c);
 }
@@ -637,6 +755,11 @@ void hb200_destroy(hb200_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->stream2) cudaStreamSynchronize(c->stream2);
+  for (size_t p = 0; p < c->peer_ptrs.size(); ++p)
+    if (c->peer_ptrs[p] && c->peer_ptrs[p] != c->mbox.p) cudaIpcCloseMemHandle(c->peer_ptrs[p]);
+  c->peer_ptrs.clear();
+  if (c->nccl && c->own_nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
+  c->nccl = nullptr;
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->graph) cudaGraphDestroy(c->graph);
@@ -980,7 +1103,7 @@ int hb200_bind(hb200_ctx* c, int* num_invalid) {
   HB_CUDA(cudaStreamSynchronize(c->stream));
   c->bound = true;
   c->invalidate();
-  return 0;
+  return sync_layout(c);   // multi-GPU: all ranks adopt the widest band (collective when a communicator is attached)
 }
 
 int hb200_get_index_maps(hb200_ctx* c, int* pixel_base, int* inertial_base, int* gyro_bias_base, int* accel_bias_base) {
@@ -1185,11 +1308,7 @@ int hb200_build_system(hb200_ctx* c) {
   if (!c->evaluated_J) return fail(-2, "call hb200_evaluate(HB200_EVAL_JACOBIANS) first");
   HB_CUDA(cudaSetDevice(c->device));
   if ((rc = enqueue_build(c))) return rc;
-  if (c->allreduce) {
-    rc = c->allreduce(c->allreduce_user, c->sys.p, static_cast<long long>(c->n) * c->n + 3LL * c->n + 2, c->stream);
-    if (rc) return fail(200 + rc, "all-reduce callback failed (%d)", rc);
-  }
-  if ((rc = enqueue_finalize(c))) return rc;
+  if ((rc = enqueue_reduce_system(c))) return rc;
   c->system_built = true;
   return 0;
 }
@@ -1198,8 +1317,9 @@ int hb200_get_system(hb200_ctx* c, double* S, double* b) {
   if (!c || !c->system_built) return fail(-2, "system not built");
   HB_CUDA(cudaSetDevice(c->device));
   const size_t n = c->n;
-  if (S) HB_CUDA(cudaMemcpyAsync(S, c->sys.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
-  if (b) HB_CUDA(cudaMemcpyAsync(b, c->sys.p + n * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  { const int rc = enqueue_densify(c); if (rc) return rc; }   // dense, damped, masked -- what the solvers factor
+  if (S) HB_CUDA(cudaMemcpyAsync(S, c->Lw.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+  if (b) HB_CUDA(cudaMemcpyAsync(b, c->Lw.p + static_cast<size_t>((n + 31) / 32) * 32 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1225,21 +1345,30 @@ namespace {
 
 int iterate_enqueue(hb200_ctx* c, int iterations) {
   int rc = 0;
-  const bool graph_ok = c->use_graph && !c->allreduce;
   for (int it = 0; it < iterations; ++it) {
+    // the callback hook cannot be captured; with NCCL the first iteration runs eagerly (NCCL finishes its lazy
+    // channel / buffer setup outside of a capture), every later one is a graph launch
+    const bool graph_ok = c->use_graph && !c->allreduce && (!c->nccl || c->comm_warm);
     if (graph_ok) {
       if (!c->graph_valid) {
         if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
         if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
-        HB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        const long long before = c->launches;
-        rc = enqueue_segment(c, 0);
-        if (!rc) rc = enqueue_segment(c, 1);
-        if (!rc) rc = enqueue_segment(c, 2);
+        HB_CUDA(cudaStreamBeginCapture(c->stream, c->nccl ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
+        const long long before = c->launches, nccl_before = c->nccl_calls;
+        rc = enqueue_iteration(c);
         cudaError_t e = cudaStreamEndCapture(c->stream, &c->graph);
         c->launches = before;  // capture does not execute
+        c->nccl_calls_per_iteration = c->nccl_calls - nccl_before;
+        c->nccl_calls = nccl_before;
         if (rc) return rc;
-        if (e != cudaSuccess) return fail(100 + static_cast<int>(e), "graph capture: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+          if (!c->nccl) return fail(100 + static_cast<int>(e), "graph capture: %s", cudaGetErrorString(e));
+          // a communicator that cannot be captured: fall back to direct launches for this context
+          cudaGetLastError();
+          c->use_graph = false; c->graph = nullptr;
+          --it;
+          continue;
+        }
         HB_CUDA(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
         c->graph_valid = true;
         c->launches_per_iteration = 0;
@@ -1249,26 +1378,20 @@ int iterate_enqueue(hb200_ctx* c, int iterations) {
         HB_CUDA(cudaGraphGetNodes(c->graph, nd, &nodes));
         for (size_t i = 0; i < nodes; ++i) { cudaGraphNodeType t; if (cudaGraphNodeGetType(nd[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) c->launches_per_iteration += 1; }
         delete[] nd;
+        c->launches_per_iteration -= c->nccl_calls_per_iteration;   // NCCL's kernel nodes are not this library's launches
         if (getenv("HB200_GRAPH_DEBUG")) {
           size_t edges = 0;
           cudaGraphGetEdges(c->graph, nullptr, nullptr, &edges);
-          std::fprintf(stderr, "[hb200] iteration graph: %zu nodes (%lld kernels), %zu edges\n", nodes, c->launches_per_iteration, edges);
+          std::fprintf(stderr, "[hb200] iteration graph: %zu nodes (%lld own kernels, %lld NCCL), %zu edges\n", nodes, c->launches_per_iteration,
+                       c->nccl_calls_per_iteration, edges);
         }
       }
       HB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
       c->launches += c->launches_per_iteration;
+      c->nccl_calls += c->nccl_calls_per_iteration;
     } else {
-      if ((rc = enqueue_segment(c, 0))) return rc;
-      if (c->allreduce) {
-        rc = c->allreduce(c->allreduce_user, c->sys.p, static_cast<long long>(c->n) * c->n + 3LL * c->n + 2, c->stream);
-        if (rc) return fail(200 + rc, "all-reduce callback failed (%d)", rc);
-      }
-      if ((rc = enqueue_segment(c, 1))) return rc;
-      if (c->allreduce) {
-        rc = c->allreduce(c->allreduce_user, c->scal.p, 4, c->stream);
-        if (rc) return fail(200 + rc, "all-reduce callback failed (%d)", rc);
-      }
-      if ((rc = enqueue_segment(c, 2))) return rc;
+      if ((rc = enqueue_iteration(c))) return rc;
+      if (c->nccl) c->comm_warm = true;
     }
   }
   c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
@@ -1405,13 +1528,8 @@ int hb200_profile_iteration(hb200_ctx* c, int reps, int max_entries, char* names
     hb200_spin_kernel<<<1, 1, 0, c->stream>>>(600000);
     c->profiling = true;
     prof_mark(c, "start");
-    if (reps_mode_evaluate) {
-      rc = enqueue_evaluate(c, true, 0);          // the plain Evaluate sweep (hb200_evaluate), Jacobians materialised
-    } else {
-      rc = enqueue_segment(c, 0);
-      if (!rc) rc = enqueue_segment(c, 1);
-      if (!rc) rc = enqueue_segment(c, 2);
-    }
+    if (reps_mode_evaluate) rc = enqueue_evaluate(c, true, 0);   // the plain Evaluate sweep (hb200_evaluate), Jacobians materialised
+    else rc = enqueue_iteration(c);
     c->profiling = false;
     if (rc) return rc;
     if (!reps_mode_evaluate) c->iter_total += 1;
@@ -1551,13 +1669,148 @@ int hb200_get_state(hb200_ctx* c, double* knots, double* gyro, double* accel, do
 
 int hb200_set_allreduce(hb200_ctx* c, hb200_allreduce_fn fn, void* user) {
   if (!c) return fail(-1, "null context");
+  if (fn && c->nccl) return fail(-2, "a NCCL communicator is attached; the callback hook is its replacement, not an addition");
   c->allreduce = fn; c->allreduce_user = user;
+  c->graph_valid = false;
+  return 0;
+}
+
+int hb200_comm_unique_id(char* id) {
+  if (!id) return fail(-1, "null argument");
+  int rc = load_nccl();
+  if (rc) return rc;
+  NcclUid u;
+  HB_NCCL(g_nccl.GetUniqueId(&u));
+  std::memcpy(id, u.internal, sizeof(u.internal));
+  return 0;
+}
+
+int hb200_set_nccl_comm(hb200_ctx* c, void* comm, int nranks, int rank) {
+  if (!c) return fail(-1, "null context");
+  if (comm && (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)) return fail(-1, "invalid rank %d of %d (at most %d ranks)", rank, nranks, kMaxRanks);
+  if (comm && c->allreduce) return fail(-2, "the all-reduce callback hook is set; clear it first");
+  if (comm) { int rc = load_nccl(); if (rc) return rc; }
+  HB_CUDA(cudaSetDevice(c->device));
+  if (c->nccl && c->own_nccl) { HB_CUDA(cudaStreamSynchronize(c->stream)); g_nccl.CommDestroy(c->nccl); }
+  c->nccl = comm; c->own_nccl = false;
+  c->nranks = comm ? nranks : 1; c->rank = comm ? rank : 0;
+  c->comm_warm = false; c->graph_valid = false;
+  return sync_layout(c);
+}
+
+int hb200_comm_init_rank(hb200_ctx* c, int nranks, int rank, const char* id) {
+  if (!c || !id) return fail(-1, "null argument");
+  if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(-1, "invalid rank %d of %d (at most %d ranks)", rank, nranks, kMaxRanks);
+  int rc = load_nccl();
+  if (rc) return rc;
+  HB_CUDA(cudaSetDevice(c->device));
+  NcclUid u;
+  std::memcpy(u.internal, id, sizeof(u.internal));
+  void* comm = nullptr;
+  HB_NCCL(g_nccl.CommInitRank(&comm, nranks, u, rank));
+  rc = hb200_set_nccl_comm(c, comm, nranks, rank);
+  if (rc) { g_nccl.CommDestroy(comm); return rc; }
+  c->own_nccl = true;
+  return 0;
+}
+
+int hb200_peer_handle(hb200_ctx* c, char* handle) {
+  if (!c || !handle) return fail(-1, "null argument");
+  HB_CUDA(cudaSetDevice(c->device));
+  HB_CUDA(c->mbox.ensure(2 * kMaxRanks * 4));
+  HB_CUDA(c->mbox_seq.ensure(1));
+  HB_CUDA(cudaMemsetAsync(c->mbox.p, 0, sizeof(double) * 2 * kMaxRanks * 4, c->stream));
+  HB_CUDA(cudaMemsetAsync(c->mbox_seq.p, 0, sizeof(unsigned long long), c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaIpcMemHandle_t h;
+  HB_CUDA(cudaIpcGetMemHandle(&h, c->mbox.p));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+
+namespace {
+void close_peers(hb200_ctx* c) {
+  for (size_t p = 0; p < c->peer_ptrs.size(); ++p)
+    if (c->peer_ptrs[p] && c->peer_ptrs[p] != c->mbox.p) cudaIpcCloseMemHandle(c->peer_ptrs[p]);
+  c->peer_ptrs.clear();
+  c->peers_open = false;
+}
+}  // namespace
+
+int hb200_peer_connect(hb200_ctx* c, int nranks, int rank, const char* handles) {
+  if (!c || !handles) return fail(-1, "null argument");
+  if (!c->nccl || nranks != c->nranks || rank != c->rank) return fail(-2, "attach the communicator first (same nranks / rank)");
+  if (!c->mbox.p) return fail(-2, "call hb200_peer_handle first");
+  HB_CUDA(cudaSetDevice(c->device));
+  close_peers(c);
+  c->peer_ptrs.assign(nranks, nullptr);
+  for (int p = 0; p < nranks; ++p) {
+    if (p == rank) { c->peer_ptrs[p] = c->mbox.p; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * static_cast<size_t>(p), sizeof(h));
+    void* ptr = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      close_peers(c);
+      return fail(100 + static_cast<int>(e), "cudaIpcOpenMemHandle(rank %d): %s (the scalar exchange falls back to a second ncclAllReduce)", p, cudaGetErrorString(e));
+    }
+    c->peer_ptrs[p] = ptr;
+  }
+  HB_CUDA(c->d_peers.ensure(kMaxRanks));
+  std::vector<double*> host(kMaxRanks, nullptr);
+  for (int p = 0; p < nranks; ++p) host[p] = static_cast<double*>(c->peer_ptrs[p]);
+  HB_CUDA(cudaMemcpyAsync(c->d_peers.p, host.data(), sizeof(double*) * kMaxRanks, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->peers_open = true;
+  c->graph_valid = false;
+  return 0;
+}
+
+int hb200_set_min_bandwidth(hb200_ctx* c, int beta) {
+  if (!c || beta < 0) return fail(-1, "invalid argument");
+  HB_CUDA(cudaSetDevice(c->device));
+  c->min_beta = beta;
+  if (c->bound) {
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    const int rc = ensure_system(c);
+    if (rc) return rc;
+    c->invalidate();
+  }
+  return 0;
+}
+
+int hb200_get_bandwidth(hb200_ctx* c, int* beta) {
+  if (!c || !beta) return fail(-1, "null argument");
+  if (!c->bound) return fail(-2, "not bound");
+  *beta = c->beta;
+  return 0;
+}
+
+int hb200_peer_disconnect(hb200_ctx* c) {
+  if (!c) return fail(-1, "null context");
+  HB_CUDA(cudaSetDevice(c->device));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  close_peers(c);
+  c->graph_valid = false;
+  return 0;
+}
+
+int hb200_comm_info(hb200_ctx* c, int* nranks, int* rank, int* nccl, int* peer_mailbox, int* graph, long long* payload_doubles) {
+  if (!c) return fail(-1, "null context");
+  if (nranks) *nranks = c->nranks;
+  if (rank) *rank = c->rank;
+  if (nccl) *nccl = c->nccl ? 1 : 0;
+  if (peer_mailbox) *peer_mailbox = (c->nccl && c->peers_open) ? 1 : 0;
+  if (graph) *graph = (c->use_graph && !c->allreduce && c->graph_valid) ? 1 : 0;
+  if (payload_doubles) *payload_doubles = c->bound ? c->lay.total : 0;
   return 0;
 }
 
 void* hb200_system_device_ptr(hb200_ctx* c, long long* count) {
   if (!c) return nullptr;
-  if (count) *count = static_cast<long long>(c->n) * c->n + 3LL * c->n + 2;
+  if (count) *count = c->lay.total;
   return c->sys.p;
 }
 

@@ -316,13 +316,14 @@ HB_DI void band_transform_row(double* v, const double* L, const double* rd) {
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* __restrict__ sys, int n, int K, int beta,
+__global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* __restrict__ sys, SysLayout lay,
                                                                   double* __restrict__ ws_global, double* __restrict__ x_out,
                                                                   int* __restrict__ spd_flag, long long* __restrict__ dbg,
                                                                   const SolverState* __restrict__ st, const unsigned char* __restrict__ fixed,
                                                                   double* __restrict__ Dout, int chunk_cols) {
   extern __shared__ double s_band[];
   double* ws = SMEM ? s_band : ws_global;
+  const int n = lay.n, K = lay.K, beta = lay.beta;
   const int np = 6 * K, m = n - np, h = 6 + 6 * beta, h6 = h * 6;
   const BandPlan pl = band_plan(K, beta);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -354,13 +355,13 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   double* XA = CC + static_cast<size_t>(m + 1) * LDc;   // (both move to shared memory after the factorisation when !SMEM)
   const BandChain C = my_chain ? C1 : C0;           // this thread's chain in the update phase (registers)
   const BandChain CP = (tid >> 8) ? C1 : C0;        // ... and in the panel phase (threads 0..255 / 256..511)
-  const double* S = sys;
-  const double* b = sys + static_cast<size_t>(n) * n;
+  const double* S = sys;                 // band-only storage: P at offset 0 in the chain-0 column layout
+  const double* b = sys + lay.ob;
   // Dout != null: the system is the raw accumulation (lower triangle of H with the Schur complement applied,
   // b = -g + ...); LM damping mu * clamp(diag H) and the constant-dof mask are applied while gathering
   // (== finalize_kernel, which then need not run), and D = clamp(diag H) is written out for accept_kernel.
   const bool damp = Dout != nullptr;
-  const double* diagH = b + n;
+  const double* diagH = sys + lay.oD;
   // stage the per-dof damping term and the mask once (the gather would otherwise chase them through L2 per element)
   double* s_dmp = XA + 2 * m;
   unsigned char* s_fix = reinterpret_cast<unsigned char*>(s_dmp + n);
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   }
   __syncthreads();
   auto Sval = [&](int row, int col) -> double {   // row >= col
-    double v = S[static_cast<size_t>(row) * n + col];
+    double v = S[sys_index(lay, row, col)];
     if (row == col) v += s_dmp[row];
     if (s_fix[row] | s_fix[col]) v = (row == col) ? 1.0 : 0.0;
     return v;
@@ -412,13 +413,12 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
         v[t] = x;
       }
     };
-    auto load6 = [&](int row, int col0, double* v) {
-      const double2* p2 = reinterpret_cast<const double2*>(S + static_cast<size_t>(row) * n + col0);   // n and col0 are even
+    auto load6 = [&](int row, int col0, double* v) {   // S[row][col0 .. col0+5], col0 a multiple of 6: one 48-byte row of P
+      const double2* p2 = reinterpret_cast<const double2*>(S + (static_cast<size_t>(col0 / 6) * h + (row - col0)) * 6);
       const double2 a0 = p2[0], a1 = p2[1], a2 = p2[2];
       v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = a2.x; v[5] = a2.y;
     };
-    const bool vec = (n % 2) == 0;   // (always: n = 6K + 3Kbg + 3Kba + 2 with Kbg == Kba; kept as a guard)
-    if (vec) {
+    {
       const int nu0 = C0.ncol * h;
       for (int u0 = tid; u0 < nu0; u0 += 2 * kBandThreads) {
         double v[2][6];
@@ -467,19 +467,6 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
           for (int t = 0; t < 6; ++t) C1.W[(static_cast<size_t>(c) * h + 6 * q + t) * 6 + j] = v[w][5 - t];   // row 6q+t <-> b = b0 + 5 - t
         }
       }
-    } else {
-    gather4(C0.ncol * h6, [&](int e) {
-      const int c = e / h6, rem = e - c * h6;
-      const int i = rem / 6, j = rem - 6 * i;
-      const int row = 6 * c + i, col = 6 * c + j;
-      return (row < C0.npc && row >= col) ? Sval(row, col) : 0.0;
-    }, [&](int e, double v) { C0.W[e] = v; });
-    gather4(C1.ncol * h6, [&](int e) {
-      const int c = e / h6, rem = e - c * h6;
-      const int i = rem / 6, j = rem - 6 * i;
-      const int rr = 6 * c + i, rc = 6 * c + j;          // reversed (chain-local) row / column
-      return (c < C1.Ke && rr < N1 && rr >= rc) ? Sval(np - 1 - rc, np - 1 - rr) : 0.0;
-    }, [&](int e, double v) { C1.W[e] = v; });
     }
     gather4((m + 1) * C0.npc, [&](int e) {
       const int r = e / C0.npc, col = e - r * C0.npc;

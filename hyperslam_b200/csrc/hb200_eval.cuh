@@ -386,8 +386,8 @@ struct PixelArgs {
   double huber;           // Huber delta of the pixel factors (reference optimizer.cpp:226)
   double huber_bearing;   // Huber delta of the bearing factors (reference optimizer.cpp:204)
   int K_knots;
-  double* sys;            // packed reduced system [S | b | diagH | g | ...] to accumulate J^T J / J^T r into, or null
-  int n_sys;              // its dimension n
+  double* sys;            // packed band-only reduced system (SysLayout) to accumulate J^T J / J^T r into, or null
+  SysLayout lay;
 };
 
 // J^T J / J^T r of up to 32 consecutive pixel factors [f0, f0 + cnt) of this CTA, accumulated into the
@@ -418,7 +418,7 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
   }
   __syncthreads();
   double* S = a.sys;
-  double* g = a.sys + static_cast<size_t>(a.n_sys) * a.n_sys + 2 * static_cast<size_t>(a.n_sys);
+  double* g = a.sys + a.lay.og;
   const int base_lo = sb[0], base_hi = sb[rows - 1];   // bound order is sorted by base
   const int lm = lane >> 2, lk = lane & 3;
   for (int base = base_lo; base <= base_hi; ++base) {
@@ -445,8 +445,8 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
       }
       const int rr = 8 * ti + lm, cc = 8 * tj + 2 * lk;
       if (rr < NB) {
-        if (cc < NB && cc <= rr) atomicAdd(&S[static_cast<size_t>(c0 + rr) * a.n_sys + c0 + cc], c0v);
-        if (cc + 1 < NB && cc + 1 <= rr) atomicAdd(&S[static_cast<size_t>(c0 + rr) * a.n_sys + c0 + cc + 1], c1v);
+        if (cc < NB && cc <= rr) atomicAdd(&S[sys_index(a.lay, c0 + rr, c0 + cc)], c0v);
+        if (cc + 1 < NB && cc + 1 <= rr) atomicAdd(&S[sys_index(a.lay, c0 + rr, c0 + cc + 1)], c1v);
       }
     }
     if (tid >= kEvalThreads - NB) {   // gradient: the last NB threads

@@ -13,16 +13,7 @@ namespace hb {
 
 namespace cg = cooperative_groups;
 
-// Packed system buffer: [S n*n | b n | diagH n | g n | cost | pad]
-struct SysView {
-  double* S; double* b; double* diagH; double* g; double* cost;
-  int n;
-};
-HB_DI SysView sys_view(double* base, int n) {
-  SysView v;
-  v.S = base; v.b = base + static_cast<size_t>(n) * n; v.diagH = v.b + n; v.g = v.diagH + n; v.cost = v.g + n; v.n = n;
-  return v;
-}
+// The packed reduced system is band-only: see SysLayout / sys_index (hb200_types.cuh).
 
 // ---------------------------------------------------------------------------------------------
 // J^T J / J^T r of the pixel factors, one CTA per spline segment (factors are sorted by knot base
@@ -32,7 +23,7 @@ constexpr int kHessThreads = 128;
 
 template <int K>
 __global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* __restrict__ seg_off, const double* __restrict__ r,
-                                                                     const double* __restrict__ Jp, const double* __restrict__ wv, double* sys, int n, int splits) {
+                                                                     const double* __restrict__ Jp, const double* __restrict__ wv, double* sys, SysLayout lay, int splits) {
   constexpr int NB = 6 * K;
   constexpr int CH = 16;
   constexpr int EPT = (NB * NB + kHessThreads - 1) / kHessThreads;
@@ -76,17 +67,16 @@ __global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* 
       gacc += s;
     }
   }
-  SysView v = sys_view(sys, n);
   const int c0 = 6 * seg;  // segment index == knot base index
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
     const int id = threadIdx.x + e * kHessThreads;
     if (id < NB * NB) {
       const int a = id / NB, b = id - a * NB;
-      if (b <= a) atomicAdd(&v.S[static_cast<size_t>(c0 + a) * n + c0 + b], acc[e]);
+      if (b <= a) atomicAdd(&sys[sys_index(lay, c0 + a, c0 + b)], acc[e]);
     }
   }
-  if (threadIdx.x < NB) atomicAdd(&v.g[c0 + threadIdx.x], gacc);
+  if (threadIdx.x < NB) atomicAdd(&sys[lay.og + c0 + threadIdx.x], gacc);
 }
 
 // Inertial factors: one CTA per (run of identical (pose base, gyro-bias base, accel-bias base), split).
@@ -100,7 +90,7 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
                                                                         const double* __restrict__ r, const double* __restrict__ Jp,
                                                                         const double* __restrict__ wg, const double* __restrict__ wa,
                                                                         const double* __restrict__ Jg, double loss_scale, double* sys,
-                                                                        int n, int o_bg, int o_ba, int o_g, int splits) {
+                                                                        SysLayout lay, int o_bg, int o_ba, int o_g, int splits) {
   constexpr int NP = 6 * K;
   constexpr int CH = 16;
   constexpr int NBP = 3 * KB * NP;                // bias-pose entries (per bias spline)
@@ -234,7 +224,7 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
     }
   }
   // ---- flush (loss scaling applied once here: J^T J and J^T r both carry loss_scale) ----
-  SysView v = sys_view(sys, n);
+  double* gv = sys + lay.og;
   const int cp = 6 * id0.x, cg = o_bg + 3 * id0.y, ca = o_ba + 3 * id0.z;
   const double ls = loss_scale;
 #pragma unroll
@@ -246,8 +236,8 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
       const int tj = tile - ti * (ti + 1) / 2;
       const int a = 8 * ti + lm, b = 8 * tj + 2 * lk;
       if (a < NP) {
-        if (b < NP && b <= a) atomicAdd(&v.S[static_cast<size_t>(cp + a) * n + cp + b], ls * a1[2 * q]);
-        if (b + 1 < NP && b + 1 <= a) atomicAdd(&v.S[static_cast<size_t>(cp + a) * n + cp + b + 1], ls * a1[2 * q + 1]);
+        if (b < NP && b <= a) atomicAdd(&sys[sys_index(lay, cp + a, cp + b)], ls * a1[2 * q]);
+        if (b + 1 < NP && b + 1 <= a) atomicAdd(&sys[sys_index(lay, cp + a, cp + b + 1)], ls * a1[2 * q + 1]);
       }
     }
   }
@@ -256,14 +246,14 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
     const int id = tid + e * kHessThreads;
     if (id < NBP) {
       const int a = id % NP, mc = id / NP;
-      atomicAdd(&v.S[static_cast<size_t>(cg + mc) * n + cp + a], ls * a2[e]);
-      atomicAdd(&v.S[static_cast<size_t>(ca + mc) * n + cp + a], ls * a3[e]);
+      atomicAdd(&sys[sys_index(lay, cg + mc, cp + a)], ls * a2[e]);
+      atomicAdd(&sys[sys_index(lay, ca + mc, cp + a)], ls * a3[e]);
     }
   }
 #pragma unroll
   for (int e = 0; e < E4; ++e) {
     const int id = tid + e * kHessThreads;
-    if (id < NGP) atomicAdd(&v.S[static_cast<size_t>(o_g + id / NP) * n + cp + id % NP], ls * a4[e]);
+    if (id < NGP) atomicAdd(&sys[sys_index(lay, o_g + id / NP, cp + id % NP)], ls * a4[e]);
   }
 #pragma unroll
   for (int e = 0; e < E5; ++e) {
@@ -279,22 +269,22 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
         const int m2 = q - m * (m + 1) / 2;
         const int c0 = acc_b ? ca : cg;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) atomicAdd(&v.S[static_cast<size_t>(c0 + 3 * m + c) * n + c0 + 3 * m2 + c], val);
+        for (int c = 0; c < 3; ++c) atomicAdd(&sys[sys_index(lay, c0 + 3 * m + c, c0 + 3 * m2 + c)], val);
       } else if ((id -= 2 * NBB) < 2 * NGB) {
         const bool acc_b = id >= NGB;
         const int q = acc_b ? id - NGB : id;
         const int gm = q / (3 * KB), mc = q - gm * 3 * KB;
-        atomicAdd(&v.S[static_cast<size_t>(o_g + gm) * n + (acc_b ? ca : cg) + mc], val);
+        atomicAdd(&sys[sys_index(lay, o_g + gm, (acc_b ? ca : cg) + mc)], val);
       } else if ((id -= 2 * NGB) < 3) {
         const int ga = (id == 0) ? 0 : 1, gb = (id == 2) ? 1 : 0;
-        atomicAdd(&v.S[static_cast<size_t>(o_g + ga) * n + o_g + gb], val);
+        atomicAdd(&sys[sys_index(lay, o_g + ga, o_g + gb)], val);
       } else if ((id -= 3) < NP) {
-        atomicAdd(&v.g[cp + id], val);
+        atomicAdd(&gv[cp + id], val);
       } else if ((id -= NP) < 2 * 3 * KB) {
         const bool acc_b = id >= 3 * KB;
-        atomicAdd(&v.g[(acc_b ? ca : cg) + (acc_b ? id - 3 * KB : id)], val);
+        atomicAdd(&gv[(acc_b ? ca : cg) + (acc_b ? id - 3 * KB : id)], val);
       } else {
-        atomicAdd(&v.g[o_g + id - 2 * 3 * KB], val);
+        atomicAdd(&gv[o_g + id - 2 * 3 * KB], val);
       }
     }
   }
@@ -304,7 +294,7 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
 constexpr int kManWarps = 4;
 template <int K>
 __global__ void __launch_bounds__(kManWarps * 32) manifold_hessian_kernel(int nf, const int2* __restrict__ idx, const double* __restrict__ r,
-                                                                         const double* __restrict__ Jp, double* sys, int n) {
+                                                                         const double* __restrict__ Jp, double* sys, SysLayout lay) {
   constexpr int NB = 6 * K;
   __shared__ double sJ[kManWarps][6][NB];
   __shared__ double sr[kManWarps][6];
@@ -315,14 +305,14 @@ __global__ void __launch_bounds__(kManWarps * 32) manifold_hessian_kernel(int nf
   if (lane < 6) sr[warp][lane] = r[6 * static_cast<size_t>(f) + lane];
   __syncwarp();
   const int c0 = 6 * idx[f].x;
-  double* g = sys + static_cast<size_t>(n) * n + 2 * static_cast<size_t>(n);
+  double* g = sys + lay.og;
   for (int e = lane; e < NB * NB; e += 32) {
     const int a = e / NB, b = e - a * NB;
     if (b > a) continue;
     double s = 0;
 #pragma unroll
     for (int q = 0; q < 6; ++q) s += sJ[warp][q][a] * sJ[warp][q][b];
-    atomicAdd(&sys[static_cast<size_t>(c0 + a) * n + c0 + b], s);
+    atomicAdd(&sys[sys_index(lay, c0 + a, c0 + b)], s);
   }
   for (int a = lane; a < NB; a += 32) {
     double s = 0;
@@ -333,12 +323,12 @@ __global__ void __launch_bounds__(kManWarps * 32) manifold_hessian_kernel(int nf
 }
 
 // diagH = diag(H), b = -g, cost = sum of the evaluation kernels' per-block partials (fixed order).
-__global__ void diag_cost_kernel(double* sys, int n, const double* __restrict__ cp_pix, int n_pix_blocks, const double* __restrict__ cp_imu,
+__global__ void diag_cost_kernel(double* sys, SysLayout lay, const double* __restrict__ cp_pix, int n_pix_blocks, const double* __restrict__ cp_imu,
                                  int n_imu_blocks) {
-  SysView v = sys_view(sys, n);
+  const int n = lay.n;
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-    v.diagH[a] = v.S[static_cast<size_t>(a) * n + a];
-    v.b[a] = -v.g[a];
+    sys[lay.oD + a] = sys[sys_index(lay, a, a)];
+    sys[lay.ob + a] = -sys[lay.og + a];
   }
   if (blockIdx.x == 0) {
     __shared__ double s[256];
@@ -351,7 +341,7 @@ __global__ void diag_cost_kernel(double* sys, int n, const double* __restrict__ 
       if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) { v.cost[0] = s[0]; v.cost[1] = 0.0; }
+    if (threadIdx.x == 0) { sys[lay.os] = s[0]; sys[lay.os + 1] = 0.0; }
   }
 }
 
@@ -367,7 +357,7 @@ template <int K>
 __global__ void __launch_bounds__(kSchurThreads) schur_kernel(const int* __restrict__ lm_off, const int* __restrict__ lm_obs,
                                                               const int4* __restrict__ idx, const double* __restrict__ r,
                                                               const double* __restrict__ Jp, const double* __restrict__ Jl, const double* __restrict__ wv,
-                                                              const SolverState* __restrict__ st, double* sys, int n,
+                                                              const SolverState* __restrict__ st, double* sys, SysLayout lay,
                                                               double* __restrict__ Vinv, double* __restrict__ gl, double* __restrict__ Dl,
                                                               int max_rows) {
   constexpr int NB = 6 * K;
@@ -440,7 +430,6 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(const int* __restr
     for (int i = 0; i < 3; ++i) gl[3 * static_cast<size_t>(l) + i] = sV[9 + i];
   }
   __syncthreads();
-  SysView v = sys_view(sys, n);
   const int r0g = 6 * cp_lo;
   for (int e = threadIdx.x; e < rows * 3; e += kSchurThreads) {
     const int row = e / 3, c = e - 3 * row;
@@ -449,41 +438,41 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(const int* __restr
   __syncthreads();
   for (int row = threadIdx.x; row < rows; row += kSchurThreads) {
     const double val = WV[3 * row] * sV[9] + WV[3 * row + 1] * sV[10] + WV[3 * row + 2] * sV[11];
-    if (val != 0.0) atomicAdd(&v.b[r0g + row], val);
+    if (val != 0.0) atomicAdd(&sys[lay.ob + r0g + row], val);
   }
   for (int e = threadIdx.x; e < rows * rows; e += kSchurThreads) {
     const int a = e / rows, b = e - a * rows;
     if (b > a) continue;
     const double val = WV[3 * a] * W[3 * b] + WV[3 * a + 1] * W[3 * b + 1] + WV[3 * a + 2] * W[3 * b + 2];
-    if (val != 0.0) atomicAdd(&v.S[static_cast<size_t>(r0g + a) * n + r0g + b], -val);
+    if (val != 0.0) atomicAdd(&sys[sys_index(lay, r0g + a, r0g + b)], -val);
   }
 }
 
-// LM damping + constant dofs; writes the damped system back to S/b and the factorisation work
-// copy Lw ((n+1) x n, last row = b).
-__global__ void finalize_kernel(double* sys, int n, const SolverState* __restrict__ st, const unsigned char* __restrict__ fixed,
-                                double* __restrict__ D, double* __restrict__ Lw, int* __restrict__ spd_flag) {
-  SysView v = sys_view(sys, n);
+// Dense fallback / inspection: expands the band-only raw system into the dense factorisation work copy
+// Lw ((32 T + 1) x n, last row = b), applying LM damping mu clamp(diag H) and the constant-dof mask on the way
+// (what the band solver does while it gathers).  st == nullptr: no damping.
+__global__ void densify_kernel(const double* __restrict__ sys, SysLayout lay, const SolverState* __restrict__ st, const unsigned char* __restrict__ fixed,
+                               double* __restrict__ D, double* __restrict__ Lw, int* __restrict__ spd_flag) {
+  const int n = lay.n;
   if (blockIdx.x == 0 && threadIdx.x == 0) *spd_flag = 1;
   const size_t brow = static_cast<size_t>((n + 31) / 32) * 32;  // row of Lw holding b (own tile row)
-  const double mu = 1.0 / st->radius;
+  const double mu = st ? 1.0 / st->radius : 0.0;
   const size_t total = static_cast<size_t>(n + 1) * n;
   for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total; e += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int i = static_cast<int>(e / n), j = static_cast<int>(e - static_cast<size_t>(i) * n);
     if (i < n) {
-      double s = (j <= i) ? v.S[e] : v.S[static_cast<size_t>(j) * n + i];   // only the lower triangle was accumulated
+      const int hi = max(i, j), lo = min(i, j);   // only the lower triangle is stored
+      double s = 0.0;
+      if (hi >= lay.np || hi - 6 * (lo / 6) < lay.h) s = sys[sys_index(lay, hi, lo)];
       if (i == j) {
-        const double d = fmin(fmax(v.diagH[i], 1e-6), 1e32);
+        const double d = fmin(fmax(sys[lay.oD + i], 1e-6), 1e32);
         D[i] = d;
         s += mu * d;
       }
       if (fixed[i] || fixed[j]) s = (i == j) ? 1.0 : 0.0;
-      v.S[e] = s;
       Lw[e] = s;
     } else {
-      const double bb = fixed[j] ? 0.0 : v.b[j];
-      v.b[j] = bb;
-      Lw[brow * n + j] = bb;
+      Lw[brow * n + j] = fixed[j] ? 0.0 : sys[lay.ob + j];
     }
   }
 }
@@ -846,11 +835,37 @@ struct ScalarArgs {   // inputs of scalars_kernel, for the fused single-GPU path
   const double* cp_pix; int n_pix_blocks; const double* cp_imu; int n_imu_blocks; const double* lm_part; int n_lm_blocks;
 };
 
+// Multi-GPU step acceptance without a second collective call: every rank's trial-cost / model-decrease partials
+// (3 doubles) travel through PEER MEMORY inside accept_kernel itself -- thread p stores this rank's triple and a
+// sequence tag into rank p's mailbox over NVLink (st.release.sys) and waits for rank p's triple in its own
+// (ld.acquire.sys); the sums are taken in rank order, so every replica computes bit-identical rho / radius.
+// Mailbox: [2 parities][kMaxRanks][4] doubles = {cost_new, dl.g_l, dl.D_l.dl, tag}.  Slots alternate with the
+// sequence parity; a slot is not reused before the next system all-reduce has synchronised all ranks.
+constexpr int kMaxRanks = 16;
+struct MailboxArgs {
+  int nranks, rank;
+  double* const* peers;        // [nranks] mailbox base of every rank, mapped into this process (cudaIpcOpenMemHandle)
+  double* local;               // this rank's own mailbox
+  unsigned long long* seq;     // exchanges completed so far (device counter, identical on every rank)
+};
+HB_DI void st_release_sys_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+HB_DI unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+HB_DI void st_relaxed_sys_f64(double* p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+HB_DI double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
 constexpr int kAcceptThreads = 1024;   // one CTA; wide so that the fused commit copies the state in a few passes
-__global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __restrict__ sys, int n, double* __restrict__ scal, const double* __restrict__ dp,
+__global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __restrict__ sys, SysLayout lay, double* __restrict__ scal, const double* __restrict__ dp,
                               const double* __restrict__ D, const unsigned char* __restrict__ fixed, SolverState* st,
                               const int* __restrict__ spd_flag, SolverState* __restrict__ record, int max_records, int fuse_scalars,
-                              ScalarArgs sa, int fuse_commit, CommitArgs ca) {
+                              ScalarArgs sa, int fuse_commit, CommitArgs ca, MailboxArgs mb) {
   // block sums: shuffle within the warp, one partial per warp, fixed order across warps (two barriers in total)
   __shared__ double s[5][kAcceptThreads / 32];
   const int wl = threadIdx.x & 31, ww = threadIdx.x >> 5;
@@ -860,7 +875,8 @@ __global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __
     for (int i = threadIdx.x; i < sa.n_imu_blocks; i += blockDim.x) v5[0] += sa.cp_imu[i];
     for (int i = threadIdx.x; i < sa.n_lm_blocks; i += blockDim.x) { v5[1] += sa.lm_part[2 * i]; v5[2] += sa.lm_part[2 * i + 1]; }
   }
-  const double* g = sys + static_cast<size_t>(n) * n + 2 * static_cast<size_t>(n);
+  const int n = lay.n;
+  const double* g = sys + lay.og;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     if (!fixed[i]) { v5[3] += dp[i] * g[i]; v5[4] += dp[i] * dp[i] * D[i]; }
 #pragma unroll
@@ -876,12 +892,43 @@ __global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __
 #pragma unroll
       for (int q = 0; q < 5; ++q) t5[q] += s[q][w];
     if (fuse_scalars) { scal[0] = t5[0]; scal[1] = t5[1]; scal[2] = t5[2]; scal[3] = 0.0; }
-    s[3][0] = t5[3]; s[4][0] = t5[4];
+    s[0][0] = t5[0]; s[1][0] = t5[1]; s[2][0] = t5[2]; s[3][0] = t5[3]; s[4][0] = t5[4];
   }
   __syncthreads();
+  if (fuse_scalars && mb.nranks > 1) {
+    __shared__ double s_peer[kMaxRanks][3];
+    __shared__ int s_timeout;
+    const unsigned long long want = *mb.seq + 1;   // every thread reads the counter before thread 0 bumps it (below)
+    const int par = static_cast<int>(want & 1);
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
+    if (static_cast<int>(threadIdx.x) < mb.nranks) {
+      const int p = threadIdx.x;
+      double* dst = mb.peers[p] + (par * kMaxRanks + mb.rank) * 4;
+      st_relaxed_sys_f64(dst + 0, s[0][0]); st_relaxed_sys_f64(dst + 1, s[1][0]); st_relaxed_sys_f64(dst + 2, s[2][0]);
+      st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst + 3), want);
+      const double* src = mb.local + (par * kMaxRanks + p) * 4;
+      const long long t0 = clock64();
+      bool ok = true;
+      while (ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(src + 3)) != want) {
+        if (clock64() - t0 > 6000000000LL) { ok = false; break; }   // ~3 s: a peer died; report instead of hanging the GPU
+      }
+      if (!ok) s_timeout = 1;
+      s_peer[p][0] = ld_relaxed_sys_f64(src + 0); s_peer[p][1] = ld_relaxed_sys_f64(src + 1); s_peer[p][2] = ld_relaxed_sys_f64(src + 2);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a0 = 0, a1 = 0, a2 = 0;
+      for (int p = 0; p < mb.nranks; ++p) { a0 += s_peer[p][0]; a1 += s_peer[p][1]; a2 += s_peer[p][2]; }   // rank order: identical on every rank
+      scal[0] = a0; scal[1] = a1; scal[2] = a2;
+      *mb.seq = want;
+      if (s_timeout) st->comm_error = 1;
+    }
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     const double mu = 1.0 / st->radius;
-    const double cost = sys[static_cast<size_t>(n) * n + 3 * static_cast<size_t>(n)];
+    const double cost = sys[lay.os];
     const double cost_new = scal[0];
     const double dg = s[3][0] + scal[1], dDd = s[4][0] + scal[2];
     const double model = 0.5 * (-dg + mu * dDd);

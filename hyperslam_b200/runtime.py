@@ -21,7 +21,8 @@ _ip = C.POINTER(C.c_int)
 
 
 class Options(C.Structure):
-    _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("use_graph", C.c_int), ("reserved", C.c_int)]
+    _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("use_graph", C.c_int), ("reserved", C.c_int),
+                ("nccl_comm", C.c_void_p), ("nranks", C.c_int), ("rank", C.c_int)]
 
 
 class Iteration(C.Structure):
@@ -41,7 +42,9 @@ EXPORTS = [
     "hb200_system_device_ptr", "hb200_stream", "hb200_launch_count", "hb200_optimize", "hb200_snapshot", "hb200_restore",
     "hb200_profile_iteration", "hb200_interpolate", "hb200_set_bearing_factors", "hb200_set_bearing_loss",
     "hb200_set_pose_sensors", "hb200_set_manifold_factors", "hb200_get_bearing_outputs", "hb200_get_manifold_outputs",
-    "hb200_ingest_stereo",
+    "hb200_ingest_stereo", "hb200_comm_unique_id", "hb200_comm_init_rank", "hb200_set_nccl_comm", "hb200_peer_handle",
+    "hb200_peer_connect", "hb200_peer_disconnect", "hb200_comm_info",
+    "hb200_get_bandwidth", "hb200_set_min_bandwidth",
 ]
 
 _lib = None
@@ -87,7 +90,7 @@ class Context:
     def __init__(self, device: int = 0, stream: int | None = None, use_graph: bool = True, force_dense: bool = False):
         self.lib = load_library()
         self.h = C.c_void_p()
-        opts = Options(device, stream, int(use_graph), int(force_dense))
+        opts = Options(device, stream, int(use_graph), int(force_dense), None, 1, 0)
         self._check(self.lib.hb200_create(C.byref(opts), C.byref(self.h)))
         self._cb = None
         self.order = self.K = self.Kbg = self.Kba = self.L = self.Nv = self.Ni = self.Nb = self.Nm = 0
@@ -339,6 +342,61 @@ class Context:
             return
         self._cb = ALLREDUCE_FN(lambda user, ptr, count, stream: int(fn(ptr, count, stream) or 0))
         self._check(self.lib.hb200_set_allreduce(self.h, self._cb, None))
+
+    # ---- multi-GPU: NCCL communicator owned by the library + peer-memory mailbox ------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.hb200_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes):
+        self._check(self.lib.hb200_comm_init_rank(self.h, int(nranks), int(rank), C.c_char_p(unique_id)))
+
+    def peer_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.hb200_peer_handle(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, nranks: int, rank: int, handles: list):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * nranks
+        self._check(self.lib.hb200_peer_connect(self.h, int(nranks), int(rank), C.c_char_p(blob)))
+
+    def bandwidth(self) -> int:
+        b = C.c_int(0)
+        self._check(self.lib.hb200_get_bandwidth(self.h, C.byref(b)))
+        return b.value
+
+    def set_min_bandwidth(self, beta: int):
+        self._check(self.lib.hb200_set_min_bandwidth(self.h, int(beta)))
+
+    def comm_info(self):
+        v = [C.c_int(0) for _ in range(5)]
+        pay = C.c_longlong(0)
+        self._check(self.lib.hb200_comm_info(self.h, *[C.byref(x) for x in v], C.byref(pay)))
+        return dict(nranks=v[0].value, rank=v[1].value, nccl=bool(v[2].value), peer_mailbox=bool(v[3].value), graph=bool(v[4].value),
+                    payload_doubles=pay.value)
+
+    def connect_torch_distributed(self, dist, peer_mailbox=True):
+        """Plumbing only: ships the NCCL unique id and the mailbox handles over an initialised torch.distributed
+        group; the communicator itself and every collective on the iteration path live inside the library."""
+        world, rank = dist.get_world_size(), dist.get_rank()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init_rank(world, rank, box[0])
+        if peer_mailbox:
+            handles = [None] * world
+            dist.all_gather_object(handles, self.peer_handle())
+            try:
+                self.peer_connect(world, rank, handles)
+                ok = 1
+            except HB200Error:
+                ok = 0
+            flags = [None] * world
+            dist.all_gather_object(flags, ok)
+            if not all(flags):   # all ranks or none: the exchange is collective
+                self._check(self.lib.hb200_peer_disconnect(self.h))
+        return self.comm_info()
 
     def system_device_ptr(self):
         cnt = C.c_longlong(0)

@@ -25,6 +25,8 @@ typedef struct hb200_options {
   void* stream;      /* cudaStream_t to run on; NULL => the context creates its own */
   int use_graph;     /* capture hb200_iterate() in a CUDA graph (1) or launch kernels directly (0) */
   int reserved;      /* bit 0: force the dense cooperative Cholesky instead of the banded-arrow solver */
+  void* nccl_comm;   /* ncclComm_t spanning the ranks that share this window, or NULL (single GPU); not owned */
+  int nranks, rank;  /* size of / position in that communicator (ignored when nccl_comm is NULL) */
 } hb200_options;
 
 /* Per-iteration record, the analogue of ceres::IterationSummary printed through
@@ -110,6 +112,7 @@ int hb200_factor_evaluate(hb200_ctx* ctx, int kind, int index, const double* con
  * requires hb200_evaluate(JACOBIANS).  System layout: [6K pose | 3Kbg | 3Kba | 2 gravity]. */
 int hb200_reduced_size(hb200_ctx* ctx);
 int hb200_build_system(hb200_ctx* ctx);
+/* dense copy of what the solver factors: damped (mu * clamp(diag H)), constant dofs masked to identity. */
 int hb200_get_system(hb200_ctx* ctx, double* S /* n x n */, double* b /* n */);
 /* dense Cholesky of the reduced system, back-substitution, landmark back-substitution. */
 int hb200_solve(hb200_ctx* ctx);
@@ -148,11 +151,48 @@ int hb200_ingest_stereo(hb200_ctx* ctx, int n, const double* stamp, const int* c
                         const double* pixel1 /* [n][2] */, double* bearing0 /* [n][3] */, double* bearing1 /* [n][3] */,
                         double* landmark /* [n][3] */, int* num_invalid);
 
-/* ---- multi-GPU hook -------------------------------------------------------------------------
- * The packed reduced system [S (n*n) | b (n) | cost (1) | pad (1)] lives in one device buffer;
- * when factors are sharded over ranks the caller sums it across ranks between build and solve
- * (one all-reduce per iteration).  The callback runs on the context's
- * stream inside hb200_iterate; it must enqueue work on that stream only. */
+/* ---- multi-GPU ---------------------------------------------------------
+ * Factors shard over ranks, the window state is replicated.  Per iteration every rank builds its partial
+ * reduced system, ONE ncclAllReduce sums it on the context's stream (enqueued from C, so the iteration stays
+ * one CUDA graph), every rank solves redundantly and retracts its replica; the three step-acceptance scalars
+ * (trial cost, landmark parts of the model decrease) are exchanged through peer memory inside accept_kernel
+ * (hb200_peer_*), with a second 4-double ncclAllReduce as the fallback when no peer mapping exists.
+ *
+ * SHARDING CONTRACT (the caller's responsibility; violating it gives silently wrong steps):
+ *   - every observation (pixel / bearing factor) of a landmark must live on ONE rank -- the landmark's owner.
+ *     The landmark block is eliminated rank-locally (Schur complement of a sum is not the sum of Schur
+ *     complements) and only the owner updates the landmark, so non-owned landmarks of a replica are stale;
+ *     read each landmark back from its owner.
+ *   - inertial and manifold factors may be split arbitrarily; every factor lives on exactly one rank.
+ *   - knots, bias splines, gravity, calibration, constancy flags and options must be identical on all ranks,
+ *     and every rank must make the same sequence of hb200_iterate / hb200_optimize / hb200_build_system calls.
+ *
+ * Reduced buffer (what is summed): the band-only packed system, hb200_system_device_ptr(), in doubles
+ *   [ P K*h*6 | A m*6K | C m*m | b n | diagH n | g n | scal 8 ],  h = 6 + 6*beta, m = n - 6K
+ * (block-banded pose part of half-bandwidth beta = longest landmark track in control points, arrowhead of
+ * the bias / gravity dofs; scal[0] = cost at the linearisation point).  K = 50: 20 k doubles (0.16 MB). */
+/* ncclGetUniqueId / ncclCommInitRank through the library (libnccl.so.2 is bound with dlopen at the first call):
+ * rank 0 creates the 128-byte id, the host program ships it to the other ranks (MPI, torch.distributed, ...). */
+int hb200_comm_unique_id(char* id /* [128] */);
+int hb200_comm_init_rank(hb200_ctx* ctx, int nranks, int rank, const char* id /* [128] */);
+/* or attach an existing ncclComm_t (not owned; NULL detaches).  Same as hb200_options.nccl_comm at creation. */
+int hb200_set_nccl_comm(hb200_ctx* ctx, void* nccl_comm, int nranks, int rank);
+/* peer-memory mailbox for the step-acceptance scalars: every rank exports a 64-byte cudaIpcMemHandle_t, the
+ * host program all-gathers them, every rank maps its peers' mailboxes.  Ranks must be processes on one node
+ * with NVLink / PCIe peer access.  Optional: without it the scalars take a second ncclAllReduce. */
+int hb200_peer_handle(hb200_ctx* ctx, char* handle /* [64] */);
+int hb200_peer_connect(hb200_ctx* ctx, int nranks, int rank, const char* handles /* [nranks][64] */);
+/* all ranks or none: when the mapping failed on any rank, every rank drops it (collective protocol). */
+int hb200_peer_disconnect(hb200_ctx* ctx);
+int hb200_comm_info(hb200_ctx* ctx, int* nranks, int* rank, int* nccl, int* peer_mailbox, int* graph, long long* payload_doubles);
+/* Block half-bandwidth beta of the packed layout.  It follows from the longest landmark track of the local factor
+ * shard; with a communicator attached hb200_bind / hb200_set_nccl_comm agree on the maximum over the ranks
+ * themselves (collective).  Hosts using the callback hook below must do that: read it after hb200_bind, take the
+ * maximum over ranks, set it as the lower bound everywhere. */
+int hb200_get_bandwidth(hb200_ctx* ctx, int* beta);
+int hb200_set_min_bandwidth(hb200_ctx* ctx, int beta);
+/* Escape hatch for hosts without NCCL: the caller sums `count_doubles` doubles at `device_buffer` across ranks
+ * on `stream` (called twice per iteration: packed system, then 4 scalars).  Disables CUDA-graph capture. */
 typedef int (*hb200_allreduce_fn)(void* user, void* device_buffer, long long count_doubles, void* stream);
 int hb200_set_allreduce(hb200_ctx* ctx, hb200_allreduce_fn fn, void* user);
 void* hb200_system_device_ptr(hb200_ctx* ctx, long long* count_doubles);

@@ -1,5 +1,6 @@
-"""Worker for tests/test_gpu_multi.py: every rank runs LM iterations on its factor shard with the
-NCCL all-reduce hook; rank 0 compares records and final state with the single-process oracle."""
+"""Worker for tests/test_gpu_multi.py: every rank runs LM iterations on its factor shard (one in-graph
+ncclAllReduce per iteration + the peer-memory scalar exchange, or one of the two fallbacks); rank 0 compares
+records and final state with the single-process oracle."""
 import json
 import os
 import sys
@@ -18,21 +19,29 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     win = synthetic.make_window(order=4, num_knots=20, num_landmarks=160, num_imu=400, seed=synthetic.SEED_BASE + 700, constant_knots=2)
-    ctx = runtime.Context(local, use_graph=False)
+    mode = sys.argv[1] if len(sys.argv) > 1 else "nccl+mailbox"
+    ctx = runtime.Context(local, use_graph=(mode != "callback"))
     ctx.load_window(win.shard(rank, world))
-    ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
-    cache = {}
+    info = {}
+    if mode == "callback":   # legacy hook: the host program reduces (torch.distributed here), no graph
+        ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+        cache = {}
 
-    def allreduce(ptr, count, stream):
-        if (ptr, count) not in cache:
-            class _Arr:
-                __cuda_array_interface__ = dict(shape=(count,), typestr="<f8", data=(ptr, False), version=2)
-            cache[(ptr, count)] = torch.as_tensor(_Arr(), device=torch.device("cuda", local))
-        with torch.cuda.stream(ext):
-            dist.all_reduce(cache[(ptr, count)])
-        return 0
+        def allreduce(ptr, count, stream):
+            if (ptr, count) not in cache:
+                class _Arr:
+                    __cuda_array_interface__ = dict(shape=(count,), typestr="<f8", data=(ptr, False), version=2)
+                cache[(ptr, count)] = torch.as_tensor(_Arr(), device=torch.device("cuda", local))
+            with torch.cuda.stream(ext):
+                dist.all_reduce(cache[(ptr, count)])
+            return 0
 
-    ctx.set_allreduce(allreduce)
+        ctx.set_allreduce(allreduce)
+        beta = torch.tensor([ctx.bandwidth()], device="cuda")   # the packed layout must agree across ranks
+        dist.all_reduce(beta, op=dist.ReduceOp.MAX)
+        ctx.set_min_bandwidth(int(beta.item()))
+    else:                    # the product path: ncclAllReduce enqueued by the library, inside the iteration's CUDA graph
+        info = ctx.connect_torch_distributed(dist, peer_mailbox=(mode == "nccl+mailbox"))
     recs = ctx.iterate(4)
     state = ctx.state()
     ok, msg = True, ""
@@ -55,7 +64,8 @@ def main():
     flag = torch.tensor([1.0 if (ok and same) else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps(dict(ok=bool(flag.item() == 1.0), msg=msg, replicas_identical=same, world=world)))
+        info = ctx.comm_info() if mode != "callback" else info
+        print(json.dumps(dict(ok=bool(flag.item() == 1.0), msg=msg, replicas_identical=same, world=world, mode=mode, comm=info)))
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
