@@ -3,6 +3,7 @@
 // (reference internal/hyper/optimizers/ceres/optimizer.cpp:189-382) but flattened: one set of
 // device arrays per variable family and two factor lists.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -149,6 +150,7 @@ struct hb200_ctx {
   DevBuf<double> cams, imu, cam_tab, imu_tab;
   DevBuf<unsigned char> fixed;
   std::vector<unsigned char> h_knot_const;
+  std::vector<double> h_knot_stamp, h_bg_stamp, h_ba_stamp;   // stamps the index maps of hb200_bind were computed from
   int gravity_const = 0, bias_const = 0;
   bool have_imu = false, have_gravity = false;
   double huber = 0.5, imu_scale = 1.6e-5, radius0 = 1e4;
@@ -758,11 +760,13 @@ void hb200_destroy(hb200_ctx* c) {
   for (size_t p = 0; p < c->peer_ptrs.size(); ++p)
     if (c->peer_ptrs[p] && c->peer_ptrs[p] != c->mbox.p) cudaIpcCloseMemHandle(c->peer_ptrs[p]);
   c->peer_ptrs.clear();
+  // the captured iteration references the communicator: NCCL waits in ncclCommDestroy until such graphs are gone
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->graph) cudaGraphDestroy(c->graph);
+  c->graph_exec = nullptr; c->graph = nullptr;
   if (c->nccl && c->own_nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
   c->nccl = nullptr;
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
-  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-  if (c->graph) cudaGraphDestroy(c->graph);
   for (int s = 0; s < 2; ++s) { c->knots[s].release(); c->bg[s].release(); c->ba[s].release(); c->grav[s].release(); c->lms[s].release(); c->tab[s].release(); c->cp_pix[s].release(); c->cp_imu[s].release(); }
   c->cams.release(); c->imu.release(); c->cam_tab.release(); c->imu_tab.release(); c->fixed.release();
   c->v_stamp.release(); c->v_pixel.release(); c->i_stamp.release(); c->i_meas.release(); c->v_cam.release(); c->v_lm.release(); c->v_idx.release(); c->i_idx.release();
@@ -796,14 +800,23 @@ int hb200_set_spline(hb200_ctx* c, int order, int K, const double* knots) {
   if (K < order) return fail(-1, "need at least %d knots, got %d", order, K);
   for (int j = 1; j < K; ++j)
     if (!(knots[8 * j + 7] > knots[8 * (j - 1) + 7])) return fail(-1, "knot stamps must be strictly increasing (knot %d)", j);
+  {   // uniform B-spline (the reference only ever creates uniformly separated knots, abstract.cpp:89,128)
+    const double dt0 = knots[8 + 7] - knots[7];
+    for (int j = 2; j < K; ++j)
+      if (std::fabs((knots[8 * j + 7] - knots[8 * (j - 1) + 7]) - dt0) > 1e-6 * dt0) return fail(-1, "knot stamps must be uniformly spaced (knot %d)", j);
+  }
   HB_CUDA(cudaSetDevice(c->device));
-  const bool reshape = (order != c->k) || (K != c->K);
+  bool reshape = (order != c->k) || (K != c->K);
+  // the index maps of hb200_bind follow from the stamps: a window shifted by one knot keeps K but needs a re-bind
+  if (!reshape) for (int j = 0; j < K && !reshape; ++j) if (c->h_knot_stamp[j] != knots[8 * j + 7]) reshape = true;
+  c->h_knot_stamp.resize(K);
+  for (int j = 0; j < K; ++j) c->h_knot_stamp[j] = knots[8 * j + 7];
   c->k = order; c->K = K;
   compute_basis(&c->basis, order);
   for (int s = 0; s < 2; ++s) { HB_CUDA(c->knots[s].ensure(8 * static_cast<size_t>(K))); HB_CUDA(c->tab[s].ensure(static_cast<size_t>(K) * kTabStride)); }
   HB_CUDA(cudaMemcpyAsync(c->knots[0].p, knots, 8 * sizeof(double) * K, cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
-  if (reshape) { c->h_knot_const.assign(K, 0); c->bound = false; c->invalidate(); int rc = update_fixed(c); if (rc) return rc; }
+  if (reshape) { c->h_knot_const.assign(K, 0); c->bound = false; c->invalidate(); c->have_snapshot = false; int rc = update_fixed(c); if (rc) return rc; }
   c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
   return 0;
 }
@@ -812,15 +825,30 @@ int hb200_set_bias_splines(hb200_ctx* c, int order, int Kg, const double* gyro, 
   if (!c || !gyro || !accel) return fail(-1, "null argument");
   if (order != 4) return fail(-4, "bias spline order %d not supported (4)", order);
   if (Kg < order || Ka < order) return fail(-1, "need at least %d bias knots", order);
+  for (int w = 0; w < 2; ++w) {
+    const double* b = w ? accel : gyro;
+    const int Kb = w ? Ka : Kg;
+    const double dt0 = b[4 + 3] - b[3];
+    if (!(dt0 > 0)) return fail(-1, "bias knot stamps must be strictly increasing");
+    for (int j = 2; j < Kb; ++j)
+      if (std::fabs((b[4 * j + 3] - b[4 * (j - 1) + 3]) - dt0) > 1e-6 * dt0) return fail(-1, "bias knot stamps must be uniformly spaced (knot %d)", j);
+  }
   HB_CUDA(cudaSetDevice(c->device));
-  const bool reshape = (Kg != c->Kbg) || (Ka != c->Kba);
+  bool reshape = (Kg != c->Kbg) || (Ka != c->Kba);
+  if (!reshape) {
+    for (int j = 0; j < Kg && !reshape; ++j) if (c->h_bg_stamp[j] != gyro[4 * j + 3]) reshape = true;
+    for (int j = 0; j < Ka && !reshape; ++j) if (c->h_ba_stamp[j] != accel[4 * j + 3]) reshape = true;
+  }
+  c->h_bg_stamp.resize(Kg); c->h_ba_stamp.resize(Ka);
+  for (int j = 0; j < Kg; ++j) c->h_bg_stamp[j] = gyro[4 * j + 3];
+  for (int j = 0; j < Ka; ++j) c->h_ba_stamp[j] = accel[4 * j + 3];
   c->kb = order; c->Kbg = Kg; c->Kba = Ka;
   compute_basis(&c->bias_basis, order);
   for (int s = 0; s < 2; ++s) { HB_CUDA(c->bg[s].ensure(4 * static_cast<size_t>(Kg))); HB_CUDA(c->ba[s].ensure(4 * static_cast<size_t>(Ka))); }
   HB_CUDA(cudaMemcpyAsync(c->bg[0].p, gyro, 4 * sizeof(double) * Kg, cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaMemcpyAsync(c->ba[0].p, accel, 4 * sizeof(double) * Ka, cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
-  if (reshape) { c->bound = false; c->invalidate(); int rc = update_fixed(c); if (rc) return rc; }
+  if (reshape) { c->bound = false; c->invalidate(); c->have_snapshot = false; int rc = update_fixed(c); if (rc) return rc; }
   c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
   return 0;
 }
@@ -866,7 +894,7 @@ int hb200_set_imu(hb200_ctx* c, const double* imu) {
 int hb200_set_landmarks(hb200_ctx* c, int L, const double* xyz) {
   if (!c || (L > 0 && !xyz) || L < 0) return fail(-1, "invalid landmarks");
   HB_CUDA(cudaSetDevice(c->device));
-  if (L != c->L) { c->bound = false; c->invalidate(); }
+  if (L != c->L) { c->bound = false; c->invalidate(); c->have_snapshot = false; }
   c->L = L;
   for (int s = 0; s < 2; ++s) HB_CUDA(c->lms[s].ensure(3 * static_cast<size_t>(std::max(L, 1))));
   if (L) HB_CUDA(cudaMemcpyAsync(c->lms[0].p, xyz, 3 * sizeof(double) * L, cudaMemcpyHostToDevice, c->stream));
@@ -1126,7 +1154,7 @@ int hb200_evaluate(hb200_ctx* c, int flags) {
   const int sel = (flags & HB200_EVAL_TRIAL) ? 1 : 0;
   rc = enqueue_evaluate(c, J, sel);
   if (rc) return rc;
-  if (J && sel == 0) c->evaluated_J = true;
+  c->evaluated_J = J && sel == 0;   // a trial-state sweep overwrites the residual / Jacobian buffers
   c->mirror_valid = false; c->system_built = false;
   return 0;
 }
@@ -1441,6 +1469,11 @@ int hb200_optimize(hb200_ctx* c, int iterations, double* knots, double* gyro, do
   if (rc) return rc;
   if (iterations < 0 || iterations > c->max_records) return fail(-1, "iterations must be in [0, %d]", c->max_records);
   HB_CUDA(cudaSetDevice(c->device));
+  // the blocks alias the caller's variables, stamps included: the bound index maps are only valid for the stamps
+  // they were computed from (a slid window needs hb200_set_spline / hb200_slide + hb200_bind first)
+  if (knots) for (int j = 0; j < c->K; ++j) if (knots[8 * j + 7] != c->h_knot_stamp[j]) return fail(-2, "knot %d: stamp differs from the bound window (re-bind after changing stamps)", j);
+  if (gyro) for (int j = 0; j < c->Kbg; ++j) if (gyro[4 * j + 3] != c->h_bg_stamp[j]) return fail(-2, "gyroscope bias knot %d: stamp differs from the bound window", j);
+  if (accel) for (int j = 0; j < c->Kba; ++j) if (accel[4 * j + 3] != c->h_ba_stamp[j]) return fail(-2, "accelerometer bias knot %d: stamp differs from the bound window", j);
   double* host[5] = {knots, (gyro && c->Kbg) ? gyro : nullptr, (accel && c->Kba) ? accel : nullptr, gravity, (landmarks && c->L) ? landmarks : nullptr};
   double* dev[5] = {c->knots[0].p, c->bg[0].p, c->ba[0].p, c->grav[0].p, c->lms[0].p};
   const size_t cnt[5] = {8 * static_cast<size_t>(c->K), 4 * static_cast<size_t>(c->Kbg), 4 * static_cast<size_t>(c->Kba), 3, 3 * static_cast<size_t>(c->L)};
@@ -1691,7 +1724,11 @@ int hb200_set_nccl_comm(hb200_ctx* c, void* comm, int nranks, int rank) {
   if (comm && c->allreduce) return fail(-2, "the all-reduce callback hook is set; clear it first");
   if (comm) { int rc = load_nccl(); if (rc) return rc; }
   HB_CUDA(cudaSetDevice(c->device));
-  if (c->nccl && c->own_nccl) { HB_CUDA(cudaStreamSynchronize(c->stream)); g_nccl.CommDestroy(c->nccl); }
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // it references the old communicator
+  if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+  c->graph_valid = false;
+  if (c->nccl && c->own_nccl) g_nccl.CommDestroy(c->nccl);
   c->nccl = comm; c->own_nccl = false;
   c->nranks = comm ? nranks : 1; c->rank = comm ? rank : 0;
   c->comm_warm = false; c->graph_valid = false;

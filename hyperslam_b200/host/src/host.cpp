@@ -199,7 +199,7 @@ std::vector<StateResult> ContinuousState::evaluate(hb200_ctx* ctx, const std::ve
 // Optimizer
 // ---------------------------------------------------------------------------------------------
 Optimizer::Optimizer(int device) {
-  hb200_options o{device, nullptr, 1, 0};
+  hb200_options o{device, nullptr, 1, 0, nullptr, 1, 0};
   check(hb200_create(&o, &ctx_), "hb200_create");
 }
 Optimizer::~Optimizer() { hb200_destroy(ctx_); }
@@ -370,6 +370,7 @@ Pointers<Scalar> ExteroceptiveCost::update() {
     auto bias_blocks = [&](std::vector<IMU::Bias>& knots) {
       auto it = std::upper_bound(knots.begin(), knots.end(), stamp, [](Stamp s, const IMU::Bias& e) { return s < e.stamp(); });
       const int base = static_cast<int>(it - knots.begin()) - 1 - 1;   // order 4: left padding 1
+      if (base < 0 || base + 3 >= static_cast<int>(knots.size())) throw std::out_of_range("inertial stamp outside the bias spline's valid range");
       for (int m = 0; m < 4; ++m) { p.push_back(knots[base + m].data()); layout_.sizes.push_back(4); }
     };
     bias_blocks(imu->gyroscopeBias());

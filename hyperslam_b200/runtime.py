@@ -377,16 +377,19 @@ class Context:
         return dict(nranks=v[0].value, rank=v[1].value, nccl=bool(v[2].value), peer_mailbox=bool(v[3].value), graph=bool(v[4].value),
                     payload_doubles=pay.value)
 
-    def connect_torch_distributed(self, dist, peer_mailbox=True):
+    def connect_torch_distributed(self, dist, peer_mailbox=True, log=lambda m: None):
         """Plumbing only: ships the NCCL unique id and the mailbox handles over an initialised torch.distributed
         group; the communicator itself and every collective on the iteration path live inside the library."""
         world, rank = dist.get_world_size(), dist.get_rank()
         box = [self.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
+        log("unique id shipped")
         self.comm_init_rank(world, rank, box[0])
+        log("communicator up")
         if peer_mailbox:
             handles = [None] * world
             dist.all_gather_object(handles, self.peer_handle())
+            log("handles gathered")
             try:
                 self.peer_connect(world, rank, handles)
                 ok = 1

@@ -53,6 +53,10 @@ int hb200_synchronize(hb200_ctx* ctx);
  * knots  [K][8] = Stamped<SE3> blocks [qx qy qz qw px py pz | stamp] ordered by stamp
  *         (reference optimizer.cpp:287-305 AddParameterBlock per state element; storage order
  *         reference settings.yaml:34-36, stamped.hpp:35-36).  order = layout().outer.size.      */
+/* Knots must be UNIFORMLY spaced (relative tolerance 1e-6; the reference only creates uniform knots,
+ * abstract.cpp:89,128), likewise the bias knots.  RE-BIND RULE: the index maps of hb200_bind follow from the
+ * stamps, so changing the order, the number of knots OR ANY STAMP (a window slid by one knot keeps K) unbinds the
+ * factor lists -- call hb200_bind again; hb200_optimize rejects blocks whose stamps differ from the bound window. */
 int hb200_set_spline(hb200_ctx* ctx, int order, int num_knots, const double* knots);
 /* bias control points [Kb][4] = Stamped<R3> [bx by bz | stamp] (reference imu.cpp:64-80). */
 int hb200_set_bias_splines(hb200_ctx* ctx, int order, int num_gyro, const double* gyro, int num_accel, const double* accel);

@@ -14,11 +14,17 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from hyperslam_b200 import runtime, synthetic  # noqa: E402
 
 
+def stage(msg):
+    if os.environ.get("HB200_DEBUG"):
+        print(f"[rank {os.environ.get('RANK')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     win = synthetic.make_window(order=4, num_knots=20, num_landmarks=160, num_imu=400, seed=synthetic.SEED_BASE + 700, constant_knots=2)
+    stage("process group up")
     mode = sys.argv[1] if len(sys.argv) > 1 else "nccl+mailbox"
     ctx = runtime.Context(local, use_graph=(mode != "callback"))
     ctx.load_window(win.shard(rank, world))
@@ -41,8 +47,10 @@ def main():
         dist.all_reduce(beta, op=dist.ReduceOp.MAX)
         ctx.set_min_bandwidth(int(beta.item()))
     else:                    # the product path: ncclAllReduce enqueued by the library, inside the iteration's CUDA graph
-        info = ctx.connect_torch_distributed(dist, peer_mailbox=(mode == "nccl+mailbox"))
+        info = ctx.connect_torch_distributed(dist, peer_mailbox=(mode == "nccl+mailbox"), log=stage)
+    stage(f"connected {info}")
     recs = ctx.iterate(4)
+    stage("iterated")
     state = ctx.state()
     ok, msg = True, ""
     if rank == 0:
