@@ -17,6 +17,7 @@
 
 #include "../../include/hyperb200.h"
 #include "hb200_band.cuh"
+#include "hb200_calib.cuh"
 
 using namespace hb;
 
@@ -188,6 +189,10 @@ struct hb200_ctx {
   DevBuf<double> cp_pix[2], cp_imu[2];
   int n_pix_blocks = 0, n_imu_blocks = 0, n_man_blocks = 0;   // manifold cost partials follow the inertial ones in cp_imu
   bool evaluated_J = false;
+  // calibration-block Jacobians (on demand, hb200_factor_evaluate) and the reference-quirk switches
+  int quirks = 0;
+  bool calib_valid = false;
+  std::vector<double> m_v_Jc, m_i_Jc, m_m_Jc;   // user order: [Np + Nb][2][14], [Ni][6][36], [Nm][6][6]
   // host mirror for hb200_factor_evaluate
   bool mirror_valid = false;
   std::vector<double> m_v_r, m_v_Jp, m_v_Jl, m_i_r, m_i_Jp, m_i_wg, m_i_wa, m_i_Jg, m_grav, m_b_r, m_b_Jp, m_b_Jl, m_m_r, m_m_Jp;
@@ -235,7 +240,7 @@ struct hb200_ctx {
   int o_bg() const { return 6 * K; }
   int o_ba() const { return 6 * K + 3 * Kbg; }
   int o_g() const { return 6 * K + 3 * Kbg + 3 * Kba; }
-  void invalidate() { graph_valid = false; system_built = false; evaluated_J = false; mirror_valid = false; }
+  void invalidate() { graph_valid = false; system_built = false; evaluated_J = false; mirror_valid = false; calib_valid = false; }
 };
 
 namespace {
@@ -393,7 +398,7 @@ int launch_inertial(hb200_ctx* c, int sel) {
   HB_LAUNCH(c, "inertial_eval_kernel");
   return 0;
 }
-// visual + inertial factors in one launch (both lists non-empty; separate launches while profiling per kernel)
+// visual + inertial factors in one launch (both lists non-empty)
 template <int K, bool J>
 int launch_factors_merged(hb200_ctx* c, int sel, bool accumulate) {
   const PixelArgs pa = pixel_args<J>(c, sel, accumulate);
@@ -436,7 +441,7 @@ int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false
   // Small windows are latency-bound: one launch for both factor families.  Large windows are throughput-bound: the
   // merged kernel would run the pixel CTAs at the inertial body's 255 registers, so the families stay separate.
   static const bool no_merge = getenv("HB200_NO_MERGE") != nullptr;   // profiling aid: one kernel per factor family
-  if (c->Nv && c->Ni && !c->profiling && !no_merge && c->n_pix_blocks + c->n_imu_blocks <= 4 * c->num_sms) {
+  if (c->Nv && c->Ni && !no_merge && c->n_pix_blocks + c->n_imu_blocks <= 4 * c->num_sms) {   // (also while profiling: same kernels as the graph)
     // visual and inertial factors side by side in one launch; pose factors (if any) on the side stream
     if (c->Nm && (rc = fork_side(c))) return rc;
     if (c->k == 4) rc = J_any ? launch_factors_merged<4, true>(c, sel, accumulate) : launch_factors_merged<4, false>(c, sel, false);
@@ -817,7 +822,7 @@ int hb200_set_spline(hb200_ctx* c, int order, int K, const double* knots) {
   HB_CUDA(cudaMemcpyAsync(c->knots[0].p, knots, 8 * sizeof(double) * K, cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   if (reshape) { c->h_knot_const.assign(K, 0); c->bound = false; c->invalidate(); c->have_snapshot = false; int rc = update_fixed(c); if (rc) return rc; }
-  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
   return 0;
 }
 
@@ -849,7 +854,7 @@ int hb200_set_bias_splines(hb200_ctx* c, int order, int Kg, const double* gyro, 
   HB_CUDA(cudaMemcpyAsync(c->ba[0].p, accel, 4 * sizeof(double) * Ka, cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   if (reshape) { c->bound = false; c->invalidate(); c->have_snapshot = false; int rc = update_fixed(c); if (rc) return rc; }
-  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
   return 0;
 }
 
@@ -859,7 +864,7 @@ int hb200_set_gravity(hb200_ctx* c, const double* g) {
   HB_CUDA(cudaMemcpyAsync(c->grav[0].p, g, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   c->have_gravity = true;
-  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
   return 0;
 }
 
@@ -871,10 +876,10 @@ int hb200_set_cameras(hb200_ctx* c, int C, const double* cams) {
   HB_CUDA(c->cams.ensure(15 * static_cast<size_t>(C)));
   HB_CUDA(c->cam_tab.ensure(kCamStride * static_cast<size_t>(C)));
   HB_CUDA(cudaMemcpyAsync(c->cams.p, cams, 15 * sizeof(double) * C, cudaMemcpyHostToDevice, c->stream));
-  calib_kernel<<<(C + 63) / 64, 64, 0, c->stream>>>(C, c->cams.p, c->cam_tab.p, nullptr, nullptr);
+  calib_kernel<<<(C + 63) / 64, 64, 0, c->stream>>>(C, c->cams.p, c->cam_tab.p, nullptr, nullptr, 0);
   HB_LAUNCH(c, "calib_kernel");
   HB_CUDA(cudaStreamSynchronize(c->stream));
-  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
   return 0;
 }
 
@@ -883,11 +888,11 @@ int hb200_set_imu(hb200_ctx* c, const double* imu) {
   HB_CUDA(cudaSetDevice(c->device));
   HB_CUDA(c->imu.ensure(37));
   HB_CUDA(cudaMemcpyAsync(c->imu.p, imu, 37 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  calib_kernel<<<1, 64, 0, c->stream>>>(0, nullptr, nullptr, c->imu.p, c->imu_tab.p);
+  calib_kernel<<<1, 64, 0, c->stream>>>(0, nullptr, nullptr, c->imu.p, c->imu_tab.p, c->quirks);
   HB_LAUNCH(c, "calib_kernel");
   HB_CUDA(cudaStreamSynchronize(c->stream));
   c->have_imu = true;
-  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
   return 0;
 }
 
@@ -899,7 +904,7 @@ int hb200_set_landmarks(hb200_ctx* c, int L, const double* xyz) {
   for (int s = 0; s < 2; ++s) HB_CUDA(c->lms[s].ensure(3 * static_cast<size_t>(std::max(L, 1))));
   if (L) HB_CUDA(cudaMemcpyAsync(c->lms[0].p, xyz, 3 * sizeof(double) * L, cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
-  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
   return 0;
 }
 
@@ -912,6 +917,20 @@ int hb200_set_constant(hb200_ctx* c, const unsigned char* knot_constant, int gra
   c->gravity_const = gravity_constant; c->bias_const = bias_constant;
   c->system_built = false;
   return update_fixed(c);
+}
+
+int hb200_set_reference_quirks(hb200_ctx* c, int quirks) {
+  if (!c) return fail(-1, "null context");
+  if (quirks < 0 || quirks > 15) return fail(-1, "quirks is a bit mask in [0, 15]");
+  HB_CUDA(cudaSetDevice(c->device));
+  c->quirks = quirks;
+  if (c->have_imu) {   // rebuild the derived IMU table with the Jacobian-side matrices of this variant
+    calib_kernel<<<1, 64, 0, c->stream>>>(0, nullptr, nullptr, c->imu.p, c->imu_tab.p, c->quirks);
+    HB_LAUNCH(c, "calib_kernel");
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
+  return 0;
 }
 
 int hb200_set_options(hb200_ctx* c, double huber_pixel, double imu_loss_scale, double radius) {
@@ -1155,7 +1174,7 @@ int hb200_evaluate(hb200_ctx* c, int flags) {
   rc = enqueue_evaluate(c, J, sel);
   if (rc) return rc;
   c->evaluated_J = J && sel == 0;   // a trial-state sweep overwrites the residual / Jacobian buffers
-  c->mirror_valid = false; c->system_built = false;
+  c->mirror_valid = false; c->calib_valid = false; c->system_built = false;
   return 0;
 }
 
@@ -1235,6 +1254,63 @@ int hb200_get_inertial_outputs(hb200_ctx* c, double* r, double* Jp, double* wg, 
   return 0;
 }
 
+}  // extern "C"
+
+namespace {
+// rows of a tangent-space SE3 Jacobian [d/dtheta | d/drho] -> ambient [q(4) | p(3)] through the SE3JacobianAdapter
+// (reference pixel.cpp:141, inertial.cpp:161): J_theta A_q(q) | J_rho
+void tangent_to_ambient_se3(const double* Jt, int ld, int rows, const double* T, double* out /*rows x 7*/) {
+  const double* q = T;
+  const double Aq[12] = {2 * q[3], -2 * q[2], 2 * q[1], -2 * q[0], 2 * q[2], 2 * q[3], -2 * q[0], -2 * q[1], -2 * q[1], 2 * q[0], 2 * q[3], -2 * q[2]};
+  for (int row = 0; row < rows; ++row) {
+    const double* jt = Jt + static_cast<size_t>(ld) * row;
+    double* o = out + 7 * row;
+    for (int col = 0; col < 4; ++col) o[col] = jt[0] * Aq[col] + jt[1] * Aq[4 + col] + jt[2] * Aq[8 + col];
+    o[4] = jt[3]; o[5] = jt[4]; o[6] = jt[5];
+  }
+}
+
+// calibration-block Jacobians of every factor at the current state, mirrored to the host in user order
+int ensure_calib_mirror(hb200_ctx* c) {
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t Nv = c->Nv, Ni = c->Ni, Nm = c->Nm;
+  DevBuf<double> dv, di, dm;
+  std::vector<double> tv(28 * Nv), ti(216 * Ni);
+  c->m_v_Jc.assign(28 * Nv, 0.0); c->m_i_Jc.assign(216 * Ni, 0.0); c->m_m_Jc.assign(36 * Nm, 0.0);
+  if (Nv) {
+    HB_CUDA(dv.ensure(28 * Nv));
+    const int blocks = static_cast<int>((Nv + kEvalThreads - 1) / kEvalThreads);
+    if (c->k == 4) pixel_calib_kernel<4><<<blocks, kEvalThreads, 0, c->stream>>>(c->Nv, c->v_stamp.p, reinterpret_cast<const double2*>(c->v_pixel.p), c->v_z.p, c->v_idx.p, c->tab[0].p, c->cam_tab.p, c->lms[0].p, c->basis, dv.p);
+    else pixel_calib_kernel<6><<<blocks, kEvalThreads, 0, c->stream>>>(c->Nv, c->v_stamp.p, reinterpret_cast<const double2*>(c->v_pixel.p), c->v_z.p, c->v_idx.p, c->tab[0].p, c->cam_tab.p, c->lms[0].p, c->basis, dv.p);
+    HB_LAUNCH(c, "pixel_calib_kernel");
+    HB_CUDA(cudaMemcpyAsync(tv.data(), dv.p, sizeof(double) * 28 * Nv, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (Ni) {
+    HB_CUDA(di.ensure(216 * Ni));
+    const int blocks = static_cast<int>((Ni + kEvalThreads - 1) / kEvalThreads);
+    if (c->k == 4) inertial_calib_kernel<4><<<blocks, kEvalThreads, 0, c->stream>>>(c->Ni, c->i_stamp.p, c->i_idx.p, c->tab[0].p, c->imu.p, c->grav[0].p, c->basis, c->quirks, di.p);
+    else inertial_calib_kernel<6><<<blocks, kEvalThreads, 0, c->stream>>>(c->Ni, c->i_stamp.p, c->i_idx.p, c->tab[0].p, c->imu.p, c->grav[0].p, c->basis, c->quirks, di.p);
+    HB_LAUNCH(c, "inertial_calib_kernel");
+    HB_CUDA(cudaMemcpyAsync(ti.data(), di.p, sizeof(double) * 216 * Ni, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (Nm) {
+    HB_CUDA(dm.ensure(36 * Nm));
+    const int blocks = static_cast<int>((Nm + kEvalThreads - 1) / kEvalThreads);
+    if (c->k == 4) manifold_calib_kernel<4><<<blocks, kEvalThreads, 0, c->stream>>>(c->Nm, c->m_stamp.p, c->m_meas.p, c->m_idx.p, c->tab[0].p, c->sensors.p, c->basis, dm.p);
+    else manifold_calib_kernel<6><<<blocks, kEvalThreads, 0, c->stream>>>(c->Nm, c->m_stamp.p, c->m_meas.p, c->m_idx.p, c->tab[0].p, c->sensors.p, c->basis, dm.p);
+    HB_LAUNCH(c, "manifold_calib_kernel");
+    HB_CUDA(cudaMemcpyAsync(c->m_m_Jc.data(), dm.p, sizeof(double) * 36 * Nm, cudaMemcpyDeviceToHost, c->stream));
+  }
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t p = 0; p < Nv; ++p) std::memcpy(&c->m_v_Jc[28 * static_cast<size_t>(c->v_perm[p])], &tv[28 * p], 28 * sizeof(double));   // pixel [0, Np), bearing after
+  for (size_t p = 0; p < Ni; ++p) std::memcpy(&c->m_i_Jc[216 * static_cast<size_t>(c->i_perm[p])], &ti[216 * p], 216 * sizeof(double));
+  c->calib_valid = true;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
 int hb200_factor_evaluate(hb200_ctx* c, int kind, int index, const double* const* parameters, double* residuals, double** jacobians) {
   if (!c || !c->bound) return fail(-2, "not bound");
   if (!c->evaluated_J) return fail(-2, "call hb200_evaluate(HB200_EVAL_JACOBIANS) first");
@@ -1259,6 +1335,13 @@ int hb200_factor_evaluate(hb200_ctx* c, int kind, int index, const double* const
   }
   const int k = c->k, kb = c->kb;
   if (kind < HB200_PIXEL || kind > HB200_MANIFOLD) return fail(-1, "unknown factor kind %d", kind);
+  if (jacobians && !c->calib_valid) {
+    // calibration blocks requested?  (constant in the live configuration, so they are produced on demand only)
+    const int first = k, count = (kind == HB200_INERTIAL) ? 5 : (kind == HB200_MANIFOLD ? 1 : 3);
+    bool want = false;
+    for (int b = 0; b < count; ++b) want = want || jacobians[first + b] != nullptr;
+    if (want) { const int rc = ensure_calib_mirror(c); if (rc) return rc; }
+  }
   const int nrs[4] = {2, 6, 1, 6};
   const int Ns[4] = {c->Np, c->Ni, c->Nb, c->Nm};
   const int nr = nrs[kind], N = Ns[kind];
@@ -1284,17 +1367,29 @@ int hb200_factor_evaluate(hb200_ctx* c, int kind, int index, const double* const
   if (kind == HB200_PIXEL || kind == HB200_BEARING) {
     const int sizes[4] = {7, 4, 4, 3};
     const double* Jl = (kind == HB200_PIXEL) ? &c->m_v_Jl[6 * static_cast<size_t>(index)] : &c->m_b_Jl[3 * static_cast<size_t>(index)];
+    // calibration blocks (reference pixel.cpp:91-135,141; bearing.cpp:76): rows of [T_bs tangent 6 | intrinsics 4 | distortion 4]
+    const double* Jc = &c->m_v_Jc[28 * static_cast<size_t>(kind == HB200_PIXEL ? index : c->Np + index)];
+    const int coff[3] = {0, 6, 10};
     for (int b = 0; b < 4; ++b) {
       double* o = jacobians[k + b];
       if (!o) continue;
-      if (b < 3) std::fill(o, o + nr * sizes[b], 0.0);  // calibration is constant in the live configuration (reference optimizer.cpp:59)
+      if (b == 0) tangent_to_ambient_se3(Jc, 14, nr, parameters[k], o);
+      else if (b < 3) { for (int row = 0; row < nr; ++row) for (int col = 0; col < sizes[b]; ++col) o[sizes[b] * row + col] = Jc[14 * row + coff[b] + col]; }
       else std::memcpy(o, Jl, 3 * nr * sizeof(double));
     }
   } else if (kind == HB200_MANIFOLD) {
-    if (jacobians[k]) std::fill(jacobians[k], jacobians[k] + 6 * 7, 0.0);   // sensor extrinsics: constant
+    if (jacobians[k]) tangent_to_ambient_se3(&c->m_m_Jc[36 * static_cast<size_t>(index)], 6, 6, parameters[k], jacobians[k]);   // reference manifold.cpp:57
   } else {
+    // reference inertial.cpp:155-194: rows of [T_bs tangent 6 | i_g 6 | i_a 6 | S_g 9 | X_a 9]
     const int sizes[5] = {7, 6, 6, 9, 9};
-    for (int b = 0; b < 5; ++b) if (jacobians[k + b]) std::fill(jacobians[k + b], jacobians[k + b] + 6 * sizes[b], 0.0);
+    const int coff[5] = {0, 6, 12, 18, 27};
+    const double* Jc = &c->m_i_Jc[216 * static_cast<size_t>(index)];
+    for (int b = 0; b < 5; ++b) {
+      double* o = jacobians[k + b];
+      if (!o) continue;
+      if (b == 0) tangent_to_ambient_se3(Jc, 36, 6, parameters[k], o);
+      else for (int row = 0; row < 6; ++row) for (int col = 0; col < sizes[b]; ++col) o[sizes[b] * row + col] = Jc[36 * row + coff[b] + col];
+    }
     for (int m = 0; m < kb; ++m) {
       if (double* o = jacobians[k + 5 + m]) {
         std::fill(o, o + 24, 0.0);
@@ -1422,7 +1517,7 @@ int iterate_enqueue(hb200_ctx* c, int iterations) {
       if (c->nccl) c->comm_warm = true;
     }
   }
-  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
   c->iter_total += iterations;
   return 0;
 }
@@ -1541,6 +1636,46 @@ int hb200_cost(hb200_ctx* c, double* cost) {
   return 0;
 }
 
+// FP64 throughput ceiling of the device ("FP64 peak not in MEASURED_PEAKS.json -- measure"):
+// 8 independent DFMA chains per thread, enough warps to hide the 8-cycle dependent latency.
+__global__ void __launch_bounds__(256) hb200_fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 1.2345e300) out[0] = s;   // never true: keeps the chains alive
+}
+
+int hb200_measure_fp64_peak(hb200_ctx* c, double* tflops) {
+  if (!c || !tflops) return fail(-1, "null argument");
+  HB_CUDA(cudaSetDevice(c->device));
+  DevBuf<double> d;
+  HB_CUDA(d.ensure(1));
+  cudaEvent_t e0, e1;
+  HB_CUDA(cudaEventCreate(&e0)); HB_CUDA(cudaEventCreate(&e1));
+  const int blocks = c->num_sms * 8, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    HB_CUDA(cudaEventRecord(e0, c->stream));
+    hb200_fp64_peak_kernel<<<blocks, 256, 0, c->stream>>>(d.p, iters, 0.999999, 1e-7);
+    HB_CUDA(cudaEventRecord(e1, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    HB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = best;
+  return 0;
+}
+
 __global__ void hb200_spin_kernel(long long cycles) {
   const long long t0 = clock64();
   while (clock64() - t0 < cycles) {}
@@ -1580,7 +1715,7 @@ int hb200_profile_iteration(hb200_ctx* c, int reps, int max_entries, char* names
     ms[n_out] = acc[i] / reps;
   }
   *count = n_out;
-  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
   return 0;
 }
 
@@ -1647,7 +1782,7 @@ int hb200_restore(hb200_ctx* c) {
   if (c->L) HB_CUDA(cudaMemcpyAsync(c->lms[0].p, c->snap_lms.p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToDevice, c->stream));
   HB_CUDA(cudaMemcpyAsync(c->st.p, c->snap_st.p, sizeof(SolverState), cudaMemcpyDeviceToDevice, c->stream));
   c->iter_total = c->snap_iter_total;
-  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false;
+  c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
   return 0;
 }
 

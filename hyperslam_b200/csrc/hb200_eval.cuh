@@ -155,8 +155,10 @@ __global__ void prep_kernel(int K, const double* __restrict__ knots, double* __r
 }
 
 // Calibration tables (once per set_cameras / set_imu).
+// quirks: reference-quirk switches of the inertial Jacobians (hb200_calib.cuh / oracle Quirks): the table carries the
+// matrices the RESIDUAL uses and, separately, the ones the state / gravity JACOBIANS use (identical when quirks = 0).
 __global__ void calib_kernel(int C, const double* __restrict__ cams, double* __restrict__ cam_tab, const double* __restrict__ imu,
-                             double* __restrict__ imu_tab) {
+                             double* __restrict__ imu_tab, int quirks) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < C) {
     const double* c = cams + 15 * t;
@@ -194,7 +196,13 @@ __global__ void calib_kernel(int C, const double* __restrict__ cams, double* __r
       for (int j = 0; j < 3; ++j) {
         imu_tab[30 + 3 * i + j] = imu[19 + i + 3 * j];            // S_g row-major from column-major
         imu_tab[39 + 3 * i + j] = imu[28 + j + 3 * i] + imu[4 + j];  // lever arm c_i = X_a[:, i] + t_bs
+        // Jacobian-side copies: (i) gyroscope intrinsics in the accelerometer rows (inertial.cpp:136,142,148),
+        // (ii) no Jacobian of the S_g a_b_m term (:135,147), (v) lever arm without X_a (:142,148)
+        imu_tab[48 + 3 * i + j] = (quirks & 1) ? IgR[3 * i + j] : IaR[3 * i + j];
+        imu_tab[57 + 3 * i + j] = (quirks & 2) ? 0.0 : imu[19 + i + 3 * j];
+        imu_tab[66 + 3 * i + j] = ((quirks & 8) ? 0.0 : imu[28 + j + 3 * i]) + imu[4 + j];
       }
+    imu_tab[75] = 0.0;
   }
 }
 
@@ -640,6 +648,9 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
   const double* IaR = I + 21;
   const double* Sg = I + 30;
   const double* lever = I + 39;  // row i = c_i
+  const double* IlinR = I + 48;  // Jacobian-side matrices (== IaR, Sg, lever unless a reference quirk is switched on)
+  const double* SgJ = I + 57;
+  const double* leverJ = I + 66;
   const double gm[3] = {pdd[0] - grav[0], pdd[1] - grav[1], pdd[2] - grav[2]};
   double a_i[3], a_m[3];
   m3_tvec(P, gm, a_i);  // R^T (pdd - g) = A_lin - R_bw g
@@ -681,7 +692,7 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
   double Kw[9], Kal[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const double* c = lever + 3 * i;
+    const double* c = leverJ + 3 * i;
     // row i of -(2 w^ c^ - c^ w^) ; (w^ c^) = c w^T - (w.c) I ; (c^ w^) = w c^T - (w.c) I
     const double wc = w[0] * c[0] + w[1] * c[1] + w[2] * c[2];
 #pragma unroll
@@ -696,16 +707,16 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
     Kal[3 * i + 2] = (i == 0) ? -c[1] : (i == 1 ? c[0] : 0.0);
   }
   double Cth[18], Cw[18], Cal[18], Cp[18];
-  m3_mul(Sg, Bm, &Cth[0]);
-  m3_mul(IaR, Bm, &Cth[9]);
-  m3_mul(Sg, Kw, &Cw[0]);
+  m3_mul(SgJ, Bm, &Cth[0]);
+  m3_mul(IlinR, Bm, &Cth[9]);
+  m3_mul(SgJ, Kw, &Cw[0]);
 #pragma unroll
   for (int i = 0; i < 9; ++i) Cw[i] += IgR[i];
-  m3_mul(IaR, Kw, &Cw[9]);
-  m3_mul(Sg, Kal, &Cal[0]);
-  m3_mul(IaR, Kal, &Cal[9]);
-  m3_mult(Sg, P, &Cp[0]);   // S_g R^T
-  m3_mult(IaR, P, &Cp[9]);  // I_a R_sb R^T
+  m3_mul(IlinR, Kw, &Cw[9]);
+  m3_mul(SgJ, Kal, &Cal[0]);
+  m3_mul(IlinR, Kal, &Cal[9]);
+  m3_mult(SgJ, P, &Cp[0]);  // S_g R^T
+  m3_mult(IaR, P, &Cp[9]);  // I_a R_sb R^T (inertial.cpp:150,198 use I_a in every variant)
   (void)Rsb;
   // gravity tangent Jacobian: -(Cp) * PlusJacobian_sphere(g)   (6x2)
   {
@@ -806,7 +817,7 @@ HB_DI void inertial_eval_body(const InertialArgs& a, const Basis& B, const Basis
   __shared__ double s_cost[kEvalThreads / 32];
   __shared__ double s_imu[kImuStride];
   __shared__ double s_grav[3];
-  if (threadIdx.x < kImuStride) s_imu[threadIdx.x] = a.imu_tab[threadIdx.x];
+  for (int i = threadIdx.x; i < kImuStride; i += kEvalThreads) s_imu[i] = a.imu_tab[i];
   if (threadIdx.x < 3) s_grav[threadIdx.x] = a.gravity[threadIdx.x];
   const int f = bid * kEvalThreads + threadIdx.x;
   const bool active = f < a.n;

@@ -16,8 +16,9 @@ constexpr int kTileRows = 16;       // knot-table rows staged per CTA (3.6 KB); 
 constexpr int kEvalThreads = 64;    // one factor per thread
 
 constexpr int kCamStride = 20;      // R_sb(9) t_bs(3) intrinsics(4) distortion(4)
-// IMU derived table: R_sb(9) t_bs(3) IgRsb(9) IaRsb(9) Sg(9,row-major) lever arms c_r (3x3 rows) = 48
-constexpr int kImuStride = 48;
+// IMU derived table: R_sb(9) t_bs(3) IgRsb(9) IaRsb(9) Sg(9,row-major) lever arms c_r (3x3 rows) = 48, then the
+// Jacobian-side copies selected by the reference-quirk switches: IlinRsb(9) SgJ(9) leverJ(9) pad = 76
+constexpr int kImuStride = 76;
 
 struct Basis {
   int k;

@@ -44,7 +44,7 @@ EXPORTS = [
     "hb200_set_pose_sensors", "hb200_set_manifold_factors", "hb200_get_bearing_outputs", "hb200_get_manifold_outputs",
     "hb200_ingest_stereo", "hb200_comm_unique_id", "hb200_comm_init_rank", "hb200_set_nccl_comm", "hb200_peer_handle",
     "hb200_peer_connect", "hb200_peer_disconnect", "hb200_comm_info",
-    "hb200_get_bandwidth", "hb200_set_min_bandwidth",
+    "hb200_get_bandwidth", "hb200_set_min_bandwidth", "hb200_measure_fp64_peak", "hb200_set_reference_quirks",
 ]
 
 _lib = None
@@ -144,6 +144,9 @@ class Context:
 
     def set_options(self, huber_pixel=0.5, imu_loss_scale=1.6e-5, radius=1e4):
         self._check(self.lib.hb200_set_options(self.h, C.c_double(huber_pixel), C.c_double(imu_loss_scale), C.c_double(radius)))
+
+    def set_reference_quirks(self, quirks: int):
+        self._check(self.lib.hb200_set_reference_quirks(self.h, int(quirks)))
 
     def set_pixel_factors(self, stamp, cam, lm, pixel):
         stamp, pixel = _f64(stamp), _f64(pixel)
@@ -361,6 +364,11 @@ class Context:
         blob = b"".join(handles)
         assert len(blob) == 64 * nranks
         self._check(self.lib.hb200_peer_connect(self.h, int(nranks), int(rank), C.c_char_p(blob)))
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0)
+        self._check(self.lib.hb200_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
 
     def bandwidth(self) -> int:
         b = C.c_int(0)

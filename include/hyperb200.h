@@ -76,6 +76,13 @@ int hb200_set_constant(hb200_ctx* ctx, const unsigned char* knot_constant, int g
  * (:267-268); radius = initial trust-region radius (Ceres default 1e4). */
 int hb200_set_options(hb200_ctx* ctx, double huber_pixel, double imu_loss_scale, double radius);
 
+/* HYPER_REFERENCE_QUIRKS: 0 (default) = the mathematically consistent inertial Jacobians;
+ * bits switch on the in-tree formulas verbatim -- 1: gyroscope intrinsics in the accelerometer rows (reference
+ * inertial.cpp:136,142,148,158), 2: no Jacobian of the S_g a_b_m term (:135,147), 4: extrinsics block without R_sb
+ * (:157-158), 8: X_a ignored in the rate / acceleration coefficients (:142,148); 15 = the reference as written.
+ * All variants coincide on the calibration every reference fixture uses (I_g = I_a = I, S_g = X_a = 0, R_bs = I). */
+int hb200_set_reference_quirks(hb200_ctx* ctx, int quirks);
+
 /* ---- factor lists: replace problem_.AddResidualBlock (reference optimizer.cpp:212-232,253-274) */
 int hb200_set_pixel_factors(hb200_ctx* ctx, int n, const double* stamp, const int* camera, const int* landmark, const double* pixel);
 int hb200_set_inertial_factors(hb200_ctx* ctx, int n, const double* stamp, const double* measurement /* [n][6] gyro|accel */);
@@ -108,8 +115,10 @@ int hb200_get_bearing_outputs(hb200_ctx* ctx, double* r, double* Jp, double* Jl)
 int hb200_get_manifold_outputs(hb200_ctx* ctx, double* r, double* Jp);
 /* Ceres-shaped copy-out of one factor after hb200_evaluate(JACOBIANS): same signature, block order
  * and row-major ambient Jacobians as ExteroceptiveCost::Evaluate (reference exteroceptive.hpp:31,
- * exteroceptive.cpp:149-156).  parameters must be the blocks the window was uploaded from; blocks
- * that are constant in the live configuration (calibration) get zero Jacobians. */
+ * exteroceptive.cpp:149-156).  parameters must be the blocks the window was uploaded from.  Every block is served,
+ * the calibration blocks too (extrinsics, intrinsics, distortion; i_g, i_a, S_g, X_a -- reference pixel.cpp:91-135,141,
+ * inertial.cpp:155-194): they are constant in the live configuration (optimizer.cpp:59-63), so their Jacobians are
+ * computed by separate kernels the first time one is requested after an evaluation, not on the iteration path. */
 int hb200_factor_evaluate(hb200_ctx* ctx, int kind, int index, const double* const* parameters, double* residuals, double** jacobians);
 
 /* normal equations + landmark Schur complement at the current linearisation point;
@@ -201,6 +210,10 @@ typedef int (*hb200_allreduce_fn)(void* user, void* device_buffer, long long cou
 int hb200_set_allreduce(hb200_ctx* ctx, hb200_allreduce_fn fn, void* user);
 void* hb200_system_device_ptr(hb200_ctx* ctx, long long* count_doubles);
 void* hb200_stream(hb200_ctx* ctx);
+
+/* Measured FP64 FMA throughput of the device in TFLOP/s (DFMA chains, all SMs): the second roofline ceiling of the
+ * FP64 factor kernels next to the HBM copy bandwidth (bench.py reports both). */
+int hb200_measure_fp64_peak(hb200_ctx* ctx, double* tflops);
 
 /* kernel-launch counter (number of this library's kernels launched since creation). */
 long long hb200_launch_count(hb200_ctx* ctx);
