@@ -16,7 +16,7 @@
 #include <dlfcn.h>
 
 #include "../../include/hyperb200.h"
-#include "hb200_band.cuh"
+#include "hb200_bcr.cuh"
 #include "hb200_calib.cuh"
 
 using namespace hb;
@@ -181,6 +181,13 @@ struct hb200_ctx {
   DevBuf<double> band_ws;
   int band_chunk_cols = 0;       // !band_smem: block columns per shared-memory chunk view (per chain)
   size_t band_chunk_smem = 0;
+  // long windows: multi-CTA block cyclic reduction instead of the single-CTA chain (hb200_bcr.cuh)
+  bool use_bcr = false;
+  BcrPlan bcr{};
+  int bcr_ctas = 0;
+  size_t bcr_smem = 0;
+  DevBuf<double> bcr_ws;
+  DevBuf<unsigned int> bcr_bar;
   DevBuf<long long> band_dbg;   // optional phase timings of band_solve_kernel (HB200_BAND_TIMING=1)
   bool bound = false;
 
@@ -328,7 +335,29 @@ int ensure_system(hb200_ctx* c) {
   const size_t ws = band_workspace_doubles(c->K, c->beta, c->n - 6 * c->K) * sizeof(double);
   c->band_solver = !c->force_dense && ((c->n <= 512) || (12 * (c->beta + 1) <= 6 * c->K));
   c->band_smem = ws <= 220 * 1024;
-  if (c->band_solver) {
+  c->use_bcr = false;
+  if (c->band_solver && !c->band_smem && 6 * c->beta <= kBcrMaxNb && c->n - 6 * c->K <= 54 && !getenv("HB200_NO_BCR")) {
+    // the band does not fit one CTA's shared memory: cyclic reduction over super-blocks of beta control points
+    const int m = c->n - 6 * c->K;
+    const int nsb = (c->K + c->beta - 1) / c->beta;
+    const int nctas = std::max(1, std::min(c->num_sms, (nsb + 1) / 2));
+    const BcrPlan pl = bcr_plan(c->K, c->beta, m, nctas);
+    const size_t nb = pl.nb;
+    const size_t p1 = nb * (nb | 1) + nb + 1 + nb * ((2 * nb + m + 1) | 1);
+    const size_t p2 = 3 * nb * nb + 2 * nb * m + 2 * nb;
+    const size_t p3 = static_cast<size_t>(m + 1) * (m | 1) + 2 * m + 4;
+    const size_t smem = std::max(p1, std::max(p2, p3)) * sizeof(double);
+    if (smem <= 220 * 1024) {
+      if (nctas != c->bcr_ctas || pl.total != c->bcr.total) {
+        HB_CUDA(c->bcr_ws.ensure(static_cast<size_t>(pl.total)));
+        HB_CUDA(c->bcr_bar.ensure(1));
+        HB_CUDA(cudaMemsetAsync(c->bcr_bar.p, 0, sizeof(unsigned int), c->stream));   // the grid-barrier counter stays a multiple of the grid size
+      }
+      c->bcr = pl; c->bcr_ctas = nctas; c->bcr_smem = smem; c->use_bcr = true;
+      HB_CUDA(cudaFuncSetAttribute(bcr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    }
+  }
+  if (c->band_solver && !c->use_bcr) {
     if (c->band_smem) HB_CUDA(cudaFuncSetAttribute(band_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ws)));
     else {
       HB_CUDA(c->band_ws.ensure(ws / sizeof(double)));
@@ -528,7 +557,14 @@ RetractArgs retract_args(hb200_ctx* c);
 // solver while it gathers, the dense fallback in densify_kernel);
 // fuse_retract: the landmark back-substitution launch also retracts knots / biases / gravity (returns *fused)
 int enqueue_solve(hb200_ctx* c, bool fuse_retract = false, bool* fused = nullptr) {
-  if (c->band_solver) {
+  if (c->use_bcr) {
+    const double* sys = c->sys.p; SysLayout lay = c->lay; BcrPlan pl = c->bcr; double* ws = c->bcr_ws.p; unsigned int* bar = c->bcr_bar.p;
+    double* x = c->dp.p; int* spd = c->spd.p; const SolverState* st = c->st.p; const unsigned char* fx = c->fixed.p; double* Dout = c->D.p;
+    void* args[] = {&sys, &lay, &pl, &ws, &bar, &x, &spd, &st, &fx, &Dout};
+    HB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bcr_solve_kernel), dim3(c->bcr_ctas), dim3(kBcrThreads), args, c->bcr_smem, c->stream));
+    c->launches += 1;
+    prof_mark(c, "bcr_solve_kernel");
+  } else if (c->band_solver) {
     const SolverState* st = c->st.p;
     const unsigned char* fx = c->fixed.p;
     double* Dout = c->D.p;
@@ -779,7 +815,7 @@ void hb200_destroy(hb200_ctx* c) {
   c->seg_off.release(); c->run_off.release(); c->lm_off.release(); c->lm_obs.release(); c->d_invalid.release();
   c->v_r.release(); c->v_Jp.release(); c->v_Jl.release(); c->i_r.release(); c->i_Jp.release(); c->i_wg.release(); c->i_wa.release(); c->i_Jg.release();
   c->sys.release(); c->D.release(); c->Lw.release(); c->Ldiag.release(); c->dp.release(); c->dl.release(); c->Vinv.release(); c->gl.release(); c->Dl.release();
-  c->band_ws.release(); c->band_dbg.release(); c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
+  c->band_ws.release(); c->band_dbg.release(); c->bcr_ws.release(); c->bcr_bar.release(); c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
   c->snap_knots.release(); c->snap_bg.release(); c->snap_ba.release(); c->snap_grav.release(); c->snap_lms.release(); c->snap_st.release();
   if (c->h_stage) cudaFreeHost(c->h_stage);
   c->d_stage.release();
