@@ -343,10 +343,13 @@ int ensure_system(hb200_ctx* c) {
     const int nctas = std::max(1, std::min(c->num_sms, (nsb + 1) / 2));
     const BcrPlan pl = bcr_plan(c->K, c->beta, m, nctas);
     const size_t nb = pl.nb;
-    const size_t p1 = nb * (nb | 1) + nb + 1 + nb * ((2 * nb + m + 1) | 1);
+    const size_t p1 = nb * (nb | 1) + nb + 1 + nb * (((2 * nb + m + 1 + 11) / 16) * 16 + 4) + static_cast<size_t>(m + 1) * m;
     const size_t p2 = 3 * nb * nb + 2 * nb * m + 2 * nb;
-    const size_t p3 = static_cast<size_t>(m + 1) * (m | 1) + 2 * m + 4;
-    const size_t smem = std::max(p1, std::max(p2, p3)) * sizeof(double);
+    const size_t mp = static_cast<size_t>((m + 5) / 6) * 6;
+    const size_t p3 = mp * (mp | 1) + 3 * (mp + 1) + 8;                       // corner: padded matrix, reciprocal diagonal, rhs, solution
+    const size_t p4 = nb * static_cast<size_t>(m + 1);                         // corner partials: staged Y_f | y
+    const size_t p5 = 2 * (nb + 1) + 2 * nb + m + 2 + nb * (nb | 1);           // way back: rv, x, staged neighbours, L
+    const size_t smem = std::max(std::max(p1, p2), std::max(p3, std::max(p4, p5))) * sizeof(double);
     if (smem <= 220 * 1024) {
       if (nctas != c->bcr_ctas || pl.total != c->bcr.total) {
         HB_CUDA(c->bcr_ws.ensure(static_cast<size_t>(pl.total)));
@@ -560,7 +563,8 @@ int enqueue_solve(hb200_ctx* c, bool fuse_retract = false, bool* fused = nullptr
   if (c->use_bcr) {
     const double* sys = c->sys.p; SysLayout lay = c->lay; BcrPlan pl = c->bcr; double* ws = c->bcr_ws.p; unsigned int* bar = c->bcr_bar.p;
     double* x = c->dp.p; int* spd = c->spd.p; const SolverState* st = c->st.p; const unsigned char* fx = c->fixed.p; double* Dout = c->D.p;
-    void* args[] = {&sys, &lay, &pl, &ws, &bar, &x, &spd, &st, &fx, &Dout};
+    long long* dbg = c->band_dbg.p;
+    void* args[] = {&sys, &lay, &pl, &ws, &bar, &x, &spd, &st, &fx, &Dout, &dbg};
     HB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bcr_solve_kernel), dim3(c->bcr_ctas), dim3(kBcrThreads), args, c->bcr_smem, c->stream));
     c->launches += 1;
     prof_mark(c, "bcr_solve_kernel");
