@@ -131,7 +131,7 @@ struct hb200_ctx {
   // side stream: the inertial / manifold factor kernels (and their J^T J) are independent of the visual ones and
   // run concurrently with them -- a fork / join inside the iteration (and inside its CUDA graph)
   cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
   bool forked = false;
   // hb200_optimize on small windows: the five variable blocks travel as ONE pinned staging buffer each way
   double* h_stage = nullptr;
@@ -377,10 +377,15 @@ int ensure_system(hb200_ctx* c) {
   if (!c->band_solver) { int rc = ensure_dense(c); if (rc) return rc; }
   if (getenv("HB200_BAND_TIMING")) {
     HB_CUDA(c->band_dbg.ensure(72));
+    long long variant = getenv("HB200_BCR_VARIANT") ? atoll(getenv("HB200_BCR_VARIANT")) : 0;
+    HB_CUDA(cudaMemcpy(c->band_dbg.p + 71, &variant, sizeof(variant), cudaMemcpyHostToDevice));
   }
   // parallelism of the J^T J kernels: aim at ~2 CTAs per SM
   c->pix_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nseg, 1) - 1) / std::max(c->nseg, 1), std::max(1, c->Nv / (16 * std::max(c->nseg, 1)))));
-  c->imu_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nruns, 1) - 1) / std::max(c->nruns, 1), std::max(1, c->Ni / (16 * std::max(c->nruns, 1)))));
+  {
+    static const int min_chunk = getenv("HB200_IMU_MIN_CHUNK") ? std::max(1, atoi(getenv("HB200_IMU_MIN_CHUNK"))) : 8;   // factors per CTA at least
+    c->imu_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nruns, 1) - 1) / std::max(c->nruns, 1), std::max(1, c->Ni / (min_chunk * std::max(c->nruns, 1)))));
+  }
   return 0;
 }
 
@@ -505,6 +510,10 @@ int enqueue_clear_system(hb200_ctx* c) {
   return 0;
 }
 
+// J^T J of the inertial / manifold factors and the cost sum on the side stream, the landmark Schur complement on
+// the main stream: both accumulate into S with atomics (commutative), diag(J^T J) is kept apart from S, so nothing
+// orders them.  after_eval_on_main: the factor Jacobians were produced by a launch on the MAIN stream (merged
+// factor kernel), so the side stream is forked here rather than before the evaluation.
 int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
   if (!pixel_fused) { int rc0 = enqueue_clear_system(c); if (rc0) return rc0; }
   if (c->Nv && !pixel_fused) {
@@ -512,6 +521,7 @@ int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
     else pixel_hessian_kernel<6><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->sys.p, c->lay, c->pix_splits);
     HB_LAUNCH(c, "pixel_hessian_kernel");
   }
+  { const int rf = fork_side(c); if (rf) return rf; }   // (no-op when already forked or while profiling)
   if (c->Ni) {
     if (c->k == 4)
       inertial_hessian_kernel<4, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
@@ -527,10 +537,12 @@ int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
     else manifold_hessian_kernel<6><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->lay);
     HB_LAUNCH(c, "manifold_hessian_kernel");
   }
-  { const int rj = join_side(c); if (rj) return rj; }
-   diag_cost_kernel<<<std::max(1, (c->n + 255) / 256), 256, 0, c->stream>>>(c->sys.p, c->lay, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p,
-                                                                         c->n_imu_blocks + c->n_man_blocks);
-  HB_LAUNCH(c, "diag_cost_kernel");
+  if (c->forked) {   // the cost partials of the visual factors come from the main stream
+    HB_CUDA(cudaEventRecord(c->ev_mid, c->stream));
+    HB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_mid, 0));
+  }
+  cost_kernel<<<1, 256, 0, side(c)>>>(c->sys.p, c->lay, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p, c->n_imu_blocks + c->n_man_blocks);
+  HB_LAUNCH(c, "cost_kernel");
   if (c->Nv && c->L) {
     const size_t smem = 2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double);
     if (c->k == 4)
@@ -541,7 +553,7 @@ int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
                                                                 c->sys.p, c->lay, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
     HB_LAUNCH(c, "schur_kernel");
   }
-  return 0;
+  return join_side(c);
 }
 
 // band-only raw system -> dense damped work copy Lw (dense fallback solver, hb200_get_system)
@@ -774,6 +786,7 @@ int create_impl(const hb200_options* options, hb200_ctx* c) {
   HB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   HB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   HB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  HB_CUDA(cudaEventCreateWithFlags(&c->ev_mid, cudaEventDisableTiming));
   int rc = ensure_placeholders(c);
   if (rc) return rc;
   if (options && options->nccl_comm && (rc = hb200_set_nccl_comm(c, options->nccl_comm, options->nranks, options->rank))) return rc;
@@ -825,6 +838,7 @@ void hb200_destroy(hb200_ctx* c) {
   c->d_stage.release();
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_mid) cudaEventDestroy(c->ev_mid);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;

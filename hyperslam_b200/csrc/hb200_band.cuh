@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     if (s_fix[row] | s_fix[col]) v = (row == col) ? 1.0 : 0.0;
     return v;
   };
-  auto bval = [&](int col) -> double { return s_fix[col] ? 0.0 : b[col]; };
+  const double* gvec = sys + lay.og;
+  auto bval = [&](int col) -> double { return s_fix[col] ? 0.0 : b[col] - gvec[col]; };   // rhs = Schur part - gradient
   __shared__ int s_ok;
   if (tid == 0) s_ok = 1;
   // ---- gather: chain 0 reads P top-down, chain 1 reads J P J (index reversal) and starts its copy of the

@@ -185,7 +185,7 @@ __device__ __noinline__ void bcr_forward_warp(const double* L, int ldl, int n, c
 // on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA.8x8x4): one 8 x 8 output tile per warp pass, contraction over
 // the n rows in steps of 4.  Deliberately a small out-of-line loop: this code runs once per node, and one-shot
 // code is bound by instruction fetch, not issue (tools/microbench).
-__device__ __noinline__ void bcr_gram(const double* Y, int ldy, int n, int nc, double* G) {
+__device__ __noinline__ void bcr_gram(const double* Y, int ldy, int n, int nc, double* G, int variant = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
   const int T = (nc + 7) / 8, ntiles = T * (T + 1) / 2;
   for (int tile = warp; tile < ntiles; tile += kBcrThreads / 32) {
@@ -195,14 +195,23 @@ __device__ __noinline__ void bcr_gram(const double* Y, int ldy, int n, int nc, d
     const int ca = 8 * ti + lr, cb = 8 * tj + lr;
     const bool va = ca < nc, vb = cb < nc;
     double c0 = 0.0, c1 = 0.0;
-    for (int k0 = 0; k0 < n; k0 += 4) {
-      const bool in = k0 + lk < n;
-      const double av = (in && va) ? Y[(k0 + lk) * ldy + ca] : 0.0;
-      const double bv = (in && vb) ? Y[(k0 + lk) * ldy + cb] : 0.0;
-      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+    const double* pa = Y + lk * ldy + (va ? ca : 0);
+    const double* pb = Y + lk * ldy + (vb ? cb : 0);
+    if (variant != 2)
+    for (int k0 = 0; k0 < n; k0 += 16) {   // four k-steps per round: eight loads in flight, then the dependent DMMA chain
+      double av[4], bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool in = k0 + 4 * u + lk < n;
+        av[u] = (in && va) ? pa[(k0 + 4 * u) * ldy] : 0.0;
+        bv[u] = (in && vb) ? pb[(k0 + 4 * u) * ldy] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(av[u]), "d"(bv[u]));
     }
     const int row = 8 * ti + lr, col = 8 * tj + 2 * lk;
-    if (row < nc) {
+    if (row < nc && variant != 1) {
       if (col <= row) G[row * nc + col] = c0;
       if (col + 1 <= row) G[row * nc + col + 1] = c1;
     }
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(kBcrThreads) bcr_solve_kernel(const double* __
     }
     for (int v = tid; v < nb; v += kBcrThreads) {
       const int col = r0 + v;
-      N[pl.ob + v] = (col < np && !fixed[col]) ? sys[lay.ob + col] : 0.0;
+      N[pl.ob + v] = (col < np && !fixed[col]) ? sys[lay.ob + col] - sys[lay.og + col] : 0.0;   // rhs = Schur part - gradient
     }
   }
   if (cta == 0) {
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(kBcrThreads) bcr_solve_kernel(const double* __
         v = (q <= r) ? sys[sys_index(lay, np + r, np + q)] : 0.0;
         if (q == r) v += mu * fmin(fmax(sys[lay.oD + np + r], 1e-6), 1e32);
         if (fixed[np + r] | fixed[np + q]) v = (q == r) ? 1.0 : 0.0;
-      } else v = fixed[np + q] ? 0.0 : sys[lay.ob + np + q];
+      } else v = fixed[np + q] ? 0.0 : sys[lay.ob + np + q] - sys[lay.og + np + q];
       CC[e] = v;
     }
     for (int a = tid; a < n; a += kBcrThreads) Dout[a] = fmin(fmax(sys[lay.oD + a], 1e-6), 1e32);
@@ -331,8 +340,10 @@ __global__ void __launch_bounds__(kBcrThreads) bcr_solve_kernel(const double* __
       }
       for (int u = tid; u < nb; u += kBcrThreads) N[pl.oy + u] = sR[u * ldr + 2 * nb + m];
       if (lv == 0) stamp();
-      bcr_gram(sR, ldr, nb, ncols, N + pl.oG);
+      bcr_gram(sR, ldr, nb, ncols, N + pl.oG, dbg ? static_cast<int>(dbg[71]) : 0);
+      if (lv == 0) stamp();
       __syncthreads();
+      if (lv == 0) stamp();
       for (int e = tid; e < nacc; e += kBcrThreads) {   // (f,f) lower and (y,f): this node's share of the corner update
         const int r = e / m, q = e - r * m;
         if (r == m || q <= r) sAcc[e] += N[pl.oG + (2 * nb + r) * ncols + 2 * nb + q];

@@ -455,6 +455,9 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
       if (rr < NB) {
         if (cc < NB && cc <= rr) atomicAdd(&S[sys_index(a.lay, c0 + rr, c0 + cc)], c0v);
         if (cc + 1 < NB && cc + 1 <= rr) atomicAdd(&S[sys_index(a.lay, c0 + rr, c0 + cc + 1)], c1v);
+        // diag(J^T J) is accumulated on its own (the LM damping needs it BEFORE the Schur complement touches S)
+        if (cc == rr) atomicAdd(&S[a.lay.oD + c0 + rr], c0v);
+        if (cc + 1 == rr) atomicAdd(&S[a.lay.oD + c0 + rr], c1v);
       }
     }
     if (tid >= kEvalThreads - NB) {   // gradient: the last NB threads

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kHessThreads) pixel_hessian_kernel(const int* 
     if (id < NB * NB) {
       const int a = id / NB, b = id - a * NB;
       if (b <= a) atomicAdd(&sys[sys_index(lay, c0 + a, c0 + b)], acc[e]);
+      if (b == a) atomicAdd(&sys[lay.oD + c0 + a], acc[e]);
     }
   }
   if (threadIdx.x < NB) atomicAdd(&sys[lay.og + c0 + threadIdx.x], gacc);
@@ -238,6 +239,8 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
       if (a < NP) {
         if (b < NP && b <= a) atomicAdd(&sys[sys_index(lay, cp + a, cp + b)], ls * a1[2 * q]);
         if (b + 1 < NP && b + 1 <= a) atomicAdd(&sys[sys_index(lay, cp + a, cp + b + 1)], ls * a1[2 * q + 1]);
+        if (b == a) atomicAdd(&sys[lay.oD + cp + a], ls * a1[2 * q]);               // diag(J^T J), kept apart from S
+        if (b + 1 == a) atomicAdd(&sys[lay.oD + cp + a], ls * a1[2 * q + 1]);
       }
     }
   }
@@ -269,7 +272,10 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
         const int m2 = q - m * (m + 1) / 2;
         const int c0 = acc_b ? ca : cg;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) atomicAdd(&sys[sys_index(lay, c0 + 3 * m + c, c0 + 3 * m2 + c)], val);
+        for (int c = 0; c < 3; ++c) {
+          atomicAdd(&sys[sys_index(lay, c0 + 3 * m + c, c0 + 3 * m2 + c)], val);
+          if (m == m2) atomicAdd(&sys[lay.oD + c0 + 3 * m + c], val);
+        }
       } else if ((id -= 2 * NBB) < 2 * NGB) {
         const bool acc_b = id >= NGB;
         const int q = acc_b ? id - NGB : id;
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
       } else if ((id -= 2 * NGB) < 3) {
         const int ga = (id == 0) ? 0 : 1, gb = (id == 2) ? 1 : 0;
         atomicAdd(&sys[sys_index(lay, o_g + ga, o_g + gb)], val);
+        if (ga == gb) atomicAdd(&sys[lay.oD + o_g + ga], val);
       } else if ((id -= 3) < NP) {
         atomicAdd(&gv[cp + id], val);
       } else if ((id -= NP) < 2 * 3 * KB) {
@@ -313,6 +320,7 @@ __global__ void __launch_bounds__(kManWarps * 32) manifold_hessian_kernel(int nf
 #pragma unroll
     for (int q = 0; q < 6; ++q) s += sJ[warp][q][a] * sJ[warp][q][b];
     atomicAdd(&sys[sys_index(lay, c0 + a, c0 + b)], s);
+    if (a == b) atomicAdd(&sys[lay.oD + c0 + a], s);
   }
   for (int a = lane; a < NB; a += 32) {
     double s = 0;
@@ -322,27 +330,23 @@ __global__ void __launch_bounds__(kManWarps * 32) manifold_hessian_kernel(int nf
   }
 }
 
-// diagH = diag(H), b = -g, cost = sum of the evaluation kernels' per-block partials (fixed order).
-__global__ void diag_cost_kernel(double* sys, SysLayout lay, const double* __restrict__ cp_pix, int n_pix_blocks, const double* __restrict__ cp_imu,
-                                 int n_imu_blocks) {
-  const int n = lay.n;
-  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-    sys[lay.oD + a] = sys[sys_index(lay, a, a)];
-    sys[lay.ob + a] = -sys[lay.og + a];
-  }
-  if (blockIdx.x == 0) {
-    __shared__ double s[256];
-    double c = 0;
-    for (int i = threadIdx.x; i < n_pix_blocks; i += blockDim.x) c += cp_pix[i];
-    for (int i = threadIdx.x; i < n_imu_blocks; i += blockDim.x) c += cp_imu[i];
-    s[threadIdx.x] = c;
+// cost at the linearisation point = sum of the evaluation kernels' per-block partials (fixed order) -> scal[0] of
+// the packed system.  (diag(J^T J) is accumulated by the J^T J kernels themselves, the right-hand side is kept as
+// b_schur - g by every consumer: nothing else has to happen between the J^T J kernels and the Schur complement, so
+// this kernel runs on the side stream next to them.)
+__global__ void cost_kernel(double* sys, SysLayout lay, const double* __restrict__ cp_pix, int n_pix_blocks, const double* __restrict__ cp_imu,
+                            int n_imu_blocks) {
+  __shared__ double s[256];
+  double c = 0;
+  for (int i = threadIdx.x; i < n_pix_blocks; i += blockDim.x) c += cp_pix[i];
+  for (int i = threadIdx.x; i < n_imu_blocks; i += blockDim.x) c += cp_imu[i];
+  s[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
     __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-      if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) { sys[lay.os] = s[0]; sys[lay.os + 1] = 0.0; }
   }
+  if (threadIdx.x == 0) { sys[lay.os] = s[0]; sys[lay.os + 1] = 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -472,7 +476,7 @@ __global__ void densify_kernel(const double* __restrict__ sys, SysLayout lay, co
       if (fixed[i] || fixed[j]) s = (i == j) ? 1.0 : 0.0;
       Lw[e] = s;
     } else {
-      Lw[brow * n + j] = fixed[j] ? 0.0 : sys[lay.ob + j];
+      Lw[brow * n + j] = fixed[j] ? 0.0 : sys[lay.ob + j] - sys[lay.og + j];   // rhs = Schur part - gradient
     }
   }
 }

@@ -20,9 +20,9 @@ t = [buf[1 + i] for i in range(n)]
 print("cfg", cfg, "K", win.knots.shape[0], "beta", ctx.bandwidth(), "stamps", n)
 labels = ["gather"]
 print("total us", (t[-1] - t[0]) / 1e3)
-sub = [round((b - a) / 1e3, 1) for a, b in zip(t[2:7], t[3:8])]
-print("level-0 phase 1 of CTA 0: stage, chol, forward, stores, gram (us):", [round((t[3] - t[2]) / 1e3, 1)] + sub[1:4] + [round((t[8] - t[6]) / 1e3, 1) if False else round((t[7] - t[6]) / 1e3, 1)])
-t = t[:3] + t[7:]
+print("level-0 phase 1 of CTA 0 (us): stage, chol, forward, stores, gram(warp 0), gram barrier, corner share + loop end:",
+      [round((t[i + 1] - t[i]) / 1e3, 2) for i in range(2, 9)])
+t = t[:3] + t[9:]
 d = [round((b - a) / 1e3, 1) for a, b in zip(t[:-1], t[1:])]
 print("work / barrier-wait pairs (us):", list(zip(d[0::2], d[1::2])))
 print("sum work", round(sum(d[0::2]), 1), "sum barrier", round(sum(d[1::2]), 1))

@@ -84,6 +84,28 @@ __global__ void icache_kernel(double* out, long long* cyc, double a, double b, i
   if (threadIdx.x == 0) cyc[0] = t1 - t0;
 }
 
+// FP64 tensor-core op (mma.sync m8n8k4 -> DMMA.8x8x4): dependent-accumulator latency and issue interval with
+// CHAINS independent accumulators, per warp and with 16 warps on the SM (512 FLOP per instruction).
+template <int CHAINS>
+__global__ void dmma_kernel(double* out, long long* cyc, double a, double b, int iters) {
+  double c0[CHAINS], c1[CHAINS];
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) { c0[c] = threadIdx.x + c; c1[c] = 0.5 * c; }
+  __syncthreads();
+  const long long t0 = clk();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[c]), "+d"(c1[c]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) s += c0[c] + c1[c];
+  const long long t1 = clk();
+  out[threadIdx.x] = s;
+  if ((threadIdx.x & 31) == 0) cyc[threadIdx.x >> 5] = t1 - t0;
+}
+
 int main() {
   double* out; long long* cyc;
   cudaMalloc(&out, 1024 * sizeof(double)); cudaMalloc(&cyc, 64 * sizeof(long long));
@@ -94,6 +116,11 @@ int main() {
   dfma_kernel<8><<<1, 32>>>(out, cyc, 1.0000001, 1e-9, it); rd(); printf("DFMA issue interval, 1 warp, 8 ILP : %.2f cycles/instr\n", (double)h[0] / (8.0 * it));
   dfma_kernel<8><<<1, 128>>>(out, cyc, 1.0000001, 1e-9, it); rd(); printf("DFMA 4 warps (one per scheduler)   : %.2f cycles/instr/warp\n", (double)h[0] / (8.0 * it));
   dfma_kernel<8><<<1, 512>>>(out, cyc, 1.0000001, 1e-9, it); rd(); printf("DFMA 16 warps (4 per scheduler)    : %.2f cycles/instr/warp  (=> %.2f cycles per warp-instr per scheduler)\n", (double)h[0] / (8.0 * it), (double)h[0] / (8.0 * it) / 4.0);
+  dmma_kernel<1><<<1, 32>>>(out, cyc, 1e-3, 1e-3, it); rd(); printf("DMMA.8x8x4 dependent latency (1 chain)       : %.2f cycles\n", (double)h[0] / it);
+  dmma_kernel<4><<<1, 32>>>(out, cyc, 1e-3, 1e-3, it); rd(); printf("DMMA.8x8x4 issue interval, 1 warp, 4 chains  : %.2f cycles/instr\n", (double)h[0] / (4.0 * it));
+  dmma_kernel<8><<<1, 32>>>(out, cyc, 1e-3, 1e-3, it); rd(); printf("DMMA.8x8x4 issue interval, 1 warp, 8 chains  : %.2f cycles/instr\n", (double)h[0] / (8.0 * it));
+  dmma_kernel<8><<<1, 128>>>(out, cyc, 1e-3, 1e-3, it); rd(); printf("DMMA.8x8x4 4 warps x 8 chains                : %.2f cycles/instr/warp\n", (double)h[0] / (8.0 * it));
+  dmma_kernel<8><<<1, 512>>>(out, cyc, 1e-3, 1e-3, it); rd(); printf("DMMA.8x8x4 16 warps x 8 chains               : %.2f cycles/instr/warp => %.2f cycles per DMMA per SM (512 FLOP each)\n", (double)h[0] / (8.0 * it), (double)h[0] / (8.0 * it) / 16.0);
   rsqrt_kernel<<<1, 32>>>(out, cyc, 1.5, it); rd(); printf("rsqrt(double)+add dependent        : %.2f cycles\n", (double)h[0] / it);
   lds_kernel<<<1, 32>>>(out, cyc, it, 1); rd(); printf("LDS dependent (pointer chase)      : %.2f cycles\n", (double)h[0] / it);
   shfl_kernel<<<1, 32>>>(out, cyc, it); rd(); printf("SHFL(double)+DADD dependent        : %.2f cycles\n", (double)h[0] / it);
