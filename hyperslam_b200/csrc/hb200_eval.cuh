@@ -409,46 +409,61 @@ struct PixelArgs {
 //     C[m = l/4][n = 2 (l%4) + {0,1}].  This replaced a scalar 3x3-register-tile loop that executed ~9 000
 //     instructions per warp (ncu smsp__inst_executed, profiles/) against ~1 400 for the factor evaluation itself.
 template <int K>
-HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[64][6K+1]*/, double* sr /*[64]*/, int* sb /*[64]*/) {
+HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[128][6K+1]*/, double* sr /*[128]*/, int* sseg /*[66]*/) {
   constexpr int NB = 6 * K, LD = NB + 1, NT = (NB + 7) / 8, NTILES = NT * (NT + 1) / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rows = 2 * cnt;
-  __syncthreads();   // previous use of the scratch is complete
-  if (tid < rows) {
-    const int f = f0 + (tid >> 1);
+  // staging: thread = one factor (two Jacobian rows), 128-bit loads, rows scaled by sqrt(w)
+  int my_base = -1;
+  if (tid < cnt) {
+    const int f = f0 + tid;
     const double sw = sqrt(a.w[f]);
-    const double2* src = reinterpret_cast<const double2*>(a.Jp + static_cast<size_t>(f) * 2 * NB + (tid & 1) * NB);   // rows are 16 B aligned
-    double* dst = sJ + tid * LD;
+    const double2 rr = reinterpret_cast<const double2*>(a.r)[f];
+    my_base = a.idx[f].x;
+    const double2* src = reinterpret_cast<const double2*>(a.Jp + static_cast<size_t>(f) * 2 * NB);   // rows are 16 B aligned
+    double* dst = sJ + 2 * tid * LD;
 #pragma unroll
     for (int e = 0; e < NB / 2; ++e) { const double2 v = src[e]; dst[2 * e] = sw * v.x; dst[2 * e + 1] = sw * v.y; }
-    sr[tid] = sw * a.r[2 * static_cast<size_t>(f) + (tid & 1)];
-    sb[tid] = a.idx[f].x;
+#pragma unroll
+    for (int e = 0; e < NB / 2; ++e) { const double2 v = src[NB / 2 + e]; dst[LD + 2 * e] = sw * v.x; dst[LD + 2 * e + 1] = sw * v.y; }
+    sr[2 * tid] = sw * rr.x; sr[2 * tid + 1] = sw * rr.y;
   }
+  // segments of equal knot base (bound order is sorted by base): factor t starts one iff its base differs from its
+  // predecessor's; positions by ballot + popc (two warps), sseg[j] = first factor of segment j, sseg[nseg] = cnt
+  const int prev = __shfl_up_sync(0xffffffffu, my_base, 1);
+  __shared__ int s_edge[2], s_warp_cnt;
+  if (lane == 31) s_edge[warp] = my_base;
+  __syncthreads();   // (also: previous use of the scratch is complete, staging visible below after the next barrier)
+  const int before = (lane == 0) ? (warp == 0 ? -2 : s_edge[0]) : prev;
+  const bool start = tid < cnt && my_base != before;
+  const unsigned mask = __ballot_sync(0xffffffffu, start);
+  if (warp == 0 && lane == 0) s_warp_cnt = __popc(mask);
   __syncthreads();
+  const int pos = __popc(mask & ((1u << lane) - 1u)) + (warp ? s_warp_cnt : 0);
+  if (start) sseg[pos] = tid;
+  if (tid == 0) sseg[65] = 0;
+  __syncthreads();
+  if (warp == 1 && lane == 0) { const int n = s_warp_cnt + __popc(mask); sseg[n] = cnt; sseg[65] = n; }
+  __syncthreads();
+  const int nseg = sseg[65];
   double* S = a.sys;
   double* g = a.sys + a.lay.og;
-  const int base_lo = sb[0], base_hi = sb[rows - 1];   // bound order is sorted by base
   const int lm = lane >> 2, lk = lane & 3;
-  for (int base = base_lo; base <= base_hi; ++base) {
-    // contiguous row range of this base inside the sub-tile
-    int r_lo = 0, r_hi;
-    while (r_lo < rows && sb[r_lo] < base) ++r_lo;
-    r_hi = r_lo;
-    while (r_hi < rows && sb[r_hi] == base) ++r_hi;
-    if (r_hi == r_lo) continue;
-    const int c0 = 6 * base;
+  for (int j = 0; j < nseg; ++j) {
+    const int r_lo = 2 * sseg[j], r_hi = 2 * sseg[j + 1];
+    const int c0 = 6 * a.idx[f0 + sseg[j]].x;
     for (int tile = warp; tile < NTILES; tile += kEvalThreads / 32) {
       int ti = 0;
       while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
       const int tj = tile - ti * (ti + 1) / 2;
       const int ma = 8 * ti + lm, nb_ = 8 * tj + lm;   // this lane's m (A) and n (B) column of J
       const bool va = ma < NB, vb = nb_ < NB;
+      const double* pa = sJ + lk * LD + (va ? ma : 0);
+      const double* pb = sJ + lk * LD + (vb ? nb_ : 0);
       double c0v = 0.0, c1v = 0.0;
-      for (int k0 = r_lo & ~3; k0 < r_hi; k0 += 4) {
-        const int row = k0 + lk;
-        const bool in = row >= r_lo && row < r_hi;
-        const double av = (in && va) ? sJ[row * LD + ma] : 0.0;
-        const double bv = (in && vb) ? sJ[row * LD + nb_] : 0.0;
+      for (int k0 = r_lo; k0 < r_hi; k0 += 4) {   // rows come in pairs: r_lo, r_hi are even; the tail of a segment is masked
+        const bool in = k0 + lk < r_hi;
+        const double av = (in && va) ? pa[k0 * LD] : 0.0;
+        const double bv = (in && vb) ? pb[k0 * LD] : 0.0;
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0v), "+d"(c1v) : "d"(av), "d"(bv));
       }
       const int rr = 8 * ti + lm, cc = 8 * tj + 2 * lk;
@@ -462,9 +477,9 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
     }
     if (tid >= kEvalThreads - NB) {   // gradient: the last NB threads
       const int c = tid - (kEvalThreads - NB);
-      double gacc = 0.0;
-      for (int row = r_lo; row < r_hi; ++row) gacc += sJ[row * LD + c] * sr[row];
-      atomicAdd(&g[c0 + c], gacc);
+      double g0 = 0.0, g1 = 0.0;
+      for (int row = r_lo; row < r_hi; row += 2) { g0 += sJ[row * LD + c] * sr[row]; g1 += sJ[(row + 1) * LD + c] * sr[row + 1]; }
+      atomicAdd(&g[c0 + c], g0 + g1);
     }
   }
 }
@@ -476,10 +491,10 @@ HB_DI void pixel_eval_body(const PixelArgs& a, const Basis& B, int bid) {
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_red[2];
   __shared__ double s_cost[kEvalThreads / 32];
-  // scratch of the fused J^T J accumulation (32 factors = 64 rows at a time)
-  __shared__ double s_J[FUSE ? 64 * (6 * K + 1) : 1];
-  __shared__ double s_r[FUSE ? 64 : 1];
-  __shared__ int s_b[FUSE ? 64 : 1];
+  // scratch of the fused J^T J accumulation (the CTA's 64 factors = 128 Jacobian rows in one pass)
+  __shared__ double s_J[FUSE ? 128 * (6 * K + 1) : 1];
+  __shared__ double s_r[FUSE ? 128 : 1];
+  __shared__ int s_b[FUSE ? 66 : 1];
   const int f = bid * kEvalThreads + threadIdx.x;
   const bool active = f < a.n;
   int4 id = make_int4(0, 0, 0, 0);
@@ -517,11 +532,10 @@ HB_DI void pixel_eval_body(const PixelArgs& a, const Basis& B, int bid) {
     a.cost_partial[bid] = c;
   }
   if (FUSE && a.sys != nullptr) {
-    // fused normal equations: this CTA's factors, two sub-tiles of 32 (residuals / Jacobians were
-    // written above; the barrier in the cost reduction ordered them for the whole CTA)
+    // fused normal equations of this CTA's factors (residuals / Jacobians were written above; the barrier in the
+    // cost reduction ordered them for the whole CTA)
     const int f_lo = bid * kEvalThreads;
-    const int total = min(kEvalThreads, a.n - f_lo);
-    for (int off = 0; off < total; off += 32) cta_pixel_hessian<K>(a, f_lo + off, min(32, total - off), s_J, s_r, s_b);
+    cta_pixel_hessian<K>(a, f_lo, min(kEvalThreads, a.n - f_lo), s_J, s_r, s_b);
   }
 }
 
