@@ -18,6 +18,7 @@
 #include "../../include/hyperb200.h"
 #include "hb200_bcr.cuh"
 #include "hb200_calib.cuh"
+#include "hb200_window.cuh"
 
 using namespace hb;
 
@@ -54,6 +55,20 @@ struct DevBuf {
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  // capacity for n elements, the first `keep` of them preserved (amortised doubling; device-to-device copy on `stream`)
+  cudaError_t grow(size_t n, size_t keep, cudaStream_t stream) {
+    if (n <= cap) return cudaSuccess;
+    const size_t ncap = std::max<size_t>(n, cap + cap / 2 + 16);
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && keep) e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (p) cudaFree(p);
+    p = q; cap = ncap;
+    return e;
+  }
+  void swap(DevBuf& o) { std::swap(p, o.p); std::swap(cap, o.cap); }
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -191,6 +206,14 @@ struct hb200_ctx {
   DevBuf<long long> band_dbg;   // optional phase timings of band_solve_kernel (HB200_BAND_TIMING=1)
   bool bound = false;
 
+  // device-side window bookkeeping (hb200_append_* / hb200_slide): the factor lists live on the device only, the host
+  // mirrors above are refreshed on demand (sync_host_mirrors)
+  bool device_managed = false;
+  DevBuf<double> alt_stamp, alt_meas, alt_lms, alt_knots;
+  DevBuf<double2> alt_pixel;
+  DevBuf<int4> alt_idx;
+  DevBuf<int> w_keep, w_pos, w_lkeep, w_lpos, w_cnt, w_scal;
+  DevBuf<unsigned long long> w_last;
   // outputs
   DevBuf<double> v_r, v_Jp, v_Jl, i_r, i_Jp, i_wg, i_wa, i_Jg, m_r, m_Jp;
   DevBuf<double> cp_pix[2], cp_imu[2];
@@ -1072,8 +1095,112 @@ int hb200_set_inertial_factors(hb200_ctx* c, int n, const double* stamp, const d
   return 0;
 }
 
+}  // extern "C"
+
+namespace {
+// After hb200_append_* / hb200_slide the factor lists exist on the device only (bound order == user order from
+// then on).  The host mirrors the copy-out calls and a later full hb200_bind need are refreshed here, on demand.
+int sync_host_mirrors(hb200_ctx* c) {
+  if (!c->device_managed) return 0;
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t Nv = c->Nv, Ni = c->Ni;
+  c->h_p_stamp.resize(Nv); c->h_p_pixel.resize(2 * Nv); c->h_p_cam.resize(Nv); c->h_p_lm.resize(Nv);
+  c->h_v_idx.resize(Nv); c->h_i_idx.resize(Ni); c->h_i_stamp.resize(Ni); c->h_i_meas.resize(6 * Ni);
+  if (Nv) {
+    HB_CUDA(cudaMemcpyAsync(c->h_p_stamp.data(), c->v_stamp.p, sizeof(double) * Nv, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->h_p_pixel.data(), c->v_pixel.p, sizeof(double) * 2 * Nv, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->h_v_idx.data(), c->v_idx.p, sizeof(int4) * Nv, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (Ni) {
+    HB_CUDA(cudaMemcpyAsync(c->h_i_stamp.data(), c->i_stamp.p, sizeof(double) * Ni, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->h_i_meas.data(), c->i_meas.p, sizeof(double) * 6 * Ni, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->h_i_idx.data(), c->i_idx.p, sizeof(int4) * Ni, cudaMemcpyDeviceToHost, c->stream));
+  }
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t f = 0; f < Nv; ++f) { c->h_p_cam[f] = c->h_v_idx[f].z; c->h_p_lm[f] = c->h_v_idx[f].y; }
+  c->h_v_stamp = c->h_p_stamp; c->h_v_pixel = c->h_p_pixel; c->h_v_cam = c->h_p_cam; c->h_v_lm = c->h_p_lm; c->h_v_z.assign(Nv, 0.0);
+  c->v_perm.resize(Nv); std::iota(c->v_perm.begin(), c->v_perm.end(), 0);
+  c->i_perm.resize(Ni); std::iota(c->i_perm.begin(), c->i_perm.end(), 0);
+  c->Np = static_cast<int>(Nv);
+  c->device_managed = false;
+  return 0;
+}
+
+// Incidence lists of the device-resident factor lists (landmark CSR, inertial runs, segment offsets, longest
+// track) by counting + scan kernels, then everything hb200_bind derives from them.  One small read-back.
+int rebuild_incidence_device(hb200_ctx* c) {
+  const int Nv = c->Nv, Ni = c->Ni, L = c->L, K = c->K;
+  c->nseg = K - c->k + 1;
+  HB_CUDA(c->w_scal.ensure(8));
+  HB_CUDA(cudaMemsetAsync(c->w_scal.p, 0, 8 * sizeof(int), c->stream));
+  HB_CUDA(c->lm_off.ensure(static_cast<size_t>(L) + 2)); HB_CUDA(c->lm_obs.ensure(std::max(Nv, 1)));
+  HB_CUDA(c->seg_off.ensure(static_cast<size_t>(c->nseg) + 2)); HB_CUDA(c->run_off.ensure(static_cast<size_t>(Ni) + 2));
+  HB_CUDA(c->w_cnt.ensure(static_cast<size_t>(std::max(std::max(L, c->nseg), 1)) + 1));
+  HB_CUDA(c->w_keep.ensure(std::max(std::max(Nv, Ni), 1))); HB_CUDA(c->w_pos.ensure(std::max(std::max(Nv, Ni), 1)));
+  // landmark CSR
+  HB_CUDA(cudaMemsetAsync(c->w_cnt.p, 0, sizeof(int) * (static_cast<size_t>(L) + 1), c->stream));
+  if (Nv) { count_kernel<<<(Nv + 255) / 256, 256, 0, c->stream>>>(Nv, c->v_idx.p, 1, c->w_cnt.p); HB_LAUNCH(c, "count_kernel"); }
+  scan_kernel<<<1, 1024, 0, c->stream>>>(c->w_cnt.p, L + 1, c->lm_off.p, c->w_scal.p + 0);
+  HB_LAUNCH(c, "scan_kernel");
+  HB_CUDA(cudaMemsetAsync(c->w_cnt.p, 0, sizeof(int) * (static_cast<size_t>(L) + 1), c->stream));
+  if (Nv) {
+    csr_fill_kernel<<<(Nv + 255) / 256, 256, 0, c->stream>>>(Nv, c->v_idx.p, c->lm_off.p, c->w_cnt.p, c->lm_obs.p);
+    HB_LAUNCH(c, "csr_fill_kernel");
+    csr_sort_kernel<<<(L + 127) / 128, 128, 0, c->stream>>>(L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->k, c->w_scal.p + 1);
+    HB_LAUNCH(c, "csr_sort_kernel");
+  }
+  // segment offsets of the visual list
+  HB_CUDA(cudaMemsetAsync(c->w_cnt.p, 0, sizeof(int) * (static_cast<size_t>(c->nseg) + 1), c->stream));
+  if (Nv) { count_kernel<<<(Nv + 255) / 256, 256, 0, c->stream>>>(Nv, c->v_idx.p, 0, c->w_cnt.p); HB_LAUNCH(c, "count_kernel"); }
+  scan_kernel<<<1, 1024, 0, c->stream>>>(c->w_cnt.p, c->nseg + 1, c->seg_off.p, c->w_scal.p + 2);
+  HB_LAUNCH(c, "scan_kernel");
+  // inertial runs
+  if (Ni) {
+    run_flag_kernel<<<(Ni + 255) / 256, 256, 0, c->stream>>>(Ni, c->i_idx.p, c->w_keep.p);
+    HB_LAUNCH(c, "run_flag_kernel");
+    scan_kernel<<<1, 1024, 0, c->stream>>>(c->w_keep.p, Ni, c->w_pos.p, c->w_scal.p + 3);
+    HB_LAUNCH(c, "scan_kernel");
+  }
+  int h[8];
+  HB_CUDA(cudaMemcpyAsync(h, c->w_scal.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->max_rows = std::max(6 * c->k, h[1]);
+  c->nruns = Ni ? h[3] : 0;
+  if (Ni) { run_fill_kernel<<<(Ni + 255) / 256, 256, 0, c->stream>>>(Ni, c->w_keep.p, c->w_pos.p, c->nruns, c->run_off.p); HB_LAUNCH(c, "run_fill_kernel"); }
+  else { const int z = 0; HB_CUDA(cudaMemcpyAsync(c->run_off.p, &z, sizeof(int), cudaMemcpyHostToDevice, c->stream)); }
+  if (2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double) > 200 * 1024) return fail(-6, "landmark track spans %d control-point dofs; exceeds the Schur kernel's shared-memory tile", c->max_rows);
+  // outputs and launch shapes (as hb200_bind)
+  const size_t k = c->k;
+  HB_CUDA(c->v_z.ensure(std::max(Nv, 1))); HB_CUDA(c->v_w.ensure(std::max(Nv, 1)));
+  HB_CUDA(c->v_r.ensure(2 * static_cast<size_t>(std::max(Nv, 1)))); HB_CUDA(c->v_Jp.ensure(12 * k * std::max(Nv, 1))); HB_CUDA(c->v_Jl.ensure(6 * static_cast<size_t>(std::max(Nv, 1))));
+  HB_CUDA(c->i_r.ensure(6 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_Jp.ensure(36 * k * std::max(Ni, 1)));
+  HB_CUDA(c->i_wg.ensure(4 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_wa.ensure(4 * static_cast<size_t>(std::max(Ni, 1)))); HB_CUDA(c->i_Jg.ensure(12 * static_cast<size_t>(std::max(Ni, 1))));
+  c->n_pix_blocks = (Nv + kEvalThreads - 1) / kEvalThreads;
+  c->n_imu_blocks = (Ni + kEvalThreads - 1) / kEvalThreads;
+  c->n_man_blocks = 0;
+  for (int s2 = 0; s2 < 2; ++s2) { HB_CUDA(c->cp_pix[s2].ensure(std::max(c->n_pix_blocks, 1))); HB_CUDA(c->cp_imu[s2].ensure(std::max(c->n_imu_blocks, 1))); }
+  if (c->max_rows * 6 * sizeof(double) > 48 * 1024) {
+    const int smem = static_cast<int>(2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double));
+    HB_CUDA(cudaFuncSetAttribute(schur_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HB_CUDA(cudaFuncSetAttribute(schur_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  int rc = update_fixed(c);
+  if (rc) return rc;
+  if ((rc = ensure_system(c))) return rc;
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->bound = true;
+  c->device_managed = true;
+  c->invalidate();
+  c->have_snapshot = false;
+  return sync_layout(c);
+}
+}  // namespace
+
+extern "C" {
+
 int hb200_bind(hb200_ctx* c, int* num_invalid) {
   if (!c) return fail(-1, "null context");
+  { const int rs = sync_host_mirrors(c); if (rs) return rs; }
   if (c->K == 0) return fail(-2, "spline not set");
   if (c->Ni && (c->Kbg == 0 || c->Kba == 0)) return fail(-2, "bias splines not set");
   if (c->Nv && (c->C == 0 || c->L == 0)) return fail(-2, "cameras / landmarks not set");
@@ -1209,6 +1336,7 @@ int hb200_bind(hb200_ctx* c, int* num_invalid) {
 
 int hb200_get_index_maps(hb200_ctx* c, int* pixel_base, int* inertial_base, int* gyro_bias_base, int* accel_bias_base) {
   if (!c || !c->bound) return fail(-2, "not bound");
+  { const int rs = sync_host_mirrors(c); if (rs) return rs; }
   for (int p = 0; p < c->Nv; ++p) if (pixel_base && c->v_perm[p] < c->Np) pixel_base[c->v_perm[p]] = c->h_v_idx[p].x;
   for (int p = 0; p < c->Ni; ++p) {
     const int u = c->i_perm[p];
@@ -1234,6 +1362,7 @@ int hb200_evaluate(hb200_ctx* c, int flags) {
 
 int hb200_get_pixel_outputs(hb200_ctx* c, double* r, double* Jp, double* Jl) {
   if (!c || !c->bound) return fail(-2, "not bound");
+  { const int rs = sync_host_mirrors(c); if (rs) return rs; }
   HB_CUDA(cudaSetDevice(c->device));
   const size_t N = c->Nv, w = 12 * static_cast<size_t>(c->k);
   std::vector<double> tr(2 * N), tJ(Jp ? w * N : 0), tl(Jl ? 6 * N : 0);
@@ -1286,6 +1415,7 @@ int hb200_get_manifold_outputs(hb200_ctx* c, double* r, double* Jp) {
 
 int hb200_get_inertial_outputs(hb200_ctx* c, double* r, double* Jp, double* wg, double* wa, double* Jg) {
   if (!c || !c->bound) return fail(-2, "not bound");
+  { const int rs = sync_host_mirrors(c); if (rs) return rs; }
   HB_CUDA(cudaSetDevice(c->device));
   const size_t N = c->Ni, w = 36 * static_cast<size_t>(c->k);
   std::vector<double> tr(6 * N), tJ(Jp ? w * N : 0), tg(wg ? 4 * N : 0), ta(wa ? 4 * N : 0), tG(Jg ? 12 * N : 0);
@@ -1886,6 +2016,215 @@ int hb200_get_state(hb200_ctx* c, double* knots, double* gyro, double* accel, do
   if (gravity) HB_CUDA(cudaMemcpyAsync(gravity, c->grav[0].p, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
   if (landmarks && c->L) HB_CUDA(cudaMemcpyAsync(landmarks, c->lms[0].p, sizeof(double) * 3 * c->L, cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- device-side sliding-window bookkeeping (hb200_window.cuh) -----------------------------------------------
+namespace {
+int check_device_window(hb200_ctx* c) {
+  if (!c) return fail(-1, "null context");
+  if (!c->bound) return fail(-2, "bind the window first (hb200_bind)");
+  if (c->Nb || c->Nm) return fail(-4, "device-side window bookkeeping covers pixel and inertial factors (bearing / manifold lists must be empty)");
+  return 0;
+}
+}  // namespace
+
+int hb200_append_knots(hb200_ctx* c, int count) {
+  int rc = check_device_window(c);
+  if (rc) return rc;
+  if (count <= 0) return fail(-1, "count must be positive");
+  HB_CUDA(cudaSetDevice(c->device));
+  const int K = c->K;
+  for (int s2 = 0; s2 < 2; ++s2) {
+    HB_CUDA(c->knots[s2].grow(8 * static_cast<size_t>(K + count), s2 == 0 ? 8 * static_cast<size_t>(K) : 0, c->stream));
+    HB_CUDA(c->tab[s2].ensure(static_cast<size_t>(K + count) * kTabStride));
+  }
+  append_knots_kernel<<<1, 32, 0, c->stream>>>(K, count, c->knots[0].p);
+  HB_LAUNCH(c, "append_knots_kernel");
+  std::vector<double> tail(8 * static_cast<size_t>(count));
+  HB_CUDA(cudaMemcpyAsync(tail.data(), c->knots[0].p + 8 * static_cast<size_t>(K), sizeof(double) * tail.size(), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < count; ++i) { c->h_knot_stamp.push_back(tail[8 * i + 7]); c->h_knot_const.push_back(0); }
+  c->K = K + count;
+  if ((rc = update_fixed(c))) return rc;
+  c->nseg = c->K - c->k + 1;
+  HB_CUDA(c->seg_off.grow(static_cast<size_t>(c->nseg) + 2, static_cast<size_t>(c->nseg - count) + 1, c->stream));
+  {   // the new segments hold no visual factor yet: their offsets equal the list length
+    std::vector<int> fill(count, c->Nv);
+    HB_CUDA(cudaMemcpyAsync(c->seg_off.p + (c->nseg - count) + 1, fill.data(), sizeof(int) * count, cudaMemcpyHostToDevice, c->stream));
+  }
+  if ((rc = ensure_system(c))) return rc;
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->invalidate(); c->have_snapshot = false;
+  return sync_layout(c);
+}
+
+int hb200_append_landmarks(hb200_ctx* c, int n, const double* xyz) {
+  int rc = check_device_window(c);
+  if (rc) return rc;
+  if (n <= 0 || !xyz) return fail(-1, "invalid landmarks");
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t L = c->L;
+  for (int s2 = 0; s2 < 2; ++s2) HB_CUDA(c->lms[s2].grow(3 * (L + n), s2 == 0 ? 3 * L : 0, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->lms[0].p + 3 * L, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->L = static_cast<int>(L) + n;
+  return rebuild_incidence_device(c);
+}
+
+int hb200_append_pixel_factors(hb200_ctx* c, int n, const double* stamp, const int* camera, const int* landmark, const double* pixel) {
+  int rc = check_device_window(c);
+  if (rc) return rc;
+  if (n <= 0 || !stamp || !camera || !landmark || !pixel) return fail(-1, "invalid pixel factors");
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t Nv = c->Nv;
+  HB_CUDA(c->v_stamp.grow(Nv + n, Nv, c->stream)); HB_CUDA(c->v_pixel.grow(2 * (Nv + n), 2 * Nv, c->stream)); HB_CUDA(c->v_idx.grow(Nv + n, Nv, c->stream));
+  DevBuf<int> d_cam, d_lm;
+  HB_CUDA(d_cam.ensure(n)); HB_CUDA(d_lm.ensure(n));
+  HB_CUDA(c->d_invalid.ensure(2));
+  HB_CUDA(cudaMemsetAsync(c->d_invalid.p, 0, 2 * sizeof(int), c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->v_stamp.p + Nv, stamp, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->v_pixel.p + 2 * Nv, pixel, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(d_cam.p, camera, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(d_lm.p, landmark, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  bind_pixel_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->v_stamp.p + Nv, d_cam.p, d_lm.p, c->knots[0].p, c->K, c->k, c->C, c->L, c->v_idx.p + Nv, c->d_invalid.p);
+  HB_LAUNCH(c, "bind_pixel_kernel");
+  tail_sorted_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(static_cast<int>(Nv), n, c->v_idx.p, c->d_invalid.p + 1);
+  HB_LAUNCH(c, "tail_sorted_kernel");
+  int bad[2] = {0, 0};
+  HB_CUDA(cudaMemcpyAsync(bad, c->d_invalid.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  if (bad[0]) return fail(2, "%d appended factor(s) reference a stamp outside the spline's valid range or an invalid camera / landmark", bad[0]);
+  if (bad[1]) return fail(3, "appended factors must arrive in stamp order (%d fall before the end of the list): use hb200_set_pixel_factors + hb200_bind", bad[1]);
+  c->Nv = static_cast<int>(Nv) + n; c->Np = c->Nv;
+  return rebuild_incidence_device(c);
+}
+
+int hb200_append_inertial_factors(hb200_ctx* c, int n, const double* stamp, const double* meas) {
+  int rc = check_device_window(c);
+  if (rc) return rc;
+  if (n <= 0 || !stamp || !meas) return fail(-1, "invalid inertial factors");
+  if (!c->have_imu || c->Kbg == 0 || c->Kba == 0) return fail(-2, "inertial factors need IMU calibration and bias splines");
+  HB_CUDA(cudaSetDevice(c->device));
+  const size_t Ni = c->Ni;
+  HB_CUDA(c->i_stamp.grow(Ni + n, Ni, c->stream)); HB_CUDA(c->i_meas.grow(6 * (Ni + n), 6 * Ni, c->stream)); HB_CUDA(c->i_idx.grow(Ni + n, Ni, c->stream));
+  HB_CUDA(c->d_invalid.ensure(2));
+  HB_CUDA(cudaMemsetAsync(c->d_invalid.p, 0, 2 * sizeof(int), c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->i_stamp.p + Ni, stamp, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(c->i_meas.p + 6 * Ni, meas, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, c->stream));
+  bind_inertial_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->i_stamp.p + Ni, c->knots[0].p, c->K, c->k, c->bg[0].p, c->Kbg, c->ba[0].p, c->Kba, c->kb,
+                                                             c->i_idx.p + Ni, c->d_invalid.p);
+  HB_LAUNCH(c, "bind_inertial_kernel");
+  tail_sorted_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(static_cast<int>(Ni), n, c->i_idx.p, c->d_invalid.p + 1);
+  HB_LAUNCH(c, "tail_sorted_kernel");
+  int bad[2] = {0, 0};
+  HB_CUDA(cudaMemcpyAsync(bad, c->d_invalid.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  if (bad[0]) return fail(2, "%d appended factor(s) reference a stamp outside the state or bias splines' valid range", bad[0]);
+  if (bad[1]) return fail(3, "appended factors must arrive in stamp order (%d fall before the end of the list): use hb200_set_inertial_factors + hb200_bind", bad[1]);
+  c->Ni = static_cast<int>(Ni) + n;
+  return rebuild_incidence_device(c);
+}
+
+int hb200_slide(hb200_ctx* c, double lower_bound, int flags, hb200_slide_stats* stats) {
+  int rc = check_device_window(c);
+  if (rc) return rc;
+  HB_CUDA(cudaSetDevice(c->device));
+  const int Nv = c->Nv, Ni = c->Ni, L = c->L, K = c->K;
+  // knot index of the last state element at or before the lower bound; the window keeps `left padding` elements in
+  // front of the one that starts the lower bound's interval (reference optimizer.cpp:289: prev(upper_bound(lower), left_padding))
+  int ub = static_cast<int>(std::upper_bound(c->h_knot_stamp.begin(), c->h_knot_stamp.end(), lower_bound) - c->h_knot_stamp.begin());
+  const int begin = std::max(0, ub - 1 - (c->k - 1) / 2);
+  const int last_const = ub - 1;   // knots 0 .. last_const have stamp <= lower bound
+  HB_CUDA(c->w_scal.ensure(8));
+  int init[8] = {0, 0, 0, 0x7fffffff, 0x7fffffff, 0, 0, 0};   // [L_new, Nv_new, Ni_new, min base visual, min base inertial]
+  HB_CUDA(cudaMemcpyAsync(c->w_scal.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(c->w_last.ensure(std::max(L, 1))); HB_CUDA(c->w_lkeep.ensure(std::max(L, 1) + 1)); HB_CUDA(c->w_lpos.ensure(std::max(L, 1) + 1));
+  HB_CUDA(c->w_keep.ensure(std::max(std::max(Nv, Ni), 1))); HB_CUDA(c->w_pos.ensure(std::max(std::max(Nv, Ni), 1)));
+  DevBuf<int> i_keep, i_pos;
+  HB_CUDA(i_keep.ensure(std::max(Ni, 1))); HB_CUDA(i_pos.ensure(std::max(Ni, 1)));
+  HB_CUDA(cudaMemsetAsync(c->w_last.p, 0, sizeof(unsigned long long) * std::max(L, 1), c->stream));
+  if (Nv) { landmark_last_stamp_kernel<<<(Nv + 255) / 256, 256, 0, c->stream>>>(Nv, c->v_stamp.p, c->v_idx.p, c->w_last.p); HB_LAUNCH(c, "landmark_last_stamp_kernel"); }
+  if (L) {
+    landmark_keep_kernel<<<(L + 255) / 256, 256, 0, c->stream>>>(L, c->w_last.p, lower_bound, c->w_lkeep.p);
+    HB_LAUNCH(c, "landmark_keep_kernel");
+    scan_kernel<<<1, 1024, 0, c->stream>>>(c->w_lkeep.p, L, c->w_lpos.p, c->w_scal.p + 0);
+    HB_LAUNCH(c, "scan_kernel");
+  }
+  if (Nv) {
+    visual_keep_kernel<<<(Nv + 255) / 256, 256, 0, c->stream>>>(Nv, c->v_idx.p, c->w_lkeep.p, c->w_keep.p, c->w_scal.p + 3);
+    HB_LAUNCH(c, "visual_keep_kernel");
+    scan_kernel<<<1, 1024, 0, c->stream>>>(c->w_keep.p, Nv, c->w_pos.p, c->w_scal.p + 1);
+    HB_LAUNCH(c, "scan_kernel");
+  }
+  if (Ni) {
+    inertial_keep_kernel<<<(Ni + 255) / 256, 256, 0, c->stream>>>(Ni, c->i_idx.p, c->k, (flags & HB200_SLIDE_DROP_INERTIAL) ? last_const : -1, i_keep.p, c->w_scal.p + 4);
+    HB_LAUNCH(c, "inertial_keep_kernel");
+    scan_kernel<<<1, 1024, 0, c->stream>>>(i_keep.p, Ni, i_pos.p, c->w_scal.p + 2);
+    HB_LAUNCH(c, "scan_kernel");
+  }
+  int h[8];
+  HB_CUDA(cudaMemcpyAsync(h, c->w_scal.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  const int L_new = L ? h[0] : 0, Nv_new = Nv ? h[1] : 0, Ni_new = Ni ? h[2] : 0;
+  // state elements in front of `begin` go once no residual touches them (reference optimizer.cpp:331-341)
+  int shift = std::min(begin, std::min(h[3], h[4]));
+  shift = std::max(0, std::min(shift, K - c->k));
+  const int K_new = K - shift;
+  // compaction into the alternate buffers, then swap
+  HB_CUDA(c->alt_stamp.ensure(std::max(std::max(Nv_new, Ni_new), 1))); HB_CUDA(c->alt_idx.ensure(std::max(std::max(Nv_new, Ni_new), 1)));
+  HB_CUDA(c->alt_pixel.ensure(std::max(Nv_new, 1)));
+  if (Nv) {
+    compact_visual_kernel<<<(Nv + 255) / 256, 256, 0, c->stream>>>(Nv, c->w_keep.p, c->w_pos.p, c->w_lpos.p, shift, c->v_stamp.p, reinterpret_cast<const double2*>(c->v_pixel.p),
+                                                                  c->v_idx.p, c->alt_stamp.p, c->alt_pixel.p, c->alt_idx.p);
+    HB_LAUNCH(c, "compact_visual_kernel");
+    // (v_pixel is a DevBuf<double>: copy the compacted pairs back instead of swapping differently typed buffers)
+    HB_CUDA(cudaMemcpyAsync(c->v_pixel.p, c->alt_pixel.p, sizeof(double2) * Nv_new, cudaMemcpyDeviceToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->v_stamp.p, c->alt_stamp.p, sizeof(double) * Nv_new, cudaMemcpyDeviceToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->v_idx.p, c->alt_idx.p, sizeof(int4) * Nv_new, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (Ni) {
+    HB_CUDA(c->alt_meas.ensure(6 * static_cast<size_t>(std::max(Ni_new, 1))));
+    compact_inertial_kernel<<<(Ni + 255) / 256, 256, 0, c->stream>>>(Ni, i_keep.p, i_pos.p, shift, c->i_stamp.p, c->i_meas.p, c->i_idx.p, c->alt_stamp.p, c->alt_meas.p, c->alt_idx.p);
+    HB_LAUNCH(c, "compact_inertial_kernel");
+    HB_CUDA(cudaMemcpyAsync(c->i_stamp.p, c->alt_stamp.p, sizeof(double) * Ni_new, cudaMemcpyDeviceToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->i_meas.p, c->alt_meas.p, sizeof(double) * 6 * Ni_new, cudaMemcpyDeviceToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->i_idx.p, c->alt_idx.p, sizeof(int4) * Ni_new, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (L) {
+    HB_CUDA(c->alt_lms.ensure(3 * static_cast<size_t>(std::max(L_new, 1))));
+    compact_landmarks_kernel<<<(L + 255) / 256, 256, 0, c->stream>>>(L, c->w_lkeep.p, c->w_lpos.p, c->lms[0].p, c->alt_lms.p);
+    HB_LAUNCH(c, "compact_landmarks_kernel");
+    HB_CUDA(cudaMemcpyAsync(c->lms[0].p, c->alt_lms.p, sizeof(double) * 3 * L_new, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (shift) {
+    HB_CUDA(c->alt_knots.ensure(8 * static_cast<size_t>(K_new)));
+    shift_knots_kernel<<<(8 * K_new + 255) / 256, 256, 0, c->stream>>>(K_new, shift, c->knots[0].p, c->alt_knots.p);
+    HB_LAUNCH(c, "shift_knots_kernel");
+    HB_CUDA(cudaMemcpyAsync(c->knots[0].p, c->alt_knots.p, sizeof(double) * 8 * K_new, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  // host bookkeeping: sizes, stamps, constancy (elements at or before the lower bound: reference optimizer.cpp:322-328;
+  // gravity once the window no longer covers the whole state range: reference abstract.cpp:57-61)
+  c->h_knot_stamp.erase(c->h_knot_stamp.begin(), c->h_knot_stamp.begin() + shift);
+  c->h_knot_const.assign(K_new, 0);
+  for (int j = 0; j < K_new; ++j) c->h_knot_const[j] = c->h_knot_stamp[j] <= lower_bound ? 1 : 0;
+  if (ub > 0) c->gravity_const = 1;
+  c->K = K_new; c->L = L_new; c->Nv = Nv_new; c->Np = Nv_new; c->Ni = Ni_new;
+  if (stats) {
+    stats->knots_dropped = shift; stats->knots_constant = std::max(0, ub - shift); stats->landmarks_dropped = L - L_new;
+    stats->visual_factors_dropped = Nv - Nv_new; stats->inertial_factors_dropped = Ni - Ni_new;
+    stats->knots = K_new; stats->landmarks = L_new; stats->visual_factors = Nv_new; stats->inertial_factors = Ni_new;
+  }
+  return rebuild_incidence_device(c);
+}
+
+int hb200_window_sizes(hb200_ctx* c, int* knots, int* landmarks, int* visual_factors, int* inertial_factors) {
+  if (!c) return fail(-1, "null context");
+  if (knots) *knots = c->K;
+  if (landmarks) *landmarks = c->L;
+  if (visual_factors) *visual_factors = c->Nv;
+  if (inertial_factors) *inertial_factors = c->Ni;
   return 0;
 }
 

@@ -25,6 +25,14 @@ class Options(C.Structure):
                 ("nccl_comm", C.c_void_p), ("nranks", C.c_int), ("rank", C.c_int)]
 
 
+class SlideStats(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("knots_dropped", "knots_constant", "landmarks_dropped", "visual_factors_dropped", "inertial_factors_dropped",
+                                       "knots", "landmarks", "visual_factors", "inertial_factors")]
+
+
+SLIDE_DROP_INERTIAL = 1
+
+
 class Iteration(C.Structure):
     _fields_ = [("cost", C.c_double), ("cost_new", C.c_double), ("model_change", C.c_double), ("rho", C.c_double),
                 ("radius", C.c_double), ("accepted", C.c_int), ("spd", C.c_int)]
@@ -45,6 +53,8 @@ EXPORTS = [
     "hb200_ingest_stereo", "hb200_comm_unique_id", "hb200_comm_init_rank", "hb200_set_nccl_comm", "hb200_peer_handle",
     "hb200_peer_connect", "hb200_peer_disconnect", "hb200_comm_info",
     "hb200_get_bandwidth", "hb200_set_min_bandwidth", "hb200_measure_fp64_peak", "hb200_set_reference_quirks",
+    "hb200_append_knots", "hb200_append_landmarks", "hb200_append_pixel_factors", "hb200_append_inertial_factors", "hb200_slide",
+    "hb200_window_sizes",
 ]
 
 _lib = None
@@ -200,6 +210,41 @@ class Context:
         self.set_manifold_factors(w.m_stamp, w.m_sensor, w.m_pose)
         self.bind()
         self.set_constant(w.knot_const, w.gravity_const, w.bias_const)
+
+    # ---- device-side sliding-window bookkeeping ------------------------------------------------------
+    def _refresh_sizes(self):
+        v = [C.c_int(0) for _ in range(4)]
+        self._check(self.lib.hb200_window_sizes(self.h, *[C.byref(x) for x in v]))
+        self.K, self.L, self.Nv, self.Ni = (x.value for x in v)
+
+    def append_knots(self, count=1):
+        self._check(self.lib.hb200_append_knots(self.h, int(count)))
+        self._refresh_sizes()
+
+    def append_landmarks(self, xyz):
+        xyz = _f64(xyz).reshape(-1, 3)
+        if xyz.shape[0]:
+            self._check(self.lib.hb200_append_landmarks(self.h, xyz.shape[0], _d(xyz)))
+            self._refresh_sizes()
+
+    def append_pixel_factors(self, stamp, cam, lm, pixel):
+        stamp, pixel = _f64(stamp), _f64(pixel)
+        cam, lm = np.ascontiguousarray(cam, dtype=np.int32), np.ascontiguousarray(lm, dtype=np.int32)
+        if stamp.size:
+            self._check(self.lib.hb200_append_pixel_factors(self.h, stamp.size, _d(stamp), _i(cam), _i(lm), _d(pixel)))
+            self._refresh_sizes()
+
+    def append_inertial_factors(self, stamp, meas):
+        stamp, meas = _f64(stamp), _f64(meas)
+        if stamp.size:
+            self._check(self.lib.hb200_append_inertial_factors(self.h, stamp.size, _d(stamp), _d(meas)))
+            self._refresh_sizes()
+
+    def slide(self, lower_bound, drop_inertial=True):
+        st = SlideStats()
+        self._check(self.lib.hb200_slide(self.h, C.c_double(lower_bound), SLIDE_DROP_INERTIAL if drop_inertial else 0, C.byref(st)))
+        self._refresh_sizes()
+        return {n: getattr(st, n) for n, _ in SlideStats._fields_}
 
     def index_maps(self):
         vb = np.zeros(self.Nv, dtype=np.int32)

@@ -102,6 +102,34 @@ int hb200_set_manifold_factors(hb200_ctx* ctx, int n, const double* stamp, const
 int hb200_bind(hb200_ctx* ctx, int* num_invalid);
 int hb200_get_index_maps(hb200_ctx* ctx, int* pixel_base, int* inertial_base, int* gyro_bias_base, int* accel_bias_base);
 
+/* ---- sliding-window bookkeeping on the device ---------------------------------
+ * What the reference does per message on its pointer graph, applied to the flattened window that already lives in
+ * HBM -- no host re-sort, no re-upload of the factor lists (pixel and inertial factors; bearing / manifold lists
+ * must be empty).  After any of these calls the factor "user order" is the bound order on the device.
+ *   hb200_append_knots:    `count` state elements appended by the reference's extrapolation -- the new elements AND
+ *                          the current last one take the variable of the second to last, stamps continue at the knot
+ *                          separation (reference internal/hyper/optimizers/abstract.cpp:126-136).
+ *   hb200_append_*:        a frame's residual blocks / new landmarks (reference optimizer.cpp:212-232,253-274,347-358).
+ *                          Stamps must not precede the end of the list they are appended to (arrival order); the new
+ *                          factors are bound on the device (index maps of the tail only).
+ *   hb200_slide:           new window lower bound -- landmarks whose observation range left the window are removed
+ *                          with their residuals (optimizer.cpp:360-382), state elements at or before the bound become
+ *                          constant (:322-328), the ones in front of the window that no residual touches are removed
+ *                          (:331-341), gravity becomes constant (abstract.cpp:57-61).  The reference never removes
+ *                          inertial residuals; HB200_SLIDE_DROP_INERTIAL additionally drops those whose control points
+ *                          are all constant, so that the window stays bounded. */
+typedef struct hb200_slide_stats {
+  int knots_dropped, knots_constant, landmarks_dropped, visual_factors_dropped, inertial_factors_dropped;
+  int knots, landmarks, visual_factors, inertial_factors;   /* sizes after the call */
+} hb200_slide_stats;
+enum { HB200_SLIDE_DROP_INERTIAL = 1 };
+int hb200_append_knots(hb200_ctx* ctx, int count);
+int hb200_append_landmarks(hb200_ctx* ctx, int n, const double* xyz);
+int hb200_append_pixel_factors(hb200_ctx* ctx, int n, const double* stamp, const int* camera, const int* landmark, const double* pixel);
+int hb200_append_inertial_factors(hb200_ctx* ctx, int n, const double* stamp, const double* measurement);
+int hb200_slide(hb200_ctx* ctx, double lower_bound, int flags, hb200_slide_stats* stats /* may be NULL */);
+int hb200_window_sizes(hb200_ctx* ctx, int* knots, int* landmarks, int* visual_factors, int* inertial_factors);
+
 /* ---- the hot path --------------------------------------------------------------------------
  * hb200_evaluate: residual (+ Jacobian) of every factor at the current state (flags 0 / JACOBIANS)
  * or at the trial state (TRIAL).  Compact outputs (DESIGN.md "HBM layout"):
