@@ -323,6 +323,71 @@ def large_section(torch, dist, runtime, local_rank, rank, world, flush, config, 
     return out
 
 
+def sliding_section(torch, runtime, local_rank, frames=20):
+    """Steady-state frame loop through the device-side window bookkeeping: per frame one state element
+    is appended, the frame's factors and new landmarks are added (bound on the device), the window's lower bound moves on
+    (expired landmarks / factors / leading state elements are compacted away), five LM iterations run and the state is
+    read back -- wall clock per frame, host bookkeeping and all copies included."""
+    K0, k = 50, 4
+    full = synthetic.make_window(order=k, num_knots=K0 + frames + 2, num_landmarks=1000 + 25 * frames, frames_per_landmark=5, num_cameras=2,
+                                 num_imu=2000 + 45 * frames, seed=synthetic.SEED_BASE + 4242)
+    st = full.knots[:, 7]
+    order_v, order_i = np.argsort(full.v_stamp, kind="stable"), np.argsort(full.i_stamp, kind="stable")
+    v = dict(stamp=full.v_stamp[order_v], cam=full.v_cam[order_v], gid=full.v_lm[order_v], pixel=full.v_pixel[order_v])
+    im = dict(stamp=full.i_stamp[order_i], meas=full.i_meas[order_i])
+    hi = st[K0 - 2]
+    vm, mm = v["stamp"] < hi, im["stamp"] < hi
+    ids = list(dict.fromkeys(v["gid"][vm].tolist()))
+    pos = {g: p for p, g in enumerate(ids)}
+    import dataclasses
+    kc = np.zeros(K0, np.uint8); kc[:2] = 1
+    win = dataclasses.replace(full, knots=full.knots[:K0].copy(), landmarks=full.landmarks[ids], v_stamp=v["stamp"][vm], v_cam=v["cam"][vm],
+                              v_lm=np.array([pos[g] for g in v["gid"][vm].tolist()], np.int32), v_pixel=v["pixel"][vm], i_stamp=im["stamp"][mm],
+                              i_meas=im["meas"][mm], knot_const=kc, truth=None)
+    ctx = runtime.Context(local_rank)
+    ctx.load_window(win)
+    ctx.iterate(5, records=False)
+    times, sizes = [], []
+    alive = list(ids)
+    last_seen = {}
+    for g, t in zip(v["gid"][vm].tolist(), v["stamp"][vm].tolist()):
+        last_seen[g] = t
+    prev_hi = hi
+    for f in range(frames):
+        hi = st[K0 + f - 1]
+        sel_v = (v["stamp"] >= prev_hi) & (v["stamp"] < hi)
+        sel_i = (im["stamp"] >= prev_hi) & (im["stamp"] < hi)
+        prev_hi = hi
+        new_ids = [g for g in dict.fromkeys(v["gid"][sel_v].tolist()) if g not in pos]
+        lower = st[f + 1] + 1e-9   # the window keeps its length: one element in, one out
+        # host-side id bookkeeping of the caller (which landmark sits where), mirrored from the rules
+        for g, t in zip(v["gid"][sel_v].tolist(), v["stamp"][sel_v].tolist()):
+            last_seen[g] = t
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.append_knots(1)
+        ctx.append_landmarks(full.landmarks[new_ids].reshape(-1, 3))
+        alive += new_ids
+        pos = {g: p for p, g in enumerate(alive)}
+        ctx.append_pixel_factors(v["stamp"][sel_v], v["cam"][sel_v], np.array([pos[g] for g in v["gid"][sel_v].tolist()], np.int32), v["pixel"][sel_v])
+        ctx.append_inertial_factors(im["stamp"][sel_i], im["meas"][sel_i])
+        stats = ctx.slide(lower, drop_inertial=True)
+        ctx.iterate(5, records=False)
+        state = ctx.state()
+        times.append(time.perf_counter() - t0)
+        alive = [g for g in alive if last_seen.get(g, np.inf) >= lower]
+        pos = {g: p for p, g in enumerate(alive)}
+        assert len(alive) == stats["landmarks"], (len(alive), stats)
+        sizes.append((stats["knots"], stats["landmarks"], stats["visual_factors"], stats["inertial_factors"]))
+    ctx.close()
+    med = statistics.median(times[3:])
+    Kw, Lw, Nvw, Niw = sizes[-1]
+    return dict(frames=frames, ms_per_frame_median=med * 1e3, ms_per_frame_min=min(times[3:]) * 1e3, window=dict(knots=Kw, landmarks=Lw, pixel_factors=Nvw, inertial_factors=Niw),
+                per_frame="append 1 state element + ~%d pixel / ~%d inertial factors + new landmarks (H2D), hb200_slide, 5 LM iterations, state read-back (D2H); wall clock" % (
+                    int(np.mean([s_[2] for s_ in sizes]) / (Kw - 3)), int(np.mean([s_[3] for s_ in sizes]) / (Kw - 3))),
+                factor_evals_per_s=5 * (Nvw + Niw) / med)
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -476,6 +541,13 @@ def main():
 
     h.close()
 
+    sliding = None
+    if world == 1 and not args.no_large:
+        try:
+            sliding = sliding_section(torch, runtime, local_rank)
+        except Exception as e:  # noqa: BLE001
+            sliding = dict(error=str(e))
+
     # ---- large windows: the BASELINE configs beyond the headline, at their GPU counts ------------------------
     large = {}
     if not args.no_large:
@@ -540,6 +612,8 @@ def main():
         line["parity"] = parity
     if dense_bar:
         line["dense_solver_bar"] = dense_bar
+    if sliding:
+        line["e2e"]["sliding_window"] = sliding
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))

@@ -158,6 +158,8 @@ struct hb200_ctx {
   long long launches = 0;
   long long launches_per_iteration = 0;
   long long iter_total = 0, snap_iter_total = 0;   // host mirror of SolverState.iteration (record ring index)
+  int last_terminated = 0, last_performed = 0;     // outcome of the last hb200_iterate / hb200_optimize that fetched records
+  double last_gmax = 0, last_step_norm = 0, last_x_norm = 0;
 
   // window state (index 0 = current, 1 = trial)
   int k = 0, K = 0, kb = 4, Kbg = 0, Kba = 0, C = 0, L = 0;
@@ -170,6 +172,9 @@ struct hb200_ctx {
   int gravity_const = 0, bias_const = 0;
   bool have_imu = false, have_gravity = false;
   double huber = 0.5, imu_scale = 1.6e-5, radius0 = 1e4;
+  // ceres::Solver::Options termination tests (off: hb200_iterate runs exactly the requested number of iterations)
+  bool term_enabled = false;
+  double term_ftol = 1e-6, term_gtol = 1e-10, term_ptol = 1e-8, term_min_radius = 1e-32;
 
   // factors (host copies in user order; device copies in bound order)
   // visual list = pixel factors [0, Np) followed by bearing factors [Np, Np + Nb): both travel through the
@@ -350,8 +355,8 @@ int ensure_system(hb200_ctx* c) {
   HB_CUDA(c->gl.ensure(3 * static_cast<size_t>(std::max(c->L, 1))));
   HB_CUDA(c->Dl.ensure(3 * static_cast<size_t>(std::max(c->L, 1))));
   c->n_lm_blocks = (c->L + kLmWarps - 1) / kLmWarps;
-  HB_CUDA(c->lm_part.ensure(2 * static_cast<size_t>(std::max(c->n_lm_blocks, 1))));
-  HB_CUDA(c->scal.ensure(4));
+  HB_CUDA(c->lm_part.ensure(5 * static_cast<size_t>(std::max(c->n_lm_blocks, 1))));
+  HB_CUDA(c->scal.ensure(8));
   HB_CUDA(c->spd.ensure(1));
   HB_CUDA(c->records.ensure(c->max_records));
   // solver selection: block-banded + arrowhead unless the band is wide on a large system
@@ -643,7 +648,7 @@ int enqueue_solve(hb200_ctx* c, bool fuse_retract = false, bool* fused = nullptr
       HB_LAUNCH(c, "lm_backsub_kernel");
     } else {
       HB_CUDA(cudaMemsetAsync(c->dl.p, 0, 3 * static_cast<size_t>(c->L) * sizeof(double), c->stream));
-      HB_CUDA(cudaMemsetAsync(c->lm_part.p, 0, 2 * static_cast<size_t>(c->n_lm_blocks) * sizeof(double), c->stream));
+      HB_CUDA(cudaMemsetAsync(c->lm_part.p, 0, 5 * static_cast<size_t>(c->n_lm_blocks) * sizeof(double), c->stream));
     }
   }
   return 0;
@@ -671,6 +676,16 @@ int enqueue_scalars(hb200_ctx* c) {
   return 0;
 }
 
+TermArgs term_args(hb200_ctx* c) {
+  TermArgs t{};
+  t.enabled = c->term_enabled ? 1 : 0;
+  t.function_tolerance = c->term_ftol; t.gradient_tolerance = c->term_gtol; t.parameter_tolerance = c->term_ptol; t.min_radius = c->term_min_radius;
+  t.K = c->K; t.Kbg = c->Kbg; t.Kba = c->Kba;
+  t.knots = c->knots[0].p; t.knots_t = c->knots[1].p; t.bg = c->bg[0].p; t.bg_t = c->bg[1].p; t.ba = c->ba[0].p; t.ba_t = c->ba[1].p;
+  t.grav = c->grav[0].p; t.grav_t = c->grav[1].p;
+  return t;
+}
+
 int enqueue_accept(hb200_ctx* c) {
   ScalarArgs sa{c->cp_pix[1].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[1].p, c->n_imu_blocks + c->n_man_blocks, c->lm_part.p, (c->L && c->Nv) ? c->n_lm_blocks : 0};
   CommitArgs a{};
@@ -686,7 +701,7 @@ int enqueue_accept(hb200_ctx* c) {
   MailboxArgs mb{};
   mb.nranks = mailbox ? c->nranks : 1; mb.rank = c->rank; mb.peers = c->d_peers.p; mb.local = c->mbox.p; mb.seq = c->mbox_seq.p;
   accept_kernel<<<1, kAcceptThreads, 0, c->stream>>>(c->sys.p, c->lay, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
-                                         (!c->multi() || mailbox) ? 1 : 0, sa, fuse_commit ? 1 : 0, a, mb);
+                                         (!c->multi() || mailbox) ? 1 : 0, sa, fuse_commit ? 1 : 0, a, mb, term_args(c));
   HB_LAUNCH(c, "accept_kernel");
   if (!fuse_commit) {
     const int blocks = static_cast<int>(std::min<size_t>((mx + 255) / 256, static_cast<size_t>(c->num_sms) * 4));
@@ -717,11 +732,11 @@ int enqueue_reduce_scalars(hb200_ctx* c) {
   int rc = enqueue_scalars(c);
   if (rc) return rc;
   if (c->nccl) {
-    HB_NCCL(g_nccl.AllReduce(c->scal.p, c->scal.p, 4, 8, 0, c->nccl, c->stream));
+    HB_NCCL(g_nccl.AllReduce(c->scal.p, c->scal.p, 8, 8, 0, c->nccl, c->stream));
     c->nccl_calls += 1;
     prof_mark(c, "ncclAllReduce(scalars)");
   } else {
-    rc = c->allreduce(c->allreduce_user, c->scal.p, 4, c->stream);
+    rc = c->allreduce(c->allreduce_user, c->scal.p, 8, c->stream);
     if (rc) return fail(200 + rc, "all-reduce callback failed (%d)", rc);
     prof_mark(c, "allreduce_callback(scalars)");
   }
@@ -1702,19 +1717,35 @@ int iterate_enqueue(hb200_ctx* c, int iterations) {
     }
   }
   c->evaluated_J = false; c->system_built = false; c->mirror_valid = false; c->calib_valid = false;
-  c->iter_total += iterations;
+  if (!c->term_enabled) c->iter_total += iterations;   // (with the termination tests on, the device counter is authoritative: pick_records)
   return 0;
 }
 
-// copies the last `iterations` records out of the device ring buffer (asynchronously)
-int fetch_records(hb200_ctx* c, int iterations, std::vector<SolverState>* rec, SolverState* pinned = nullptr) {
-  rec->resize(iterations);
-  SolverState* dst = pinned ? pinned : rec->data();   // pinned destination: the copies are truly asynchronous
-  for (int i = 0; i < iterations; ++i) {
-    const long long idx = (c->iter_total - iterations + i) % c->max_records;
-    HB_CUDA(cudaMemcpyAsync(dst + i, c->records.p + idx, sizeof(SolverState), cudaMemcpyDeviceToHost, c->stream));
-  }
+// The device ring buffer of iteration records and the solver state, fetched in one batch (asynchronously); the
+// records of the iterations PERFORMED since `it_before` are picked out after the synchronisation (with the
+// termination tests on, fewer iterations than requested may have been performed).
+struct RecordFetch {
+  std::vector<SolverState> ring;
+  SolverState st{};
+};
+int fetch_records(hb200_ctx* c, RecordFetch* f, SolverState* pinned = nullptr) {
+  f->ring.resize(c->max_records);
+  SolverState* dst = pinned ? pinned : f->ring.data();
+  HB_CUDA(cudaMemcpyAsync(dst, c->records.p, sizeof(SolverState) * c->max_records, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaMemcpyAsync(pinned ? pinned + c->max_records : &f->st, c->st.p, sizeof(SolverState), cudaMemcpyDeviceToHost, c->stream));
   return 0;
+}
+// after the stream synchronisation: records of iterations it_before+1 .. st.iteration in order; returns their number
+int pick_records(hb200_ctx* c, RecordFetch* f, long long it_before, int requested, std::vector<SolverState>* rec, const SolverState* pinned = nullptr) {
+  if (pinned) { std::copy(pinned, pinned + c->max_records, f->ring.begin()); f->st = pinned[c->max_records]; }
+  const long long it_after = f->st.iteration;
+  const int performed = static_cast<int>(std::max<long long>(0, std::min<long long>(it_after - it_before, requested)));
+  rec->resize(performed);
+  for (int i = 0; i < performed; ++i) (*rec)[i] = f->ring[(it_before + i) % c->max_records];
+  c->iter_total = it_after;
+  c->last_terminated = f->st.terminated; c->last_performed = performed;
+  c->last_gmax = f->st.gradient_max_norm; c->last_step_norm = f->st.step_norm; c->last_x_norm = f->st.x_norm;
+  return performed;
 }
 
 void convert_records(const std::vector<SolverState>& rec, hb200_iteration* records) {
@@ -1732,12 +1763,22 @@ int hb200_iterate(hb200_ctx* c, int iterations, hb200_iteration* records) {
   if (rc) return rc;
   if (iterations < 0 || iterations > c->max_records) return fail(-1, "iterations must be in [0, %d]", c->max_records);
   HB_CUDA(cudaSetDevice(c->device));
+  if (c->term_enabled) {   // a new call continues the trust region but starts with a clean termination state
+    new_solve_kernel<<<1, 1, 0, c->stream>>>(c->st.p, c->radius0, 0);
+    HB_LAUNCH(c, "new_solve_kernel");
+  }
+  const long long it_before = c->iter_total;
   if ((rc = iterate_enqueue(c, iterations))) return rc;
-  if (records && iterations) {
+  if (iterations && (records || c->term_enabled)) {
+    RecordFetch f;
     std::vector<SolverState> rec;
-    if ((rc = fetch_records(c, iterations, &rec))) return rc;
+    if ((rc = fetch_records(c, &f))) return rc;
     HB_CUDA(cudaStreamSynchronize(c->stream));
-    convert_records(rec, records);
+    const int performed = pick_records(c, &f, it_before, iterations, &rec);
+    if (records) {
+      convert_records(rec, records);
+      for (int i = performed; i < iterations; ++i) records[i] = hb200_iteration{};   // not performed: the solve terminated earlier
+    }
   }
   return 0;
 }
@@ -1767,7 +1808,7 @@ int hb200_optimize(hb200_ctx* c, int iterations, double* knots, double* gyro, do
     if (c->h_stage_cap < total) {
       if (c->h_stage) cudaFreeHost(c->h_stage);
       c->h_stage = nullptr; c->h_stage_cap = 0;
-      HB_CUDA(cudaMallocHost(&c->h_stage, sizeof(double) * 8192 + sizeof(SolverState) * c->max_records));
+      HB_CUDA(cudaMallocHost(&c->h_stage, sizeof(double) * 8192 + sizeof(SolverState) * (c->max_records + 1)));
       c->h_stage_cap = 8192;
     }
     HB_CUDA(c->d_stage.ensure(8192));
@@ -1784,6 +1825,10 @@ int hb200_optimize(hb200_ctx* c, int iterations, double* knots, double* gyro, do
     for (int i = 0; i < 5; ++i)
       if (host[i]) HB_CUDA(cudaMemcpyAsync(dev[i], host[i], sizeof(double) * cnt[i], cudaMemcpyHostToDevice, c->stream));
   }
+  // every ceres::Solve starts from the initial trust-region radius and a clean termination state
+  new_solve_kernel<<<1, 1, 0, c->stream>>>(c->st.p, c->radius0, 1);
+  HB_LAUNCH(c, "new_solve_kernel");
+  const long long it_before = c->iter_total;
   if ((rc = iterate_enqueue(c, iterations))) return rc;
   if (staged) {
     copy_segments_kernel<<<4, 256, 0, c->stream>>>(out);
@@ -1794,15 +1839,40 @@ int hb200_optimize(hb200_ctx* c, int iterations, double* knots, double* gyro, do
       if (host[i]) HB_CUDA(cudaMemcpyAsync(host[i], dev[i], sizeof(double) * cnt[i], cudaMemcpyDeviceToHost, c->stream));
   }
   std::vector<SolverState> rec;
+  RecordFetch fetch;
   SolverState* rec_pinned = staged ? reinterpret_cast<SolverState*>(c->h_stage + 8192) : nullptr;
-  if (records && iterations && (rc = fetch_records(c, iterations, &rec, rec_pinned))) return rc;
+  const bool want_records = (records && iterations) || c->term_enabled;
+  if (want_records && (rc = fetch_records(c, &fetch, rec_pinned))) return rc;
   HB_CUDA(cudaStreamSynchronize(c->stream));
   if (staged) {
     for (int i = 0; i < 5; ++i)
       if (host[i]) std::memcpy(host[i], c->h_stage + off[i], sizeof(double) * cnt[i]);
-    if (records && iterations) std::copy(rec_pinned, rec_pinned + iterations, rec.begin());
   }
-  if (records && iterations) convert_records(rec, records);
+  if (want_records) {
+    const int performed = pick_records(c, &fetch, it_before, iterations, &rec, rec_pinned);
+    if (records) {
+      convert_records(rec, records);
+      for (int i = performed; i < iterations; ++i) records[i] = hb200_iteration{};
+    }
+  }
+  return 0;
+}
+
+int hb200_set_termination(hb200_ctx* c, double function_tolerance, double gradient_tolerance, double parameter_tolerance, double min_trust_region_radius) {
+  if (!c) return fail(-1, "null context");
+  c->term_ftol = function_tolerance; c->term_gtol = gradient_tolerance; c->term_ptol = parameter_tolerance; c->term_min_radius = min_trust_region_radius;
+  c->term_enabled = function_tolerance > 0 || gradient_tolerance > 0 || parameter_tolerance > 0 || min_trust_region_radius > 0;
+  c->graph_valid = false;   // baked into kernel arguments
+  return 0;
+}
+
+int hb200_get_termination(hb200_ctx* c, int* type, int* iterations_performed, double* gradient_max_norm, double* step_norm, double* x_norm) {
+  if (!c) return fail(-1, "null context");
+  if (type) *type = c->last_terminated;
+  if (iterations_performed) *iterations_performed = c->last_performed;
+  if (gradient_max_norm) *gradient_max_norm = c->last_gmax;
+  if (step_norm) *step_norm = c->last_step_norm;
+  if (x_norm) *x_norm = c->last_x_norm;
   return 0;
 }
 
@@ -2282,9 +2352,9 @@ int hb200_comm_init_rank(hb200_ctx* c, int nranks, int rank, const char* id) {
 int hb200_peer_handle(hb200_ctx* c, char* handle) {
   if (!c || !handle) return fail(-1, "null argument");
   HB_CUDA(cudaSetDevice(c->device));
-  HB_CUDA(c->mbox.ensure(2 * kMaxRanks * 4));
+  HB_CUDA(c->mbox.ensure(2 * kMaxRanks * kMboxSlot));
   HB_CUDA(c->mbox_seq.ensure(1));
-  HB_CUDA(cudaMemsetAsync(c->mbox.p, 0, sizeof(double) * 2 * kMaxRanks * 4, c->stream));
+  HB_CUDA(cudaMemsetAsync(c->mbox.p, 0, sizeof(double) * 2 * kMaxRanks * kMboxSlot, c->stream));
   HB_CUDA(cudaMemsetAsync(c->mbox_seq.p, 0, sizeof(unsigned long long), c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   cudaIpcMemHandle_t h;

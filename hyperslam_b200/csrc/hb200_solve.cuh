@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const 
                                                                   const double* __restrict__ Jp, const double* __restrict__ Jl, const double* __restrict__ wv,
                                                                   const double* __restrict__ Vinv, const double* __restrict__ gl,
                                                                   const double* __restrict__ Dl, const double* __restrict__ dp,
-                                                                  double* __restrict__ dl, double* __restrict__ part /*[n_lm_blocks][2]*/,
+                                                                  double* __restrict__ dl, double* __restrict__ part /*[n_lm_blocks][5]*/,
                                                                   const double* __restrict__ lms, double* __restrict__ lms_t,
                                                                   int n_lm_blocks, RetractArgs ra) {
   // blocks past the landmark range retract the knots / biases / gravity in the same launch (they only need dp)
@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const 
   constexpr int CG = NB / 4;  // columns per lane group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int l = blockIdx.x * kLmWarps + warp;
-  double s_g = 0, s_d = 0;
+  double s_g = 0, s_d = 0, s_step = 0, s_x = 0, s_gmax = 0;   // + |dl|^2, |x_l|^2, |g_l|_inf of the OBSERVED landmarks (termination tests)
   if (l < L) {
     const int o_lo = lm_off[l], o_hi = lm_off[l + 1];
     const int og = lane >> 2, cg = lane & 3;
@@ -797,35 +797,53 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const 
         if (lms_t) lms_t[3 * static_cast<size_t>(l) + c] = lms[3 * static_cast<size_t>(l) + c] + v;   // Manifold::Plus of the landmark block
         s_g += v * g[c];
         s_d += v * v * Dl[3 * static_cast<size_t>(l) + c];
+        if (o_hi > o_lo) {
+          const double xl = lms[3 * static_cast<size_t>(l) + c];
+          s_step += v * v; s_x += xl * xl; s_gmax = fmax(s_gmax, fabs(g[c]));
+        }
       }
     }
   }
-  __shared__ double sg[kLmWarps], sd[kLmWarps];
-  if (lane == 0) { sg[warp] = s_g; sd[warp] = s_d; }
+  __shared__ double sg[kLmWarps][5];
+  if (lane == 0) { sg[warp][0] = s_g; sg[warp][1] = s_d; sg[warp][2] = s_step; sg[warp][3] = s_x; sg[warp][4] = s_gmax; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double a = 0, b = 0;
-    for (int w = 0; w < kLmWarps; ++w) { a += sg[w]; b += sd[w]; }
-    part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int w = 0; w < kLmWarps; ++w) { a[0] += sg[w][0]; a[1] += sg[w][1]; a[2] += sg[w][2]; a[3] += sg[w][3]; a[4] = fmax(a[4], sg[w][4]); }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) part[5 * blockIdx.x + q] = a[q];
   }
 }
 
 
-// scal = [cost_new, dl.g_l, dl.D_l.dl, 0] (rank-local partial sums, fixed order).
+// scal = [cost_new, dl.g_l, dl.D_l.dl, |dl|^2, |x_l|^2, |g_l|_inf, 0, 0] (rank-local partials, fixed order).
+// Fallback paths only (callback hook / no peer mapping): the sums are reduced across ranks, the maximum is then only
+// rank-local -- the gradient-tolerance test of hb200_set_termination needs the peer mailbox at N > 1.
 __global__ void scalars_kernel(const double* __restrict__ cp_pix, int n_pix_blocks, const double* __restrict__ cp_imu, int n_imu_blocks,
                                const double* __restrict__ lm_part, int n_lm_blocks, double* __restrict__ scal) {
-  __shared__ double s[3][256];
-  double c = 0, a = 0, b = 0;
-  for (int i = threadIdx.x; i < n_pix_blocks; i += blockDim.x) c += cp_pix[i];
-  for (int i = threadIdx.x; i < n_imu_blocks; i += blockDim.x) c += cp_imu[i];
-  for (int i = threadIdx.x; i < n_lm_blocks; i += blockDim.x) { a += lm_part[2 * i]; b += lm_part[2 * i + 1]; }
-  s[0][threadIdx.x] = c; s[1][threadIdx.x] = a; s[2][threadIdx.x] = b;
+  __shared__ double s[6][256];
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n_pix_blocks; i += blockDim.x) v[0] += cp_pix[i];
+  for (int i = threadIdx.x; i < n_imu_blocks; i += blockDim.x) v[0] += cp_imu[i];
+  for (int i = threadIdx.x; i < n_lm_blocks; i += blockDim.x) {
+    v[1] += lm_part[5 * i]; v[2] += lm_part[5 * i + 1]; v[3] += lm_part[5 * i + 2]; v[4] += lm_part[5 * i + 3]; v[5] = fmax(v[5], lm_part[5 * i + 4]);
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) s[q][threadIdx.x] = v[q];
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { s[0][threadIdx.x] += s[0][threadIdx.x + o]; s[1][threadIdx.x] += s[1][threadIdx.x + o]; s[2][threadIdx.x] += s[2][threadIdx.x + o]; }
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) s[q][threadIdx.x] += s[q][threadIdx.x + o];
+      s[5][threadIdx.x] = fmax(s[5][threadIdx.x], s[5][threadIdx.x + o]);
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { scal[0] = s[0][0]; scal[1] = s[1][0]; scal[2] = s[2][0]; scal[3] = 0.0; }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) scal[q] = s[q][0];
+    scal[6] = 0.0; scal[7] = 0.0;
+  }
 }
 
 // Step acceptance (Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy::StepAccepted/Rejected).
@@ -843,9 +861,11 @@ struct ScalarArgs {   // inputs of scalars_kernel, for the fused single-GPU path
 // (3 doubles) travel through PEER MEMORY inside accept_kernel itself -- thread p stores this rank's triple and a
 // sequence tag into rank p's mailbox over NVLink (st.release.sys) and waits for rank p's triple in its own
 // (ld.acquire.sys); the sums are taken in rank order, so every replica computes bit-identical rho / radius.
-// Mailbox: [2 parities][kMaxRanks][4] doubles = {cost_new, dl.g_l, dl.D_l.dl, tag}.  Slots alternate with the
+// Mailbox: [2 parities][kMaxRanks][8] doubles = {cost_new, dl.g_l, dl.D_l.dl, |dl|^2, |x_l|^2, |g_l|_inf, -, tag}
+// (sums for the first five, maximum for the sixth: the landmark parts of Ceres' termination tests).  Slots alternate with the
 // sequence parity; a slot is not reused before the next system all-reduce has synchronised all ranks.
 constexpr int kMaxRanks = 16;
+constexpr int kMboxSlot = 8;
 struct MailboxArgs {
   int nranks, rank;
   double* const* peers;        // [nranks] mailbox base of every rank, mapped into this process (cudaIpcOpenMemHandle)
@@ -866,41 +886,120 @@ HB_DI double ld_relaxed_sys_f64(const double* p) {
 }
 
 constexpr int kAcceptThreads = 1024;   // one CTA; wide so that the fused commit copies the state in a few passes
+
+// ceres::TrustRegionMinimizer termination tests (Ceres 2.x trust_region_minimizer.cc, restated from the public
+// sources -- the reference leaves them at their defaults, reference optimizer.cpp:38-54):
+//   gradient tolerance   |x - Plus(x, -g)|_inf <= gradient_tolerance at the linearisation point (IterationZero /
+//                        HandleSuccessfulStep): the solve ends BEFORE this iteration's step is taken;
+//   parameter tolerance  |x - x_trial| <= parameter_tolerance (|x| + parameter_tolerance), ambient norms over the
+//                        non-constant parameter blocks: ends without applying the trial step;
+//   function tolerance   |cost - cost_trial| <= function_tolerance cost: ends without applying the trial step;
+//   minimum trust-region radius, five consecutive invalid (non positive definite) steps.
+struct TermArgs {
+  int enabled;
+  double function_tolerance, gradient_tolerance, parameter_tolerance, min_radius;
+  int K, Kbg, Kba;
+  const double *knots, *knots_t, *bg, *bg_t, *ba, *ba_t, *grav, *grav_t;
+};
+
 __global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __restrict__ sys, SysLayout lay, double* __restrict__ scal, const double* __restrict__ dp,
                               const double* __restrict__ D, const unsigned char* __restrict__ fixed, SolverState* st,
                               const int* __restrict__ spd_flag, SolverState* __restrict__ record, int max_records, int fuse_scalars,
-                              ScalarArgs sa, int fuse_commit, CommitArgs ca, MailboxArgs mb) {
-  // block sums: shuffle within the warp, one partial per warp, fixed order across warps (two barriers in total)
-  __shared__ double s[5][kAcceptThreads / 32];
+                              ScalarArgs sa, int fuse_commit, CommitArgs ca, MailboxArgs mb, TermArgs ta) {
+  // block reductions: shuffle within the warp, one partial per warp, fixed order across warps.
+  // v[0..5]: cost_new, dl.g_l, dl.D_l.dl, |dl|^2, |x_l|^2, |g_l|_inf (landmark partials of this rank)
+  // v[6..7]: dp.g, dp.D.dp        v[8..10]: |x_trial - x|^2, |x|^2, |x - Plus(x, -g)|_inf of the knots / biases / gravity
+  constexpr int NV = 11;
+  __shared__ double s[NV][kAcceptThreads / 32];
+  __shared__ int s_done;
   const int wl = threadIdx.x & 31, ww = threadIdx.x >> 5;
-  double v5[5] = {0, 0, 0, 0, 0};   // cost_new, dl.g_l, dl.D_l.dl, dp.g, dp.D.dp
+  if (st->terminated) {   // the solve has ended: later iterations of the same call leave everything alone
+    if (threadIdx.x == 0 && mb.nranks > 1 && fuse_scalars) *mb.seq += 1;   // (the peers skip their exchange too: keep the counters aligned)
+    return;
+  }
+  double v[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = 0.0;
   if (fuse_scalars) {   // == scalars_kernel (no all-reduce between the two on a single GPU)
-    for (int i = threadIdx.x; i < sa.n_pix_blocks; i += blockDim.x) v5[0] += sa.cp_pix[i];
-    for (int i = threadIdx.x; i < sa.n_imu_blocks; i += blockDim.x) v5[0] += sa.cp_imu[i];
-    for (int i = threadIdx.x; i < sa.n_lm_blocks; i += blockDim.x) { v5[1] += sa.lm_part[2 * i]; v5[2] += sa.lm_part[2 * i + 1]; }
+    for (int i = threadIdx.x; i < sa.n_pix_blocks; i += blockDim.x) v[0] += sa.cp_pix[i];
+    for (int i = threadIdx.x; i < sa.n_imu_blocks; i += blockDim.x) v[0] += sa.cp_imu[i];
+    for (int i = threadIdx.x; i < sa.n_lm_blocks; i += blockDim.x) {
+      v[1] += sa.lm_part[5 * i]; v[2] += sa.lm_part[5 * i + 1]; v[3] += sa.lm_part[5 * i + 2]; v[4] += sa.lm_part[5 * i + 3];
+      v[5] = fmax(v[5], sa.lm_part[5 * i + 4]);
+    }
   }
   const int n = lay.n;
   const double* g = sys + lay.og;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
-    if (!fixed[i]) { v5[3] += dp[i] * g[i]; v5[4] += dp[i] * dp[i] * D[i]; }
+    if (!fixed[i]) { v[6] += dp[i] * g[i]; v[7] += dp[i] * dp[i] * D[i]; }
+  if (ta.enabled) {
+    // ambient norms over the non-constant blocks (Stamped<SE3>: 8 coordinates, the stamp included; bias knots 4; gravity 3)
+    // and the projected gradient step: Ceres' local rotation coordinate is half of this library's theta, so
+    // Plus(x, -g_ceres) is a rotation by -4 g_theta.
+    const int i = threadIdx.x;
+    for (int j = i; j < ta.K; j += blockDim.x) {
+      if (fixed[6 * j]) continue;
+      const double* x = ta.knots + 8 * static_cast<size_t>(j);
+      const double* t = ta.knots_t + 8 * static_cast<size_t>(j);
 #pragma unroll
-  for (int q = 0; q < 5; ++q) {
+      for (int c = 0; c < 8; ++c) { const double d = t[c] - x[c]; v[8] += d * d; v[9] += x[c] * x[c]; }
+      const double th[3] = {-4.0 * g[6 * j], -4.0 * g[6 * j + 1], -4.0 * g[6 * j + 2]};
+      const double q[4] = {x[0], x[1], x[2], x[3]};
+      double qe[4], qn[4];
+      quat_exp(th, qe);
+      quat_mul(qe, q, qn);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v5[q] += __shfl_xor_sync(0xffffffffu, v5[q], o);
-    if (wl == 0) s[q][ww] = v5[q];
+      for (int c = 0; c < 4; ++c) v[10] = fmax(v[10], fabs(qn[c] - q[c]));
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[10] = fmax(v[10], fabs(g[6 * j + 3 + c]));
+    }
+    const int o_bg = 6 * ta.K, o_ba = o_bg + 3 * ta.Kbg, o_g = o_ba + 3 * ta.Kba;
+    for (int j = i; j < ta.Kbg + ta.Kba; j += blockDim.x) {
+      const bool acc = j >= ta.Kbg;
+      const int jj = acc ? j - ta.Kbg : j, o = (acc ? o_ba : o_bg) + 3 * jj;
+      if (fixed[o]) continue;
+      const double* x = (acc ? ta.ba : ta.bg) + 4 * static_cast<size_t>(jj);
+      const double* t = (acc ? ta.ba_t : ta.bg_t) + 4 * static_cast<size_t>(jj);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { const double d = t[c] - x[c]; v[8] += d * d; v[9] += x[c] * x[c]; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[10] = fmax(v[10], fabs(g[o + c]));
+    }
+    if (i == 0 && !fixed[o_g]) {
+      const double x[3] = {ta.grav[0], ta.grav[1], ta.grav[2]};
+      const double dd[2] = {-g[o_g], -g[o_g + 1]};
+      double xp[3];
+      sphere_plus(x, dd, xp);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const double d = ta.grav_t[c] - x[c]; v[8] += d * d; v[9] += x[c] * x[c]; v[10] = fmax(v[10], fabs(xp[c] - x[c])); }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const bool is_max = (q == 5 || q == 10);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(0xffffffffu, v[q], o); v[q] = is_max ? fmax(v[q], y) : v[q] + y; }
+    if (wl == 0) s[q][ww] = v[q];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double t5[5] = {0, 0, 0, 0, 0};
+    double t[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) t[q] = 0.0;
     for (int w = 0; w < kAcceptThreads / 32; ++w)
 #pragma unroll
-      for (int q = 0; q < 5; ++q) t5[q] += s[q][w];
-    if (fuse_scalars) { scal[0] = t5[0]; scal[1] = t5[1]; scal[2] = t5[2]; scal[3] = 0.0; }
-    s[0][0] = t5[0]; s[1][0] = t5[1]; s[2][0] = t5[2]; s[3][0] = t5[3]; s[4][0] = t5[4];
+      for (int q = 0; q < NV; ++q) t[q] = (q == 5 || q == 10) ? fmax(t[q], s[q][w]) : t[q] + s[q][w];
+    if (fuse_scalars) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) scal[q] = t[q];
+      scal[6] = 0.0; scal[7] = 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) s[q][0] = t[q];
   }
   __syncthreads();
   if (fuse_scalars && mb.nranks > 1) {
-    __shared__ double s_peer[kMaxRanks][3];
+    __shared__ double s_peer[kMaxRanks][6];
     __shared__ int s_timeout;
     const unsigned long long want = *mb.seq + 1;   // every thread reads the counter before thread 0 bumps it (below)
     const int par = static_cast<int>(want & 1);
@@ -908,58 +1007,92 @@ __global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __
     __syncthreads();
     if (static_cast<int>(threadIdx.x) < mb.nranks) {
       const int p = threadIdx.x;
-      double* dst = mb.peers[p] + (par * kMaxRanks + mb.rank) * 4;
-      st_relaxed_sys_f64(dst + 0, s[0][0]); st_relaxed_sys_f64(dst + 1, s[1][0]); st_relaxed_sys_f64(dst + 2, s[2][0]);
-      st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst + 3), want);
-      const double* src = mb.local + (par * kMaxRanks + p) * 4;
+      double* dst = mb.peers[p] + (par * kMaxRanks + mb.rank) * kMboxSlot;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) st_relaxed_sys_f64(dst + q, s[q][0]);
+      st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst + 7), want);
+      const double* src = mb.local + (par * kMaxRanks + p) * kMboxSlot;
       const long long t0 = clock64();
       bool ok = true;
-      while (ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(src + 3)) != want) {
+      while (ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(src + 7)) != want) {
         if (clock64() - t0 > 6000000000LL) { ok = false; break; }   // ~3 s: a peer died; report instead of hanging the GPU
       }
       if (!ok) s_timeout = 1;
-      s_peer[p][0] = ld_relaxed_sys_f64(src + 0); s_peer[p][1] = ld_relaxed_sys_f64(src + 1); s_peer[p][2] = ld_relaxed_sys_f64(src + 2);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s_peer[p][q] = ld_relaxed_sys_f64(src + q);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      double a0 = 0, a1 = 0, a2 = 0;
-      for (int p = 0; p < mb.nranks; ++p) { a0 += s_peer[p][0]; a1 += s_peer[p][1]; a2 += s_peer[p][2]; }   // rank order: identical on every rank
-      scal[0] = a0; scal[1] = a1; scal[2] = a2;
+      double a[6] = {0, 0, 0, 0, 0, 0};
+      for (int p = 0; p < mb.nranks; ++p) {   // rank order: identical on every rank
+#pragma unroll
+        for (int q = 0; q < 5; ++q) a[q] += s_peer[p][q];
+        a[5] = fmax(a[5], s_peer[p][5]);
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) scal[q] = a[q];
       *mb.seq = want;
       if (s_timeout) st->comm_error = 1;
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    s_done = 0;
     const double mu = 1.0 / st->radius;
     const double cost = sys[lay.os];
     const double cost_new = scal[0];
-    const double dg = s[3][0] + scal[1], dDd = s[4][0] + scal[2];
+    const double dg = s[6][0] + scal[1], dDd = s[7][0] + scal[2];
     const double model = 0.5 * (-dg + mu * dDd);
     const double rho = (cost - cost_new) / model;
     const int spd = *spd_flag;
-    st->cost = cost; st->cost_new = cost_new; st->model_change = model; st->rho = rho; st->spd = spd;
-    if (spd && model > 0.0 && rho > 1e-3) {
-      st->accepted = 1;
-      const double t = 2.0 * rho - 1.0;
-      st->radius = fmin(1e16, st->radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
-      st->decrease_factor = 2.0;
-    } else {
-      st->accepted = 0;
-      st->radius = st->radius / st->decrease_factor;
-      st->decrease_factor *= 2.0;
+    int term = 0;
+    if (ta.enabled) {
+      const double gmax = fmax(s[10][0], scal[5]);
+      const double step_norm = sqrt(s[8][0] + scal[3]), x_norm = sqrt(s[9][0] + scal[4]);
+      st->gradient_max_norm = gmax; st->step_norm = step_norm; st->x_norm = x_norm;
+      if (ta.gradient_tolerance > 0.0 && gmax <= ta.gradient_tolerance) term = 3;
+      else if (spd && ta.parameter_tolerance > 0.0 && step_norm <= ta.parameter_tolerance * (x_norm + ta.parameter_tolerance)) term = 2;
+      else if (spd && ta.function_tolerance > 0.0 && fabs(cost - cost_new) <= ta.function_tolerance * cost) term = 1;
     }
-    st->iteration += 1;
-    if (record) record[(st->iteration - 1) % max_records] = *st;   // ring buffer, host tracks the index
+    if (term) {   // the solve ends here; this iteration's step is not applied and not counted (Ceres returns before IsStepSuccessful)
+      st->terminated = term; st->accepted = 0;
+      st->cost = cost; st->cost_new = cost_new; st->model_change = model; st->rho = rho; st->spd = spd;
+      s_done = 1;
+    } else {
+      st->cost = cost; st->cost_new = cost_new; st->model_change = model; st->rho = rho; st->spd = spd;
+      if (spd && model > 0.0 && rho > 1e-3) {
+        st->accepted = 1;
+        const double t = 2.0 * rho - 1.0;
+        st->radius = fmin(1e16, st->radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+        st->decrease_factor = 2.0;
+      } else {
+        st->accepted = 0;
+        st->radius = st->radius / st->decrease_factor;
+        st->decrease_factor *= 2.0;
+      }
+      st->invalid_steps = spd ? 0 : st->invalid_steps + 1;
+      st->iteration += 1;
+      if (ta.enabled) {
+        if (st->invalid_steps >= 5) st->terminated = 5;
+        else if (ta.min_radius > 0.0 && st->radius <= ta.min_radius) st->terminated = 4;
+      }
+      if (record) record[(st->iteration - 1) % max_records] = *st;   // ring buffer, host tracks the index
+    }
   }
   if (fuse_commit) {   // small windows: the accepted trial state is committed by this CTA (== commit_kernel)
     __syncthreads();
-    if (st->accepted) {
+    if (st->accepted && !s_done) {
 #pragma unroll
       for (int q = 0; q < 5; ++q)
         for (size_t i = threadIdx.x; i < ca.count[q]; i += blockDim.x) ca.dst[q][i] = ca.src[q][i];
     }
   }
+}
+
+// start of a solve: clean termination state; reset_radius: ceres::Solve starts every call at initial_trust_region_radius
+__global__ void new_solve_kernel(SolverState* st, double radius0, int reset_radius) {
+  st->terminated = 0; st->invalid_steps = 0;
+  if (reset_radius) { st->radius = radius0; st->decrease_factor = 2.0; }
 }
 
 // unconditional segmented copy (host staging buffer <-> variable blocks in hb200_optimize)

@@ -67,6 +67,10 @@ struct SolverState {  // lives on the device; updated by accept_kernel
   int spd;
   int iteration;
   int comm_error;     // a peer-memory exchange timed out (multi-GPU): the records of this solve are invalid
+  // ceres::TrustRegionMinimizer termination tests (hb200_set_termination); terminated != 0 turns accept_kernel into a no-op
+  int terminated;     // 0 running, 1 function tolerance, 2 parameter tolerance, 3 gradient tolerance, 4 minimum trust-region radius, 5 invalid steps
+  int invalid_steps;  // consecutive non-positive-definite systems
+  double gradient_max_norm, step_norm, x_norm;
 };
 
 }  // namespace hb

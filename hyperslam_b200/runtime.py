@@ -54,7 +54,7 @@ EXPORTS = [
     "hb200_peer_connect", "hb200_peer_disconnect", "hb200_comm_info",
     "hb200_get_bandwidth", "hb200_set_min_bandwidth", "hb200_measure_fp64_peak", "hb200_set_reference_quirks",
     "hb200_append_knots", "hb200_append_landmarks", "hb200_append_pixel_factors", "hb200_append_inertial_factors", "hb200_slide",
-    "hb200_window_sizes",
+    "hb200_window_sizes", "hb200_set_termination", "hb200_get_termination",
 ]
 
 _lib = None
@@ -328,6 +328,17 @@ class Context:
                                             rec if records else None))
         return [dict(cost=r.cost, cost_new=r.cost_new, rho=r.rho, radius=r.radius, accepted=r.accepted, spd=r.spd)
                 for r in rec[:iterations]] if records else None
+
+    def set_termination(self, function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8, min_trust_region_radius=1e-32):
+        """Ceres' termination tests (defaults = ceres::Solver::Options defaults); all <= 0 switches them off."""
+        self._check(self.lib.hb200_set_termination(self.h, C.c_double(function_tolerance), C.c_double(gradient_tolerance), C.c_double(parameter_tolerance),
+                                                   C.c_double(min_trust_region_radius)))
+
+    def termination(self):
+        t, n = C.c_int(0), C.c_int(0)
+        g, s_, x = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._check(self.lib.hb200_get_termination(self.h, C.byref(t), C.byref(n), C.byref(g), C.byref(s_), C.byref(x)))
+        return dict(type=t.value, iterations=n.value, gradient_max_norm=g.value, step_norm=s_.value, x_norm=x.value)
 
     def snapshot(self):
         self._check(self.lib.hb200_snapshot(self.h))

@@ -162,6 +162,18 @@ int hb200_get_delta(hb200_ctx* ctx, double* delta_pose /* n */, double* delta_la
  * accept/reject, all on the device.  records may be NULL. */
 int hb200_iterate(hb200_ctx* ctx, int iterations, hb200_iteration* records);
 int hb200_cost(hb200_ctx* ctx, double* cost);
+/* ceres::Solver::Options termination tests (the reference leaves them at Ceres' defaults, optimizer.cpp:38-54:
+ * function_tolerance 1e-6, gradient_tolerance 1e-10, parameter_tolerance 1e-8, min_trust_region_radius 1e-32), evaluated
+ * on the device in the step-acceptance kernel exactly where ceres::TrustRegionMinimizer evaluates them; a value <= 0
+ * switches a test off, all four off (the default of this library) makes hb200_iterate / hb200_optimize run exactly the
+ * requested number of iterations.  Once a test fires the remaining iterations of the call are no-ops and their records
+ * are zero.  hb200_get_termination: 0 none (iteration limit), 1 function, 2 parameter, 3 gradient tolerance, 4 minimum
+ * trust-region radius, 5 five consecutive invalid steps; plus the number of iterations performed by the last call
+ * that fetched records and the last |x - Plus(x, -g)|_inf, |step|, |x| the tests saw.
+ * hb200_optimize starts every call at the initial radius of hb200_set_options (as ceres::Solve does); hb200_iterate
+ * continues the trust region of the previous call.  At N > 1 the gradient test needs the peer mailbox. */
+int hb200_set_termination(hb200_ctx* ctx, double function_tolerance, double gradient_tolerance, double parameter_tolerance, double min_trust_region_radius);
+int hb200_get_termination(hb200_ctx* ctx, int* type, int* iterations_performed, double* gradient_max_norm, double* step_norm, double* x_norm);
 /* The drop-in for CeresOptimizer::optimize() (reference optimizer.cpp:276-280) with the parameter
  * blocks in HOST memory, as Ceres aliases them: uploads the five variable families, runs
  * `iterations` LM iterations on the device, downloads the updated blocks into the same buffers and

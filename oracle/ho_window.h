@@ -239,6 +239,17 @@ inline void window_eval_inertial(const Window& w, int f, bool want_J, double* r,
 // Reduced-system dof layout: [6K pose | 3Kbg | 3Kba | 2 gravity].
 inline int reduced_size(const Window& w) { return 6 * w.K + 3 * w.Kbg + 3 * w.Kba + 2; }
 
+// ceres::TrustRegionMinimizer termination tests (Ceres 2.x trust_region_minimizer.cc: IterationZero,
+// ParameterToleranceReached, FunctionToleranceReached, HandleSuccessfulStep, FinalizeIterationAndCheckIfMinimizerCanContinue)
+// restated from the public sources -- PARITY UNPINNED like the rest of the LM loop.  The reference leaves the
+// tolerances at Ceres' defaults (reference internal/hyper/optimizers/ceres/optimizer.cpp:38-54).
+struct Termination {
+  double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8, min_radius = 1e-32;
+  int type = 0;            // 0 running, 1 function, 2 parameter, 3 gradient tolerance, 4 minimum radius, 5 invalid steps
+  int invalid_steps = 0;
+  double gradient_max_norm = 0, step_norm = 0, x_norm = 0;
+};
+
 struct IterationOutput {
   std::vector<double> S, b;        // reduced system (n x n row-major full symmetric, n)
   std::vector<double> delta_p;     // n
@@ -340,7 +351,8 @@ inline void retract(Window* w, const std::vector<double>& dp, const std::vector<
 }
 
 // One LM iteration.  If apply == 0 the state is left untouched (used for parity of S, b, delta).
-inline void window_iterate(Window* w, IterationOutput* out, int apply) {
+inline void retract(Window* w, const std::vector<double>& dp, const std::vector<double>& dl);
+inline void window_iterate(Window* w, IterationOutput* out, int apply, Termination* term = nullptr) {
   const int k = w->k, kb = w->k_b, K = w->K, n = reduced_size(*w), L = w->L;
   const int o_bg = 6 * K, o_ba = o_bg + 3 * w->Kbg, o_g = o_ba + 3 * w->Kba;
   std::vector<double> H((size_t)n * n, 0.0), g(n, 0.0);
@@ -457,8 +469,34 @@ inline void window_iterate(Window* w, IterationOutput* out, int apply) {
       S[(size_t)a * n + a] = 1.0; b[a] = 0.0;
     }
   out->S = S; out->b = b;
+  if (term) {
+    // |x - Plus(x, -g)|_inf at the linearisation point, in Ceres' local coordinates (its rotation coordinate is half of
+    // this restatement's theta: Plus(x, -g_ceres) rotates by -4 g_theta); fixed dofs do not move.
+    std::vector<double> dpg(n), dlg((size_t)3 * L);
+    for (int a = 0; a < n; ++a) dpg[a] = fixed[a] ? 0.0 : -g[a];
+    for (int j = 0; j < K; ++j) for (int c = 0; c < 3; ++c) dpg[6 * j + c] *= 4.0;
+    for (int i = 0; i < 3 * L; ++i) dlg[i] = -gl[i];
+    Window xp = *w;
+    retract(&xp, dpg, dlg);
+    double gmax = 0;
+    for (size_t i = 0; i < w->knots.size(); ++i) gmax = std::max(gmax, std::fabs(xp.knots[i] - w->knots[i]));
+    for (size_t i = 0; i < w->bg.size(); ++i) gmax = std::max(gmax, std::fabs(xp.bg[i] - w->bg[i]));
+    for (size_t i = 0; i < w->ba.size(); ++i) gmax = std::max(gmax, std::fabs(xp.ba[i] - w->ba[i]));
+    for (int c = 0; c < 3; ++c) gmax = std::max(gmax, std::fabs(xp.gravity[c] - w->gravity[c]));
+    for (int l = 0; l < L; ++l) if (!lm_obs[l].empty()) for (int c = 0; c < 3; ++c) gmax = std::max(gmax, std::fabs(gl[3 * l + c]));
+    term->gradient_max_norm = gmax;
+    if (term->gradient_tolerance > 0 && gmax <= term->gradient_tolerance) { term->type = 3; return; }
+  }
   std::vector<double> Lc = S, dp = b;
-  if (!cholesky(Lc, n)) { out->spd = 0; out->delta_p.assign(n, 0.0); out->delta_l.assign((size_t)3 * L, 0.0); return; }
+  if (!cholesky(Lc, n)) {
+    out->spd = 0; out->delta_p.assign(n, 0.0); out->delta_l.assign((size_t)3 * L, 0.0);
+    if (apply) {   // HandleInvalidStep: the strategy shrinks the radius as for a rejected step
+      w->radius /= w->decrease_factor; w->decrease_factor *= 2.0; out->radius = w->radius;
+      if (term && ++term->invalid_steps >= 5) term->type = 5;
+    }
+    return;
+  }
+  if (term) term->invalid_steps = 0;
   cholesky_solve(Lc, n, dp);
   // Back-substitution: dl = V^{-1} (-g_l - W^T dp)
   std::vector<double> dl((size_t)3 * L, 0.0), rhs((size_t)3 * L);
@@ -485,6 +523,21 @@ inline void window_iterate(Window* w, IterationOutput* out, int apply) {
   retract(&trial, dp, dl);
   out->cost_new = window_cost(trial);
   out->rho = (out->cost - out->cost_new) / out->model_change;
+  if (term) {
+    // ambient norms over the non-constant parameter blocks (Stamped blocks count their stamp coordinate)
+    double s2 = 0, x2 = 0;
+    auto acc = [&](const double* t, const double* x, int cnt) { for (int c = 0; c < cnt; ++c) { s2 += (t[c] - x[c]) * (t[c] - x[c]); x2 += x[c] * x[c]; } };
+    for (int j = 0; j < K; ++j) if (!w->knot_const[j]) acc(&trial.knots[8 * j], &w->knots[8 * j], 8);
+    if (!w->bias_const) {
+      for (int j = 0; j < w->Kbg; ++j) acc(&trial.bg[4 * j], &w->bg[4 * j], 4);
+      for (int j = 0; j < w->Kba; ++j) acc(&trial.ba[4 * j], &w->ba[4 * j], 4);
+    }
+    if (!w->gravity_const) acc(trial.gravity, w->gravity, 3);
+    for (int l = 0; l < L; ++l) if (!lm_obs[l].empty()) acc(&trial.landmarks[3 * l], &w->landmarks[3 * l], 3);
+    term->step_norm = std::sqrt(s2); term->x_norm = std::sqrt(x2);
+    if (term->parameter_tolerance > 0 && term->step_norm <= term->parameter_tolerance * (term->x_norm + term->parameter_tolerance)) { term->type = 2; return; }
+    if (term->function_tolerance > 0 && std::fabs(out->cost - out->cost_new) <= term->function_tolerance * out->cost) { term->type = 1; return; }
+  }
   // Ceres TrustRegionMinimizer / LevenbergMarquardtStrategy step acceptance (min_relative_decrease 1e-3).
   if (out->model_change > 0 && out->rho > 1e-3) {
     out->accepted = 1;
@@ -500,6 +553,20 @@ inline void window_iterate(Window* w, IterationOutput* out, int apply) {
     w->decrease_factor *= 2.0;
   }
   out->radius = w->radius;
+  if (term && term->min_radius > 0 && w->radius <= term->min_radius) term->type = 4;
+}
+
+// ceres::Solve with max_num_iterations = max_iter: iterations until a termination test fires.  Returns the number performed.
+inline int window_optimize(Window* w, int max_iter, Termination* term, std::vector<IterationOutput>* outs) {
+  int performed = 0;
+  for (int it = 0; it < max_iter && term->type == 0; ++it) {
+    IterationOutput out;
+    window_iterate(w, &out, 1, term);
+    if (term->type == 1 || term->type == 2 || term->type == 3) break;   // ended before this iteration's step was applied / counted
+    outs->push_back(out);
+    performed += 1;
+  }
+  return performed;
 }
 
 

@@ -217,6 +217,14 @@ class OracleWindow:
         return dict(S=S, b=b, delta_p=dp, delta_l=dl, cost=stats[0], cost_new=stats[1], model_change=stats[2], rho=stats[3],
                     radius=stats[4], accepted=int(stats[5]), spd=int(stats[6]), stats=stats)
 
+    def optimize(self, max_iter, function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8, min_radius=1e-32, nthreads=0):
+        """ceres::Solve restated: iterations until one of Ceres' termination tests fires (or max_iter)."""
+        stats, per = np.zeros(6), np.zeros((max_iter, 4))
+        n = lib().ho_window_optimize(self.h, int(max_iter), C.c_double(function_tolerance), C.c_double(gradient_tolerance), C.c_double(parameter_tolerance),
+                                     C.c_double(min_radius), _d(stats), _d(per), nthreads)
+        return dict(type=int(stats[0]), iterations=int(n), gradient_max_norm=stats[2], step_norm=stats[3], x_norm=stats[4], radius=stats[5],
+                    cost=per[:n, 0].copy(), cost_new=per[:n, 1].copy(), accepted=per[:n, 2].astype(int), radii=per[:n, 3].copy())
+
     def build_packed(self):
         n = self.n
         packed = np.zeros(n * n + 3 * n + 2)

@@ -15,5 +15,7 @@ for k, v in r.get("large_windows", {}).items():
 for key in ("comm", "parity", "dense_solver_bar"):
     if d.get(key):
         print(key, d[key])
+if d["e2e"].get("sliding_window"):
+    print("sliding", d["e2e"]["sliding_window"])
 if d.get("cpu_baseline"):
     print("cpu", {k: d["cpu_baseline"][k] for k in ("value", "cores", "gn_iters_per_s")})
