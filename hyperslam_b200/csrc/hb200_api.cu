@@ -431,7 +431,7 @@ int reset_solver_state(hb200_ctx* c) {
 template <bool J>
 PixelArgs pixel_args(hb200_ctx* c, int sel, bool accumulate) {
   PixelArgs a{};
-  a.sys = accumulate ? c->sys.p : nullptr; a.lay = c->lay;
+  a.sys = accumulate ? c->sys.p : nullptr; a.lay = c->lay; a.tiles_per_cta = 1;
   a.n = c->Nv; a.stamp = c->v_stamp.p; a.pixel = reinterpret_cast<const double2*>(c->v_pixel.p); a.meas_z = c->v_z.p; a.idx = c->v_idx.p;
   a.tab = c->tab[sel].p; a.cam_tab = c->cam_tab.p; a.landmarks = c->lms[sel].p;
   a.r = J ? c->v_r.p : nullptr; a.Jp = c->v_Jp.p; a.Jl = c->v_Jl.p; a.w = c->v_w.p; a.cost_partial = c->cp_pix[J ? 0 : 1].p; a.huber = c->huber; a.huber_bearing = c->huber_bearing; a.K_knots = c->K;
@@ -449,9 +449,14 @@ InertialArgs inertial_args(hb200_ctx* c, int sel) {
 template <int K, bool J>
 int launch_pixel(hb200_ctx* c, int sel, bool accumulate = false) {
   if (c->Nv == 0) return 0;
-  const PixelArgs a = pixel_args<J>(c, sel, accumulate);
-  if (J && accumulate) pixel_eval_kernel<K, J, J><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
-  else pixel_eval_kernel<K, J, false><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
+  PixelArgs a = pixel_args<J>(c, sel, accumulate);
+  if (J && accumulate) {
+    // optional (HB200_PIX_TILES): a CTA walks several consecutive tiles and flushes its J^T J accumulators once per knot base
+    static const int tiles_env = getenv("HB200_PIX_TILES") ? atoi(getenv("HB200_PIX_TILES")) : 0;
+    a.tiles_per_cta = tiles_env > 0 ? tiles_env : 1;   // measured on the 1 M-factor window: 1 tile 0.41 ms, 11 tiles 0.50 ms (fewer, longer CTAs lose more than the saved atomics win)
+    const int grid = (c->n_pix_blocks + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    pixel_eval_kernel<K, J, J><<<grid, kEvalThreads, 0, c->stream>>>(a, c->basis);
+  } else pixel_eval_kernel<K, J, false><<<c->n_pix_blocks, kEvalThreads, 0, c->stream>>>(a, c->basis);
   HB_LAUNCH(c, "pixel_eval_kernel");
   return 0;
 }
@@ -459,7 +464,7 @@ template <int K, bool J>
 int launch_inertial(hb200_ctx* c, int sel) {
   if (c->Ni == 0) return 0;
   const InertialArgs a = inertial_args<J>(c, sel);
-  inertial_eval_kernel<K, 4, J><<<c->n_imu_blocks, kEvalThreads, 0, side(c)>>>(a, c->basis, c->bias_basis);
+  inertial_eval_kernel<K, 4, J><<<c->n_imu_blocks, kEvalThreads, J ? inertial_stash_bytes(K) : 0, side(c)>>>(a, c->basis, c->bias_basis);
   HB_LAUNCH(c, "inertial_eval_kernel");
   return 0;
 }
@@ -469,8 +474,9 @@ int launch_factors_merged(hb200_ctx* c, int sel, bool accumulate) {
   const PixelArgs pa = pixel_args<J>(c, sel, accumulate);
   const InertialArgs ia = inertial_args<J>(c, sel);
   const int blocks = c->n_pix_blocks + c->n_imu_blocks;
-  if (J && accumulate) factor_eval_kernel<K, 4, J, J><<<blocks, kEvalThreads, 0, c->stream>>>(pa, ia, c->basis, c->bias_basis, c->n_pix_blocks);
-  else factor_eval_kernel<K, 4, J, false><<<blocks, kEvalThreads, 0, c->stream>>>(pa, ia, c->basis, c->bias_basis, c->n_pix_blocks);
+  const size_t smem = J ? inertial_stash_bytes(K) : 0;
+  if (J && accumulate) factor_eval_kernel<K, 4, J, J><<<blocks, kEvalThreads, smem, c->stream>>>(pa, ia, c->basis, c->bias_basis, c->n_pix_blocks);
+  else factor_eval_kernel<K, 4, J, false><<<blocks, kEvalThreads, smem, c->stream>>>(pa, ia, c->basis, c->bias_basis, c->n_pix_blocks);
   HB_LAUNCH(c, "factor_eval_kernel");
   return 0;
 }
@@ -694,7 +700,7 @@ int enqueue_accept(hb200_ctx* c) {
   double* dsts[5] = {c->knots[0].p, c->bg[0].p, c->ba[0].p, c->grav[0].p, c->lms[0].p};
   size_t mx = 1, total = 0;
   for (int i = 0; i < 5; ++i) { a.count[i] = counts[i]; a.src[i] = srcs[i]; a.dst[i] = dsts[i]; mx = std::max(mx, counts[i]); total += counts[i]; }
-  const bool fuse_commit = total <= 16384;   // small windows: one CTA commits the accepted state right away
+  const bool fuse_commit = total <= 65536;   // small windows: one CTA commits the accepted state right away
   // scalars: summed inside this kernel on one GPU and, across GPUs, exchanged by it through peer memory; only the
   // fallbacks (callback hook, no peer mapping) run scalars_kernel + a second reduction before it
   const bool mailbox = c->nccl && c->peers_open;
@@ -746,8 +752,12 @@ int enqueue_reduce_scalars(hb200_ctx* c) {
 // One LM iteration enqueued on the stream (graph-capturable unless the callback hook is in use).
 int enqueue_iteration(hb200_ctx* c) {
   int rc = 0;
-  if ((rc = enqueue_evaluate(c, true, 0, true, /*keep_fork=*/true, /*clear_system=*/true))) return rc;
-  if ((rc = enqueue_build(c, true))) return rc;
+  // pixel J^T J: fused into the factor kernel (small windows: one launch less on the latency chain) or a separate
+  // segment-wise pass over the Jacobians (large windows); HB200_FUSE=0/1 overrides the choice
+  static const int fuse_env = getenv("HB200_FUSE") ? atoi(getenv("HB200_FUSE")) : -1;
+  const bool fuse = fuse_env >= 0 ? fuse_env != 0 : true;
+  if ((rc = enqueue_evaluate(c, true, 0, fuse, /*keep_fork=*/true, /*clear_system=*/fuse))) return rc;
+  if ((rc = enqueue_build(c, fuse))) return rc;
   if ((rc = enqueue_reduce_system(c))) return rc;
   bool retracted = false;
   if ((rc = enqueue_solve(c, /*fuse_retract=*/true, &retracted))) return rc;
@@ -829,6 +839,14 @@ int create_impl(const hb200_options* options, hb200_ctx* c) {
   if (rc) return rc;
   if (options && options->nccl_comm && (rc = hb200_set_nccl_comm(c, options->nccl_comm, options->nranks, options->rank))) return rc;
   HB_CUDA(cudaFuncSetAttribute(cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCholSmem)));
+  // the Jacobian passes of the inertial factors park their forward-sweep state in dynamic shared memory (41.5 KB at
+  // order 4, 69 KB at order 6); together with the static scratch of the merged kernel that is above the 48 KB default
+  HB_CUDA(cudaFuncSetAttribute(inertial_eval_kernel<4, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(inertial_stash_bytes(4))));
+  HB_CUDA(cudaFuncSetAttribute(inertial_eval_kernel<6, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(inertial_stash_bytes(6))));
+  HB_CUDA(cudaFuncSetAttribute(factor_eval_kernel<4, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(inertial_stash_bytes(4))));
+  HB_CUDA(cudaFuncSetAttribute(factor_eval_kernel<4, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(inertial_stash_bytes(4))));
+  HB_CUDA(cudaFuncSetAttribute(factor_eval_kernel<6, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(inertial_stash_bytes(6))));
+  HB_CUDA(cudaFuncSetAttribute(factor_eval_kernel<6, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(inertial_stash_bytes(6))));
   return reset_solver_state(c);
 }
 }  // namespace

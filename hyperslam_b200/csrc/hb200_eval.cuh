@@ -396,6 +396,8 @@ struct PixelArgs {
   int K_knots;
   double* sys;            // packed band-only reduced system (SysLayout) to accumulate J^T J / J^T r into, or null
   SysLayout lay;
+  int tiles_per_cta;      // consecutive 64-factor tiles one CTA of pixel_eval_kernel walks (large windows: its J^T J accumulators
+                          // stay in registers across tiles of the same knot base, one flush per base instead of one per tile)
 };
 
 // J^T J / J^T r of up to 32 consecutive pixel factors [f0, f0 + cnt) of this CTA, accumulated into the
@@ -408,8 +410,47 @@ struct PixelArgs {
 //     J[k][m] and B[k = l%4][n = l/4] = J[k][n] -- the same shared-memory access pattern -- and
 //     C[m = l/4][n = 2 (l%4) + {0,1}].  This replaced a scalar 3x3-register-tile loop that executed ~9 000
 //     instructions per warp (ncu smsp__inst_executed, profiles/) against ~1 400 for the factor evaluation itself.
+// J^T J tiles / gradient entry a thread carries across the tiles of one knot base (registers)
 template <int K>
-HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[128][6K+1]*/, double* sr /*[128]*/, int* sseg /*[66]*/) {
+struct PixelHessAcc {
+  static constexpr int NB = 6 * K, NT = (NB + 7) / 8, NTILES = NT * (NT + 1) / 2, PER_WARP = (NTILES + 1) / 2;
+  double c0[PER_WARP], c1[PER_WARP], g;
+  int base;
+};
+template <int K>
+HB_DI void pixel_hess_reset(PixelHessAcc<K>& acc, int base) {
+#pragma unroll
+  for (int q = 0; q < PixelHessAcc<K>::PER_WARP; ++q) { acc.c0[q] = 0.0; acc.c1[q] = 0.0; }
+  acc.g = 0.0; acc.base = base;
+}
+template <int K>
+HB_DI void pixel_hess_flush(const PixelArgs& a, const PixelHessAcc<K>& acc) {
+  constexpr int NB = 6 * K, NTILES = PixelHessAcc<K>::NTILES;
+  if (acc.base < 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lm = lane >> 2, lk = lane & 3;
+  double* S = a.sys;
+  const int c0 = 6 * acc.base;
+#pragma unroll
+  for (int q = 0; q < PixelHessAcc<K>::PER_WARP; ++q) {
+    const int tile = warp + 2 * q;
+    if (tile >= NTILES) continue;
+    int ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+    const int tj = tile - ti * (ti + 1) / 2;
+    const int rr = 8 * ti + lm, cc = 8 * tj + 2 * lk;
+    if (rr < NB) {
+      if (cc < NB && cc <= rr) atomicAdd(&S[sys_index(a.lay, c0 + rr, c0 + cc)], acc.c0[q]);
+      if (cc + 1 < NB && cc + 1 <= rr) atomicAdd(&S[sys_index(a.lay, c0 + rr, c0 + cc + 1)], acc.c1[q]);
+      // diag(J^T J) is accumulated on its own (the LM damping needs it BEFORE the Schur complement touches S)
+      if (cc == rr) atomicAdd(&S[a.lay.oD + c0 + rr], acc.c0[q]);
+      if (cc + 1 == rr) atomicAdd(&S[a.lay.oD + c0 + rr], acc.c1[q]);
+    }
+  }
+  if (tid >= kEvalThreads - NB) atomicAdd(&S[a.lay.og + c0 + tid - (kEvalThreads - NB)], acc.g);
+}
+
+template <int K>
+HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[128][6K+1]*/, double* sr /*[128]*/, int* sseg /*[66]*/, PixelHessAcc<K>& acc) {
   constexpr int NB = 6 * K, LD = NB + 1, NT = (NB + 7) / 8, NTILES = NT * (NT + 1) / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // staging: thread = one factor (two Jacobian rows), 128-bit loads, rows scaled by sqrt(w)
@@ -445,13 +486,15 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
   if (warp == 1 && lane == 0) { const int n = s_warp_cnt + __popc(mask); sseg[n] = cnt; sseg[65] = n; }
   __syncthreads();
   const int nseg = sseg[65];
-  double* S = a.sys;
-  double* g = a.sys + a.lay.og;
   const int lm = lane >> 2, lk = lane & 3;
   for (int j = 0; j < nseg; ++j) {
     const int r_lo = 2 * sseg[j], r_hi = 2 * sseg[j + 1];
-    const int c0 = 6 * a.idx[f0 + sseg[j]].x;
-    for (int tile = warp; tile < NTILES; tile += kEvalThreads / 32) {
+    const int base = a.idx[f0 + sseg[j]].x;
+    if (base != acc.base) { pixel_hess_flush<K>(a, acc); pixel_hess_reset<K>(acc, base); }   // (uniform across the CTA)
+#pragma unroll
+    for (int q = 0; q < PixelHessAcc<K>::PER_WARP; ++q) {
+      const int tile = warp + 2 * q;
+      if (tile >= NTILES) continue;
       int ti = 0;
       while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
       const int tj = tile - ti * (ti + 1) / 2;
@@ -459,34 +502,27 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
       const bool va = ma < NB, vb = nb_ < NB;
       const double* pa = sJ + lk * LD + (va ? ma : 0);
       const double* pb = sJ + lk * LD + (vb ? nb_ : 0);
-      double c0v = 0.0, c1v = 0.0;
+      double c0v = acc.c0[q], c1v = acc.c1[q];
       for (int k0 = r_lo; k0 < r_hi; k0 += 4) {   // rows come in pairs: r_lo, r_hi are even; the tail of a segment is masked
         const bool in = k0 + lk < r_hi;
         const double av = (in && va) ? pa[k0 * LD] : 0.0;
         const double bv = (in && vb) ? pb[k0 * LD] : 0.0;
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0v), "+d"(c1v) : "d"(av), "d"(bv));
       }
-      const int rr = 8 * ti + lm, cc = 8 * tj + 2 * lk;
-      if (rr < NB) {
-        if (cc < NB && cc <= rr) atomicAdd(&S[sys_index(a.lay, c0 + rr, c0 + cc)], c0v);
-        if (cc + 1 < NB && cc + 1 <= rr) atomicAdd(&S[sys_index(a.lay, c0 + rr, c0 + cc + 1)], c1v);
-        // diag(J^T J) is accumulated on its own (the LM damping needs it BEFORE the Schur complement touches S)
-        if (cc == rr) atomicAdd(&S[a.lay.oD + c0 + rr], c0v);
-        if (cc + 1 == rr) atomicAdd(&S[a.lay.oD + c0 + rr], c1v);
-      }
+      acc.c0[q] = c0v; acc.c1[q] = c1v;
     }
     if (tid >= kEvalThreads - NB) {   // gradient: the last NB threads
       const int c = tid - (kEvalThreads - NB);
       double g0 = 0.0, g1 = 0.0;
       for (int row = r_lo; row < r_hi; row += 2) { g0 += sJ[row * LD + c] * sr[row]; g1 += sJ[(row + 1) * LD + c] * sr[row + 1]; }
-      atomicAdd(&g[c0 + c], g0 + g1);
+      acc.g += g0 + g1;
     }
   }
 }
 
 // bid: the CTA's index within the pixel grid (the merged factor kernel offsets it)
 template <int K, bool WANT_J, bool FUSE>
-HB_DI void pixel_eval_body(const PixelArgs& a, const Basis& B, int bid) {
+HB_DI void pixel_eval_body(const PixelArgs& a, const Basis& B, int bid0) {
   __shared__ __align__(16) double s_tab[kTileRows * kTabStride];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_red[2];
@@ -495,6 +531,13 @@ HB_DI void pixel_eval_body(const PixelArgs& a, const Basis& B, int bid) {
   __shared__ double s_J[FUSE ? 128 * (6 * K + 1) : 1];
   __shared__ double s_r[FUSE ? 128 : 1];
   __shared__ int s_b[FUSE ? 66 : 1];
+  const int T = (FUSE && a.tiles_per_cta > 1) ? a.tiles_per_cta : 1;
+  PixelHessAcc<K> acc;
+  if (FUSE) pixel_hess_reset<K>(acc, -1);
+  for (int tt = 0; tt < T; ++tt) {
+  const int bid = bid0 * T + tt;
+  if (bid * kEvalThreads >= a.n) break;
+  if (tt) __syncthreads();   // the previous tile's shared-memory state (table tile, mbarrier, J^T J scratch) is done with
   const int f = bid * kEvalThreads + threadIdx.x;
   const bool active = f < a.n;
   int4 id = make_int4(0, 0, 0, 0);
@@ -535,8 +578,10 @@ HB_DI void pixel_eval_body(const PixelArgs& a, const Basis& B, int bid) {
     // fused normal equations of this CTA's factors (residuals / Jacobians were written above; the barrier in the
     // cost reduction ordered them for the whole CTA)
     const int f_lo = bid * kEvalThreads;
-    cta_pixel_hessian<K>(a, f_lo, min(kEvalThreads, a.n - f_lo), s_J, s_r, s_b);
+    cta_pixel_hessian<K>(a, f_lo, min(kEvalThreads, a.n - f_lo), s_J, s_r, s_b, acc);
   }
+  }   // tiles
+  if (FUSE && a.sys != nullptr) pixel_hess_flush<K>(a, acc);
 }
 
 template <int K, bool WANT_J, bool FUSE = false>
@@ -589,7 +634,8 @@ template <int K, int KB, bool WANT_J>
 HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const Basis& BB, int base, int gb, int ab, double t,
                            const double* __restrict__ z, const double* __restrict__ I, const double* __restrict__ bg,
                            const double* __restrict__ ba, const double* __restrict__ grav, double* r, double* __restrict__ Jp,
-                           double* __restrict__ wg_out, double* __restrict__ wa_out, double* __restrict__ Jg) {
+                           double* __restrict__ wg_out, double* __restrict__ wa_out, double* __restrict__ Jg,
+                           double* __restrict__ stash /* shared memory, kInertialStash(K) doubles per thread, or null when !WANT_J */) {
   constexpr int left = (K - 1) / 2;
   const double* row0 = T + static_cast<size_t>(base) * kTabStride;
   const double t0 = row0[left * kTabStride + 24], t1 = row0[(left + 1) * kTabStride + 24];
@@ -602,26 +648,24 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
   double P[9], pdd[3] = {0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 9; ++i) P[i] = row0[i];
-  double A[(K - 1) * 9], LJ[(K - 1) * 9];          // A_j, lambda_j Jr(lambda_j d_j)
-  double ATw[(K - 1) * 3], ATwd[(K - 1) * 3], Wat[(K - 1) * 3];
+  // What the backward sweep needs from step j -- A_j, lambda_j Jr(lambda_j d_j), A_j^T w, A_j^T wd, w_j: 27 doubles --
+  // is parked in SHARED memory (slot s of this thread at stash[s * kEvalThreads]: conflict-free) instead of staying
+  // live in registers across the residual and coefficient computations: with 81 (K = 4) / 135 (K = 6) more doubles
+  // live the kernel sat at 255 registers and spilled 2.7 KB per thread, doubling its DRAM traffic.
   double w[3] = {0, 0, 0}, wd[3] = {0, 0, 0};
-#pragma unroll
+#pragma unroll 1
   for (int j = 1; j < K; ++j) {
     const double* rj = row0 + j * kTabStride;
     const double d[3] = {rj[12], rj[13], rj[14]};
     const double lw[3] = {lam[j] * d[0], lam[j] * d[1], lam[j] * d[2]};
-    double Jr[9], Pn[9];
-    so3_exp_and_Jr(lw, &A[(j - 1) * 9], WANT_J ? Jr : nullptr);
-    if (WANT_J) {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) LJ[(j - 1) * 9 + i] = lam[j] * Jr[i];
-    }
-    m3_mul(P, &A[(j - 1) * 9], Pn);
+    double Aj[9], Jr[9], Pn[9];
+    so3_exp_and_Jr(lw, Aj, WANT_J ? Jr : nullptr);
+    m3_mul(P, Aj, Pn);
 #pragma unroll
     for (int i = 0; i < 9; ++i) P[i] = Pn[i];
     double aw[3], awd[3], wn[3], cr[3];
-    m3_tvec(&A[(j - 1) * 9], w, aw);
-    m3_tvec(&A[(j - 1) * 9], wd, awd);
+    m3_tvec(Aj, w, aw);
+    m3_tvec(Aj, wd, awd);
 #pragma unroll
     for (int c = 0; c < 3; ++c) wn[c] = aw[c] + lamd[j] * d[c];
     cross(wn, d, cr);
@@ -629,8 +673,14 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
     for (int c = 0; c < 3; ++c) {
       wd[c] = awd[c] + lamd[j] * cr[c] + lamdd[j] * d[c];
       w[c] = wn[c];
-      ATw[(j - 1) * 3 + c] = aw[c]; ATwd[(j - 1) * 3 + c] = awd[c]; Wat[(j - 1) * 3 + c] = wn[c];
       pdd[c] += lamdd[j] * (rj[9 + c] - rj[9 + c - kTabStride]);
+    }
+    if (WANT_J) {
+      double* sj = stash + (j - 1) * 27 * kEvalThreads;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { sj[i * kEvalThreads] = Aj[i]; sj[(9 + i) * kEvalThreads] = lam[j] * Jr[i]; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { sj[(18 + c) * kEvalThreads] = aw[c]; sj[(21 + c) * kEvalThreads] = awd[c]; sj[(24 + c) * kEvalThreads] = wn[c]; }
     }
   }
   // ---- bias splines (value + basis weights) ----
@@ -723,15 +773,11 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
     Kal[3 * i + 1] = (i == 0) ? c[2] : (i == 1 ? 0.0 : -c[0]);
     Kal[3 * i + 2] = (i == 0) ? -c[1] : (i == 1 ? c[0] : 0.0);
   }
-  double Cth[18], Cw[18], Cal[18], Cp[18];
-  m3_mul(SgJ, Bm, &Cth[0]);
-  m3_mul(IlinR, Bm, &Cth[9]);
-  m3_mul(SgJ, Kw, &Cw[0]);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) Cw[i] += IgR[i];
-  m3_mul(IlinR, Kw, &Cw[9]);
-  m3_mul(SgJ, Kal, &Cal[0]);
-  m3_mul(IlinR, Kal, &Cal[9]);
+  // The 6 x 3 coefficient matrices [S_g ; I R_sb] {Bm, Kw, Kal} (+ I_g R_sb for the rate) are NOT materialised: with
+  //   M_j = Bm TG_j + Kw XG_j + Kal YG_j      the block of step j is   [S_g M_j + I_g R_sb XG_j ; I_lin R_sb M_j]
+  // -- 54 fewer live doubles across the backward sweep (the calibration matrices sit in shared memory) and six 3x3
+  // products per step instead of nine 6x3x3 ones.
+  double Cp[18];
   m3_mult(SgJ, P, &Cp[0]);  // S_g R^T
   m3_mult(IaR, P, &Cp[9]);  // I_a R_sb R^T (inertial.cpp:150,198 use I_a in every variant)
   (void)Rsb;
@@ -750,18 +796,23 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
   for (int i = 0; i < 9; ++i) { Pc[i] = P[i]; QT[i] = (i % 4 == 0) ? 1.0 : 0.0; Z[i] = 0.0; }
 #pragma unroll
   for (int i = 0; i < 18; ++i) Dprev[i] = 0.0;
-#pragma unroll
+#pragma unroll 1   // one step's live set at a time: fully unrolled, the scheduler interleaved the steps and spilled 2.4 KB per thread
   for (int j = K - 1; j >= 1; --j) {
     const double* rj = row0 + j * kTabStride;
     const double d[3] = {rj[12], rj[13], rj[14]};
-    const double* lj = &LJ[(j - 1) * 9];
+    const double* sj = stash + (j - 1) * 27 * kEvalThreads;
+    double lj[9], atw[3], atwd[3], wat[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) lj[i] = sj[(9 + i) * kEvalThreads];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { atw[c] = sj[(18 + c) * kEvalThreads]; atwd[c] = sj[(21 + c) * kEvalThreads]; wat[c] = sj[(24 + c) * kEvalThreads]; }
     double X[9], Y[9], tmp[9], tmp2[9];
-    hat_mul(&ATw[(j - 1) * 3], lj, X);
+    hat_mul(atw, lj, X);
 #pragma unroll
     for (int i = 0; i < 3; ++i) X[4 * i] += lamd[j];
-    hat_mul(&ATwd[(j - 1) * 3], lj, Y);
+    hat_mul(atwd, lj, Y);
     hat_mul(d, X, tmp);
-    hat(&Wat[(j - 1) * 3], tmp2);
+    hat(wat, tmp2);
 #pragma unroll
     for (int i = 0; i < 9; ++i) Y[i] += lamd[j] * (tmp2[i] - tmp[i]);
 #pragma unroll
@@ -780,13 +831,21 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
     m3_mul(Xf, G, XG);
     m3_mul(Yf, G, YG);
     double D[18];
+    {
+      double M[9], t9[9];
+      m3_mul(Bm, TG, M);
+      m3_mul(Kw, XG, t9);
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 9; ++i) M[i] += t9[i];
+      m3_mul(Kal, YG, t9);
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        D[3 * i + c] = Cth[3 * i] * TG[c] + Cth[3 * i + 1] * TG[3 + c] + Cth[3 * i + 2] * TG[6 + c] + Cw[3 * i] * XG[c] +
-                       Cw[3 * i + 1] * XG[3 + c] + Cw[3 * i + 2] * XG[6 + c] + Cal[3 * i] * YG[c] + Cal[3 * i + 1] * YG[3 + c] +
-                       Cal[3 * i + 2] * YG[6 + c];
+      for (int i = 0; i < 9; ++i) M[i] += t9[i];
+      m3_mul(SgJ, M, &D[0]);
+      m3_mul(IgR, XG, t9);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) D[i] += t9[i];
+      m3_mul(IlinR, M, &D[9]);
+    }
     // block m = j : rotation = D_j - D_{j+1}, translation = (lamdd_m - lamdd_{m+1}) * Cp
     {
       const double wdd = lamdd[j] - lamdd[j + 1];
@@ -801,7 +860,9 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
 #pragma unroll
     for (int i = 0; i < 18; ++i) Dprev[i] = D[i];
     // Pc <- Pc A_j^T ; Z <- (Z - lamd_j QT d^) A_j^T ; QT <- QT A_j^T
-    const double* Aj = &A[(j - 1) * 9];
+    double Aj[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Aj[i] = sj[i * kEvalThreads];
     m3_mult(Pc, Aj, tmp);
 #pragma unroll
     for (int i = 0; i < 9; ++i) Pc[i] = tmp[i];
@@ -813,8 +874,11 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
 #pragma unroll
     for (int i = 0; i < 9; ++i) QT[i] = tmp[i];
   }
-  // block m = 0 : rotation = Cth - D_1
+  // block m = 0 : rotation = [S_g ; I_lin R_sb] Bm - D_1
   {
+    double Cth[18];
+    m3_mul(SgJ, Bm, &Cth[0]);
+    m3_mul(IlinR, Bm, &Cth[9]);
     const double wdd = lamdd[0] - lamdd[1];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -826,8 +890,13 @@ HB_DI void inertial_factor(const double* __restrict__ T, const Basis& B, const B
   }
 }
 
+// dynamic shared memory of the Jacobian pass of the inertial factors (the merged factor kernel carries it too)
+constexpr size_t inertial_stash_bytes(int K) { return static_cast<size_t>(27) * (K - 1) * kEvalThreads * sizeof(double); }
+
 template <int K, int KB, bool WANT_J>
 HB_DI void inertial_eval_body(const InertialArgs& a, const Basis& B, const Basis& BB, int bid) {
+  extern __shared__ double s_dyn_eval[];
+  double* stash = WANT_J ? s_dyn_eval + threadIdx.x : nullptr;
   __shared__ __align__(16) double s_tab[kTileRows * kTabStride];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_red[2];
@@ -861,9 +930,9 @@ HB_DI void inertial_eval_body(const InertialArgs& a, const Basis& B, const Basis
     double* Jg = WANT_J ? a.Jg + static_cast<size_t>(f) * 12 : nullptr;
     if (staged)
       inertial_factor<K, KB, WANT_J>(s_tab - static_cast<ptrdiff_t>(bmin) * kTabStride, B, BB, id.x, id.y, id.z, t, z, s_imu, a.bg, a.ba,
-                                     s_grav, r, Jp, wg, wa, Jg);
+                                     s_grav, r, Jp, wg, wa, Jg, stash);
     else
-      inertial_factor<K, KB, WANT_J>(a.tab, B, BB, id.x, id.y, id.z, t, z, s_imu, a.bg, a.ba, s_grav, r, Jp, wg, wa, Jg);
+      inertial_factor<K, KB, WANT_J>(a.tab, B, BB, id.x, id.y, id.z, t, z, s_imu, a.bg, a.ba, s_grav, r, Jp, wg, wa, Jg, stash);
     double s = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) s += r[i] * r[i];
