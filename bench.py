@@ -280,11 +280,15 @@ def roofline_entry(name, nbytes, ms, peak):
 
 def comm_entry(h, agg, reps_total=1):
     """NVLink side of the iteration: payload and bus bandwidth of the one system all-reduce."""
-    pay = h.ctx.comm_info()["payload_doubles"] * 8
-    ms = agg.get("ncclAllReduce(system)")
+    info = h.ctx.comm_info()
+    pay = info["payload_doubles"] * 8
+    peer = info.get("peer_reduce")
+    ms = agg.get("peer_reduce_kernel") if peer else agg.get("ncclAllReduce(system)")
     n = h.world
-    out = dict(allreduce_bytes=pay, collectives_per_iteration="1 ncclAllReduce (packed band-only system)" + (
-        " + peer-memory scalar exchange fused in accept_kernel" if h.comm.get("peer_mailbox") else " + 1 ncclAllReduce (4 scalars)"),
+    what = ("1 fused barrier + all-reduce kernel over NVLink peer memory (peer_reduce_kernel: flag exchange, then every rank sums the N partial "
+            "systems out of its peers' HBM in rank order); no NCCL call on the iteration path") if peer else "1 ncclAllReduce (packed band-only system)"
+    out = dict(allreduce_bytes=pay, mode="peer-memory" if peer else "nccl", collectives_per_iteration=what + (
+        " + peer-memory scalar exchange fused in accept_kernel" if info.get("peer_mailbox") else " + 1 ncclAllReduce (8 scalars)"),
         comm_ms=ms)
     if ms:
         out["nvlink_algbw_gbs"] = pay / (ms * 1e-3) / 1e9
@@ -591,7 +595,7 @@ def main():
                    sample=f"{reps} full LM iterations + {r2} all-core and {r3} single-thread Evaluate sweeps of {nf_total} factors (oracle restatement; Ceres cannot be built here)",
                    gn_iters_per_s=1.0 / it_s, evaluate_only_all_cores=ev_all, evaluate_only_cores=ev_cores, evaluate_only_one_thread=ev_one)
 
-    step_desc = "one LM iteration (evaluate r+J, JtJ, Schur, " + ("1 NCCL all-reduce, " if world > 1 else "") + \
+    step_desc = "one LM iteration (evaluate r+J, JtJ, Schur, " + (("1 peer-memory all-reduce kernel, " if info.get("peer_reduce") else "1 NCCL all-reduce, ") if world > 1 else "") + \
                 "banded Cholesky, retract, trial cost, accept) " + ("as one CUDA graph" if info["graph"] else "direct launches (graph capture unavailable)")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",

@@ -251,7 +251,17 @@ struct hb200_ctx {
   long long nccl_calls = 0, nccl_calls_per_iteration = 0;
   int nranks = 1, rank = 0;
   bool comm_warm = false;        // one eager all-reduce has run (NCCL's lazy setup is done: safe to capture)
-  DevBuf<double> mbox;           // [2][kMaxRanks][4]
+  DevBuf<double> mbox;           // the peer arena: [mailbox | flags | partial system A | partial system B] (hb200_solve.cuh)
+  long long arena_cap = 0;       // doubles per partial
+  int peer_par = 0;              // arena half the NEXT iteration assembles into
+  bool peer_reduce_wanted = true;
+  DevBuf<unsigned long long> red_round;
+  DevBuf<unsigned int> red_arrive;
+  cudaGraph_t graph_b = nullptr;            // second capture of the iteration (arena half B)
+  cudaGraphExec_t graph_exec_b = nullptr;
+  bool graph_b_valid = false;
+  bool peer_reduce() const { return nccl && peers_open && peer_reduce_wanted && lay.total <= arena_cap; }
+  double* assembly() { return peer_reduce() ? mbox.p + kArenaParts + static_cast<long long>(peer_par) * arena_cap : sys.p; }
   DevBuf<unsigned long long> mbox_seq;
   DevBuf<double*> d_peers;
   std::vector<void*> peer_ptrs;  // cudaIpcOpenMemHandle mappings (own entry = mbox.p)
@@ -431,7 +441,7 @@ int reset_solver_state(hb200_ctx* c) {
 template <bool J>
 PixelArgs pixel_args(hb200_ctx* c, int sel, bool accumulate) {
   PixelArgs a{};
-  a.sys = accumulate ? c->sys.p : nullptr; a.lay = c->lay; a.tiles_per_cta = 1;
+  a.sys = accumulate ? c->assembly() : nullptr; a.lay = c->lay; a.tiles_per_cta = 1;
   a.n = c->Nv; a.stamp = c->v_stamp.p; a.pixel = reinterpret_cast<const double2*>(c->v_pixel.p); a.meas_z = c->v_z.p; a.idx = c->v_idx.p;
   a.tab = c->tab[sel].p; a.cam_tab = c->cam_tab.p; a.landmarks = c->lms[sel].p;
   a.r = J ? c->v_r.p : nullptr; a.Jp = c->v_Jp.p; a.Jl = c->v_Jl.p; a.w = c->v_w.p; a.cost_partial = c->cp_pix[J ? 0 : 1].p; a.huber = c->huber; a.huber_bearing = c->huber_bearing; a.K_knots = c->K;
@@ -504,7 +514,7 @@ int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false
   if (!skip_prep) {
     const size_t nclear = clear_system ? static_cast<size_t>(c->lay.total) : 0;
     const int blocks = clear_system ? static_cast<int>(std::min<size_t>((nclear / 4 + 255) / 256, static_cast<size_t>(c->num_sms) * 4)) : (c->K + 255) / 256;
-    prep_kernel<<<std::max(blocks, (c->K + 255) / 256), 256, 0, c->stream>>>(c->K, c->knots[sel].p, c->tab[sel].p, clear_system ? c->sys.p : nullptr, nclear);
+    prep_kernel<<<std::max(blocks, (c->K + 255) / 256), 256, 0, c->stream>>>(c->K, c->knots[sel].p, c->tab[sel].p, clear_system ? c->assembly() : nullptr, nclear);
     HB_LAUNCH(c, "prep_kernel");
   }
   int rc = 0;
@@ -539,7 +549,7 @@ int enqueue_evaluate(hb200_ctx* c, bool want_J, int sel, bool accumulate = false
 }
 
 int enqueue_clear_system(hb200_ctx* c) {
-  HB_CUDA(cudaMemsetAsync(c->sys.p, 0, static_cast<size_t>(c->lay.total) * sizeof(double), c->stream));
+  HB_CUDA(cudaMemsetAsync(c->assembly(), 0, static_cast<size_t>(c->lay.total) * sizeof(double), c->stream));
   prof_mark(c, "memset(system)");
   return 0;
 }
@@ -551,40 +561,40 @@ int enqueue_clear_system(hb200_ctx* c) {
 int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
   if (!pixel_fused) { int rc0 = enqueue_clear_system(c); if (rc0) return rc0; }
   if (c->Nv && !pixel_fused) {
-    if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->sys.p, c->lay, c->pix_splits);
-    else pixel_hessian_kernel<6><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->sys.p, c->lay, c->pix_splits);
+    if (c->k == 4) pixel_hessian_kernel<4><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->assembly(), c->lay, c->pix_splits);
+    else pixel_hessian_kernel<6><<<c->nseg * c->pix_splits, kHessThreads, 0, c->stream>>>(c->seg_off.p, c->v_r.p, c->v_Jp.p, c->v_w.p, c->assembly(), c->lay, c->pix_splits);
     HB_LAUNCH(c, "pixel_hessian_kernel");
   }
   { const int rf = fork_side(c); if (rf) return rf; }   // (no-op when already forked or while profiling)
   if (c->Ni) {
     if (c->k == 4)
       inertial_hessian_kernel<4, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+                                                                             c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     else
       inertial_hessian_kernel<6, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                             c->i_Jg.p, c->imu_scale, c->sys.p, c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+                                                                             c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     HB_LAUNCH(c, "inertial_hessian_kernel");
   }
   if (c->Nm) {
     const int blocks = (c->Nm + kManWarps - 1) / kManWarps;
-    if (c->k == 4) manifold_hessian_kernel<4><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->lay);
-    else manifold_hessian_kernel<6><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->sys.p, c->lay);
+    if (c->k == 4) manifold_hessian_kernel<4><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->assembly(), c->lay);
+    else manifold_hessian_kernel<6><<<blocks, kManWarps * 32, 0, side(c)>>>(c->Nm, c->m_idx.p, c->m_r.p, c->m_Jp.p, c->assembly(), c->lay);
     HB_LAUNCH(c, "manifold_hessian_kernel");
   }
   if (c->forked) {   // the cost partials of the visual factors come from the main stream
     HB_CUDA(cudaEventRecord(c->ev_mid, c->stream));
     HB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_mid, 0));
   }
-  cost_kernel<<<1, 256, 0, side(c)>>>(c->sys.p, c->lay, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p, c->n_imu_blocks + c->n_man_blocks);
+  cost_kernel<<<1, 256, 0, side(c)>>>(c->assembly(), c->lay, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p, c->n_imu_blocks + c->n_man_blocks);
   HB_LAUNCH(c, "cost_kernel");
   if (c->Nv && c->L) {
     const size_t smem = 2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double);
     if (c->k == 4)
       schur_kernel<4><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p, c->st.p,
-                                                                c->sys.p, c->lay, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
+                                                                c->assembly(), c->lay, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
     else
       schur_kernel<6><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p, c->st.p,
-                                                                c->sys.p, c->lay, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
+                                                                c->assembly(), c->lay, c->Vinv.p, c->gl.p, c->Dl.p, c->max_rows);
     HB_LAUNCH(c, "schur_kernel");
   }
   return join_side(c);
@@ -719,6 +729,19 @@ int enqueue_accept(hb200_ctx* c) {
 
 // Sum of the packed partial systems over the ranks: ONE ncclAllReduce on the context's stream (capturable).
 int enqueue_reduce_system(hb200_ctx* c) {
+  if (c->peer_reduce()) {
+    // fused barrier + reduction over peer memory (peer_reduce_kernel); the next iteration assembles into the other half
+    PeerReduceArgs a{};
+    a.nranks = c->nranks; a.rank = c->rank; a.peers = c->d_peers.p; a.local = c->mbox.p;
+    a.part_offset = kArenaParts + static_cast<long long>(c->peer_par) * c->arena_cap; a.total = c->lay.total;
+    a.out = c->sys.p; a.round = c->red_round.p; a.arrive = c->red_arrive.p; a.st = c->st.p;
+    const long long pairs = c->lay.total / 2;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(2LL * c->num_sms, (pairs + kReduceThreads - 1) / kReduceThreads)));
+    peer_reduce_kernel<<<grid, kReduceThreads, 0, c->stream>>>(a);
+    HB_LAUNCH(c, "peer_reduce_kernel");
+    c->peer_par ^= 1;
+    return 0;
+  }
   if (c->nccl) {
     HB_NCCL(g_nccl.AllReduce(c->sys.p, c->sys.p, static_cast<size_t>(c->lay.total), /*ncclDouble*/ 8, /*ncclSum*/ 0, c->nccl, c->stream));
     c->nccl_calls += 1;
@@ -877,7 +900,9 @@ void hb200_destroy(hb200_ctx* c) {
   // the captured iteration references the communicator: NCCL waits in ncclCommDestroy until such graphs are gone
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->graph) cudaGraphDestroy(c->graph);
-  c->graph_exec = nullptr; c->graph = nullptr;
+  if (c->graph_exec_b) cudaGraphExecDestroy(c->graph_exec_b);
+  if (c->graph_b) cudaGraphDestroy(c->graph_b);
+  c->graph_exec = nullptr; c->graph = nullptr; c->graph_exec_b = nullptr; c->graph_b = nullptr;
   if (c->nccl && c->own_nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
   c->nccl = nullptr;
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
@@ -1687,46 +1712,55 @@ int iterate_enqueue(hb200_ctx* c, int iterations) {
   int rc = 0;
   for (int it = 0; it < iterations; ++it) {
     // the callback hook cannot be captured; with NCCL the first iteration runs eagerly (NCCL finishes its lazy
-    // channel / buffer setup outside of a capture), every later one is a graph launch
-    const bool graph_ok = c->use_graph && !c->allreduce && (!c->nccl || c->comm_warm);
+    // channel / buffer setup outside of a capture), every later one is a graph launch.  With the peer-memory
+    // reduction the iteration exists twice: it assembles into arena half A or B by parity.
+    const bool graph_ok = c->use_graph && !c->allreduce && (!c->nccl || c->comm_warm || c->peer_reduce());
     if (graph_ok) {
-      if (!c->graph_valid) {
-        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-        if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+      const bool slot_b = c->peer_reduce() && c->peer_par == 1;
+      cudaGraph_t& graph = slot_b ? c->graph_b : c->graph;
+      cudaGraphExec_t& exec = slot_b ? c->graph_exec_b : c->graph_exec;
+      bool& valid = slot_b ? c->graph_b_valid : c->graph_valid;
+      if (!c->graph_valid) c->graph_b_valid = false;   // (invalidate() only knows the first slot)
+      if (!valid) {
+        if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
+        if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+        const int par_before = c->peer_par;
         HB_CUDA(cudaStreamBeginCapture(c->stream, c->nccl ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
         const long long before = c->launches, nccl_before = c->nccl_calls;
         rc = enqueue_iteration(c);
-        cudaError_t e = cudaStreamEndCapture(c->stream, &c->graph);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
         c->launches = before;  // capture does not execute
         c->nccl_calls_per_iteration = c->nccl_calls - nccl_before;
         c->nccl_calls = nccl_before;
+        c->peer_par = par_before;   // (enqueue_iteration toggled it: the toggle happens again at the launch below)
         if (rc) return rc;
         if (e != cudaSuccess) {
           if (!c->nccl) return fail(100 + static_cast<int>(e), "graph capture: %s", cudaGetErrorString(e));
           // a communicator that cannot be captured: fall back to direct launches for this context
           cudaGetLastError();
-          c->use_graph = false; c->graph = nullptr;
+          c->use_graph = false; graph = nullptr;
           --it;
           continue;
         }
-        HB_CUDA(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
-        c->graph_valid = true;
+        HB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        valid = true;
         c->launches_per_iteration = 0;
         size_t nodes = 0;
-        HB_CUDA(cudaGraphGetNodes(c->graph, nullptr, &nodes));
+        HB_CUDA(cudaGraphGetNodes(graph, nullptr, &nodes));
         cudaGraphNode_t* nd = new cudaGraphNode_t[nodes];
-        HB_CUDA(cudaGraphGetNodes(c->graph, nd, &nodes));
+        HB_CUDA(cudaGraphGetNodes(graph, nd, &nodes));
         for (size_t i = 0; i < nodes; ++i) { cudaGraphNodeType t; if (cudaGraphNodeGetType(nd[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) c->launches_per_iteration += 1; }
         delete[] nd;
         c->launches_per_iteration -= c->nccl_calls_per_iteration;   // NCCL's kernel nodes are not this library's launches
         if (getenv("HB200_GRAPH_DEBUG")) {
           size_t edges = 0;
-          cudaGraphGetEdges(c->graph, nullptr, nullptr, &edges);
-          std::fprintf(stderr, "[hb200] iteration graph: %zu nodes (%lld own kernels, %lld NCCL), %zu edges\n", nodes, c->launches_per_iteration,
-                       c->nccl_calls_per_iteration, edges);
+          cudaGraphGetEdges(graph, nullptr, nullptr, &edges);
+          std::fprintf(stderr, "[hb200] iteration graph%s: %zu nodes (%lld own kernels, %lld NCCL), %zu edges\n", slot_b ? " (arena half B)" : "", nodes,
+                       c->launches_per_iteration, c->nccl_calls_per_iteration, edges);
         }
       }
-      HB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
+      HB_CUDA(cudaGraphLaunch(exec, c->stream));
+      if (c->peer_reduce()) c->peer_par ^= 1;
       c->launches += c->launches_per_iteration;
       c->nccl_calls += c->nccl_calls_per_iteration;
     } else {
@@ -2343,7 +2377,9 @@ int hb200_set_nccl_comm(hb200_ctx* c, void* comm, int nranks, int rank) {
   HB_CUDA(cudaStreamSynchronize(c->stream));
   if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // it references the old communicator
   if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
-  c->graph_valid = false;
+  if (c->graph_exec_b) { cudaGraphExecDestroy(c->graph_exec_b); c->graph_exec_b = nullptr; }
+  if (c->graph_b) { cudaGraphDestroy(c->graph_b); c->graph_b = nullptr; }
+  c->graph_valid = false; c->graph_b_valid = false;
   if (c->nccl && c->own_nccl) g_nccl.CommDestroy(c->nccl);
   c->nccl = comm; c->own_nccl = false;
   c->nranks = comm ? nranks : 1; c->rank = comm ? rank : 0;
@@ -2370,10 +2406,19 @@ int hb200_comm_init_rank(hb200_ctx* c, int nranks, int rank, const char* id) {
 int hb200_peer_handle(hb200_ctx* c, char* handle) {
   if (!c || !handle) return fail(-1, "null argument");
   HB_CUDA(cudaSetDevice(c->device));
-  HB_CUDA(c->mbox.ensure(2 * kMaxRanks * kMboxSlot));
-  HB_CUDA(c->mbox_seq.ensure(1));
-  HB_CUDA(cudaMemsetAsync(c->mbox.p, 0, sizeof(double) * 2 * kMaxRanks * kMboxSlot, c->stream));
+  // the arena: mailbox + flag row + two partial-system halves (capacity HB200_PEER_ARENA_DOUBLES each, default 600 k doubles =
+  // 4.8 MB: a K = 1000 window; larger systems fall back to ncclAllReduce)
+  const long long cap = getenv("HB200_PEER_ARENA_DOUBLES") ? std::max(0LL, atoll(getenv("HB200_PEER_ARENA_DOUBLES"))) & ~1LL : 600000LL;
+  const size_t arena = static_cast<size_t>(kArenaParts) + 2 * static_cast<size_t>(cap);
+  HB_CUDA(c->mbox.ensure(arena));
+  c->arena_cap = cap;
+  HB_CUDA(c->mbox_seq.ensure(1)); HB_CUDA(c->red_round.ensure(1)); HB_CUDA(c->red_arrive.ensure(1));
+  HB_CUDA(cudaMemsetAsync(c->mbox.p, 0, sizeof(double) * kArenaParts, c->stream));
   HB_CUDA(cudaMemsetAsync(c->mbox_seq.p, 0, sizeof(unsigned long long), c->stream));
+  HB_CUDA(cudaMemsetAsync(c->red_round.p, 0, sizeof(unsigned long long), c->stream));
+  HB_CUDA(cudaMemsetAsync(c->red_arrive.p, 0, sizeof(unsigned int), c->stream));
+  c->peer_par = 0;
+  c->peer_reduce_wanted = !(getenv("HB200_PEER_REDUCE") && atoi(getenv("HB200_PEER_REDUCE")) == 0);
   HB_CUDA(cudaStreamSynchronize(c->stream));
   cudaIpcMemHandle_t h;
   HB_CUDA(cudaIpcGetMemHandle(&h, c->mbox.p));
@@ -2455,7 +2500,7 @@ int hb200_comm_info(hb200_ctx* c, int* nranks, int* rank, int* nccl, int* peer_m
   if (nranks) *nranks = c->nranks;
   if (rank) *rank = c->rank;
   if (nccl) *nccl = c->nccl ? 1 : 0;
-  if (peer_mailbox) *peer_mailbox = (c->nccl && c->peers_open) ? 1 : 0;
+  if (peer_mailbox) *peer_mailbox = (c->nccl && c->peers_open) ? (c->peer_reduce() ? 2 : 1) : 0;   // 2: the system reduction runs over peer memory too
   if (graph) *graph = (c->use_graph && !c->allreduce && c->graph_valid) ? 1 : 0;
   if (payload_doubles) *payload_doubles = c->bound ? c->lay.total : 0;
   return 0;

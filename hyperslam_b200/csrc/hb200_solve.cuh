@@ -885,6 +885,69 @@ HB_DI double ld_relaxed_sys_f64(const double* p) {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The system reduction over peer memory: barrier + all-reduce in ONE kernel, no library call.
+// Every rank's partial packed system sits in its peer arena (mapped into every process with cudaIpcOpenMemHandle).
+// CTA 0 tells every peer "my partial of round `want` is complete" (one st.release.sys per peer into the peer's flag
+// row); every CTA waits until all ranks' flags of this round have arrived in the LOCAL flag row, then the grid sums
+// the N partials straight out of the peers' HBM over NVLink (ld.relaxed.sys, 16 B per lane) in RANK ORDER -- every
+// replica computes bit-identical sums -- into the local reduced system the solver reads.  Nothing is written to a
+// peer except the flags, so no second barrier is needed: partials alternate between two arena halves (A / B by
+// iteration parity) and a rank cannot run two rounds ahead of a peer it has to wait for.
+// The last CTA to finish advances the round counter (all CTAs read it first: no CTA can see the new value early).
+// Arena layout (doubles): [mailbox 2 x kMaxRanks x kMboxSlot | flags kMaxRanks | partial A cap | partial B cap].
+// ---------------------------------------------------------------------------------------------
+constexpr int kArenaFlags = 2 * kMaxRanks * kMboxSlot;        // offset of the flag row
+constexpr int kArenaParts = kArenaFlags + 2 * kMaxRanks;      // offset of partial A (16-byte aligned)
+constexpr int kReduceThreads = 256;
+struct PeerReduceArgs {
+  int nranks, rank;
+  double* const* peers;          // arena base of every rank in this process' address space
+  double* local;                 // own arena
+  long long part_offset, total;  // active partial (offset in doubles inside the arena), doubles to reduce
+  double* out;                   // local reduced system
+  unsigned long long* round;     // rounds completed (device counter, identical on every rank)
+  unsigned int* arrive;          // CTAs finished in this launch
+  SolverState* st;               // comm_error on a timeout
+};
+HB_DI double2 ld_relaxed_sys_f64x2(const double* p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(kReduceThreads) peer_reduce_kernel(PeerReduceArgs a) {
+  __shared__ int s_bad;
+  const unsigned long long want = *reinterpret_cast<volatile unsigned long long*>(a.round) + 1;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < a.nranks)
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(a.peers[tid] + kArenaFlags) + a.rank, want);
+  if (tid < a.nranks) {
+    const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(a.local + kArenaFlags) + tid;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(flag) < want) {
+      if (clock64() - t0 > 6000000000LL) { s_bad = 1; break; }   // ~3 s: a peer died; report instead of hanging the GPU
+    }
+  }
+  __syncthreads();
+  const long long pairs = a.total / 2;   // total is even (SysLayout)
+  for (long long e = blockIdx.x * static_cast<long long>(kReduceThreads) + tid; e < pairs; e += static_cast<long long>(gridDim.x) * kReduceThreads) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int p = 0; p < a.nranks; ++p) {
+      const double2 v = ld_relaxed_sys_f64x2(a.peers[p] + a.part_offset + 2 * e);
+      acc.x += v.x; acc.y += v.y;
+    }
+    reinterpret_cast<double2*>(a.out)[e] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (s_bad) a.st->comm_error = 1;
+    __threadfence();
+    if (atomicAdd(a.arrive, 1u) == gridDim.x - 1) { *a.arrive = 0; __threadfence(); *a.round = want; }
+  }
+}
+
 constexpr int kAcceptThreads = 1024;   // one CTA; wide so that the fused commit copies the state in a few passes
 
 // ceres::TrustRegionMinimizer termination tests (Ceres 2.x trust_region_minimizer.cc, restated from the public

@@ -438,8 +438,8 @@ class Context:
         v = [C.c_int(0) for _ in range(5)]
         pay = C.c_longlong(0)
         self._check(self.lib.hb200_comm_info(self.h, *[C.byref(x) for x in v], C.byref(pay)))
-        return dict(nranks=v[0].value, rank=v[1].value, nccl=bool(v[2].value), peer_mailbox=bool(v[3].value), graph=bool(v[4].value),
-                    payload_doubles=pay.value)
+        return dict(nranks=v[0].value, rank=v[1].value, nccl=bool(v[2].value), peer_mailbox=bool(v[3].value), peer_reduce=(v[3].value == 2),
+                    graph=bool(v[4].value), payload_doubles=pay.value)
 
     def connect_torch_distributed(self, dist, peer_mailbox=True, log=lambda m: None):
         """Plumbing only: ships the NCCL unique id and the mailbox handles over an initialised torch.distributed

@@ -25,7 +25,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     win = synthetic.make_window(order=4, num_knots=20, num_landmarks=160, num_imu=400, seed=synthetic.SEED_BASE + 700, constant_knots=2)
     stage("process group up")
-    mode = sys.argv[1] if len(sys.argv) > 1 else "nccl+mailbox"
+    mode = sys.argv[1] if len(sys.argv) > 1 else "peer"
+    if mode != "peer":   # "peer": barrier + system reduction + scalar exchange all over peer memory, no NCCL call per iteration
+        os.environ["HB200_PEER_REDUCE"] = "0"
     ctx = runtime.Context(local, use_graph=(mode != "callback"))
     ctx.load_window(win.shard(rank, world))
     info = {}
@@ -47,7 +49,7 @@ def main():
         dist.all_reduce(beta, op=dist.ReduceOp.MAX)
         ctx.set_min_bandwidth(int(beta.item()))
     else:                    # the product path: ncclAllReduce enqueued by the library, inside the iteration's CUDA graph
-        info = ctx.connect_torch_distributed(dist, peer_mailbox=(mode == "nccl+mailbox"), log=stage)
+        info = ctx.connect_torch_distributed(dist, peer_mailbox=(mode in ("peer", "nccl+mailbox")), log=stage)
     stage(f"connected {info}")
     recs = ctx.iterate(4)
     stage("iterated")

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode", ["nccl+mailbox", "nccl", "callback"])
+@pytest.mark.parametrize("mode", ["peer", "nccl+mailbox", "nccl", "callback"])
 def test_two_rank_iterations_match_single_rank_oracle(built, mode):
     import torch
     if torch.cuda.device_count() < 2:
@@ -24,4 +24,5 @@ def test_two_rank_iterations_match_single_rank_oracle(built, mode):
     assert out["ok"] and out["replicas_identical"], out
     if mode != "callback":
         assert out["comm"]["nccl"] and out["comm"]["graph"], out          # the iteration ran as a CUDA graph with NCCL inside
-        assert out["comm"]["peer_mailbox"] == (mode == "nccl+mailbox"), out
+        assert out["comm"]["peer_mailbox"] == (mode in ("peer", "nccl+mailbox")), out
+        assert out["comm"]["peer_reduce"] == (mode == "peer"), out
