@@ -194,6 +194,10 @@ struct hb200_ctx {
   std::vector<int4> h_v_idx, h_i_idx;       // bound order
   std::vector<int> v_perm, i_perm;          // bound position -> user index
   DevBuf<int> seg_off, run_off, lm_off, lm_obs, d_invalid;
+  // large windows: landmarks ordered by first knot base and cut into groups for schur_group_kernel
+  DevBuf<int> lm_order, lm_group_off;
+  int n_lm_groups = 0, schur_rt = 0;
+  bool schur_groups = false;
   int nseg = 0, nruns = 0, max_rows = 6;
   int pix_splits = 1, imu_splits = 1;
   int beta = 3, min_beta = 0;   // min_beta: lower bound agreed across ranks (the packed layout must be identical everywhere)
@@ -587,7 +591,16 @@ int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
   }
   cost_kernel<<<1, 256, 0, side(c)>>>(c->assembly(), c->lay, c->cp_pix[0].p, c->Nv ? c->n_pix_blocks : 0, c->cp_imu[0].p, c->n_imu_blocks + c->n_man_blocks);
   HB_LAUNCH(c, "cost_kernel");
-  if (c->Nv && c->L) {
+  if (c->Nv && c->L && c->schur_groups) {
+    const size_t smem = (3 * static_cast<size_t>(kSchurGroup) * (c->schur_rt + 1) + 3 * kSchurGroup + 4 * 3 * static_cast<size_t>(c->schur_rt)) * sizeof(double);
+    if (c->k == 4)
+      schur_group_kernel<4><<<c->n_lm_groups, kSchurGThreads, smem, c->stream>>>(c->lm_group_off.p, c->lm_order.p, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p,
+                                                                                 c->v_Jl.p, c->v_w.p, c->st.p, c->assembly(), c->lay, c->Vinv.p, c->gl.p, c->Dl.p, c->schur_rt);
+    else
+      schur_group_kernel<6><<<c->n_lm_groups, kSchurGThreads, smem, c->stream>>>(c->lm_group_off.p, c->lm_order.p, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p,
+                                                                                 c->v_Jl.p, c->v_w.p, c->st.p, c->assembly(), c->lay, c->Vinv.p, c->gl.p, c->Dl.p, c->schur_rt);
+    HB_LAUNCH(c, "schur_group_kernel");
+  } else if (c->Nv && c->L) {
     const size_t smem = 2 * 3 * static_cast<size_t>(c->max_rows) * sizeof(double);
     if (c->k == 4)
       schur_kernel<4><<<c->L, kSchurThreads, smem, c->stream>>>(c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p, c->st.p,
@@ -910,7 +923,7 @@ void hb200_destroy(hb200_ctx* c) {
   c->cams.release(); c->imu.release(); c->cam_tab.release(); c->imu_tab.release(); c->fixed.release();
   c->v_stamp.release(); c->v_pixel.release(); c->i_stamp.release(); c->i_meas.release(); c->v_cam.release(); c->v_lm.release(); c->v_idx.release(); c->i_idx.release();
   c->v_z.release(); c->v_w.release(); c->m_stamp.release(); c->m_meas.release(); c->sensors.release(); c->m_sensor.release(); c->m_idx.release(); c->m_r.release(); c->m_Jp.release();
-  c->seg_off.release(); c->run_off.release(); c->lm_off.release(); c->lm_obs.release(); c->d_invalid.release();
+  c->seg_off.release(); c->run_off.release(); c->lm_off.release(); c->lm_obs.release(); c->d_invalid.release(); c->lm_order.release(); c->lm_group_off.release();
   c->v_r.release(); c->v_Jp.release(); c->v_Jl.release(); c->i_r.release(); c->i_Jp.release(); c->i_wg.release(); c->i_wa.release(); c->i_Jg.release();
   c->sys.release(); c->D.release(); c->Lw.release(); c->Ldiag.release(); c->dp.release(); c->dl.release(); c->Vinv.release(); c->gl.release(); c->Dl.release();
   c->band_ws.release(); c->band_dbg.release(); c->bcr_ws.release(); c->bcr_bar.release(); c->lm_part.release(); c->scal.release(); c->spd.release(); c->st.release(); c->records.release();
@@ -1223,6 +1236,7 @@ int rebuild_incidence_device(hb200_ctx* c) {
   HB_CUDA(cudaMemcpyAsync(h, c->w_scal.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   c->max_rows = std::max(6 * c->k, h[1]);
+  c->schur_groups = false;   // (the groups are cut on the host at hb200_bind; after device-side bookkeeping the per-landmark kernel runs)
   c->nruns = Ni ? h[3] : 0;
   if (Ni) { run_fill_kernel<<<(Ni + 255) / 256, 256, 0, c->stream>>>(Ni, c->w_keep.p, c->w_pos.p, c->nruns, c->run_off.p); HB_LAUNCH(c, "run_fill_kernel"); }
   else { const int z = 0; HB_CUDA(cudaMemcpyAsync(c->run_off.p, &z, sizeof(int), cudaMemcpyHostToDevice, c->stream)); }
@@ -1367,6 +1381,41 @@ int hb200_bind(hb200_ctx* c, int* num_invalid) {
   HB_CUDA(cudaMemcpyAsync(c->run_off.p, runs.data(), sizeof(int) * runs.size(), cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaMemcpyAsync(c->lm_off.p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaMemcpyAsync(c->lm_obs.p, obs.data(), sizeof(int) * obs.size(), cudaMemcpyHostToDevice, c->stream));
+  {
+    // landmark groups for the large-window Schur kernel: observed landmarks ordered by their first knot base, cut so that
+    // a group has at most kSchurGroup members and its control-point rows fit one window of RT rows
+    static const int min_lm = getenv("HB200_SCHUR_GROUP_MIN") ? atoi(getenv("HB200_SCHUR_GROUP_MIN")) : 8192;
+    c->schur_groups = false;
+    c->schur_rt = ((c->max_rows + 12 + 7) / 8) * 8;
+    if (c->L >= min_lm && Nv) {
+      std::vector<int> order;
+      order.reserve(c->L);
+      for (int l = 0; l < c->L; ++l) if (off[l + 1] > off[l]) order.push_back(l);
+      auto first_base = [&](int l) { return c->h_v_idx[obs[off[l]]].x; };
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return first_base(a) < first_base(b); });
+      std::vector<int> goff;
+      const int win = c->schur_rt / 6;   // control points per window
+      int glo = 0;
+      for (size_t i = 0; i < order.size(); ++i) {
+        const int l = order[i];
+        const int lo = first_base(l), hi = c->h_v_idx[obs[off[l + 1] - 1]].x + c->k;
+        if (goff.empty() || static_cast<int>(i) - goff.back() >= kSchurGroup || hi - glo > win) { goff.push_back(static_cast<int>(i)); glo = lo; }
+      }
+      c->n_lm_groups = static_cast<int>(goff.size());
+      goff.push_back(static_cast<int>(order.size()));
+      HB_CUDA(c->lm_order.ensure(std::max<size_t>(order.size(), 1))); HB_CUDA(c->lm_group_off.ensure(goff.size()));
+      HB_CUDA(cudaMemcpyAsync(c->lm_order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(c->lm_group_off.p, goff.data(), sizeof(int) * goff.size(), cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaStreamSynchronize(c->stream));
+      c->schur_groups = c->n_lm_groups > 0;
+      const size_t smem = (3 * static_cast<size_t>(kSchurGroup) * (c->schur_rt + 1) + 3 * kSchurGroup + 4 * 3 * static_cast<size_t>(c->schur_rt)) * sizeof(double);
+      if (smem > 200 * 1024) c->schur_groups = false;
+      else {
+        HB_CUDA(cudaFuncSetAttribute(schur_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        HB_CUDA(cudaFuncSetAttribute(schur_group_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      }
+    }
+  }
   // outputs
   const size_t k = c->k;
   HB_CUDA(c->v_r.ensure(2 * static_cast<size_t>(std::max(Nv, 1)))); HB_CUDA(c->v_Jp.ensure(12 * k * std::max(Nv, 1))); HB_CUDA(c->v_Jl.ensure(6 * static_cast<size_t>(std::max(Nv, 1))));
@@ -1386,6 +1435,11 @@ int hb200_bind(hb200_ctx* c, int* num_invalid) {
   if (rc) return rc;
   rc = ensure_system(c);
   if (rc) return rc;
+  if (c->schur_groups) {   // unobserved landmarks are not in any group: their blocks stay zero (no step)
+    HB_CUDA(cudaMemsetAsync(c->Vinv.p, 0, sizeof(double) * 9 * static_cast<size_t>(std::max(c->L, 1)), c->stream));
+    HB_CUDA(cudaMemsetAsync(c->gl.p, 0, sizeof(double) * 3 * static_cast<size_t>(std::max(c->L, 1)), c->stream));
+    HB_CUDA(cudaMemsetAsync(c->Dl.p, 0, sizeof(double) * 3 * static_cast<size_t>(std::max(c->L, 1)), c->stream));
+  }
   HB_CUDA(cudaStreamSynchronize(c->stream));
   c->bound = true;
   c->invalidate();

@@ -452,6 +452,154 @@ __global__ void __launch_bounds__(kSchurThreads) schur_kernel(const int* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Landmark Schur complement for LARGE windows: a CTA takes a GROUP of landmarks whose control-point ranges fall into
+// one window of RT rows (groups are cut on the host from the landmarks ordered by their first knot base) and
+// accumulates the whole group's contribution on the FP64 tensor cores before touching the system once.
+// Per landmark (one warp each, four in flight): V, g_l, W as in schur_kernel; then with V^-1 = Lc Lc^T
+//   W V^-1 W^T = Y Y^T,  Y = W Lc (rows x 3)         W V^-1 g_l = Y z,  z = Lc^T g_l
+// Y's three columns become three rows of the group's stack Ys[3 G][RT] (zero outside the landmark's rows), so
+//   S[tile] -= Ys^T Ys  (mma.sync m8n8k4 -> DMMA, contraction over 3 G)        b[tile] += Ys^T zs
+// and the group flushes RT (RT + 1) / 2 lower entries with one atomic each instead of ~rows^2 / 2 per landmark
+// (83 k landmarks: 75 M FP64 atomics on a few hundred cache lines were the whole cost of schur_kernel).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSchurGroup = 32;       // landmarks per group (3 * 32 = 96 contraction rows)
+constexpr int kSchurGThreads = 128;
+template <int K>
+__global__ void __launch_bounds__(kSchurGThreads) schur_group_kernel(const int* __restrict__ group_off, const int* __restrict__ lm_order,
+                                                                    const int* __restrict__ lm_off, const int* __restrict__ lm_obs,
+                                                                    const int4* __restrict__ idx, const double* __restrict__ r,
+                                                                    const double* __restrict__ Jp, const double* __restrict__ Jl, const double* __restrict__ wv,
+                                                                    const SolverState* __restrict__ st, double* sys, SysLayout lay,
+                                                                    double* __restrict__ Vinv, double* __restrict__ gl, double* __restrict__ Dl, int RT) {
+  constexpr int NB = 6 * K;
+  extern __shared__ double s_grp[];
+  const int LD = RT + 1;
+  double* Ys = s_grp;                                  // [3 G][LD]
+  double* zs = Ys + 3 * kSchurGroup * LD;              // [3 G]
+  double* Ws = zs + 3 * kSchurGroup;                   // per warp: W [RT][3]
+  __shared__ int s_lo;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g0 = group_off[blockIdx.x], g1 = group_off[blockIdx.x + 1];
+  const int cnt = g1 - g0;
+  if (tid == 0) {   // window origin = first knot base of the group's first landmark (the order is ascending in it)
+    const int l = lm_order[g0];
+    s_lo = idx[lm_obs[lm_off[l]]].x;
+  }
+  for (int e = tid; e < 3 * kSchurGroup * LD; e += kSchurGThreads) Ys[e] = 0.0;
+  for (int e = tid; e < 3 * kSchurGroup; e += kSchurGThreads) zs[e] = 0.0;
+  __syncthreads();
+  const int tile_lo = s_lo;
+  const double mu = 1.0 / st->radius;
+  double* W = Ws + warp * RT * 3;
+  for (int gi = warp; gi < cnt; gi += kSchurGThreads / 32) {
+    const int l = lm_order[g0 + gi];
+    const int o_lo = lm_off[l], o_hi = lm_off[l + 1];
+    const int cp_lo = idx[lm_obs[o_lo]].x, cp_hi = idx[lm_obs[o_hi - 1]].x + K;
+    const int rows = 6 * (cp_hi - cp_lo), roff = 6 * (cp_lo - tile_lo);
+    // V (9) and g_l (3): lanes 0..11
+    double vg = 0.0;
+    if (lane < 12) {
+      for (int o = o_lo; o < o_hi; ++o) {
+        const int f = lm_obs[o];
+        const double wgt = wv[f];
+        const double* jl = Jl + 6 * static_cast<size_t>(f);
+        if (lane < 9) { const int a = lane / 3, b = lane % 3; vg += wgt * (jl[a] * jl[b] + jl[3 + a] * jl[3 + b]); }
+        else { const int a = lane - 9; vg += wgt * (jl[a] * r[2 * f] + jl[3 + a] * r[2 * f + 1]); }
+      }
+    }
+    // W rows (rows x 3)
+    for (int e = lane; e < rows * 3; e += 32) {
+      const int row = e / 3, c = e - 3 * row;
+      double acc = 0.0;
+      for (int o = o_lo; o < o_hi; ++o) {
+        const int f = lm_obs[o];
+        const int a = row - 6 * (idx[f].x - cp_lo);
+        if (a >= 0 && a < NB) {
+          const double* jp = Jp + static_cast<size_t>(f) * 2 * NB;
+          const double* jl = Jl + 6 * static_cast<size_t>(f);
+          acc += wv[f] * (jp[a] * jl[c] + jp[NB + a] * jl[3 + c]);
+        }
+      }
+      W[e] = acc;
+    }
+    // lane 0: damped V, its inverse, Cholesky of the inverse; everything the back substitution needs goes to global memory
+    double V[9], g3[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) V[i] = __shfl_sync(0xffffffffu, vg, i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) g3[i] = __shfl_sync(0xffffffffu, vg, 9 + i);
+    double Lc[6] = {0, 0, 0, 0, 0, 0}, z[3] = {0, 0, 0};   // Lc: lower 3x3 packed (00, 10, 11, 20, 21, 22)
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double d = fmin(fmax(V[4 * a], 1e-6), 1e32);
+        Dl[3 * static_cast<size_t>(l) + a] = d;
+        V[4 * a] += mu * d;
+      }
+      const double a = V[0], b = V[1], c = V[2], d = V[4], e = V[5], f = V[8];
+      const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+      const double id = 1.0 / (a * c00 + b * c01 + c * c02);
+      double Vi[9];
+      Vi[0] = c00 * id; Vi[1] = c01 * id; Vi[2] = c02 * id;
+      Vi[3] = Vi[1]; Vi[4] = (a * f - c * c) * id; Vi[5] = (b * c - a * e) * id;
+      Vi[6] = Vi[2]; Vi[7] = Vi[5]; Vi[8] = (a * d - b * b) * id;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Vinv[9 * static_cast<size_t>(l) + i] = Vi[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gl[3 * static_cast<size_t>(l) + i] = g3[i];
+      // Vi = Lc Lc^T
+      Lc[0] = sqrt(Vi[0]); Lc[1] = Vi[3] / Lc[0]; Lc[3] = Vi[6] / Lc[0];
+      Lc[2] = sqrt(Vi[4] - Lc[1] * Lc[1]); Lc[4] = (Vi[7] - Lc[3] * Lc[1]) / Lc[2];
+      Lc[5] = sqrt(Vi[8] - Lc[3] * Lc[3] - Lc[4] * Lc[4]);
+      z[0] = Lc[0] * g3[0] + Lc[1] * g3[1] + Lc[3] * g3[2];
+      z[1] = Lc[2] * g3[1] + Lc[4] * g3[2];
+      z[2] = Lc[5] * g3[2];
+      zs[3 * gi] = z[0]; zs[3 * gi + 1] = z[1]; zs[3 * gi + 2] = z[2];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Lc[i] = __shfl_sync(0xffffffffu, Lc[i], 0);
+    __syncwarp();
+    // Y = W Lc into the stack: row k = 3 gi + c holds column c of Y at the landmark's rows
+    for (int row = lane; row < rows; row += 32) {
+      const double w0 = W[3 * row], w1 = W[3 * row + 1], w2 = W[3 * row + 2];
+      Ys[(3 * gi) * LD + roff + row] = w0 * Lc[0] + w1 * Lc[1] + w2 * Lc[3];
+      Ys[(3 * gi + 1) * LD + roff + row] = w1 * Lc[2] + w2 * Lc[4];
+      Ys[(3 * gi + 2) * LD + roff + row] = w2 * Lc[5];
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // the group's Schur complement: lower 8 x 8 tiles of Ys^T Ys on the FP64 tensor cores, contraction over 3 cnt rows
+  const int NT = RT / 8, ntiles = NT * (NT + 1) / 2, kk = 3 * cnt;
+  const int lm = lane >> 2, lk = lane & 3;
+  const int r0g = 6 * tile_lo;
+  for (int tile = warp; tile < ntiles; tile += kSchurGThreads / 32) {
+    int ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+    const int tj = tile - ti * (ti + 1) / 2;
+    const double* pa = Ys + lk * LD + 8 * ti + lm;
+    const double* pb = Ys + lk * LD + 8 * tj + lm;
+    double c0 = 0.0, c1 = 0.0;
+    for (int k0 = 0; k0 < kk; k0 += 4) {
+      const bool in = k0 + lk < kk;
+      const double av = in ? pa[k0 * LD] : 0.0, bv = in ? pb[k0 * LD] : 0.0;
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+    }
+    const int m = 8 * ti + lm, n = 8 * tj + 2 * lk;
+    const int row = r0g + m;
+    if (row < lay.np) {
+      if (n <= m && c0 != 0.0 && row - 6 * ((r0g + n) / 6) < lay.h) atomicAdd(&sys[sys_index(lay, row, r0g + n)], -c0);
+      if (n + 1 <= m && c1 != 0.0 && row - 6 * ((r0g + n + 1) / 6) < lay.h) atomicAdd(&sys[sys_index(lay, row, r0g + n + 1)], -c1);
+    }
+  }
+  for (int m = tid; m < RT; m += kSchurGThreads) {
+    double acc = 0.0;
+    for (int k = 0; k < kk; ++k) acc += Ys[k * LD + m] * zs[k];
+    if (acc != 0.0 && r0g + m < lay.np) atomicAdd(&sys[lay.ob + r0g + m], acc);
+  }
+}
+
 // Dense fallback / inspection: expands the band-only raw system into the dense factorisation work copy
 // Lw ((32 T + 1) x n, last row = b), applying LM damping mu clamp(diag H) and the constant-dof mask on the way
 // (what the band solver does while it gathers).  st == nullptr: no damping.

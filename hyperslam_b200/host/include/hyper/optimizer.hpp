@@ -89,6 +89,12 @@ class Optimizer {   // OptimizerSuite::B200
   // CeresOptimizer::optimize (reference optimizer.cpp:276-280): <= max_num_iterations LM iterations,
   // variables updated in place.
   std::vector<IterationSummary> optimize(int max_num_iterations = 5);
+  // ceres::Solver::Options termination tests, evaluated on the device (hb200_set_termination); the reference keeps Ceres'
+  // defaults (reference optimizer.cpp:38-54): setSolverTolerances() with no arguments switches exactly those on.
+  void setSolverTolerances(double function_tolerance = 1e-6, double gradient_tolerance = 1e-10, double parameter_tolerance = 1e-8,
+                           double min_trust_region_radius = 1e-32);
+  // summary.termination_type of the last optimize(): 0 iteration limit, 1 function, 2 parameter, 3 gradient tolerance, 4 radius, 5 invalid steps
+  int terminationType() const;
 
   hb200_ctx* context() { return ctx_; }
   const ContinuousState& state() const { return *state_; }

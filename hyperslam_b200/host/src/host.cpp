@@ -204,6 +204,15 @@ Optimizer::Optimizer(int device) {
 }
 Optimizer::~Optimizer() { hb200_destroy(ctx_); }
 
+void Optimizer::setSolverTolerances(double function_tolerance, double gradient_tolerance, double parameter_tolerance, double min_trust_region_radius) {
+  check(hb200_set_termination(ctx_, function_tolerance, gradient_tolerance, parameter_tolerance, min_trust_region_radius), "hb200_set_termination");
+}
+int Optimizer::terminationType() const {
+  int type = 0;
+  hb200_get_termination(ctx_, &type, nullptr, nullptr, nullptr, nullptr);
+  return type;
+}
+
 Index Optimizer::cameraIndex(const Camera* camera) const {
   for (size_t i = 0; i < cameras_.size(); ++i) if (cameras_[i] == camera) return static_cast<Index>(i);
   throw std::invalid_argument("observation refers to an unknown camera");
@@ -325,8 +334,13 @@ std::vector<IterationSummary> Optimizer::optimize(int max_num_iterations) {
   std::vector<hb200_iteration> rec(max_num_iterations);
   check(hb200_iterate(ctx_, max_num_iterations, rec.data()), "hb200_iterate");
   download();
+  int performed = max_num_iterations, type = 0;
+  hb200_get_termination(ctx_, &type, &performed, nullptr, nullptr, nullptr);   // fewer when a termination test fired
   std::vector<IterationSummary> out;
-  for (auto& r : rec) out.push_back({r.cost, r.cost_new, r.rho, r.radius, r.accepted != 0, r.spd != 0});
+  for (int i = 0; i < std::min(performed, max_num_iterations); ++i) {
+    const auto& r = rec[i];
+    out.push_back({r.cost, r.cost_new, r.rho, r.radius, r.accepted != 0, r.spd != 0});
+  }
   return out;
 }
 
