@@ -744,7 +744,53 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     int u0 = 0, v0 = m;   // this thread's first element (v0 = m: none)
     if (tid < nel) decode(tid, &u0, &v0);
     double* own0 = CC + static_cast<size_t>(u0) * LDc + v0;
-    for (int q = 0; q < m; ++q) {
+    // Leading full blocks of six columns: the diagonal block in registers (chol6, one thread), one thread per row for the
+    // panel, the fixed element ownership for the 6-term trailing update -- three barriers per SIX columns instead of two
+    // per column (the scalar loop below spent ~560 cycles per column on barriers and exposed shared-memory latency).
+    const int q_blocked = (m / 6) * 6;
+    double* cinv = DG + m;   // scratch behind DG: reciprocal diagonal of the current block (6 doubles; the staged damping terms are dead by now)
+    for (int k0 = 0; k0 < q_blocked; k0 += 6) {
+      if (tid == 0) {
+        if (!chol6(CC + static_cast<size_t>(k0) * LDc + k0, LDc, cinv)) s_ok = 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) DG[k0 + j] = CC[static_cast<size_t>(k0 + j) * LDc + k0 + j];
+      }
+      __syncthreads();
+      for (int r = k0 + 6 + tid; r <= m; r += kBandThreads) {   // panel rows, the rhs row (r == m) included
+        double* a = CC + static_cast<size_t>(r) * LDc + k0;
+        double v[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v[q] = a[q];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          v[j] *= cinv[j];
+#pragma unroll
+          for (int q = j + 1; q < 6; ++q) v[q] -= v[j] * CC[static_cast<size_t>(k0 + q) * LDc + k0 + j];
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a[q] = v[q];
+      }
+      __syncthreads();
+      if (v0 >= k0 + 6 && v0 < m) {
+        const double* pu = CC + static_cast<size_t>(u0) * LDc + k0;
+        const double* pv = CC + static_cast<size_t>(v0) * LDc + k0;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc += pu[j] * pv[j];
+        *own0 -= acc;
+      }
+      for (int e = tid + kBandThreads; e < nel; e += kBandThreads) {   // only for m > 30
+        int u, v;
+        decode(e, &u, &v);
+        if (v >= k0 + 6) {
+          double acc = 0.0;
+          for (int j = 0; j < 6; ++j) acc += CC[static_cast<size_t>(u) * LDc + k0 + j] * CC[static_cast<size_t>(v) * LDc + k0 + j];
+          CC[static_cast<size_t>(u) * LDc + v] -= acc;
+        }
+      }
+      __syncthreads();
+    }
+    for (int q = q_blocked; q < m; ++q) {   // the remaining (m mod 6) columns, one at a time
       const double d = CC[static_cast<size_t>(q) * LDc + q];
       const double iv = rsqrt(d);
       if (tid == 0) { if (!(d > 0.0)) s_ok = 0; DG[q] = d * iv; }

@@ -497,32 +497,59 @@ __global__ void __launch_bounds__(kSchurGThreads) schur_group_kernel(const int* 
     const int o_lo = lm_off[l], o_hi = lm_off[l + 1];
     const int cp_lo = idx[lm_obs[o_lo]].x, cp_hi = idx[lm_obs[o_hi - 1]].x + K;
     const int rows = 6 * (cp_hi - cp_lo), roff = 6 * (cp_lo - tile_lo);
-    // V (9) and g_l (3): lanes 0..11
+    // observation-major: per observation the warp reads the factor's two Jacobian rows coalesced (lane = column) and adds
+    // w (jp0 jl_c + jp1 jl_{3+c}) into W's rows of that factor's control points; lanes 0..11 keep V (9) and g_l (3)
+    for (int e = lane; e < rows * 3; e += 32) W[e] = 0.0;
+    __syncwarp();
     double vg = 0.0;
-    if (lane < 12) {
-      for (int o = o_lo; o < o_hi; ++o) {
-        const int f = lm_obs[o];
-        const double wgt = wv[f];
-        const double* jl = Jl + 6 * static_cast<size_t>(f);
-        if (lane < 9) { const int a = lane / 3, b = lane % 3; vg += wgt * (jl[a] * jl[b] + jl[3 + a] * jl[3 + b]); }
-        else { const int a = lane - 9; vg += wgt * (jl[a] * r[2 * f] + jl[3 + a] * r[2 * f + 1]); }
-      }
-    }
-    // W rows (rows x 3)
-    for (int e = lane; e < rows * 3; e += 32) {
-      const int row = e / 3, c = e - 3 * row;
-      double acc = 0.0;
-      for (int o = o_lo; o < o_hi; ++o) {
-        const int f = lm_obs[o];
-        const int a = row - 6 * (idx[f].x - cp_lo);
-        if (a >= 0 && a < NB) {
-          const double* jp = Jp + static_cast<size_t>(f) * 2 * NB;
-          const double* jl = Jl + 6 * static_cast<size_t>(f);
-          acc += wv[f] * (jp[a] * jl[c] + jp[NB + a] * jl[3 + c]);
+    // four observations per round: all their loads are issued before anything is accumulated (the loop is a chain of
+    // dependent L2 round trips otherwise: lm_obs -> idx / w / Jl / Jp)
+    for (int o0 = o_lo; o0 < o_hi; o0 += 4) {
+      int fq[4], bq[4];
+      double wq[4], jlq[4][6], j0q[4][2], j1q[4][2], rq[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) fq[u] = (o0 + u < o_hi) ? lm_obs[o0 + u] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int f = fq[u];
+        const bool on = f >= 0;
+        wq[u] = on ? wv[f] : 0.0;
+        bq[u] = on ? 6 * (idx[f].x - cp_lo) : 0;
+        const double* jlp = Jl + 6 * static_cast<size_t>(on ? f : 0);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) jlq[u][c] = on ? jlp[c] : 0.0;
+        const double* jp = Jp + static_cast<size_t>(on ? f : 0) * 2 * NB;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {   // NB <= 64 columns: lane, lane + 32
+          const int a = lane + 32 * t;
+          j0q[u][t] = (on && a < NB) ? jp[a] : 0.0;
+          j1q[u][t] = (on && a < NB) ? jp[NB + a] : 0.0;
         }
+        rq[u][0] = (on && lane >= 9 && lane < 12) ? r[2 * f] : 0.0;
+        rq[u][1] = (on && lane >= 9 && lane < 12) ? r[2 * f + 1] : 0.0;
       }
-      W[e] = acc;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (fq[u] < 0) continue;
+        const double wgt = wq[u];
+        const double* jl = jlq[u];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int a = lane + 32 * t;
+          if (a < NB) {
+            const double j0 = wgt * j0q[u][t], j1 = wgt * j1q[u][t];
+            double* wr = W + (bq[u] + a) * 3;
+            wr[0] += j0 * jl[0] + j1 * jl[3];
+            wr[1] += j0 * jl[1] + j1 * jl[4];
+            wr[2] += j0 * jl[2] + j1 * jl[5];
+          }
+        }
+        if (lane < 9) { const int a = lane / 3, b = lane % 3; vg += wgt * (jl[a] * jl[b] + jl[3 + a] * jl[3 + b]); }
+        else if (lane < 12) { const int a = lane - 9; vg += wgt * (jl[a] * rq[u][0] + jl[3 + a] * rq[u][1]); }
+        __syncwarp();   // the next observation may touch the same rows of W
+      }
     }
+    __syncwarp();
     // lane 0: damped V, its inverse, Cholesky of the inverse; everything the back substitution needs goes to global memory
     double V[9], g3[3];
 #pragma unroll
