@@ -3,7 +3,7 @@
 import collections, csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
@@ -43,7 +43,9 @@ def to_bytes(val, unit):
 
 traffic = {}
 md = [f"# {R}: ncu --set full captures (clock-control none)\n"]
-for tag, title in (("eval_cfg1", "factor kernels on BASELINE config 1 (bench.py workload: 10k pixel + 2k IMU factors)"),
+for tag, title in (("iter_cfg1", "the kernels of one LM iteration of the timed graph on BASELINE config 1 (bench.py workload: 10k pixel + 2k IMU factors)"),
+                   ("iter_cfg4", "the kernels of one LM iteration on the 1M-factor window (833k pixel + 167k IMU, one GPU)"),
+                   ("eval_cfg1", "factor kernels on BASELINE config 1 (bench.py workload: 10k pixel + 2k IMU factors)"),
                    ("eval_cfg4", "factor kernels on the 1M-factor window (833k pixel + 167k IMU)"),
                    ("band_cfg1", "band_solve_kernel on config 1 (dominant kernel of the step by time)"),
                    ("jtj_cfg1", "inertial J^T J and landmark Schur complement on config 1")):
@@ -90,6 +92,10 @@ if os.path.exists(lst):
 
 tr = {}
 if "cfg1" in traffic:
+    # the roofline kernel of the bench line: the merged factor kernel WITH Jacobians (template <K, KB, WANT_J = 1, FUSE>)
+    pe = [v for k, v in traffic["cfg1"].items() if k.startswith("factor_eval_kernel<4, 4, 1") or k.startswith("factor_eval_kernel<4, 4, true")]
+    if pe:
+        tr["factor_eval_kernel_dram_bytes"] = pe[0]["dram_bytes"]
     pe = [v for k, v in traffic["cfg1"].items() if k.startswith("pixel_eval_kernel<4, 1")]
     if pe:
         tr["pixel_eval_kernel_dram_bytes"] = pe[0]["dram_bytes"]
