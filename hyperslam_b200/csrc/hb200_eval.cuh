@@ -414,6 +414,9 @@ struct PixelArgs {
 template <int K>
 struct PixelHessAcc {
   static constexpr int NB = 6 * K, NT = (NB + 7) / 8, NTILES = NT * (NT + 1) / 2, PER_WARP = (NTILES + 1) / 2;
+  // row pitch of the staged Jacobian rows: the fragment loads touch word (k0 + l%4) * LD + l/4, conflict-free when
+  // LD = 4 or 12 (mod 16); 6K = 24 -> 28.  (6K = 36 would need 44: 45 KB, over the static shared-memory limit -> 37)
+  static constexpr int LD = (NB == 24) ? 28 : NB + 1;
   double c0[PER_WARP], c1[PER_WARP], g;
   int base;
 };
@@ -449,23 +452,46 @@ HB_DI void pixel_hess_flush(const PixelArgs& a, const PixelHessAcc<K>& acc) {
   if (tid >= kEvalThreads - NB) atomicAdd(&S[a.lay.og + c0 + tid - (kEvalThreads - NB)], acc.g);
 }
 
+// lower-triangle tile number -> (tile row, tile column), compile time
+__host__ __device__ constexpr int tile_row(int tile) { int ti = 0; while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti; return ti; }
+__host__ __device__ constexpr int tile_col(int tile) { return tile - tile_row(tile) * (tile_row(tile) + 1) / 2; }
+
+// one k-step (4 Jacobian rows) of every tile warp W owns: the NT column fragments are loaded once and serve as A and B
+// operand of all of them; the PER_WARP accumulators are independent, so the DMMAs of a step overlap
+template <int K, int W>
+HB_DI void pixel_hess_steps(PixelHessAcc<K>& acc, const double* sJ, int r_lo, int r_hi, int lm, int lk) {
+  constexpr int NB = 6 * K, LD = PixelHessAcc<K>::LD, NT = PixelHessAcc<K>::NT, NTILES = PixelHessAcc<K>::NTILES;
+#pragma unroll 1
+  for (int k0 = r_lo; k0 < r_hi; k0 += 4) {   // rows come in pairs: r_lo, r_hi are even; the tail of a segment is masked
+    const bool in = k0 + lk < r_hi;
+    const double* p = sJ + (k0 + lk) * LD + lm;
+    double fr[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) fr[t] = (in && (8 * t + 8 <= NB || 8 * t + lm < NB)) ? p[8 * t] : 0.0;
+#pragma unroll
+    for (int q = 0; q < PixelHessAcc<K>::PER_WARP; ++q) {
+      const int tile = W + 2 * q;
+      if (tile < NTILES) {
+        const double av = fr[tile_row(W + 2 * q < NTILES ? W + 2 * q : 0)], bv = fr[tile_col(W + 2 * q < NTILES ? W + 2 * q : 0)];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc.c0[q]), "+d"(acc.c1[q]) : "d"(av), "d"(bv));
+      }
+    }
+  }
+}
+
 template <int K>
-HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[128][6K+1]*/, double* sr /*[128]*/, int* sseg /*[66]*/, PixelHessAcc<K>& acc) {
-  constexpr int NB = 6 * K, LD = NB + 1, NT = (NB + 7) / 8, NTILES = NT * (NT + 1) / 2;
+HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[128][LD]*/, double* sr /*[128]*/, int* sseg /*[66]*/, PixelHessAcc<K>& acc) {
+  constexpr int NB = 6 * K, LD = PixelHessAcc<K>::LD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // staging: thread = one factor (two Jacobian rows), 128-bit loads, rows scaled by sqrt(w)
+  __shared__ double s_sw[kEvalThreads];
+  // per-factor scalars: sqrt(w), knot base, scaled residual
   int my_base = -1;
   if (tid < cnt) {
     const int f = f0 + tid;
     const double sw = sqrt(a.w[f]);
     const double2 rr = reinterpret_cast<const double2*>(a.r)[f];
     my_base = a.idx[f].x;
-    const double2* src = reinterpret_cast<const double2*>(a.Jp + static_cast<size_t>(f) * 2 * NB);   // rows are 16 B aligned
-    double* dst = sJ + 2 * tid * LD;
-#pragma unroll
-    for (int e = 0; e < NB / 2; ++e) { const double2 v = src[e]; dst[2 * e] = sw * v.x; dst[2 * e + 1] = sw * v.y; }
-#pragma unroll
-    for (int e = 0; e < NB / 2; ++e) { const double2 v = src[NB / 2 + e]; dst[LD + 2 * e] = sw * v.x; dst[LD + 2 * e + 1] = sw * v.y; }
+    s_sw[tid] = sw;
     sr[2 * tid] = sw * rr.x; sr[2 * tid + 1] = sw * rr.y;
   }
   // segments of equal knot base (bound order is sorted by base): factor t starts one iff its base differs from its
@@ -473,7 +499,20 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
   const int prev = __shfl_up_sync(0xffffffffu, my_base, 1);
   __shared__ int s_edge[2], s_warp_cnt;
   if (lane == 31) s_edge[warp] = my_base;
-  __syncthreads();   // (also: previous use of the scratch is complete, staging visible below after the next barrier)
+  __syncthreads();   // (also: previous use of the scratch is complete; s_sw is visible)
+  // staging: the CTA's 2 * cnt Jacobian rows are one contiguous run of global memory (just written: L2 hits) -- copied
+  // cooperatively with coalesced 128-bit loads, scaled by sqrt(w) of their factor, pitch LD in shared memory
+  {
+    const double2* src = reinterpret_cast<const double2*>(a.Jp + static_cast<size_t>(f0) * 2 * NB);   // 16 B aligned
+    const int total = cnt * NB;   // double2 elements
+#pragma unroll 4
+    for (int e = tid; e < total; e += kEvalThreads) {
+      const double2 v = src[e];
+      const int row = (2 * e) / NB, col = 2 * e - row * NB;   // NB is even: a pair never straddles two rows
+      const double sw = s_sw[row >> 1];
+      sJ[row * LD + col] = sw * v.x; sJ[row * LD + col + 1] = sw * v.y;
+    }
+  }
   const int before = (lane == 0) ? (warp == 0 ? -2 : s_edge[0]) : prev;
   const bool start = tid < cnt && my_base != before;
   const unsigned mask = __ballot_sync(0xffffffffu, start);
@@ -491,26 +530,8 @@ HB_DI void cta_pixel_hessian(const PixelArgs& a, int f0, int cnt, double* sJ /*[
     const int r_lo = 2 * sseg[j], r_hi = 2 * sseg[j + 1];
     const int base = a.idx[f0 + sseg[j]].x;
     if (base != acc.base) { pixel_hess_flush<K>(a, acc); pixel_hess_reset<K>(acc, base); }   // (uniform across the CTA)
-#pragma unroll
-    for (int q = 0; q < PixelHessAcc<K>::PER_WARP; ++q) {
-      const int tile = warp + 2 * q;
-      if (tile >= NTILES) continue;
-      int ti = 0;
-      while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
-      const int tj = tile - ti * (ti + 1) / 2;
-      const int ma = 8 * ti + lm, nb_ = 8 * tj + lm;   // this lane's m (A) and n (B) column of J
-      const bool va = ma < NB, vb = nb_ < NB;
-      const double* pa = sJ + lk * LD + (va ? ma : 0);
-      const double* pb = sJ + lk * LD + (vb ? nb_ : 0);
-      double c0v = acc.c0[q], c1v = acc.c1[q];
-      for (int k0 = r_lo; k0 < r_hi; k0 += 4) {   // rows come in pairs: r_lo, r_hi are even; the tail of a segment is masked
-        const bool in = k0 + lk < r_hi;
-        const double av = (in && va) ? pa[k0 * LD] : 0.0;
-        const double bv = (in && vb) ? pb[k0 * LD] : 0.0;
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0v), "+d"(c1v) : "d"(av), "d"(bv));
-      }
-      acc.c0[q] = c0v; acc.c1[q] = c1v;
-    }
+    if (warp == 0) pixel_hess_steps<K, 0>(acc, sJ, r_lo, r_hi, lm, lk);
+    else pixel_hess_steps<K, 1>(acc, sJ, r_lo, r_hi, lm, lk);
     if (tid >= kEvalThreads - NB) {   // gradient: the last NB threads
       const int c = tid - (kEvalThreads - NB);
       double g0 = 0.0, g1 = 0.0;
@@ -528,7 +549,7 @@ HB_DI void pixel_eval_body(const PixelArgs& a, const Basis& B, int bid0) {
   __shared__ int s_red[2];
   __shared__ double s_cost[kEvalThreads / 32];
   // scratch of the fused J^T J accumulation (the CTA's 64 factors = 128 Jacobian rows in one pass)
-  __shared__ double s_J[FUSE ? 128 * (6 * K + 1) : 1];
+  __shared__ double s_J[FUSE ? 128 * PixelHessAcc<K>::LD : 1];
   __shared__ double s_r[FUSE ? 128 : 1];
   __shared__ int s_b[FUSE ? 66 : 1];
   const int T = (FUSE && a.tiles_per_cta > 1) ? a.tiles_per_cta : 1;
@@ -585,7 +606,7 @@ HB_DI void pixel_eval_body(const PixelArgs& a, const Basis& B, int bid0) {
 }
 
 template <int K, bool WANT_J, bool FUSE = false>
-__global__ void __launch_bounds__(kEvalThreads) pixel_eval_kernel(PixelArgs a, Basis B) { pixel_eval_body<K, WANT_J, FUSE>(a, B, blockIdx.x); }
+__global__ void __launch_bounds__(kEvalThreads, (K == 4 && FUSE) ? 6 : 1) pixel_eval_kernel(PixelArgs a, Basis B) { pixel_eval_body<K, WANT_J, FUSE>(a, B, blockIdx.x); }
 
 // ---------------------------------------------------------------------------------------------
 // Inertial factor (a6 + a3 with value/velocity/acceleration Jacobian stacks fused).
