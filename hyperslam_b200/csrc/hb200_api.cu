@@ -749,7 +749,7 @@ int enqueue_reduce_system(hb200_ctx* c) {
     a.part_offset = kArenaParts + static_cast<long long>(c->peer_par) * c->arena_cap; a.total = c->lay.total;
     a.out = c->sys.p; a.round = c->red_round.p; a.arrive = c->red_arrive.p; a.st = c->st.p;
     const long long pairs = c->lay.total / 2;
-    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(2LL * c->num_sms, (pairs + kReduceThreads - 1) / kReduceThreads)));
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(4LL * c->num_sms, (pairs + kReduceThreads - 1) / kReduceThreads)));
     peer_reduce_kernel<<<grid, kReduceThreads, 0, c->stream>>>(a);
     HB_LAUNCH(c, "peer_reduce_kernel");
     c->peer_par ^= 1;

@@ -1090,11 +1090,20 @@ HB_DI double2 ld_relaxed_sys_f64x2(const double* p) {
   asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
   return v;
 }
+// 16-byte asynchronous copy global -> shared, L2 only (LDGSTS.BYPASS): the eight peers' reads of one element group are all
+// in flight before the first one is waited for.  (Plain or asm loads do not achieve that here: ptxas schedules the rank-order
+// additions between the STRONG.SYS loads and the in-order issue then serialises the NVLink round trips.)
+HB_DI void cp_async_16(void* smem, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gptr) : "memory");
+}
 __global__ void __launch_bounds__(kReduceThreads) peer_reduce_kernel(PeerReduceArgs a) {
   __shared__ int s_bad;
+  __shared__ const double* s_part[kMaxRanks];   // every rank's active partial (the pointer table is read once, before the wait)
+  __shared__ __align__(16) double2 s_v[8][kReduceThreads];
   const unsigned long long want = *reinterpret_cast<volatile unsigned long long*>(a.round) + 1;
   const int tid = threadIdx.x;
   if (tid == 0) s_bad = 0;
+  if (tid < a.nranks) s_part[tid] = a.peers[tid] + a.part_offset;
   __syncthreads();
   if (blockIdx.x == 0 && tid < a.nranks)
     st_release_sys_u64(reinterpret_cast<unsigned long long*>(a.peers[tid] + kArenaFlags) + a.rank, want);
@@ -1109,9 +1118,15 @@ __global__ void __launch_bounds__(kReduceThreads) peer_reduce_kernel(PeerReduceA
   const long long pairs = a.total / 2;   // total is even (SysLayout)
   for (long long e = blockIdx.x * static_cast<long long>(kReduceThreads) + tid; e < pairs; e += static_cast<long long>(gridDim.x) * kReduceThreads) {
     double2 acc = make_double2(0.0, 0.0);
-    for (int p = 0; p < a.nranks; ++p) {
-      const double2 v = ld_relaxed_sys_f64x2(a.peers[p] + a.part_offset + 2 * e);
-      acc.x += v.x; acc.y += v.y;
+    // eight peers' loads are in flight together (one NVLink round trip per group, not one per rank); the sum stays in rank order
+    for (int p0 = 0; p0 < a.nranks; p0 += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (p0 + u < a.nranks) cp_async_16(&s_v[u][tid], s_part[p0 + u] + 2 * e);
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (p0 + u < a.nranks) { const double2 v = s_v[u][tid]; acc.x += v.x; acc.y += v.y; }
     }
     reinterpret_cast<double2*>(a.out)[e] = acc;
   }
