@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
                                                                   const SolverState* __restrict__ st, const unsigned char* __restrict__ fixed,
                                                                   double* __restrict__ Dout, int chunk_cols) {
   extern __shared__ double s_band[];
+  const long long t_entry = clock64();
   double* ws = SMEM ? s_band : ws_global;
   const int n = lay.n, K = lay.K, beta = lay.beta;
   const int np = 6 * K, m = n - np, h = 6 + 6 * beta, h6 = h * 6;
@@ -375,6 +376,8 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
     }
   }
   __syncthreads();
+  const long long t_staged = clock64();
+  long long t_g[4] = {0, 0, 0, 0};
   auto Sval = [&](int row, int col) -> double {   // row >= col
     double v = S[sys_index(lay, row, col)];
     if (row == col) v += s_dmp[row];
@@ -420,10 +423,16 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
       v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = a2.x; v[5] = a2.y;
     };
     {
+      // chain 0: unit u = row i of block column c (a 48-byte row of P).  chain 1 = J P J: unit (c, q, j) = column j of the
+      // 6-row group q of block column c of the reversed band; its six entries are S[a][b0 .. b0+5] (a = np-1-(6c+j), b
+      // descending with the row), contiguous in S.  Two units of each chain per thread and pass: twelve 128-bit loads in
+      // flight before the first store.
       const int nu0 = C0.ncol * h;
-      for (int u0 = tid; u0 < nu0; u0 += 2 * kBandThreads) {
-        double v[2][6];
-        int rowv[2], cv[2];
+      const int hq = h / 6, nu1 = C1.Ke * hq * 6;
+      for (int e = tid; e < (C1.ncol - C1.Ke) * h6; e += kBandThreads) C1.W[static_cast<size_t>(C1.Ke) * h6 + e] = 0.0;   // separator copy
+      for (int u0 = tid; u0 < max(nu0, nu1); u0 += 2 * kBandThreads) {
+        double v[2][6], v1[2][6];
+        int rowv[2], cv[2], av[2], b0v[2];
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           const int u = u0 + w * kBandThreads;
@@ -435,49 +444,74 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           const int u = u0 + w * kBandThreads;
+          const int c = u / (hq * 6), rem = u - c * hq * 6, q = rem / 6, j = rem - 6 * q;
+          av[w] = np - 1 - (6 * c + j);
+          b0v[w] = np - 6 * (c + q) - 6;
+          if (u < nu1 && b0v[w] >= 0) load6(av[w], b0v[w], v1[w]);
+          else { for (int t = 0; t < 6; ++t) v1[w][t] = 0.0; av[w] = -1; }
+        }
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int u = u0 + w * kBandThreads;
           if (u >= nu0) continue;
           if (rowv[w] >= 0) fix6(rowv[w], 6 * cv[w], v[w]);
           double* dst = C0.W + static_cast<size_t>(u) * 6;
 #pragma unroll
           for (int t = 0; t < 6; ++t) dst[t] = v[w][t];
         }
-      }
-      // chain 1 = J P J: unit (c, q, j) = column j of the 6-row group q of block column c of the reversed band; its six
-      // entries are S[a][b0 .. b0+5] (a = np-1-(6c+j), b descending with the row), contiguous in S
-      const int hq = h / 6, nu1 = C1.Ke * hq * 6;
-      for (int e = tid; e < (C1.ncol - C1.Ke) * h6; e += kBandThreads) C1.W[static_cast<size_t>(C1.Ke) * h6 + e] = 0.0;   // separator copy
-      for (int u0 = tid; u0 < nu1; u0 += 2 * kBandThreads) {
-        double v[2][6];
-        int av[2], b0v[2];
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const int u = u0 + w * kBandThreads;
-          const int c = u / (hq * 6), rem = u - c * hq * 6, q = rem / 6, j = rem - 6 * q;
-          av[w] = np - 1 - (6 * c + j);
-          b0v[w] = np - 6 * (c + q) - 6;
-          if (u < nu1 && b0v[w] >= 0) load6(av[w], b0v[w], v[w]);
-          else { for (int t = 0; t < 6; ++t) v[w][t] = 0.0; av[w] = -1; }
-        }
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           const int u = u0 + w * kBandThreads;
           if (u >= nu1) continue;
           const int c = u / (hq * 6), rem = u - c * hq * 6, q = rem / 6, j = rem - 6 * q;
-          if (av[w] >= 0) fix6(av[w], b0v[w], v[w]);
+          if (av[w] >= 0) fix6(av[w], b0v[w], v1[w]);
 #pragma unroll
-          for (int t = 0; t < 6; ++t) C1.W[(static_cast<size_t>(c) * h + 6 * q + t) * 6 + j] = v[w][5 - t];   // row 6q+t <-> b = b0 + 5 - t
+          for (int t = 0; t < 6; ++t) C1.W[(static_cast<size_t>(c) * h + 6 * q + t) * 6 + j] = v1[w][5 - t];   // row 6q+t <-> b = b0 + 5 - t
+        }
+      }
+      t_g[0] = clock64();
+    }
+    t_g[1] = clock64();
+    // arrow rows + the right-hand-side row (row m): one warp per row, lanes along the columns (rows of A are contiguous in
+    // the packed system) -- chain 0 reads columns 0 .. N0-1, chain 1 the mirrored ones; six loads per lane in flight.
+    // (An element-indexed loop through sys_index() spent 9 of the gather's 13.6 us here at K = 50.)
+    {
+      const int N0 = C0.npc, n1v = 6 * C1.Ke;
+      const double* Arows = sys + lay.oA;
+      constexpr int NW = kBandThreads / 32;
+      for (int r0 = warp; r0 <= m; r0 += 2 * NW) {   // two rows per warp and pass: 24 loads per lane in flight
+        for (int c0 = 0; c0 < max(N0, N1); c0 += 192) {
+          double v0[2][6], v1[2][6];
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int r = r0 + w * NW;
+            const bool on = r <= m, rhs = (r == m);
+            const double* src = Arows + static_cast<size_t>((on && !rhs) ? r : 0) * np;
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+              const int col = c0 + lane + 32 * u;
+              v0[w][u] = (on && col < N0) ? (rhs ? b[col] - gvec[col] : src[col]) : 0.0;
+              const int col1 = np - 1 - col;
+              v1[w][u] = (on && col < n1v) ? (rhs ? b[col1] - gvec[col1] : src[col1]) : 0.0;
+            }
+          }
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int r = r0 + w * NW;
+            if (r > m) continue;
+            const bool rfix = (r < m) && s_fix[np + r];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+              const int col = c0 + lane + 32 * u, col1 = np - 1 - col;
+              if (col < N0) C0.AR[static_cast<size_t>(r) * N0 + col] = (rfix || s_fix[col]) ? 0.0 : v0[w][u];
+              if (col < N1) C1.AR[static_cast<size_t>(r) * N1 + col] = (col < n1v && !(rfix || s_fix[col1])) ? v1[w][u] : 0.0;
+            }
+          }
         }
       }
     }
-    gather4((m + 1) * C0.npc, [&](int e) {
-      const int r = e / C0.npc, col = e - r * C0.npc;
-      return (r < m) ? Sval(np + r, col) : bval(col);
-    }, [&](int e, double v) { C0.AR[e] = v; });
-    gather4((m + 1) * N1, [&](int e) {
-      const int r = e / N1, rc = e - r * N1;
-      const int col = np - 1 - rc;
-      return (rc < 6 * C1.Ke) ? ((r < m) ? Sval(np + r, col) : bval(col)) : 0.0;
-    }, [&](int e, double v) { C1.AR[e] = v; });
+    t_g[2] = clock64();
+    t_g[3] = clock64();
     for (int e = tid; e < (m + 1) * m; e += kBandThreads) {
       const int r = e / m, q = e - r * m;
       CC[static_cast<size_t>(r) * LDc + q] = (r < m) ? ((q <= r) ? Sval(np + r, np + q) : 0.0) : bval(np + q);
@@ -485,6 +519,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   }
   __syncthreads();
   long long t_mark = clock64(), t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_gathered = t_mark;
 #define HB_TICKD(i, addr) do { if (dbg && tid == 0) { const long long now = clock_after(*reinterpret_cast<const volatile double*>(addr)); t_acc[i] += now - t_mark; t_mark = now; } } while (0)
 #define HB_TICK(i) do { if (dbg && tid == 0) { const long long now = clock64(); t_acc[i] += now - t_mark; t_mark = now; } } while (0)
   // ---- two-sided factorisation + forward substitution: step s eliminates block column s of BOTH chains.
@@ -871,7 +906,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
   for (int e = tid; e < C0.npc; e += kBandThreads) x_out[e] = C0.X[e];
   for (int e = tid; e < 6 * C1.Ke; e += kBandThreads) x_out[np - 1 - e] = C1.X[e];
   for (int e = tid; e < m; e += kBandThreads) x_out[np + e] = XA[e];
-  if (dbg && tid == 0) { for (int i = 0; i < 8; ++i) dbg[i] = t_acc[i]; }
+  if (dbg && tid == 0) { for (int i = 0; i < 8; ++i) dbg[i] = t_acc[i]; dbg[8 + 6] = t_staged - t_entry; dbg[8 + 7] = t_gathered - t_staged; dbg[8 + 14] = clock64() - t_entry; dbg[8 + 15] = t_g[0] - t_staged; dbg[8 + 22] = t_g[1] - t_g[0]; dbg[8 + 23] = t_g[2] - t_g[1]; dbg[8 + 30] = t_g[3] - t_g[2]; dbg[8 + 31] = t_gathered - t_g[3]; }
   if (tid == 0) *spd_flag = s_ok;
 }
 

@@ -22,3 +22,6 @@ for i in range(8):
     print(f"{i+4:4d} {r[1]-b:9d} {r[2]-b:9d} {r[3]-b:8d} | {r[4]-b:9d} {r[5]-b:8d} | {(nxt-b) if nxt else 0:9d}")
 
 print("TOTAL cycles", tot, "us", tot/1.965e3)
+print(f"before the first tick: staging (damping, mask) {cyc[14]} cycles {cyc[14]/1.965e3:.1f} us, gather {cyc[15]} cycles {cyc[15]/1.965e3:.1f} us; kernel entry -> exit {cyc[22]} cycles {cyc[22]/1.965e3:.1f} us")
+
+print("gather split (thread 0): chain-0 band", cyc[23], "chain-1 band", cyc[30], "chain-0 arrow", cyc[31], "chain-1 arrow", cyc[38], "corner + barrier", cyc[39])
