@@ -316,6 +316,24 @@ int check_launch(hb200_ctx* c, const char* what) {
     if (rc__) return rc__;                         \
   } while (0)
 
+// Launch on the context's stream as a PROGRAMMATIC dependent of the previous kernel in that stream: the grid may become
+// resident while its predecessor still runs and blocks in pdl_wait() until the predecessor has completed (inside stream
+// capture the edge becomes a programmatic graph dependency).  Only for kernels whose sole dependency is that predecessor
+// and that call pdl_wait() first.  OFF by default: measured at cfg1 (profiles/r02_experiments.md) the step got slower
+// (0.164 vs 0.155 ms) with the four single-dependency edges of the iteration (knot table -> factors, solve ->
+// back-substitution -> trial factors -> accept) made programmatic; HB200_PDL=1 switches it on.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_dependent(hb200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  static const bool off = !(getenv("HB200_PDL") != nullptr && atoi(getenv("HB200_PDL")) != 0);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (off || c->profiling) ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 cudaStream_t side(hb200_ctx* c) { return c->forked ? c->stream2 : c->stream; }
 int fork_side(hb200_ctx* c) {
   static const bool no_fork = getenv("HB200_NO_FORK") != nullptr;   // A/B switch for measurements
@@ -489,8 +507,8 @@ int launch_factors_merged(hb200_ctx* c, int sel, bool accumulate) {
   const InertialArgs ia = inertial_args<J>(c, sel);
   const int blocks = c->n_pix_blocks + c->n_imu_blocks;
   const size_t smem = J ? inertial_stash_bytes(K) : 0;
-  if (J && accumulate) factor_eval_kernel<K, 4, J, J><<<blocks, kEvalThreads, smem, c->stream>>>(pa, ia, c->basis, c->bias_basis, c->n_pix_blocks);
-  else factor_eval_kernel<K, 4, J, false><<<blocks, kEvalThreads, smem, c->stream>>>(pa, ia, c->basis, c->bias_basis, c->n_pix_blocks);
+  if (J && accumulate) HB_CUDA(launch_dependent(c, factor_eval_kernel<K, 4, J, J>, dim3(blocks), dim3(kEvalThreads), smem, pa, ia, c->basis, c->bias_basis, c->n_pix_blocks));
+  else HB_CUDA(launch_dependent(c, factor_eval_kernel<K, 4, J, false>, dim3(blocks), dim3(kEvalThreads), smem, pa, ia, c->basis, c->bias_basis, c->n_pix_blocks));
   HB_LAUNCH(c, "factor_eval_kernel");
   return 0;
 }
@@ -669,11 +687,11 @@ int enqueue_solve(hb200_ctx* c, bool fuse_retract = false, bool* fused = nullptr
         if (fused) *fused = true;
       }
       if (c->k == 4)
-        lm_backsub_kernel<4><<<c->n_lm_blocks + extra, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
-                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p, c->n_lm_blocks, ra);
+        HB_CUDA(launch_dependent(c, lm_backsub_kernel<4>, dim3(c->n_lm_blocks + extra), dim3(kLmWarps * 32), 0, c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
+                                 c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p, c->n_lm_blocks, ra));
       else
-        lm_backsub_kernel<6><<<c->n_lm_blocks + extra, kLmWarps * 32, 0, c->stream>>>(c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
-                                                                    c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p, c->n_lm_blocks, ra);
+        HB_CUDA(launch_dependent(c, lm_backsub_kernel<6>, dim3(c->n_lm_blocks + extra), dim3(kLmWarps * 32), 0, c->L, c->lm_off.p, c->lm_obs.p, c->v_idx.p, c->v_r.p, c->v_Jp.p, c->v_Jl.p, c->v_w.p,
+                                 c->Vinv.p, c->gl.p, c->Dl.p, c->dp.p, c->dl.p, c->lm_part.p, c->lms[0].p, c->lms[1].p, c->n_lm_blocks, ra));
       HB_LAUNCH(c, "lm_backsub_kernel");
     } else {
       HB_CUDA(cudaMemsetAsync(c->dl.p, 0, 3 * static_cast<size_t>(c->L) * sizeof(double), c->stream));
@@ -729,8 +747,8 @@ int enqueue_accept(hb200_ctx* c) {
   const bool mailbox = c->nccl && c->peers_open;
   MailboxArgs mb{};
   mb.nranks = mailbox ? c->nranks : 1; mb.rank = c->rank; mb.peers = c->d_peers.p; mb.local = c->mbox.p; mb.seq = c->mbox_seq.p;
-  accept_kernel<<<1, kAcceptThreads, 0, c->stream>>>(c->sys.p, c->lay, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
-                                         (!c->multi() || mailbox) ? 1 : 0, sa, fuse_commit ? 1 : 0, a, mb, term_args(c));
+  HB_CUDA(launch_dependent(c, accept_kernel, dim3(1), dim3(kAcceptThreads), 0, c->sys.p, c->lay, c->scal.p, c->dp.p, c->D.p, c->fixed.p, c->st.p, c->spd.p, c->records.p, c->max_records,
+                           (!c->multi() || mailbox) ? 1 : 0, sa, fuse_commit ? 1 : 0, a, mb, term_args(c)));
   HB_LAUNCH(c, "accept_kernel");
   if (!fuse_commit) {
     const int blocks = static_cast<int>(std::min<size_t>((mx + 255) / 256, static_cast<size_t>(c->num_sms) * 4));

@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(kBandThreads) band_solve_kernel(const double* 
                                                                   const SolverState* __restrict__ st, const unsigned char* __restrict__ fixed,
                                                                   double* __restrict__ Dout, int chunk_cols) {
   extern __shared__ double s_band[];
+  pdl_launch_dependents();   // the back-substitution grid behind the solve may become resident (it waits for this grid's completion)
   const long long t_entry = clock64();
   double* ws = SMEM ? s_band : ws_global;
   const int n = lay.n, K = lay.K, beta = lay.beta;

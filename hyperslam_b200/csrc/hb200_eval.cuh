@@ -143,6 +143,7 @@ HB_DI void knot_table_row(const double* q, const double* p, double stamp, const 
 // clear / nclear: optional buffer zeroed by the same launch (the packed reduced system at the start of an
 // iteration -- saves the separate memset node).
 __global__ void prep_kernel(int K, const double* __restrict__ knots, double* __restrict__ tab, double* __restrict__ clear, size_t nclear) {
+  pdl_launch_dependents();   // the factor kernel behind it may become resident now (it waits for this grid's completion)
   const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   for (size_t e = gid; e < nclear; e += static_cast<size_t>(gridDim.x) * blockDim.x) clear[e] = 0.0;
   const int j = static_cast<int>(gid);
@@ -981,6 +982,8 @@ __global__ void __launch_bounds__(kEvalThreads) inertial_eval_kernel(InertialArg
 // side they cost the longer of the two.
 template <int K, int KB, bool WANT_J, bool FUSE>
 __global__ void __launch_bounds__(kEvalThreads) factor_eval_kernel(PixelArgs pa, InertialArgs ia, Basis B, Basis BB, int n_pix_blocks) {
+  pdl_launch_dependents();
+  pdl_wait();   // (launched as a programmatic dependent of the knot-table / retraction kernel on the iteration path)
   if (static_cast<int>(blockIdx.x) < n_pix_blocks) pixel_eval_body<K, WANT_J, FUSE>(pa, B, blockIdx.x);
   else inertial_eval_body<K, KB, WANT_J>(ia, B, BB, blockIdx.x - n_pix_blocks);
 }

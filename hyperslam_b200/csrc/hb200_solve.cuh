@@ -921,6 +921,8 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_backsub_kernel(int L, const 
                                                                   double* __restrict__ dl, double* __restrict__ part /*[n_lm_blocks][5]*/,
                                                                   const double* __restrict__ lms, double* __restrict__ lms_t,
                                                                   int n_lm_blocks, RetractArgs ra) {
+  pdl_launch_dependents();
+  pdl_wait();   // (programmatic dependent of the solver kernel on the iteration path: resident early, starts when the solve is complete)
   // blocks past the landmark range retract the knots / biases / gravity in the same launch (they only need dp)
   if (static_cast<int>(blockIdx.x) >= n_lm_blocks) { retract_body(ra, (blockIdx.x - n_lm_blocks) * blockDim.x + threadIdx.x); return; }
   constexpr int NB = 6 * K;
@@ -1166,6 +1168,7 @@ __global__ void __launch_bounds__(kAcceptThreads) accept_kernel(const double* __
   __shared__ double s[NV][kAcceptThreads / 32];
   __shared__ int s_done;
   const int wl = threadIdx.x & 31, ww = threadIdx.x >> 5;
+  pdl_wait();   // (programmatic dependent of the trial-cost factor kernel)
   if (st->terminated) {   // the solve has ended: later iterations of the same call leave everything alone
     if (threadIdx.x == 0 && mb.nranks > 1 && fuse_scalars) *mb.seq += 1;   // (the peers skip their exchange too: keep the counters aligned)
     return;
