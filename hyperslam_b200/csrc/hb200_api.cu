@@ -589,12 +589,27 @@ int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
   }
   { const int rf = fork_side(c); if (rf) return rf; }   // (no-op when already forked or while profiling)
   if (c->Ni) {
-    if (c->k == 4)
-      inertial_hessian_kernel<4, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                             c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
-    else
-      inertial_hessian_kernel<6, 4><<<c->nruns * c->imu_splits, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                             c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+    // the augmented product on the FP64 tensor cores when a CTA has at least two full chunks of factors to walk (1 M-factor
+    // window: 0.295 -> 0.178 ms); the scalar block-by-block kernel for short runs (cfg1, ~9 factors per CTA: 16.4 vs 18.3 us).
+    // HB200_IMU_HESS=0 / 1 forces the scalar / tensor-core kernel (A/B switch)
+    static const int hess_env = getenv("HB200_IMU_HESS") != nullptr ? atoi(getenv("HB200_IMU_HESS")) : -1;
+    const int grid = c->nruns * c->imu_splits;
+    const bool scalar_hess = hess_env >= 0 ? hess_env == 0 : c->Ni < 32 * static_cast<size_t>(grid);
+    if (scalar_hess) {
+      if (c->k == 4)
+        inertial_hessian_kernel<4, 4><<<grid, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+                                                                          c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+      else
+        inertial_hessian_kernel<6, 4><<<grid, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+                                                                          c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+    } else {
+      if (c->k == 4)
+        inertial_hessian_mma_kernel<4, 4><<<grid, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+                                                                              c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+      else
+        inertial_hessian_mma_kernel<6, 4><<<grid, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
+                                                                              c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+    }
     HB_LAUNCH(c, "inertial_hessian_kernel");
   }
   if (c->Nm) {

@@ -297,6 +297,134 @@ __global__ void __launch_bounds__(kHessThreads) inertial_hessian_kernel(const in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Inertial J^T J / J^T r as ONE product on the FP64 tensor cores.  The factor's full Jacobian is written out as an
+// augmented row block  Ja = [ Jp (6K) | gyro-bias (3KB: w_g[m] in gyro row c, column 3m+c) | accel-bias (3KB) |
+// gravity (2) | r (1) ]  -- NA = 6K + 6KB + 3 columns, 6 rows per factor -- and  H = Ja^T Ja  (lower triangle, 8 x 8
+// DMMA tiles) holds every block the scalar kernel above accumulates one loop at a time: pose-pose, bias-pose,
+// gravity-pose, bias-bias, gravity-bias, gravity-gravity, and in its last row the gradients J^T r.  The bias columns
+// are zero except one entry per row, written once per chunk; the zero pattern of the product (gyro-bias x accel-bias,
+// bias components c != c') is skipped at the flush.  k-step-outer loop as in the fused pixel J^T J: the NT column
+// fragments of a step are loaded once and feed every tile the warp owns.
+// ---------------------------------------------------------------------------------------------
+template <int K, int KB>
+struct ImuHess {
+  static constexpr int NP = 6 * K, NBG = 3 * KB, NA = NP + 2 * NBG + 3, NT = (NA + 7) / 8, NTL = NT * (NT + 1) / 2;
+  static constexpr int NW = kHessThreads / 32, PER_WARP = (NTL + NW - 1) / NW;
+  static constexpr int CH = (K == 4) ? 16 : 12;                   // factors per chunk (static shared memory <= 48 KB)
+};
+// row pitch of the staged rows: >= 8 NT and = 4 or 12 (mod 16) doubles (conflict-free fragment loads): K = 4: 60, K = 6: 68
+template <int K, int KB> struct ImuHessLD { static constexpr int value = 8 * ImuHess<K, KB>::NT + 4; };
+
+template <int K, int KB, int W>
+HB_DI void imu_hess_steps(double (&c0)[ImuHess<K, KB>::PER_WARP], double (&c1)[ImuHess<K, KB>::PER_WARP], const double* sJ, int krows, int lm, int lk) {
+  using H = ImuHess<K, KB>;
+  constexpr int LD = ImuHessLD<K, KB>::value;
+#pragma unroll 1
+  for (int k0 = 0; k0 < krows; k0 += 4) {
+    const bool in = k0 + lk < krows;
+    const double* p = sJ + (k0 + lk) * LD + lm;
+    double fr[H::NT];
+#pragma unroll
+    for (int t = 0; t < H::NT; ++t) fr[t] = in ? p[8 * t] : 0.0;   // (columns NA .. 8 NT - 1 are zero in shared memory)
+#pragma unroll
+    for (int q = 0; q < H::PER_WARP; ++q) {
+      if (W + H::NW * q < H::NTL) {
+        const double av = fr[tile_row(W + H::NW * q < H::NTL ? W + H::NW * q : 0)], bv = fr[tile_col(W + H::NW * q < H::NTL ? W + H::NW * q : 0)];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[q]), "+d"(c1[q]) : "d"(av), "d"(bv));
+      }
+    }
+  }
+}
+
+template <int K, int KB>
+__global__ void __launch_bounds__(kHessThreads) inertial_hessian_mma_kernel(const int* __restrict__ run_off, const int4* __restrict__ idx,
+                                                                            const double* __restrict__ r, const double* __restrict__ Jp,
+                                                                            const double* __restrict__ wg, const double* __restrict__ wa,
+                                                                            const double* __restrict__ Jg, double loss_scale, double* sys,
+                                                                            SysLayout lay, int o_bg, int o_ba, int o_g, int splits) {
+  using H = ImuHess<K, KB>;
+  constexpr int NP = H::NP, NBG = H::NBG, NA = H::NA, NT = H::NT, NTL = H::NTL, CH = H::CH, LD = ImuHessLD<K, KB>::value;
+  static_assert(LD >= 8 * NT && (LD % 16 == 4 || LD % 16 == 12), "row pitch: conflict-free fragment loads");
+  __shared__ double sJ[6 * CH * LD];
+  const int run = blockIdx.x / splits, part = blockIdx.x - run * splits;
+  const int rlo = run_off[run], rhi = run_off[run + 1];
+  const int len = (rhi - rlo + splits - 1) / splits;
+  const int lo = rlo + part * len, hi = min(rhi, lo + len);
+  if (lo >= hi) return;
+  const int4 id0 = idx[lo];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lm = lane >> 2, lk = lane & 3;
+  // the augmented columns are zero except the entries rewritten per chunk
+  for (int e = tid; e < 6 * CH * (LD - NP); e += kHessThreads) { const int row = e / (LD - NP), col = NP + e - row * (LD - NP); sJ[row * LD + col] = 0.0; }
+  double c0[H::PER_WARP], c1[H::PER_WARP];
+#pragma unroll
+  for (int q = 0; q < H::PER_WARP; ++q) { c0[q] = 0.0; c1[q] = 0.0; }
+  for (int f0 = lo; f0 < hi; f0 += CH) {
+    const int cnt = min(CH, hi - f0);
+    __syncthreads();   // previous chunk's fragment loads are done (first pass: the zero fill is complete)
+    {   // pose block: the chunk's 6 cnt rows are one contiguous run of global memory
+      const double2* src = reinterpret_cast<const double2*>(Jp + static_cast<size_t>(f0) * 6 * NP);
+      const int total = cnt * 3 * NP;
+#pragma unroll 4
+      for (int e = tid; e < total; e += kHessThreads) {
+        const double2 v = src[e];
+        const int row = (2 * e) / NP, col = 2 * e - row * NP;
+        sJ[row * LD + col] = v.x; sJ[row * LD + col + 1] = v.y;
+      }
+    }
+    for (int e = tid; e < cnt * KB * 3; e += kHessThreads) {   // bias entries: factor ff, knot m, component c
+      const int ff = e / (KB * 3), rem = e - ff * KB * 3, m = rem / 3, c = rem - 3 * m;
+      sJ[(6 * ff + c) * LD + NP + 3 * m + c] = wg[static_cast<size_t>(f0 + ff) * KB + m];
+      sJ[(6 * ff + 3 + c) * LD + NP + NBG + 3 * m + c] = wa[static_cast<size_t>(f0 + ff) * KB + m];
+    }
+    for (int e = tid; e < cnt * 12; e += kHessThreads) {       // gravity: Jg[ff][row][gm]
+      const int ff = e / 12, rem = e - 12 * ff, row = rem >> 1, gm = rem & 1;
+      sJ[(6 * ff + row) * LD + NP + 2 * NBG + gm] = Jg[static_cast<size_t>(f0) * 12 + e];
+    }
+    for (int e = tid; e < cnt * 6; e += kHessThreads) sJ[e * LD + NP + 2 * NBG + 2] = r[static_cast<size_t>(f0) * 6 + e];
+    __syncthreads();
+    const int krows = 6 * cnt;
+    if (warp == 0) imu_hess_steps<K, KB, 0>(c0, c1, sJ, krows, lm, lk);
+    else if (warp == 1) imu_hess_steps<K, KB, 1>(c0, c1, sJ, krows, lm, lk);
+    else if (warp == 2) imu_hess_steps<K, KB, 2>(c0, c1, sJ, krows, lm, lk);
+    else imu_hess_steps<K, KB, 3>(c0, c1, sJ, krows, lm, lk);
+  }
+  // ---- flush: entry (a, b), a >= b, of the augmented product (loss scaling applied once here) ----
+  double* gv = sys + lay.og;
+  const int cp = 6 * id0.x, cg = o_bg + 3 * id0.y, ca = o_ba + 3 * id0.z;
+  const double ls = loss_scale;
+  auto dof = [&](int a) -> int {   // augmented column -> reduced-system dof
+    if (a < NP) return cp + a;
+    if (a < NP + NBG) return cg + (a - NP);
+    if (a < NP + 2 * NBG) return ca + (a - NP - NBG);
+    return o_g + (a - NP - 2 * NBG);
+  };
+  auto flush = [&](int a, int b, double v) {
+    if (a >= NA || b > a) return;
+    if (a == NA - 1) {                         // last row: J^T r
+      if (b < NA - 1) atomicAdd(&gv[dof(b)], ls * v);
+      return;
+    }
+    if (a >= NP && a < NP + 2 * NBG && b >= NP) {   // bias x bias: only equal components of the same sensor
+      if ((a >= NP + NBG) != (b >= NP + NBG)) return;
+      if ((a - NP) % 3 != (b - NP) % 3) return;
+    }
+    const int da = dof(a), db = dof(b);
+    atomicAdd(&sys[sys_index(lay, da, db)], ls * v);
+    if (a == b) atomicAdd(&sys[lay.oD + da], ls * v);   // diag(J^T J), kept apart from S
+  };
+#pragma unroll
+  for (int q = 0; q < H::PER_WARP; ++q) {
+    const int tile = warp + H::NW * q;
+    if (tile < NTL) {
+      const int ti = tile_row(tile), tj = tile_col(tile);
+      const int a = 8 * ti + lm, b = 8 * tj + 2 * lk;
+      flush(a, b, c0[q]);
+      flush(a, b + 1, c1[q]);
+    }
+  }
+}
+
 // J^T J / J^T r of the manifold (pose) factors: one warp per factor, lower triangle of its 6K x 6K block.
 constexpr int kManWarps = 4;
 template <int K>
