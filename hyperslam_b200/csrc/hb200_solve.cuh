@@ -630,6 +630,7 @@ __global__ void __launch_bounds__(kSchurGThreads) schur_group_kernel(const int* 
     for (int e = lane; e < rows * 3; e += 32) W[e] = 0.0;
     __syncwarp();
     double vg = 0.0;
+    const int va = lane < 9 ? lane / 3 : lane - 9, vb = lane % 3;   // this lane's entry of V (lanes 0..8) or of g (9..11)
     // four observations per round: all their loads are issued before anything is accumulated (the loop is a chain of
     // dependent L2 round trips otherwise: lm_obs -> idx / w / Jl / Jp)
     for (int o0 = o_lo; o0 < o_hi; o0 += 4) {
@@ -672,8 +673,14 @@ __global__ void __launch_bounds__(kSchurGThreads) schur_group_kernel(const int* 
             wr[2] += j0 * jl[2] + j1 * jl[5];
           }
         }
-        if (lane < 9) { const int a = lane / 3, b = lane % 3; vg += wgt * (jl[a] * jl[b] + jl[3 + a] * jl[3 + b]); }
-        else if (lane < 12) { const int a = lane - 9; vg += wgt * (jl[a] * rq[u][0] + jl[3 + a] * rq[u][1]); }
+        // lanes 0..8: V[a][b]; lanes 9..11: g[a].  The row picks are SELECT chains on purpose: `jl[a]` with a lane-dependent
+        // index put the whole jlq array into local memory (ncu: 250 M local sectors, a third of the kernel's stall samples)
+        if (lane < 12) {
+          const double ja0 = va == 0 ? jl[0] : (va == 1 ? jl[1] : jl[2]), ja1 = va == 0 ? jl[3] : (va == 1 ? jl[4] : jl[5]);
+          const double x0 = lane < 9 ? (vb == 0 ? jl[0] : (vb == 1 ? jl[1] : jl[2])) : rq[u][0];
+          const double x1 = lane < 9 ? (vb == 0 ? jl[3] : (vb == 1 ? jl[4] : jl[5])) : rq[u][1];
+          vg += wgt * (ja0 * x0 + ja1 * x1);
+        }
         __syncwarp();   // the next observation may touch the same rows of W
       }
     }
