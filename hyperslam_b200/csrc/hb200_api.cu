@@ -199,7 +199,7 @@ struct hb200_ctx {
   int n_lm_groups = 0, schur_rt = 0;
   bool schur_groups = false;
   int nseg = 0, nruns = 0, max_rows = 6;
-  int pix_splits = 1, imu_splits = 1;
+  int pix_splits = 1, imu_splits = 1, imu_splits_mma = 1;
   int beta = 3, min_beta = 0;   // min_beta: lower bound agreed across ranks (the packed layout must be identical everywhere)
   bool band_solver = true, band_smem = true, force_dense = false;
   DevBuf<double> band_ws;
@@ -445,6 +445,9 @@ int ensure_system(hb200_ctx* c) {
   {
     static const int min_chunk = getenv("HB200_IMU_MIN_CHUNK") ? std::max(1, atoi(getenv("HB200_IMU_MIN_CHUNK"))) : 8;   // factors per CTA at least
     c->imu_splits = std::max(1, std::min((2 * c->num_sms + std::max(c->nruns, 1) - 1) / std::max(c->nruns, 1), std::max(1, c->Ni / (min_chunk * std::max(c->nruns, 1)))));
+    // tensor-core kernel (large windows): ~6 CTAs per SM, at least two 8-factor chunks per CTA
+    static const int per_sm = getenv("HB200_IMU_CTAS_PER_SM") ? std::max(1, atoi(getenv("HB200_IMU_CTAS_PER_SM"))) : 6;
+    c->imu_splits_mma = std::max(1, std::min((per_sm * c->num_sms + std::max(c->nruns, 1) - 1) / std::max(c->nruns, 1), std::max(1, c->Ni / (16 * std::max(c->nruns, 1)))));
   }
   return 0;
 }
@@ -589,12 +592,15 @@ int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
   }
   { const int rf = fork_side(c); if (rf) return rf; }   // (no-op when already forked or while profiling)
   if (c->Ni) {
-    // the augmented product on the FP64 tensor cores when a CTA has at least two full chunks of factors to walk (1 M-factor
-    // window: 0.295 -> 0.178 ms); the scalar block-by-block kernel for short runs (cfg1, ~9 factors per CTA: 16.4 vs 18.3 us).
-    // HB200_IMU_HESS=0 / 1 forces the scalar / tensor-core kernel (A/B switch)
+    // large windows (>= 16 384 inertial factors): the augmented product on the FP64 tensor cores, ~6 CTAs per SM of 8-factor
+    // chunks (1 M-factor window: 0.295 -> 0.16 ms); small windows: the scalar block-by-block kernel on short runs (cfg1, ~9
+    // factors per CTA: 16.4 vs 18.3 us).  HB200_IMU_HESS=0 / 1 forces the scalar / tensor-core kernel (A/B switch)
     static const int hess_env = getenv("HB200_IMU_HESS") != nullptr ? atoi(getenv("HB200_IMU_HESS")) : -1;
-    const int grid = c->nruns * c->imu_splits;
-    const bool scalar_hess = hess_env >= 0 ? hess_env == 0 : c->Ni < 32 * static_cast<size_t>(grid);
+    const bool scalar_hess = hess_env >= 0 ? hess_env == 0 : c->Ni < 16384;
+    // (order 6 keeps the configuration it was measured with: 12-factor chunks, ~2 CTAs per SM -- order-6 window 0.045 ms; with
+    // 8-factor chunks and ~6 CTAs per SM 0.053 ms)
+    const int splits = (scalar_hess || c->k != 4) ? c->imu_splits : c->imu_splits_mma;
+    const int grid = c->nruns * splits;
     if (scalar_hess) {
       if (c->k == 4)
         inertial_hessian_kernel<4, 4><<<grid, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
@@ -603,12 +609,12 @@ int enqueue_build(hb200_ctx* c, bool pixel_fused = false) {
         inertial_hessian_kernel<6, 4><<<grid, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
                                                                           c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
     } else {
-      if (c->k == 4)
-        inertial_hessian_mma_kernel<4, 4><<<grid, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                              c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
-      else
-        inertial_hessian_mma_kernel<6, 4><<<grid, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p,
-                                                                              c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), c->imu_splits);
+      static const bool small_chunks = !(getenv("HB200_IMU_CH") != nullptr && atoi(getenv("HB200_IMU_CH")) != 8);   // 8-factor chunks (HB200_IMU_CH=16: 16 / 12)
+#define HB_IMU_MMA(KK, CHH) inertial_hessian_mma_kernel<KK, 4, CHH><<<grid, kHessThreads, 0, side(c)>>>(c->run_off.p, c->i_idx.p, c->i_r.p, c->i_Jp.p, c->i_wg.p, c->i_wa.p, \
+                                                    c->i_Jg.p, c->imu_scale, c->assembly(), c->lay, c->o_bg(), c->o_ba(), c->o_g(), splits)
+      if (c->k == 4) { if (small_chunks) HB_IMU_MMA(4, 8); else HB_IMU_MMA(4, 16); }
+      else HB_IMU_MMA(6, 12);
+#undef HB_IMU_MMA
     }
     HB_LAUNCH(c, "inertial_hessian_kernel");
   }

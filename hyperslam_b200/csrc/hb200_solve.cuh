@@ -311,7 +311,6 @@ template <int K, int KB>
 struct ImuHess {
   static constexpr int NP = 6 * K, NBG = 3 * KB, NA = NP + 2 * NBG + 3, NT = (NA + 7) / 8, NTL = NT * (NT + 1) / 2;
   static constexpr int NW = kHessThreads / 32, PER_WARP = (NTL + NW - 1) / NW;
-  static constexpr int CH = (K == 4) ? 16 : 12;                   // factors per chunk (static shared memory <= 48 KB)
 };
 // row pitch of the staged rows: >= 8 NT and = 4 or 12 (mod 16) doubles (conflict-free fragment loads): K = 4: 60, K = 6: 68
 template <int K, int KB> struct ImuHessLD { static constexpr int value = 8 * ImuHess<K, KB>::NT + 4; };
@@ -337,14 +336,15 @@ HB_DI void imu_hess_steps(double (&c0)[ImuHess<K, KB>::PER_WARP], double (&c1)[I
   }
 }
 
-template <int K, int KB>
+// CH: factors per chunk (static shared memory: 6 CH rows of pitch 60 / 68 doubles, <= 48 KB -> 16 / 12 at most)
+template <int K, int KB, int CH>
 __global__ void __launch_bounds__(kHessThreads) inertial_hessian_mma_kernel(const int* __restrict__ run_off, const int4* __restrict__ idx,
                                                                             const double* __restrict__ r, const double* __restrict__ Jp,
                                                                             const double* __restrict__ wg, const double* __restrict__ wa,
                                                                             const double* __restrict__ Jg, double loss_scale, double* sys,
                                                                             SysLayout lay, int o_bg, int o_ba, int o_g, int splits) {
   using H = ImuHess<K, KB>;
-  constexpr int NP = H::NP, NBG = H::NBG, NA = H::NA, NT = H::NT, NTL = H::NTL, CH = H::CH, LD = ImuHessLD<K, KB>::value;
+  constexpr int NP = H::NP, NBG = H::NBG, NA = H::NA, NT = H::NT, NTL = H::NTL, LD = ImuHessLD<K, KB>::value;
   static_assert(LD >= 8 * NT && (LD % 16 == 4 || LD % 16 == 12), "row pitch: conflict-free fragment loads");
   __shared__ double sJ[6 * CH * LD];
   const int run = blockIdx.x / splits, part = blockIdx.x - run * splits;
