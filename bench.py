@@ -487,7 +487,8 @@ def main():
                     kernel_ms_source="hb200_profile_iteration: the graph's launch sequence run with a CUDA event after every launch (measured live)",
                     whole_step=dict(algorithmic_bytes=ab["factor_eval_kernel"], ms=ms_per_step, achieved=ab["factor_eval_kernel"] / (ms_per_step * 1e-3) / 1e9,
                                     frac=ab["factor_eval_kernel"] / (ms_per_step * 1e-3) / 1e9 / peak),
-                    note="cfg1 moves 7.8 MB per sweep (1.2 us at peak): latency-bound by construction (SURVEY.md 8d); large_windows holds the bandwidth-relevant fractions of the same in-iteration kernels")
+                    note="cfg1 moves 7.8 MB per sweep (1.2 us at peak): latency-bound by construction (SURVEY.md 8d); large_windows holds the bandwidth-relevant fractions of the same in-iteration kernels",
+                    traffic_note="dram__bytes_read + write of one launch from the committed ncu capture (profiles/traffic.json): far below the algorithmic bytes at cfg1 because the 7 MB of residuals / Jacobians the launch writes stay in the 126 MB L2 until the J^T J / Schur kernels have consumed them; on the 1M-factor window the same kernels write through (profiles/r02_ncu_full.md)")
     try:
         roofline["fp64_peak_tflops_measured"] = ctx.measure_fp64_peak()
     except Exception as e:  # noqa: BLE001
